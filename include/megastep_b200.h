@@ -1,0 +1,138 @@
+/* megastep_b200.h — C ABI of the B200-native simulation core (libmegastep_b200.so).
+ *
+ * This is the drop-in boundary for the reference's per-step hot path. The reference exposes that path as a
+ * pybind11/ATen extension (`megastepcuda`, megastep/src/wrappers.cpp:30-172); the entry points below are what a
+ * binding for it binds, with every at::Tensor flattened to a raw DEVICE pointer plus sizes, and the reference's
+ * process-global `initialize()` constants (megastep/src/kernels.cu:12-27) turned into an explicit per-call params
+ * struct. No torch types, no globals, no allocation: the caller owns every buffer; kernels are enqueued on the
+ * caller's stream and return without synchronising (as the reference: kernels.cu:30-32, no device sync anywhere).
+ *
+ * All functions return 0 on success, non-zero on failure (msb_last_error() describes it). Pointer arguments are
+ * device pointers unless marked [host]. All float data is fp32; all index data int32 unless stated (texel
+ * offsets are int64 so scenes beyond 2^31 texels work, which the reference's 32-bit accessors —
+ * megastep/src/common.h:30,43 — cannot address).
+ *
+ * INTEGRATION.md shows the binding a reference maintainer would add on top of this header.
+ */
+#ifndef MEGASTEP_B200_H
+#define MEGASTEP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSB_ABI_VERSION 1
+
+/* Replaces initialize(agent_radius, res, fov, fps) — megastep/src/wrappers.cpp:53, kernels.cu:18-27. */
+typedef struct msb_params {
+    int32_t res;            /* R: rays (pixels) per agent; any R >= 1 (the reference caps at 1024, core.py:61-64) */
+    float agent_radius;     /* collision radius and near plane; megastep/core.py:14 */
+    float half_screen;      /* tanf(pi/180*fov/2.) — filled by msb_params_init exactly as kernels.cu:22 does */
+    float fps;              /* steps per second */
+    float fov;              /* degrees, kept for reference */
+    int32_t reserved[3];
+} msb_params;
+
+/* The Scenery struct of megastep/src/common.h:185-214, as raw ragged arrays.
+ *   lines   : ragged per env  — vals (sum L, 2, 2) = one float4 {ax, ay, bx, by} per segment; the first
+ *             n_agents*n_model lines of every env are the agents' model lines (render() rewrites them).
+ *   lights  : ragged per env  — vals (sum I, 3) = {x, y, intensity}
+ *   textures: ragged per LINE — vals (sum T, 3) linear RGB; widths (sum L) texels per line
+ *   baked   : (sum T) baked light per texel, same raggedness as textures
+ *   model   : (n_model, 2, 2) the agent outline in agent-local coordinates
+ */
+typedef struct msb_scenery {
+    int32_t n_envs;             /* N */
+    int32_t n_agents;           /* A: agents per env */
+    int32_t n_model;            /* F: lines in the agent model */
+    int32_t max_lines;          /* max over envs of line_widths (shared-memory sizing) */
+    int32_t max_lights;         /* max over envs of light_widths */
+    int32_t reserved;
+    float* lines;               /* (sum L, 4) — render()/step() write the agents' lines in place */
+    const int32_t* line_widths; /* (N) */
+    const int32_t* line_starts; /* (N) exclusive prefix sum of line_widths */
+    const float* lights;        /* (sum I, 3) */
+    const int32_t* light_widths;/* (N) */
+    const int32_t* light_starts;/* (N) */
+    const float* textures;      /* (sum T, 3) */
+    const int32_t* tex_widths;  /* (sum L) */
+    const int64_t* tex_starts;  /* (sum L) exclusive prefix sum of tex_widths, 64-bit */
+    float* baked;               /* (sum T) — written by msb_bake, read by msb_render */
+    const float* model;         /* (F, 4) */
+    int64_t n_lines;            /* sum L */
+    int64_t n_texels;           /* sum T */
+} msb_scenery;
+
+/* The Agents struct of megastep/src/common.h:162-177. Updated in place by msb_physics. */
+typedef struct msb_agents {
+    float* angles;       /* (N, A)    degrees in [-180, 180) */
+    float* positions;    /* (N, A, 2) metres */
+    float* angvelocity;  /* (N, A)    degrees / s */
+    float* velocity;     /* (N, A, 2) metres / s */
+} msb_agents;
+
+/* The Render struct of megastep/src/common.h:216-222. Any pointer may be NULL to skip that output. */
+typedef struct msb_render_out {
+    int32_t* indices;    /* (N, A, R)   line index of the nearest hit, -1 for none */
+    float* locations;    /* (N, A, R)   position along the hit line in [0, 1], NaN for none */
+    float* dots;         /* (N, A, R)   cosine between ray and line, NaN for none */
+    float* distances;    /* (N, A, R)   metres to the hit, +inf for none */
+    float* screen;       /* (N, A, R, 3) linear RGB */
+} msb_render_out;
+
+/* Optional fused observation heads (reference: megastep/modules.py:170-184 Depth, :211-224 RGB, :263-270 IMU),
+ * produced by msb_render / msb_step in the same pass when the pointers are non-NULL. */
+typedef struct msb_obs_out {
+    float* rgb;          /* (N, A, 3, R/subsample)  mean over `subsample` adjacent pixels */
+    float* depth;        /* (N, A, R/subsample)     1 - clamp((distance - agent_radius)/max_depth, 0, 1), mean-pooled */
+    float* imu;          /* (N, A, 3)               {angvelocity/ang_scale, local-frame velocity/speed_scale} */
+    int32_t subsample;   /* >= 1, divides R */
+    float max_depth;     /* modules.py:147 default 10 */
+    float speed_scale;   /* modules.py:242 default 10 */
+    float ang_scale;     /* modules.py:242 default 360 */
+} msb_obs_out;
+
+/* MomentumMovement (megastep/modules.py:68-118), fused into msb_step ahead of the physics. */
+typedef struct msb_movement {
+    const int32_t* actions; /* (N, A) in [0, 7): noop, forward, back, strafe right(+x local y?) … see modules.py:95-96 */
+    float accel;            /* m/s^2, default 5 */
+    float ang_accel;        /* deg/s^2, default 180 */
+    float decay;            /* default 0.125 */
+} msb_movement;
+
+int msb_abi_version(void);
+const char* msb_last_error(void);
+
+/* [host] Fills *p. half_screen = tanf(CUDART_PI_F/180.f*fov/2.) evaluated as the reference does. fov must be < 180. */
+int msb_params_init(msb_params* p, float agent_radius, int32_t res, float fov, float fps);
+
+/* bake(scenery) — megastep/src/wrappers.cpp:61, kernels.cu:270-293. Writes scenery->baked for every texel. */
+int msb_bake(const msb_params* p, const msb_scenery* s, void* cuda_stream);
+
+/* physics(scenery, agents) -> Physics{progress} — wrappers.cpp:69, kernels.cu:179-230.
+ * progress: (N, A) out. Agents are advanced in place (positions, angles) and stopped where progress < 1. */
+int msb_physics(const msb_params* p, const msb_scenery* s, const msb_agents* a, float* progress, void* cuda_stream);
+
+/* render(scenery, agents) -> Render — wrappers.cpp:82, kernels.cu:297-475. Also rewrites the agents' model
+ * lines inside s->lines (the reference's draw_kernel side effect). obs may be NULL. */
+int msb_render(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_render_out* out,
+               const msb_obs_out* obs, void* cuda_stream);
+
+/* One whole environment tick in a single launch: MomentumMovement -> physics -> render -> observation heads.
+ * mv may be NULL (velocities are then taken as already set, i.e. plain physics+render). out/obs as msb_render. */
+int msb_step(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_movement* mv,
+             float* progress, const msb_render_out* out, const msb_obs_out* obs, void* cuda_stream);
+
+/* Tuning/diagnostics: selects kernel variants (0 = default). Affects speed only, never results. */
+int msb_set_option(const char* name, int64_t value);
+int64_t msb_get_option(const char* name);
+
+/* Number of kernels launched by this library since load (bench.py's `gpu_launches`). */
+int64_t msb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEGASTEP_B200_H */

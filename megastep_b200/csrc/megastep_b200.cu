@@ -1,0 +1,789 @@
+// megastep_b200.cu — sm_100a kernels + C ABI (include/megastep_b200.h) for megastep's per-step hot path.
+//
+// Replaces, from scratch, the reference's megastep/src/kernels.cu:
+//   physics()  = collision_kernel (:179-210) + ~15 ATen elementwise launches (:223-227)      -> ONE kernel
+//   render()   = draw_kernel (:297-318) + raycast_kernel (:326-383) + shader_kernel (:407-450) -> ONE kernel
+//   msb_step() = MomentumMovement (modules.py:106-118) + physics + render + RGB/Depth/IMU heads -> ONE kernel
+//   bake()     = baking_kernel (:270-284)
+//
+// Layout / mapping:
+//   * one CTA per environment; the env's static segments are staged once from the ragged-packed HBM array into
+//     shared memory with a single 1-D bulk (TMA) copy + mbarrier, and shared by all of the env's agents;
+//   * one warp per agent (x ray block): lanes are SEGMENTS while binning (each lane projects one segment onto the
+//     agent's 1-D screen and gets the conservative interval of rays it can touch), then lanes are RAYS while
+//     testing; a __ballot over "segment overlaps this 32-ray chunk" yields the candidates in ascending line order,
+//     which preserves the reference's order-dependent nearest-hit rule exactly while skipping ~90% of the tests;
+//   * per-(agent, segment) terms of the intersection are hoisted out of the per-ray work; the ray/line cosine and
+//     its sqrt are computed for the winning line only (the reference computes them for every line);
+//   * rays that hit another agent need the dynamic light at the hit point (I lights x W occluders); the warp does
+//     that cooperatively (lanes = occluders, early exit on the first occluder) instead of one lane doing I*W tests;
+//   * physics: the CTA's threads stride the env's segments for each agent, warp-shuffle min, fused integration.
+//
+// No tensor cores: nothing on this path is a dense contraction.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../include/megastep_b200.h"
+#include "msb_math.cuh"
+
+using namespace msb;
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernel arguments
+// ---------------------------------------------------------------------------------------------------------------
+struct KArgs {
+    msb_params p;
+    msb_scenery s;
+    msb_agents a;
+    float* progress;
+    msb_render_out out;
+    msb_obs_out obs;
+    msb_movement mv;
+    int32_t has_obs;
+    int32_t has_mv;
+    int32_t ray_blocks;     // RB: warps per agent in the render stage
+    int32_t seg_cap;        // float4 slots reserved for segments in shared memory (>= max_lines)
+    float inv_fps;          // IEEE 1/fps (ATen's tensor/scalar == tensor*(1/scalar), kernels.cu:224,226)
+    float mv_keep, mv_dv, mv_dw;   // 1-decay, accel/fps, ang_accel/fps evaluated in double like the Python does
+    float inv_max_depth, inv_speed, inv_ang, inv_sub;   // reciprocals ATen would multiply by
+    unsigned long long* stats;  // optional diagnostics counters (may be null)
+};
+
+enum { MODE_PHYSICS = 1, MODE_RENDER = 2, MODE_STEP = 3 };
+enum { ST_ANG = 0, ST_PX = 1, ST_PY = 2, ST_AV = 3, ST_VX = 4, ST_VY = 5, ST_STRIDE = 8 };
+enum { STAT_TESTS = 0, STAT_GROUPS = 1, STAT_DYN_RAYS = 2, STAT_DYN_ITERS = 3, STAT_COLL = 4 };
+
+struct Smem {
+    float4* seg;        // [seg_cap] this env's segments {ax, ay, bx, by}
+    float4* scratch;    // [nwarps][64] per-warp per-segment terms
+    float* st_in;       // [A][8] start-of-step agent state
+    float* st_out;      // [A][8] post-physics agent state
+    int* xmin;          // [A] progress, as ordered int bits
+    uint64_t* bar;
+};
+
+__device__ __forceinline__ Smem carve(unsigned char* base, int seg_cap, int nwarps, int A) {
+    Smem m;
+    m.seg = reinterpret_cast<float4*>(base);
+    m.scratch = m.seg + seg_cap;
+    m.st_in = reinterpret_cast<float*>(m.scratch + nwarps * 64);
+    m.st_out = m.st_in + A * ST_STRIDE;
+    m.xmin = reinterpret_cast<int*>(m.st_out + A * ST_STRIDE);
+    uintptr_t p = reinterpret_cast<uintptr_t>(m.xmin + A);
+    p = (p + 15) & ~uintptr_t(15);
+    m.bar = reinterpret_cast<uint64_t*>(p);
+    return m;
+}
+
+static size_t smem_bytes(int seg_cap, int nwarps, int A) {
+    size_t b = (size_t)seg_cap * 16 + (size_t)nwarps * 64 * 16 + (size_t)A * ST_STRIDE * 4 * 2 + (size_t)A * 4;
+    b = (b + 15) & ~size_t(15);
+    return b + 16;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// physics
+// ---------------------------------------------------------------------------------------------------------------
+
+// collision(p0, v0, p1, v1) — kernels.cu:119-133 (+ project :92-106), op order per docs/REFERENCE_ARITHMETIC.md
+__device__ __forceinline__ float collide_agents(float p0x, float p0y, float m0x, float m0y, float p1x, float p1y,
+                                                float m1x, float m1y, float rF, float r2) {
+    const float Ux = ffma(m0x, rF, -fmul(m1x, rF));
+    const float Uy = ffma(m0y, rF, -fmul(m1y, rF));
+    const float ulen = sqrt_(ffma(Ux, Ux, fmul(Uy, Uy)));
+    const float u = fadd(ulen, 1e-6f);
+    const float PQx = fsub(p1x, p0x), PQy = fsub(p1y, p0y);
+    const float s = fmul(dot2(Ux, PQx, Uy, PQy), rcp(fmul(u, u)));
+    const float d = fmul(fabsf(cross2(Uy, PQx, Ux, PQy)), rcp(u));
+    float x = 1.f;
+    if ((s > 0.f) && (d < r2)) {
+        const float back = sqrt_(ffma(-d, d, fmul(r2, r2)));
+        x = fminf(x, sens(ffma(-back, rcp(ulen), s)));
+    }
+    return x;
+}
+
+// collision(p, v, l) — kernels.cu:135-171. v is already velocity/fps; vlen = |v|.
+__device__ __forceinline__ float collide_line(float px, float py, float vx, float vy, float vlen, float u, float uu,
+                                              float4 l, float r1, float r1sq) {
+    const float Vx = fsub(l.z, l.x), Vy = fsub(l.w, l.y);
+    float x = 1.f;
+
+    // passing through l (:143-146)
+    {
+        const float PQx = fsub(l.x, px), PQy = fsub(l.y, py);
+        const Hit mid = intersect_pre(vx, vy, Vx, Vy, PQx, PQy, cross2(Vy, PQx, Vx, PQy));
+        if ((0.f < mid.s) && (mid.s < 1.f) && (0.f < mid.t) && (mid.t < 1.f)) {
+            const float cr = cross2(Vy, fsub(px, l.x), Vx, fsub(py, l.y));
+            const float uV = fadd(sqrt_(ffma(Vx, Vx, fmul(Vy, Vy))), 1e-6f);
+            const float d = fmul(fabsf(cr), rcp(uV));
+            x = fminf(x, sens(fmul(ffma(rcp(d), -r1, 1.f), mid.s)));
+        }
+    }
+    // passing within r of l.a, then l.b (:149-160)
+    const float ruu = rcp(uu), ru = rcp(u);
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const float ex = e ? l.z : l.x, ey = e ? l.w : l.y;
+        const float PQx = fsub(ex, px), PQy = fsub(ey, py);
+        const float s = fmul(dot2(vx, PQx, vy, PQy), ruu);
+        const float d = fmul(fabsf(cross2(vy, PQx, vx, PQy)), ru);
+        if ((0.f < s) && (d < r1)) {
+            const float back = sqrt_(ffma(-d, d, r1sq));
+            x = fminf(x, sens(ffma(-back, rcp(vlen), s)));
+        }
+    }
+    // end point within r of the interior of l (:163-168)
+    {
+        const float PQx = fsub(fadd(px, vx), l.x), PQy = fsub(fadd(py, vy), l.y);
+        const float uV = fadd(sqrt_(ffma(Vx, Vx, fmul(Vy, Vy))), 1e-6f);
+        const float s = fmul(dot2(Vx, PQx, Vy, PQy), rcp(fmul(uV, uV)));
+        const float rV = rcp(uV);
+        const float dq = fmul(fabsf(cross2(Vy, PQx, Vx, PQy)), rV);
+        if ((0.f < s) && (s < 1.f) && (dq < r1)) {
+            const float cr = fabsf(cross2(Vy, fsub(px, l.x), Vx, fsub(py, l.y)));
+            x = fminf(x, sens(fmul(ffma(cr, rV, -r1), rcp(ffma(cr, rV, -dq)))));
+        }
+    }
+    return x;
+}
+
+// One env's physics tick. st_in holds the start-of-step state of all A agents; results go to global memory and to
+// st_out (for a following render stage).
+__device__ __forceinline__ void physics_stage(const KArgs& k, const Smem& m, int n, int L) {
+    const int A = k.s.n_agents, AF = A * k.s.n_model;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const float rF = rcp(k.p.fps);
+    const float r2 = fmul(k.p.agent_radius, 2.0020000934600830078f);
+    const float r1 = fmul(k.p.agent_radius, 1.0010000467300415039f);
+    const float r1sq = fmul(r1, r1);
+
+    for (int a = 0; a < A; a++) {
+        const float* me = m.st_in + a * ST_STRIDE;
+        const float px = me[ST_PX], py = me[ST_PY], mx = me[ST_VX], my = me[ST_VY];
+        float x = 1.f;
+        // other agents (:193-200): start-of-step state, no sequential resolution
+        for (int d1 = tid; d1 < A; d1 += blockDim.x) {
+            if (d1 != a) {
+                const float* o = m.st_in + d1 * ST_STRIDE;
+                x = fminf(x, collide_agents(px, py, mx, my, o[ST_PX], o[ST_PY], o[ST_VX], o[ST_VY], rF, r2));
+            }
+        }
+        // static lines (:203-205); the agents' own model lines [0, AF) are skipped
+        const float vx = fmul(mx, rF), vy = fmul(my, rF);
+        const float vlen = sqrt_(ffma(vx, vx, fmul(vy, vy)));
+        const float u = fadd(vlen, 1e-6f), uu = fmul(u, u);
+        for (int l = AF + tid; l < L; l += blockDim.x) {
+            x = fminf(x, collide_line(px, py, vx, vy, vlen, u, uu, m.seg[l], r1, r1sq));
+        }
+        x = warp_min(x);
+        if (lane == 0) atomicMin(m.xmin + a, __float_as_int(x));   // x in [0, 1]: int order == float order
+    }
+    __syncthreads();
+
+    // integration (kernels.cu:223-227), one thread per agent, plain in-place stores (no storage swap)
+    for (int a = tid; a < A; a += blockDim.x) {
+        const float* me = m.st_in + a * ST_STRIDE;
+        float* o = m.st_out + a * ST_STRIDE;
+        const float x = __int_as_float(m.xmin[a]);
+        const int64_t i = (int64_t)n * A + a;
+        const float npx = __fadd_rn(me[ST_PX], __fmul_rn(__fmul_rn(x, me[ST_VX]), k.inv_fps));
+        const float npy = __fadd_rn(me[ST_PY], __fmul_rn(__fmul_rn(x, me[ST_VY]), k.inv_fps));
+        float ang = __fadd_rn(me[ST_ANG], __fmul_rn(__fmul_rn(x, me[ST_AV]), k.inv_fps));
+        ang = __fsub_rn(remainder_(__fadd_rn(remainder_(ang, 360.f), 180.f), 360.f), 180.f);
+        const bool hit = x < 1.f;
+        const float nvx = hit ? 0.f : me[ST_VX], nvy = hit ? 0.f : me[ST_VY], nav = hit ? 0.f : me[ST_AV];
+        k.a.angles[i] = ang;
+        reinterpret_cast<float2*>(k.a.positions)[i] = make_float2(npx, npy);
+        k.a.angvelocity[i] = nav;
+        reinterpret_cast<float2*>(k.a.velocity)[i] = make_float2(nvx, nvy);
+        if (k.progress) k.progress[i] = x;
+        o[ST_ANG] = ang; o[ST_PX] = npx; o[ST_PY] = npy; o[ST_AV] = nav; o[ST_VX] = nvx; o[ST_VY] = nvy;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// render
+// ---------------------------------------------------------------------------------------------------------------
+
+// light_intensity() (kernels.cu:238-268) at point C, evaluated by a whole warp: lanes stride the static lines,
+// the first occluder found ends that light. Returns the same value in every lane.
+__device__ __forceinline__ float light_intensity_warp(const KArgs& k, const Smem& m, int n, int L, int AF, float Cx,
+                                                      float Cy, int lane, unsigned& iters) {
+    const int I = k.s.light_widths[n];
+    const float* lt = k.s.lights + 3 * (int64_t)k.s.light_starts[n];
+    float acc = 0.1f;   // AMBIENT (kernels.cu:9)
+    for (int i = 0; i < I; i++) {
+        const float Ix = __ldg(lt + 3 * i), Iy = __ldg(lt + 3 * i + 1), Ii = __ldg(lt + 3 * i + 2);
+        const float Ux = fsub(Cx, Ix), Uy = fsub(Cy, Iy);
+        bool occluded = false;
+        for (int base = AF; base < L; base += 32) {
+            const int l = base + lane;
+            bool ob = false;
+            if (l < L) {
+                const Hit h = intersect(Ix, Iy, Ux, Uy, m.seg[l]);
+                ob = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
+            }
+            iters++;
+            if (__any_sync(0xffffffffu, ob)) { occluded = true; break; }
+        }
+        if (!occluded) {
+            const float dx = fsub(Ix, Cx), dy = fsub(Iy, Cy);
+            acc = ffma(fadd(Ii, Ii), rcp(fmaxf(ffma(dx, dx, fmul(dy, dy)), 1.f)), acc);   // LUMINANCE = 2 (:240)
+        }
+    }
+    return fminf(acc, 1.f);
+}
+
+// light_intensity() evaluated by a single thread (bake: every lane has its own texel).
+__device__ __forceinline__ float light_intensity_thread(const float4* seg, int AF, int L, const float* lt, int I,
+                                                        float Cx, float Cy) {
+    float acc = 0.1f;
+    for (int i = 0; i < I; i++) {
+        const float Ix = __ldg(lt + 3 * i), Iy = __ldg(lt + 3 * i + 1), Ii = __ldg(lt + 3 * i + 2);
+        const float Ux = fsub(Cx, Ix), Uy = fsub(Cy, Iy);
+        bool occluded = false;
+        for (int l = AF; l < L; l++) {
+            const Hit h = intersect(Ix, Iy, Ux, Uy, seg[l]);
+            if ((h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f)) { occluded = true; break; }
+        }
+        if (!occluded) {
+            const float dx = fsub(Ix, Cx), dy = fsub(Iy, Cy);
+            acc = ffma(fadd(Ii, Ii), rcp(fmaxf(ffma(dx, dx, fmul(dy, dy)), 1.f)), acc);
+        }
+    }
+    return fminf(acc, 1.f);
+}
+
+// draw_kernel (kernels.cu:297-318): the agents' model lines, at their current poses, into shared and global memory.
+__device__ __forceinline__ void draw_stage(const KArgs& k, const Smem& m, int n, int64_t g0) {
+    const int A = k.s.n_agents, F = k.s.n_model;
+    float* seg = reinterpret_cast<float*>(m.seg);
+    for (int t = threadIdx.x; t < A * F * 2; t += blockDim.x) {
+        const int e = t & 1, mm = (t >> 1) % F, a = (t >> 1) / F;
+        const float* st = m.st_out + a * ST_STRIDE;
+        float s, c;
+        sincos_deg(st[ST_ANG], s, c);
+        const float mx = __ldg(k.s.model + 4 * mm + 2 * e), my = __ldg(k.s.model + 4 * mm + 2 * e + 1);
+        const float2 pt = make_float2(fadd(st[ST_PX], cross2(c, mx, s, my)), fadd(st[ST_PY], dot2(s, mx, c, my)));
+        reinterpret_cast<float2*>(seg)[2 * (a * F + mm) + e] = pt;
+        reinterpret_cast<float2*>(k.s.lines)[2 * (g0 + a * F + mm) + e] = pt;
+    }
+}
+
+template <int NCH, bool STATS>
+__device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int n, int64_t g0, int L, int a, int rb,
+                                             float4* __restrict__ scr, int lane) {
+    const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
+    const float* st = m.st_out + a * ST_STRIDE;
+    const float px = st[ST_PX], py = st[ST_PY];
+    float sn, cs;
+    sincos_deg(st[ST_ANG], sn, cs);
+
+    // ---- rays (kernels.cu:341-344, ray_y :234-236). Lane = ray within each of this warp's NCH 32-ray chunks.
+    const float Rf = (float)R;
+    const float rcpR = rcp(Rf);
+    const int r0 = rb * (32 * NCH);
+    float rux[NCH], ruy[NCH], rlen[NCH], nearp[NCH], best[NCH], loc[NCH];
+    int idx[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        const int r = r0 + 32 * c + lane;
+        const float y = fmul(fmul(fadd(fsub(Rf, (float)(unsigned)(2 * r)), -1.f), k.p.half_screen), rcpR);
+        rux[c] = ffma(sn, -y, cs);
+        ruy[c] = ffma(cs, y, sn);
+        rlen[c] = sqrt_(ffma(rux[c], rux[c], fmul(ruy[c], ruy[c])));
+        nearp[c] = fmul(rcp(rlen[c]), k.p.agent_radius);
+        best[c] = CUDART_INF_F;
+        loc[c] = __int_as_float(0x7fffffff);
+        idx[c] = -1;
+    }
+
+    // ---- conservative screen-space binning constants (never affect results, only which exact tests are skipped)
+    const float hs = k.p.half_screen;
+    const float kappa = Rf / (2.f * hs);                 // rays per unit of screen coordinate
+    const float rmid = 0.5f * (Rf - 1.f);
+    const float xclip = 0.5f * k.p.agent_radius * rsqrtf(1.f + hs * hs);   // well inside every ray's near plane
+    const float delta = 0.05f;
+    const float lo_chunk = (float)r0, hi_chunk = (float)(r0 + 32 * NCH - 1);
+    unsigned tests = 0, groups = 0;
+
+    for (int gbase = 0; gbase < L; gbase += 32) {
+        const int l = gbase + lane;
+        int rlo = 1, rhi = 0;
+        if (l < L) {
+            const float4 s4 = m.seg[l];
+            // exact per-(agent, line) terms of intersect() (kernels.cu:83-85), hoisted out of the per-ray loop
+            const float Vx = fsub(s4.z, s4.x), Vy = fsub(s4.w, s4.y);
+            const float PQx = fsub(s4.x, px), PQy = fsub(s4.y, py);
+            scr[lane] = make_float4(Vx, Vy, PQx, PQy);
+            scr[32 + lane].x = cross2(Vy, PQx, Vx, PQy);
+            // approximate camera-space endpoints: x' forward, y' left; screen coordinate = y'/x'
+            const float bxr = s4.z - px, byr = s4.w - py;
+            float xa = PQx * cs + PQy * sn, ya = PQy * cs - PQx * sn;
+            float xb = bxr * cs + byr * sn, yb = byr * cs - bxr * sn;
+            const bool behind = (xa < xclip) && (xb < xclip);
+            if (!behind) {
+                if (xa < xclip) { const float tt = (xclip - xa) / (xb - xa); ya = ya + tt * (yb - ya); xa = xclip; }
+                if (xb < xclip) { const float tt = (xclip - xb) / (xa - xb); yb = yb + tt * (ya - yb); xb = xclip; }
+                const float sa = ya / xa, sb = yb / xb;
+                const float rf_first = rmid - fmaxf(sa, sb) * kappa - delta;
+                const float rf_last = rmid - fminf(sa, sb) * kappa + delta;
+                // NaN-safe: any comparison failing leaves the full range, i.e. the exact test still runs
+                rlo = (rf_first > lo_chunk) ? ((rf_first < hi_chunk + 1.f) ? (int)ceilf(rf_first) : (int)hi_chunk + 1) : (int)lo_chunk;
+                rhi = (rf_last < hi_chunk) ? ((rf_last > lo_chunk - 1.f) ? (int)floorf(rf_last) : (int)lo_chunk - 1) : (int)hi_chunk;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const int c_lo = r0 + 32 * c, c_hi = c_lo + 31;
+            unsigned mask = __ballot_sync(0xffffffffu, (rlo <= c_hi) && (rhi >= c_lo) && (rlo <= rhi));
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float4 q = scr[j];
+                const float snum = scr[32 + j].x;
+                // raycast_kernel inner loop (kernels.cu:353-376)
+                const Hit h = intersect_pre(rux[c], ruy[c], q.x, q.y, q.z, q.w, snum);
+                const bool hit = (h.t >= 0.f) && (h.t <= 1.f);
+                const bool better = (nearp[c] < h.s) && (h.s < fadd(best[c], -1.e-4f));
+                if (hit && better) { best[c] = h.s; loc[c] = h.t; idx[c] = gbase + j; }
+                if (STATS) tests++;
+            }
+        }
+        if (STATS) groups++;
+        __syncwarp();
+    }
+
+    // ---- shade + store (shader_kernel, kernels.cu:407-450)
+    unsigned dyn_rays = 0, dyn_iters = 0;
+    const int sub_ = k.has_obs ? k.obs.subsample : 1;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        const int r = r0 + 32 * c + lane;
+        const bool live = r < R;
+        const int l0 = idx[c];
+        float dotv = __int_as_float(0x7fffffff);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        float lw = 0.f, rw = 0.f, tl0 = 0.f, tl1 = 0.f, tl2 = 0.f, tr0 = 0.f, tr1 = 0.f, tr2 = 0.f, intensity = 0.f;
+        float Cx = 0.f, Cy = 0.f;
+        const bool hitany = live && (l0 >= 0);
+        if (hitany) {
+            const float4 s4 = m.seg[l0];
+            const float Vx = fsub(s4.z, s4.x), Vy = fsub(s4.w, s4.y);
+            // ray . line cosine for the winner only (kernels.cu:362-364)
+            dotv = fmul(dot2(rux[c], Vx, ruy[c], Vy), rcp(ffma(rlen[c], sqrt_(ffma(Vx, Vx, fmul(Vy, Vy))), 1.e-6f)));
+            const int64_t g = g0 + l0;
+            const int w = __ldg(k.s.tex_widths + g);
+            const int64_t ts = __ldg(k.s.tex_starts + g);
+            // filter() (kernels.cu:394-405)
+            const float yy = fminf(fmul(loc[c], (float)(w + 1)), (float)(w - 1));
+            const int fl = __float2int_rz(fmaxf(fadd(yy, -1.f), 0.f));
+            const int fr = __float2int_rz(yy);
+            const float ld = fadd(fabsf(fsub(yy, (float)(fl + 1))), 1.e-3f);
+            const float rd = fadd(fabsf(fsub(yy, (float)(fr + 1))), 1.e-3f);
+            const float rc = rcp(fadd(rd, ld));
+            lw = fmul(rd, rc);
+            rw = fmul(ld, rc);
+            const float* tl = k.s.textures + 3 * (ts + fl);
+            const float* tr = k.s.textures + 3 * (ts + fr);
+            tl0 = __ldg(tl); tl1 = __ldg(tl + 1); tl2 = __ldg(tl + 2);
+            tr0 = __ldg(tr); tr1 = __ldg(tr + 1); tr2 = __ldg(tr + 2);
+            if (l0 >= AF) {
+                intensity = ffma(rw, __ldg(k.s.baked + ts + fr), fmul(lw, __ldg(k.s.baked + ts + fl)));   // :438
+            } else {
+                const float om = fsub(1.f, loc[c]);                                                       // :435
+                Cx = ffma(s4.x, om, fmul(loc[c], s4.z));
+                Cy = ffma(s4.y, om, fmul(loc[c], s4.w));
+            }
+        }
+        // dynamic lighting for rays that hit an agent's model (:434-436), one ray at a time, whole warp
+        unsigned dm = __ballot_sync(0xffffffffu, hitany && (l0 < AF));
+        while (dm) {
+            const int j = __ffs(dm) - 1;
+            dm &= dm - 1;
+            const float cx = __shfl_sync(0xffffffffu, Cx, j), cy = __shfl_sync(0xffffffffu, Cy, j);
+            const float v = light_intensity_warp(k, m, n, L, AF, cx, cy, lane, dyn_iters);
+            if (lane == j) intensity = v;
+            dyn_rays++;
+        }
+        if (hitany) {
+            const float kk = fmul(ffma(-dotv, dotv, 1.f), intensity);                                       // :442-445
+            s0 = fmul(kk, ffma(rw, tr0, fmul(lw, tl0)));
+            s1 = fmul(kk, ffma(rw, tr1, fmul(lw, tl1)));
+            s2 = fmul(kk, ffma(rw, tr2, fmul(lw, tl2)));
+        }
+        const float dist = fmul(rlen[c], best[c]);
+        if (live) {
+            const int64_t o = ((int64_t)n * A + a) * R + r;
+            if (k.out.indices) k.out.indices[o] = l0;
+            if (k.out.locations) k.out.locations[o] = loc[c];
+            if (k.out.dots) k.out.dots[o] = dotv;
+            if (k.out.distances) k.out.distances[o] = dist;
+            if (k.out.screen) { float* sc = k.out.screen + 3 * o; sc[0] = s0; sc[1] = s1; sc[2] = s2; }
+        }
+        // fused observation heads: Depth (modules.py:181-183) and RGB (:222-223), mean over `subsample` pixels
+        if (k.has_obs) {
+            float d = 0.f;
+            if (live) {
+                const float z = __fmul_rn(__fsub_rn(dist, k.p.agent_radius), k.inv_max_depth);
+                d = __fsub_rn(1.f, fminf(fmaxf(z, 0.f), 1.f));
+            }
+            float v0 = s0, v1 = s1, v2 = s2, v3 = d;
+            for (int o = 1; o < sub_; o <<= 1) {
+                v0 = __fadd_rn(v0, __shfl_xor_sync(0xffffffffu, v0, o));
+                v1 = __fadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+                v2 = __fadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
+                v3 = __fadd_rn(v3, __shfl_xor_sync(0xffffffffu, v3, o));
+            }
+            if (live && (lane % sub_) == 0) {
+                const int Ro = R / sub_, ro = r / sub_;
+                const float inv = k.inv_sub;
+                const int64_t ag = (int64_t)n * A + a;
+                if (k.obs.rgb) {
+                    float* q = k.obs.rgb + ag * 3 * Ro + ro;
+                    q[0] = v0 * inv; q[Ro] = v1 * inv; q[2 * Ro] = v2 * inv;
+                }
+                if (k.obs.depth) k.obs.depth[ag * Ro + ro] = v3 * inv;
+            }
+        }
+    }
+    if (STATS && k.stats && lane == 0) {
+        atomicAdd(k.stats + STAT_TESTS, (unsigned long long)tests);
+        atomicAdd(k.stats + STAT_GROUPS, (unsigned long long)groups);
+        atomicAdd(k.stats + STAT_DYN_RAYS, (unsigned long long)dyn_rays);
+        atomicAdd(k.stats + STAT_DYN_ITERS, (unsigned long long)dyn_iters);
+    }
+}
+
+// IMU head (modules.py:263-270): {angvelocity/ang_scale, to_local_frame(angles, velocity)/speed_scale}
+__device__ __forceinline__ void imu_stage(const KArgs& k, const Smem& m, int n) {
+    const int A = k.s.n_agents;
+    for (int a = threadIdx.x; a < A; a += blockDim.x) {
+        const float* st = m.st_out + a * ST_STRIDE;
+        const float ang = __fmul_rn(0.017453292519943295f, st[ST_ANG]);
+        const float c = cosf(ang), s = sinf(ang);
+        const float vx = st[ST_VX], vy = st[ST_VY];
+        float* q = k.obs.imu + 3 * ((int64_t)n * A + a);
+        q[0] = __fmul_rn(st[ST_AV], k.inv_ang);
+        q[1] = __fmul_rn(__fadd_rn(__fmul_rn(c, vx), __fmul_rn(s, vy)), k.inv_speed);
+        q[2] = __fmul_rn(__fadd_rn(__fmul_rn(-s, vx), __fmul_rn(c, vy)), k.inv_speed);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the per-env kernel: any of physics / render / both
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE, int NCH, bool STATS>
+__global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ KArgs k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = blockIdx.x;
+    const int A = k.s.n_agents, AF = A * k.s.n_model;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const Smem m = carve(smem_raw, k.seg_cap, nwarps, A);
+
+    const int L = __ldg(k.s.line_widths + n);
+    const int64_t g0 = __ldg(k.s.line_starts + n);
+    const int W = L - AF;
+
+    // stage this env's static segments: one bulk (TMA) copy, ragged-packed HBM -> shared memory
+    if (tid == 0) {
+        mbar_init(m.bar, 1);
+        if (W > 0) {
+            mbar_expect_tx(m.bar, (uint32_t)W * 16u);
+            bulk_g2s(m.seg + AF, k.s.lines + 4 * (g0 + AF), (uint32_t)W * 16u, m.bar);
+        }
+    }
+    // agent state -> shared memory (and the MomentumMovement update when fused, modules.py:106-118)
+    for (int a = tid; a < A; a += blockDim.x) {
+        const int64_t i = (int64_t)n * A + a;
+        float ang = k.a.angles[i], av = k.a.angvelocity[i];
+        float2 pos = reinterpret_cast<const float2*>(k.a.positions)[i];
+        float2 vel = reinterpret_cast<const float2*>(k.a.velocity)[i];
+        if (MODE == MODE_STEP && k.has_mv) {
+            const int act = k.mv.actions[i];
+            const float keep = k.mv_keep, dv = k.mv_dv, dw = k.mv_dw;
+            // action table of modules.py:95-96: 0 noop, 1 +y, 2 -y, 3 +x, 4 -x (agent-local), 5 +turn, 6 -turn
+            const float lx = (act == 3) ? dv : ((act == 4) ? -dv : 0.f);
+            const float ly = (act == 1) ? dv : ((act == 2) ? -dv : 0.f);
+            const float lw = (act == 5) ? dw : ((act == 6) ? -dw : 0.f);
+            const float rad = __fmul_rn(0.017453292519943295f, ang);
+            const float c = cosf(rad), s = sinf(rad);
+            av = __fadd_rn(__fmul_rn(keep, av), lw);
+            vel.x = __fadd_rn(__fmul_rn(keep, vel.x), __fsub_rn(__fmul_rn(c, lx), __fmul_rn(s, ly)));
+            vel.y = __fadd_rn(__fmul_rn(keep, vel.y), __fadd_rn(__fmul_rn(s, lx), __fmul_rn(c, ly)));
+        }
+        float* st = ((MODE & MODE_PHYSICS) ? m.st_in : m.st_out) + a * ST_STRIDE;
+        st[ST_ANG] = ang; st[ST_PX] = pos.x; st[ST_PY] = pos.y; st[ST_AV] = av; st[ST_VX] = vel.x; st[ST_VY] = vel.y;
+        m.xmin[a] = __float_as_int(1.f);
+    }
+    __syncthreads();
+    if (W > 0) mbar_wait(m.bar, 0);
+
+    if (MODE & MODE_PHYSICS) {
+        physics_stage(k, m, n, L);
+        if (MODE & MODE_RENDER) __syncthreads();
+    }
+    if (MODE & MODE_RENDER) {
+        draw_stage(k, m, n, g0);
+        __syncthreads();
+        const int RB = k.ray_blocks;
+        for (int w = warp; w < A * RB; w += nwarps) {
+            render_agent<NCH, STATS>(k, m, n, g0, L, w / RB, w % RB, m.scratch + warp * 64, lane);
+        }
+        if (k.has_obs && k.obs.imu) imu_stage(k, m, n);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bake (kernels.cu:270-293): one CTA per env, one warp per line, one lane per texel
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bake_kernel(const __grid_constant__ KArgs k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = blockIdx.x;
+    const int A = k.s.n_agents, AF = A * k.s.n_model;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const Smem m = carve(smem_raw, k.seg_cap, nwarps, A);
+    const int L = __ldg(k.s.line_widths + n);
+    const int64_t g0 = __ldg(k.s.line_starts + n);
+    if (tid == 0) {
+        mbar_init(m.bar, 1);
+        if (L > 0) {
+            mbar_expect_tx(m.bar, (uint32_t)L * 16u);
+            bulk_g2s(m.seg, k.s.lines + 4 * g0, (uint32_t)L * 16u, m.bar);
+        }
+    }
+    __syncthreads();
+    if (L > 0) mbar_wait(m.bar, 0);
+    const int I = k.s.light_widths[n];
+    const float* lt = k.s.lights + 3 * (int64_t)k.s.light_starts[n];
+    for (int l = warp; l < L; l += nwarps) {
+        const int w = __ldg(k.s.tex_widths + g0 + l);
+        const int64_t ts = __ldg(k.s.tex_starts + g0 + l);
+        const float4 s4 = m.seg[l];
+        const float rw = rcp((float)w);
+        for (int t = lane; t < w; t += 32) {
+            const float loc = fmul(fadd((float)(unsigned)t, 0.5f), rw);                     // :278
+            const float om = fsub(1.f, loc);
+            const float Cx = ffma(s4.x, om, fmul(loc, s4.z)), Cy = ffma(s4.y, om, fmul(loc, s4.w));   // :279
+            k.s.baked[ts + t] = light_intensity_thread(m.seg, AF, L, lt, I, Cx, Cy);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side: C ABI
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static long long g_launches = 0;
+static long long g_opt_nch = 0;          // 0 = auto
+static long long g_opt_threads = 0;      // 0 = auto
+static unsigned long long* g_stats = nullptr;   // device counters, enabled by option "stats"
+
+static int fail(const char* fmt, const char* detail) {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return 1;
+}
+static int check(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return 1;
+}
+
+extern "C" int msb_abi_version(void) { return MSB_ABI_VERSION; }
+extern "C" const char* msb_last_error(void) { return g_err; }
+extern "C" int64_t msb_launch_count(void) { return g_launches; }
+
+extern "C" int msb_params_init(msb_params* p, float agent_radius, int32_t res, float fov, float fps) {
+    if (!p) return fail("%s", "msb_params_init: null params");
+    if (!(fov < 180.f) || !(fov > 0.f)) return fail("%s", "msb_params_init: fov must be in (0, 180)");
+    if (res < 1) return fail("%s", "msb_params_init: res must be >= 1");
+    if (!(fps > 0.f)) return fail("%s", "msb_params_init: fps must be positive");
+    memset(p, 0, sizeof(*p));
+    p->res = res;
+    p->agent_radius = agent_radius;
+    p->half_screen = tanf(CUDART_PI_F / 180.f * fov / 2.);   // exactly kernels.cu:22
+    p->fps = fps;
+    p->fov = fov;
+    return 0;
+}
+
+extern "C" int msb_set_option(const char* name, int64_t value) {
+    if (!strcmp(name, "nch")) { g_opt_nch = value; return 0; }
+    if (!strcmp(name, "threads")) { g_opt_threads = value; return 0; }
+    if (!strcmp(name, "stats")) {
+        if (value && !g_stats) {
+            if (check(cudaMalloc(&g_stats, 8 * sizeof(unsigned long long)), "cudaMalloc(stats)")) return 1;
+            return check(cudaMemset(g_stats, 0, 8 * sizeof(unsigned long long)), "cudaMemset(stats)");
+        }
+        if (!value && g_stats) { cudaFree(g_stats); g_stats = nullptr; }
+        return 0;
+    }
+    if (!strcmp(name, "stats_reset")) {
+        if (g_stats) return check(cudaMemset(g_stats, 0, 8 * sizeof(unsigned long long)), "cudaMemset(stats)");
+        return 0;
+    }
+    return fail("msb_set_option: unknown option '%s'", name);
+}
+
+extern "C" int64_t msb_get_option(const char* name) {
+    if (!strcmp(name, "nch")) return g_opt_nch;
+    if (!strcmp(name, "threads")) return g_opt_threads;
+    if (!strncmp(name, "stat", 4) && g_stats) {
+        unsigned long long h[8];
+        if (cudaMemcpy(h, g_stats, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        if (!strcmp(name, "stat_tests")) return (int64_t)h[STAT_TESTS];
+        if (!strcmp(name, "stat_groups")) return (int64_t)h[STAT_GROUPS];
+        if (!strcmp(name, "stat_dyn_rays")) return (int64_t)h[STAT_DYN_RAYS];
+        if (!strcmp(name, "stat_dyn_iters")) return (int64_t)h[STAT_DYN_ITERS];
+    }
+    return -1;
+}
+
+static int validate(const msb_params* p, const msb_scenery* s) {
+    if (!p || !s) return fail("%s", "null params/scenery");
+    if (s->n_envs < 0 || s->n_agents < 1 || s->n_model < 0) return fail("%s", "bad scenery dimensions");
+    if (s->max_lines < s->n_agents * s->n_model) return fail("%s", "scenery.max_lines is smaller than n_agents*n_model");
+    return 0;
+}
+
+template <int MODE>
+static int launch_env(const KArgs& k, int nch, int threads, cudaStream_t st) {
+    const size_t sm = smem_bytes(k.seg_cap, threads / 32, k.s.n_agents);
+    if (sm > 227 * 1024) return fail("%s", "scene too large: an env's segments do not fit in shared memory (227 KB)");
+#define MSB_LAUNCH(N)                                                                                            \
+    {                                                                                                            \
+        auto fn = k.stats ? env_kernel<MODE, N, true> : env_kernel<MODE, N, false>;                              \
+        if (sm > 48 * 1024 && check(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), \
+                                    "cudaFuncSetAttribute"))                                                     \
+            return 1;                                                                                            \
+        fn<<<k.s.n_envs, threads, sm, st>>>(k);                                                                  \
+    }
+    switch (nch) {
+        case 1: MSB_LAUNCH(1); break;
+        case 2: MSB_LAUNCH(2); break;
+        default: MSB_LAUNCH(4); break;
+    }
+#undef MSB_LAUNCH
+    g_launches++;
+    return check(cudaGetLastError(), "kernel launch");
+}
+
+static void plan_render(const msb_params* p, const msb_scenery* s, int* nch, int* rb, int* threads) {
+    const int chunks = (p->res + 31) / 32;
+    int n = 4;
+    if (g_opt_nch == 1 || g_opt_nch == 2 || g_opt_nch == 4) n = (int)g_opt_nch;
+    else {
+        // largest chunk count per warp that still leaves the env's CTA at least 4 warps of work
+        while (n > 1 && (s->n_agents * ((chunks + n - 1) / n) < 4 || n > chunks)) n >>= 1;
+    }
+    *nch = n;
+    *rb = (chunks + n - 1) / n;
+    int t = 32 * s->n_agents * (*rb);
+    if (t < 64) t = 64;
+    if (t > 256) t = 256;
+    if (g_opt_threads >= 32 && g_opt_threads <= 256) t = (int)(g_opt_threads / 32) * 32;
+    *threads = t;
+}
+
+static void fill(KArgs& k, const msb_params* p, const msb_scenery* s, const msb_agents* a) {
+    memset(&k, 0, sizeof(k));
+    k.p = *p;
+    k.s = *s;
+    if (a) k.a = *a;
+    k.seg_cap = s->max_lines > 0 ? s->max_lines : 1;
+    k.inv_fps = 1.0f / p->fps;
+    k.ray_blocks = 1;
+    k.stats = g_stats;
+}
+
+extern "C" int msb_physics(const msb_params* p, const msb_scenery* s, const msb_agents* a, float* progress,
+                           void* cuda_stream) {
+    if (validate(p, s)) return 1;
+    if (!a || !a->angles || !a->positions || !a->angvelocity || !a->velocity) return fail("%s", "msb_physics: null agents");
+    if (s->n_envs == 0) return 0;
+    KArgs k;
+    fill(k, p, s, a);
+    k.progress = progress;
+    int threads = 128;
+    if (g_opt_threads >= 32 && g_opt_threads <= 256) threads = (int)(g_opt_threads / 32) * 32;
+    return launch_env<MODE_PHYSICS>(k, 1, threads, (cudaStream_t)cuda_stream);
+}
+
+static void set_obs(KArgs& k, const msb_obs_out* obs) {
+    if (!obs) return;
+    k.obs = *obs;
+    k.has_obs = 1;
+    k.inv_max_depth = 1.0f / obs->max_depth;
+    k.inv_speed = 1.0f / obs->speed_scale;
+    k.inv_ang = 1.0f / obs->ang_scale;
+    k.inv_sub = 1.0f / (float)obs->subsample;
+}
+
+static int check_obs(const msb_params* p, const msb_obs_out* obs) {
+    if (!obs) return 0;
+    const int sub = obs->subsample;
+    if (sub < 1 || sub > 32 || (sub & (sub - 1)) || p->res % sub) return fail("%s", "obs.subsample must be a power of two <= 32 dividing res");
+    return 0;
+}
+
+extern "C" int msb_render(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_render_out* out,
+                          const msb_obs_out* obs, void* cuda_stream) {
+    if (validate(p, s) || check_obs(p, obs)) return 1;
+    if (!a || !a->angles || !a->positions) return fail("%s", "msb_render: null agents");
+    if (s->n_envs == 0) return 0;
+    KArgs k;
+    fill(k, p, s, a);
+    if (out) k.out = *out;
+    set_obs(k, obs);
+    int nch, rb, threads;
+    plan_render(p, s, &nch, &rb, &threads);
+    k.ray_blocks = rb;
+    return launch_env<MODE_RENDER>(k, nch, threads, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int msb_step(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_movement* mv,
+                        float* progress, const msb_render_out* out, const msb_obs_out* obs, void* cuda_stream) {
+    if (validate(p, s) || check_obs(p, obs)) return 1;
+    if (!a || !a->angles || !a->positions || !a->angvelocity || !a->velocity) return fail("%s", "msb_step: null agents");
+    if (mv && !mv->actions) return fail("%s", "msb_step: movement without actions");
+    if (s->n_envs == 0) return 0;
+    KArgs k;
+    fill(k, p, s, a);
+    k.progress = progress;
+    if (out) k.out = *out;
+    set_obs(k, obs);
+    if (mv) {
+        k.mv = *mv;
+        k.has_mv = 1;
+        k.mv_keep = (float)(1.0 - (double)mv->decay);
+        k.mv_dv = (float)((double)mv->accel / (double)p->fps);
+        k.mv_dw = (float)((double)mv->ang_accel / (double)p->fps);
+    }
+    int nch, rb, threads;
+    plan_render(p, s, &nch, &rb, &threads);
+    k.ray_blocks = rb;
+    return launch_env<MODE_STEP>(k, nch, threads, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int msb_bake(const msb_params* p, const msb_scenery* s, void* cuda_stream) {
+    if (validate(p, s)) return 1;
+    if (!s->baked) return fail("%s", "msb_bake: null baked");
+    if (s->n_envs == 0) return 0;
+    KArgs k;
+    fill(k, p, s, nullptr);
+    const int threads = 256;
+    const size_t sm = smem_bytes(k.seg_cap, threads / 32, s->n_agents);
+    if (sm > 227 * 1024) return fail("%s", "scene too large: an env's segments do not fit in shared memory (227 KB)");
+    if (sm > 48 * 1024 &&
+        check(cudaFuncSetAttribute(bake_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "cudaFuncSetAttribute"))
+        return 1;
+    bake_kernel<<<s->n_envs, threads, sm, (cudaStream_t)cuda_stream>>>(k);
+    g_launches++;
+    return check(cudaGetLastError(), "bake launch");
+}

@@ -1,0 +1,438 @@
+"""The native interface: same names, arguments and error behaviour as the reference's `megastep.cuda` extension
+module (megastep/src/wrappers.cpp:30-172), implemented over the C ABI of libmegastep_b200.so
+(include/megastep_b200.h) instead of pybind11/ATen.
+
+    initialize(agent_radius, res, fov, fps)      wrappers.cpp:53
+    bake(scenery)                                wrappers.cpp:61
+    physics(scenery, agents) -> Physics          wrappers.cpp:69
+    render(scenery, agents) -> Render            wrappers.cpp:82
+    Ragged1D / Ragged2D / Ragged3D               wrappers.cpp:14-28,99-101 (common.h:102-155)
+    Agents, Scenery, Render, Physics             wrappers.cpp:103-172 (common.h:162-226)
+
+There is no CPU path and no fallback: physics/render/bake on anything but CUDA tensors raise RuntimeError, as the
+reference's TensorProxy does (common.h:12-14,33-37), and a missing library makes the import itself fail.
+ctypes releases the GIL for the duration of each foreign call, like the reference's `gil_scoped_release` guards.
+
+Beyond the reference: `step(...)` runs movement + physics + render + observation heads as one launch, the optional
+`params=` keyword lets several Cores with different res/fov coexist (the reference keeps those in process globals,
+wrappers.cpp:57-59), and texel offsets are 64-bit.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, 'libmegastep_b200.so')
+
+c_f32p = ctypes.c_void_p
+
+
+class Params(ctypes.Structure):
+    _fields_ = [('res', ctypes.c_int32), ('agent_radius', ctypes.c_float), ('half_screen', ctypes.c_float),
+                ('fps', ctypes.c_float), ('fov', ctypes.c_float), ('reserved', ctypes.c_int32 * 3)]
+
+
+class _Scenery(ctypes.Structure):
+    _fields_ = [('n_envs', ctypes.c_int32), ('n_agents', ctypes.c_int32), ('n_model', ctypes.c_int32),
+                ('max_lines', ctypes.c_int32), ('max_lights', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('lines', ctypes.c_void_p), ('line_widths', ctypes.c_void_p), ('line_starts', ctypes.c_void_p),
+                ('lights', ctypes.c_void_p), ('light_widths', ctypes.c_void_p), ('light_starts', ctypes.c_void_p),
+                ('textures', ctypes.c_void_p), ('tex_widths', ctypes.c_void_p), ('tex_starts', ctypes.c_void_p),
+                ('baked', ctypes.c_void_p), ('model', ctypes.c_void_p),
+                ('n_lines', ctypes.c_int64), ('n_texels', ctypes.c_int64)]
+
+
+class _Agents(ctypes.Structure):
+    _fields_ = [('angles', ctypes.c_void_p), ('positions', ctypes.c_void_p), ('angvelocity', ctypes.c_void_p),
+                ('velocity', ctypes.c_void_p)]
+
+
+class _RenderOut(ctypes.Structure):
+    _fields_ = [('indices', ctypes.c_void_p), ('locations', ctypes.c_void_p), ('dots', ctypes.c_void_p),
+                ('distances', ctypes.c_void_p), ('screen', ctypes.c_void_p)]
+
+
+class _ObsOut(ctypes.Structure):
+    _fields_ = [('rgb', ctypes.c_void_p), ('depth', ctypes.c_void_p), ('imu', ctypes.c_void_p),
+                ('subsample', ctypes.c_int32), ('max_depth', ctypes.c_float), ('speed_scale', ctypes.c_float),
+                ('ang_scale', ctypes.c_float)]
+
+
+class _Movement(ctypes.Structure):
+    _fields_ = [('actions', ctypes.c_void_p), ('accel', ctypes.c_float), ('ang_accel', ctypes.c_float),
+                ('decay', ctypes.c_float)]
+
+
+def _load():
+    if not os.path.exists(_LIBPATH):
+        raise ImportError(
+            f'{_LIBPATH} is missing. Build it with `python -m megastep_b200.build` (needs nvcc); '
+            'there is no CPU or PyTorch fallback for the simulation kernels.')
+    lib = ctypes.CDLL(_LIBPATH)
+    P = ctypes.POINTER
+    lib.msb_abi_version.restype = ctypes.c_int
+    lib.msb_last_error.restype = ctypes.c_char_p
+    lib.msb_launch_count.restype = ctypes.c_int64
+    lib.msb_params_init.argtypes = [P(Params), ctypes.c_float, ctypes.c_int32, ctypes.c_float, ctypes.c_float]
+    lib.msb_bake.argtypes = [P(Params), P(_Scenery), ctypes.c_void_p]
+    lib.msb_physics.argtypes = [P(Params), P(_Scenery), P(_Agents), ctypes.c_void_p, ctypes.c_void_p]
+    lib.msb_render.argtypes = [P(Params), P(_Scenery), P(_Agents), P(_RenderOut), P(_ObsOut), ctypes.c_void_p]
+    lib.msb_step.argtypes = [P(Params), P(_Scenery), P(_Agents), P(_Movement), ctypes.c_void_p, P(_RenderOut),
+                             P(_ObsOut), ctypes.c_void_p]
+    lib.msb_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
+    lib.msb_get_option.argtypes = [ctypes.c_char_p]
+    lib.msb_get_option.restype = ctypes.c_int64
+    if lib.msb_abi_version() != 1:
+        raise ImportError(f'{_LIBPATH} has ABI version {lib.msb_abi_version()}, expected 1; rebuild it')
+    return lib
+
+
+_lib = _load()
+
+
+def _check(code):
+    if code != 0:
+        raise RuntimeError(_lib.msb_last_error().decode())
+
+
+def _require(cond, msg):
+    if not cond:
+        raise RuntimeError(msg)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Ragged (common.h:88-155)
+# --------------------------------------------------------------------------------------------------------------
+def _inverses(widths, total):
+    # common.h:88-99: scatter ones at the row starts, cumsum, minus one
+    starts = widths.cumsum(0) - widths.to(torch.long)
+    flags = torch.ones(starts.size(0), dtype=torch.int32, device=widths.device)
+    indices = torch.zeros(total, dtype=torch.int32, device=widths.device)
+    return (indices.scatter(0, starts, flags).cumsum(0).to(torch.int32) - 1)
+
+
+class _Ragged:
+    _ndim = None
+
+    def __init__(self, vals, widths):
+        _require(isinstance(vals, torch.Tensor) and isinstance(widths, torch.Tensor), 'vals and widths must be tensors')
+        _require(vals.is_contiguous(), 'vals must be contiguous')
+        _require(widths.is_contiguous(), 'widths must be contiguous')
+        _require(widths.dtype == torch.int32, 'widths must be an int32 tensor')
+        _require(widths.dim() == 1, 'widths must be 1-dimensional')
+        _require(vals.dtype == torch.float32, 'vals must be a float32 tensor')
+        _require(vals.dim() == self._ndim, f'vals must be {self._ndim}-dimensional')
+        total = int(widths.sum(0).item()) if widths.numel() else 0
+        _require(total == vals.size(0), 'the widths must sum to the length of vals')
+        with torch.no_grad():
+            ends = widths.cumsum(0).to(torch.int32)
+            self._vals, self._widths = vals, widths
+            self._starts, self._ends = ends - widths, ends
+            self._inverse = _inverses(widths, total)
+        self._starts64 = None
+
+    vals = property(lambda self: self._vals)
+    widths = property(lambda self: self._widths)
+    starts = property(lambda self: self._starts)
+    ends = property(lambda self: self._ends)
+    inverse = property(lambda self: self._inverse)
+
+    def _long_starts(self):
+        """64-bit exclusive prefix sum of the widths (the kernels' texel offsets); int32 `starts` wraps at 2^31."""
+        if self._starts64 is None:
+            w = self._widths.to(torch.long)
+            self._starts64 = (w.cumsum(0) - w).contiguous()
+        return self._starts64
+
+    def __getitem__(self, x):
+        if isinstance(x, slice):
+            start, stop, step = x.indices(self._widths.size(0))
+            _require(step == 1, 'ragged slices must have step 1')
+            lo, hi = int(self._starts[start].item()), int(self._ends[stop - 1].item())
+            return type(self)(self._vals[lo:hi], self._widths[start:stop])
+        n = int(x)
+        return self._vals[int(self._starts[n].item()):int(self._ends[n].item())]
+
+    def clone(self):
+        return type(self)(self._vals.clone(), self._widths.clone())
+
+    def numpyify(self):
+        from .ragged import RaggedNumpy
+        from .arrdict import numpyify
+        return RaggedNumpy(numpyify(self._vals), numpyify(self._widths))
+
+    def __len__(self):
+        return self._widths.size(0)
+
+
+class Ragged1D(_Ragged):
+    _ndim = 1
+
+
+class Ragged2D(_Ragged):
+    _ndim = 2
+
+
+class Ragged3D(_Ragged):
+    _ndim = 3
+
+
+# --------------------------------------------------------------------------------------------------------------
+# state containers (common.h:162-226)
+# --------------------------------------------------------------------------------------------------------------
+def _proxy(t, ndim, name, dtype=torch.float32):
+    """TensorProxy's checks (common.h:33-37)."""
+    _require(isinstance(t, torch.Tensor), f'{name} must be a tensor')
+    _require(t.is_cuda, f'{name} must be a CUDA tensor')
+    _require(t.is_contiguous(), f'{name} must be contiguous')
+    _require(t.dtype == dtype, f'{name} must have dtype {dtype}')
+    _require(t.dim() == ndim, f'{name} must be {ndim}-dimensional')
+    return t
+
+
+class Agents:
+    """Holds the state of the agents; the four tensors stay caller-visible and are updated in place."""
+
+    def __init__(self, angles, positions, angvelocity, velocity):
+        self._angles = _proxy(angles, 2, 'angles')
+        self._positions = _proxy(positions, 3, 'positions')
+        self._angvelocity = _proxy(angvelocity, 2, 'angvelocity')
+        self._velocity = _proxy(velocity, 3, 'velocity')
+        n, a = angles.shape
+        _require(tuple(positions.shape) == (n, a, 2) and tuple(velocity.shape) == (n, a, 2)
+                 and tuple(angvelocity.shape) == (n, a), 'agent tensors disagree on (n_envs, n_agents)')
+        self._c = _Agents(angles.data_ptr(), positions.data_ptr(), angvelocity.data_ptr(), velocity.data_ptr())
+
+    angles = property(lambda self: self._angles)
+    positions = property(lambda self: self._positions)
+    angvelocity = property(lambda self: self._angvelocity)
+    velocity = property(lambda self: self._velocity)
+
+    def state(self, e):
+        from .arrdict import arrdict
+        return arrdict(angles=self._angles[e], positions=self._positions[e],
+                       angvelocity=self._angvelocity[e], velocity=self._velocity[e])
+
+
+class Scenery:
+    """Holds the static scene plus the agents' model lines (common.h:185-214)."""
+
+    def __init__(self, n_agents, lights, lines, textures, model):
+        _require(isinstance(lights, Ragged2D), 'lights must be a Ragged2D')
+        _require(isinstance(lines, Ragged3D), 'lines must be a Ragged3D')
+        _require(isinstance(textures, Ragged2D), 'textures must be a Ragged2D')
+        self._n_agents = int(n_agents)
+        self._lights, self._lines, self._textures = lights, lines, textures
+        self._model = _proxy(model, 3, 'model')
+        _require(tuple(lines.vals.shape[1:]) == (2, 2), 'lines.vals must be (n, 2, 2)')
+        _require(lights.vals.shape[1] == 3 and textures.vals.shape[1] == 3, 'lights/textures vals must be (n, 3)')
+        _require(tuple(model.shape[1:]) == (2, 2), 'model must be (n, 2, 2)')
+        _require(len(lights) == len(lines), 'lights and lines disagree on the number of environments')
+        _require(len(textures) == lines.vals.size(0), 'textures must have one row per line')
+        self._baked = Ragged1D(torch.ones_like(textures.vals[:, 0]).contiguous(), textures.widths)
+        self._params = None   # set by core.Core so that several Cores can coexist
+        self._c = None
+
+    n_agents = property(lambda self: self._n_agents)
+    lights = property(lambda self: self._lights)
+    lines = property(lambda self: self._lines)
+    textures = property(lambda self: self._textures)
+    baked = property(lambda self: self._baked)
+    model = property(lambda self: self._model)
+
+    def state(self, e):
+        from .dotdict import dotdict
+        se, ee = int(self._lines.starts[e].item()), int(self._lines.ends[e].item())
+        return dotdict(n_agents=self._n_agents, lights=self._lights[e], lines=self._lines[e],
+                       textures=self._textures[se:ee], model=self._model, baked=self._baked[se:ee])
+
+    def _struct(self):
+        """The msb_scenery view of this object; built once (device pointers are stable, we hold the tensors)."""
+        if self._c is None:
+            for name, t in (('lines', self._lines.vals), ('lights', self._lights.vals), ('textures', self._textures.vals)):
+                _require(t.is_cuda, f'{name} must be a CUDA tensor')
+            lw, iw = self._lines.widths, self._lights.widths
+            self._tex_starts = self._textures._long_starts()
+            self._c = _Scenery(
+                n_envs=len(self._lines), n_agents=self._n_agents, n_model=self._model.size(0),
+                max_lines=int(lw.max().item()) if lw.numel() else 0,
+                max_lights=int(iw.max().item()) if iw.numel() else 0, reserved=0,
+                lines=self._lines.vals.data_ptr(), line_widths=lw.data_ptr(), line_starts=self._lines.starts.data_ptr(),
+                lights=self._lights.vals.data_ptr(), light_widths=iw.data_ptr(), light_starts=self._lights.starts.data_ptr(),
+                textures=self._textures.vals.data_ptr(), tex_widths=self._textures.widths.data_ptr(),
+                tex_starts=self._tex_starts.data_ptr(), baked=self._baked.vals.data_ptr(), model=self._model.data_ptr(),
+                n_lines=self._lines.vals.size(0), n_texels=self._textures.vals.size(0))
+        return self._c
+
+
+class Render:
+    """The result of a render() call. Exactly five public attributes (modules.unpack walks dir())."""
+    __slots__ = ('screen', 'indices', 'locations', 'dots', 'distances')
+
+    def __init__(self, indices, locations, dots, distances, screen):
+        self.indices, self.locations, self.dots, self.distances, self.screen = indices, locations, dots, distances, screen
+
+
+class Physics:
+    __slots__ = ('progress',)
+
+    def __init__(self, progress):
+        self.progress = progress
+
+
+# --------------------------------------------------------------------------------------------------------------
+# functions
+# --------------------------------------------------------------------------------------------------------------
+_PARAMS = None
+
+
+def make_params(agent_radius, res, fov, fps):
+    p = Params()
+    _check(_lib.msb_params_init(ctypes.byref(p), float(agent_radius), int(res), float(fov), float(fps)))
+    return p
+
+
+def initialize(agent_radius, res, fov, fps):
+    """Sets the process-wide default parameters used by bake/physics/render (kernels.cu:18-27)."""
+    global _PARAMS
+    _PARAMS = make_params(agent_radius, res, fov, fps)
+
+
+def _params(scenery, params):
+    p = params if params is not None else _PARAMS
+    _require(p is not None, 'initialize(agent_radius, res, fov, fps) must be called before bake/physics/render')
+    return p
+
+
+class _on_device:
+    """Makes the tensors' device current for the launch (the reference launches on whatever is current)."""
+    __slots__ = ('idx', 'prev')
+
+    def __init__(self, tensor):
+        self.idx = tensor.device.index
+
+    def __enter__(self):
+        self.prev = torch.cuda.current_device()
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.idx)
+        return torch.cuda.current_stream(self.idx).cuda_stream
+
+    def __exit__(self, *exc):
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.prev)
+
+
+def bake(scenery, params=None):
+    """Pre-computes the lighting of the static geometry into scenery.baked."""
+    _require(isinstance(scenery, Scenery), 'scenery must be a Scenery')
+    p = _params(scenery, params)
+    s = scenery._struct()
+    with _on_device(scenery.model) as stream:
+        _check(_lib.msb_bake(ctypes.byref(p), ctypes.byref(s), stream))
+
+
+def physics(scenery, agents, params=None):
+    """Advances the agents by one tick, resolving collisions; returns Physics(progress)."""
+    _require(isinstance(scenery, Scenery) and isinstance(agents, Agents), 'expected (Scenery, Agents)')
+    p = _params(scenery, params)
+    s = scenery._struct()
+    n, a = agents._angles.shape
+    _require(n == s.n_envs and a == s.n_agents, 'agents and scenery disagree on (n_envs, n_agents)')
+    progress = torch.empty((n, a), dtype=torch.float32, device=agents._angles.device)
+    with _on_device(agents._angles) as stream:
+        _check(_lib.msb_physics(ctypes.byref(p), ctypes.byref(s), ctypes.byref(agents._c), progress.data_ptr(), stream))
+    return Physics(progress)
+
+
+def _alloc_render(n, a, r, device):
+    f = dict(dtype=torch.float32, device=device)
+    return Render(indices=torch.empty((n, a, r), dtype=torch.int32, device=device),
+                  locations=torch.empty((n, a, r), **f), dots=torch.empty((n, a, r), **f),
+                  distances=torch.empty((n, a, r), **f), screen=torch.empty((n, a, r, 3), **f))
+
+
+def _render_struct(r):
+    return _RenderOut(r.indices.data_ptr(), r.locations.data_ptr(), r.dots.data_ptr(), r.distances.data_ptr(),
+                      r.screen.data_ptr())
+
+
+def render(scenery, agents, params=None):
+    """Renders the scenery onto the agents' cameras; returns a Render. Also moves the agents' model lines inside
+    scenery.lines to the agents' current poses (the reference's draw_kernel side effect)."""
+    _require(isinstance(scenery, Scenery) and isinstance(agents, Agents), 'expected (Scenery, Agents)')
+    p = _params(scenery, params)
+    s = scenery._struct()
+    n, a = agents._angles.shape
+    _require(n == s.n_envs and a == s.n_agents, 'agents and scenery disagree on (n_envs, n_agents)')
+    out = _alloc_render(n, a, p.res, agents._angles.device)
+    c = _render_struct(out)
+    with _on_device(agents._angles) as stream:
+        _check(_lib.msb_render(ctypes.byref(p), ctypes.byref(s), ctypes.byref(agents._c), ctypes.byref(c), None, stream))
+    return out
+
+
+class StepPlan:
+    """A pre-bound fused step: MomentumMovement -> physics -> render -> RGB/Depth/IMU heads in ONE kernel launch,
+    writing into persistent output buffers (so it can also be captured in a CUDA graph).
+
+    Built by `modules.FusedStep`; kept here because it owns ctypes structs.
+    """
+
+    def __init__(self, scenery, agents, params, actions=None, accel=5., ang_accel=180., decay=.125,
+                 raw=True, subsample=None, max_depth=10., speed_scale=10., ang_scale=360.):
+        n, a = agents.angles.shape
+        dev = agents.angles.device
+        self.scenery, self.agents, self.params = scenery, agents, params
+        self.progress = torch.empty((n, a), dtype=torch.float32, device=dev)
+        self.render = _alloc_render(n, a, params.res, dev) if raw else None
+        self._out = _render_struct(self.render) if raw else None
+        self.actions = actions
+        self._mv = None
+        if actions is not None:
+            _proxy(actions, 2, 'actions', torch.int32)
+            self._mv = _Movement(actions.data_ptr(), accel, ang_accel, decay)
+        self.rgb = self.depth = self.imu = None
+        self._obs = None
+        if subsample is not None:
+            ro = params.res // subsample
+            self.rgb = torch.empty((n, a, 3, 1, ro), dtype=torch.float32, device=dev)
+            self.depth = torch.empty((n, a, 1, 1, ro), dtype=torch.float32, device=dev)
+            self.imu = torch.empty((n, a, 3), dtype=torch.float32, device=dev)
+            self._obs = _ObsOut(self.rgb.data_ptr(), self.depth.data_ptr(), self.imu.data_ptr(), subsample,
+                                max_depth, speed_scale, ang_scale)
+        self._s = scenery._struct()
+
+    def step(self):
+        """movement (if actions were bound) + physics + render + heads, one launch"""
+        with _on_device(self.progress) as stream:
+            _check(_lib.msb_step(ctypes.byref(self.params), ctypes.byref(self._s), ctypes.byref(self.agents._c),
+                                 ctypes.byref(self._mv) if self._mv is not None else None, self.progress.data_ptr(),
+                                 ctypes.byref(self._out) if self._out is not None else None,
+                                 ctypes.byref(self._obs) if self._obs is not None else None, stream))
+
+    __call__ = step
+
+    def render_only(self):
+        """render + heads, one launch; the agents are not moved"""
+        with _on_device(self.progress) as stream:
+            _check(_lib.msb_render(ctypes.byref(self.params), ctypes.byref(self._s), ctypes.byref(self.agents._c),
+                                   ctypes.byref(self._out) if self._out is not None else None,
+                                   ctypes.byref(self._obs) if self._obs is not None else None, stream))
+
+
+def set_option(name, value):
+    _check(_lib.msb_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    return int(_lib.msb_get_option(name.encode()))
+
+
+def launch_count():
+    return int(_lib.msb_launch_count())
+
+
+def library_path():
+    return _LIBPATH

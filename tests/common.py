@@ -1,0 +1,115 @@
+"""Shared scene/state builders for the tests (seeded, deterministic)."""
+import glob
+import importlib.machinery
+import importlib.util
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+AGENT_RADIUS = .15 / 2 ** .5
+
+
+def synthetic_scene(n_envs, n_agents, seed=1, bake=True):
+    """(geometries, scene arrays incl. oracle-baked lighting)"""
+    from megastep_b200 import scene, synthetic
+    from oracle import oracle
+    gs = synthetic.sample(n_envs, seed=seed)
+    arrays = scene.scene_arrays(gs, n_agents, np.random.RandomState(seed))
+    if bake:
+        arrays['baked'] = oracle.bake(arrays)
+    return gs, arrays
+
+
+def toy_scene(kind, n_envs, n_agents, seed=1):
+    from megastep_b200 import scene, toys
+    from oracle import oracle
+    gs = [getattr(toys, kind)()] * n_envs
+    arrays = scene.scene_arrays(gs, n_agents, np.random.RandomState(seed))
+    arrays['baked'] = oracle.bake(arrays)
+    return gs, arrays
+
+
+def random_state(gs, n_agents, seed=2, speed=3., angspeed=200.):
+    """Agents at random free poses with random velocities (m/s, deg/s)."""
+    from megastep_b200 import synthetic
+    rng = np.random.RandomState(seed)
+    if 'rooms' in gs[0]:
+        pos, ang = synthetic.spawns(gs, n_agents, rng)
+    else:
+        pos = rng.uniform(1.6, 5.4, (len(gs), n_agents, 2)).astype(np.float32)
+        ang = rng.uniform(-180, 180, (len(gs), n_agents)).astype(np.float32)
+    N = len(gs)
+    return dict(angles=ang, positions=pos,
+                angvelocity=rng.uniform(-angspeed, angspeed, (N, n_agents)).astype(np.float32),
+                velocity=(speed * rng.normal(size=(N, n_agents, 2))).astype(np.float32))
+
+
+def copy_state(st):
+    return {k: v.copy() for k, v in st.items()}
+
+
+def to_device(arrays, st, res, fov, fps=10., device='cuda'):
+    """Scene arrays + state -> (core, cuda module); the Core's agents are loaded with `st` and the scenery's baked
+    light map with arrays['baked'] (so lighting parity is tested separately from render parity)."""
+    import torch
+    from megastep_b200 import core as core_, scene
+    s = scene.upload(arrays, device)
+    if 'baked' in arrays:
+        s.baked.vals.copy_(torch.as_tensor(arrays['baked']))
+    c = core_.Core(s, res=res, fov=fov, fps=fps)
+    load_state(c, st)
+    return c
+
+
+def load_state(c, st):
+    import torch
+    for k in ('angles', 'positions', 'angvelocity', 'velocity'):
+        getattr(c.agents, k).copy_(torch.as_tensor(st[k]))
+
+
+def read_state(c):
+    return {k: getattr(c.agents, k).cpu().numpy() for k in ('angles', 'positions', 'angvelocity', 'velocity')}
+
+
+def reference_module():
+    """The reference's own extension (oracle/_ref, built from its unmodified sources), or None when not built."""
+    hits = glob.glob(os.path.join(ROOT, 'oracle', '_ref', 'megastepcuda*.so'))
+    if not hits:
+        return None
+    import torch  # noqa: F401  (the extension links against libtorch)
+    loader = importlib.machinery.ExtensionFileLoader('megastepcuda', hits[0])
+    spec = importlib.util.spec_from_loader('megastepcuda', loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    return mod
+
+
+def reference_scenery(ref, arrays, device='cuda'):
+    import torch
+    t = lambda k, dtype: torch.as_tensor(arrays[k], dtype=dtype).contiguous().to(device)
+    s = ref.Scenery(n_agents=arrays['n_agents'],
+                    lights=ref.Ragged2D(t('lights', torch.float32), t('light_widths', torch.int32)),
+                    lines=ref.Ragged3D(t('lines', torch.float32), t('line_widths', torch.int32)),
+                    textures=ref.Ragged2D(t('textures', torch.float32), t('tex_widths', torch.int32)),
+                    model=t('model', torch.float32))
+    if 'baked' in arrays:
+        s.baked.vals.copy_(torch.as_tensor(arrays['baked']))
+    return s
+
+
+def reference_agents(ref, st, device='cuda'):
+    import torch
+    return ref.Agents(**{k: torch.as_tensor(st[k]).contiguous().to(device) for k in ('angles', 'positions', 'angvelocity', 'velocity')})
+
+
+def index_agreement(a, b, dist_a, dist_b, tol=2e-3):
+    """Fraction of rays whose hit index differs AND whose hit distance differs by more than `tol` (i.e. real
+    disagreements rather than ties between coincident/abutting segments)."""
+    a, b = np.asarray(a), np.asarray(b)
+    diff = a != b
+    da, db = np.asarray(dist_a), np.asarray(dist_b)
+    with np.errstate(invalid='ignore'):
+        far = np.abs(da - db) > tol * np.maximum(1., np.minimum(np.abs(da), np.abs(db)))
+    far |= np.isinf(da) != np.isinf(db)
+    return float(diff.mean()), float((diff & far).mean())

@@ -1,0 +1,243 @@
+"""Host-side logic, on CPU: ragged containers, dict containers, scene construction, geometry, the module-level
+maths, the C-ABI library's exported surface. No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import common
+from megastep_b200 import arrdict as ad
+from megastep_b200 import cuda, dotdict as dd, geometry, modules, ragged, scene, spaces, synthetic, toys
+
+
+# ---- the reference's own ragged tests (megastep/ragged.py:77-103), restated against this package -------------
+def test_ragged():
+    vals = torch.as_tensor([0, 1, 2, 3, 4, 5]).float()
+    widths = torch.as_tensor([3, 1, 2]).int()
+    r = ragged.Ragged(vals, widths)
+    assert isinstance(r, cuda.Ragged1D)
+    torch.testing.assert_close(r[1], torch.tensor([3.]))
+    torch.testing.assert_close(r[-1], torch.tensor([4., 5.]))
+    torch.testing.assert_close(r[:2].vals, torch.tensor([0., 1., 2., 3.]))
+    torch.testing.assert_close(r[:2].widths, torch.tensor([3, 1], dtype=torch.int32))
+    torch.testing.assert_close(r[1:].vals, torch.tensor([3., 4., 5.]))
+    torch.testing.assert_close(r[1:].widths, torch.tensor([1, 2], dtype=torch.int32))
+
+
+def test_ragged_numpy():
+    r = ragged.RaggedNumpy(np.array([0, 1, 2, 3, 4, 5]), np.array([3, 1, 2]))
+    np.testing.assert_allclose(r[1], [3])
+    np.testing.assert_allclose(r[-1], [4, 5])
+    np.testing.assert_allclose(r[:2].vals, [0, 1, 2, 3])
+    np.testing.assert_allclose(r[:2].widths, [3, 1])
+    np.testing.assert_allclose(r[1:].vals, [3, 4, 5])
+    np.testing.assert_allclose(r[1:].widths, [1, 2])
+
+
+def test_ragged_metadata_and_roundtrip():
+    vals = torch.arange(12.).reshape(6, 2)
+    r = ragged.Ragged(vals, torch.tensor([2, 0, 3, 1], dtype=torch.int32))
+    assert isinstance(r, cuda.Ragged2D)
+    assert r.starts.dtype == r.ends.dtype == r.inverse.dtype == torch.int32
+    assert r.starts.tolist() == [0, 2, 2, 5] and r.ends.tolist() == [2, 2, 5, 6]
+    assert r._long_starts().dtype == torch.int64 and r._long_starts().tolist() == [0, 2, 2, 5]
+    n = r.numpyify()
+    assert isinstance(n, ragged.RaggedNumpy) and n.starts.tolist() == [0, 2, 2, 5]
+    back = n.torchify()
+    assert isinstance(back, cuda.Ragged2D) and torch.equal(back.vals, vals)
+    c = r.clone()
+    c.vals[0, 0] = 99.
+    assert r.vals[0, 0] == 0.
+
+
+def test_ragged_validation_errors():
+    with pytest.raises(RuntimeError):
+        cuda.Ragged1D(torch.zeros(5), torch.tensor([3, 1], dtype=torch.int32))       # widths do not sum to len
+    with pytest.raises(RuntimeError):
+        cuda.Ragged1D(torch.zeros(4), torch.tensor([3, 1]))                           # int64 widths
+    with pytest.raises(RuntimeError):
+        cuda.Ragged2D(torch.zeros(4), torch.tensor([3, 1], dtype=torch.int32))       # wrong ndim
+    with pytest.raises(RuntimeError):
+        cuda.Ragged1D(torch.zeros(8)[::2], torch.tensor([3, 1], dtype=torch.int32))  # non-contiguous
+
+
+def test_cpu_tensors_are_refused_by_the_kernels():
+    # the reference's TensorProxy insists on CUDA tensors (common.h:12-14,33-37); there is no CPU path here either
+    z = torch.zeros
+    with pytest.raises(RuntimeError, match='CUDA'):
+        cuda.Agents(z(2, 1), z(2, 1, 2), z(2, 1), z(2, 1, 2))
+    arrays = scene.scene_arrays([toys.box()], 1, np.random.RandomState(0))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        scene.upload(arrays, 'cpu')
+
+
+def test_render_result_exposes_exactly_the_reference_attributes():
+    r = cuda.Render(*[torch.zeros(1)] * 5)
+    assert sorted(k for k in dir(r) if not k.startswith('_')) == ['distances', 'dots', 'indices', 'locations', 'screen']
+    assert sorted(modules.unpack(r).keys()) == ['distances', 'dots', 'indices', 'locations', 'screen']
+    assert [k for k in dir(cuda.Physics(torch.zeros(1))) if not k.startswith('_')] == ['progress']
+
+
+# ---- C ABI -------------------------------------------------------------------------------------------------------
+def test_library_exports_every_symbol_the_header_declares():
+    header = open(os.path.join(common.ROOT, 'include', 'megastep_b200.h')).read()
+    declared = set(re.findall(r'\b(msb_[a-z_]+)\s*\(', header))
+    assert {'msb_physics', 'msb_render', 'msb_step', 'msb_bake', 'msb_params_init'} <= declared
+    lib = ctypes.CDLL(cuda.library_path())
+    for name in declared:
+        assert hasattr(lib, name), f'{name} is declared in the header but not exported'
+    assert lib.msb_abi_version() == 1
+
+
+def test_params_init_matches_reference_formula_and_validates():
+    from oracle import oracle
+    for fov in (60., 70., 130.):
+        p = cuda.make_params(common.AGENT_RADIUS, 128, fov, 10.)
+        assert p.half_screen == pytest.approx(oracle.half_screen(fov), abs=0)   # same host expression
+        assert p.res == 128 and p.fps == 10.
+    with pytest.raises(RuntimeError, match='fov'):
+        cuda.make_params(.1, 64, 180., 10.)
+    with pytest.raises(RuntimeError, match='res'):
+        cuda.make_params(.1, 0, 90., 10.)
+
+
+def test_struct_layouts_match_the_header():
+    # sizes the C compiler gives the structs (LP64): guards the ctypes mirrors against drift
+    assert ctypes.sizeof(cuda.Params) == 32
+    assert ctypes.sizeof(cuda._Scenery) == 24 + 11 * 8 + 16
+    assert ctypes.sizeof(cuda._Agents) == 32
+    assert ctypes.sizeof(cuda._RenderOut) == 40
+    assert ctypes.sizeof(cuda._ObsOut) == 40
+    assert ctypes.sizeof(cuda._Movement) == 24
+
+
+# ---- containers --------------------------------------------------------------------------------------------------
+def test_dotdict_and_arrdict_behaviour():
+    d = dd.dotdict(a=1, b=dd.dotdict(c=2))
+    assert d.a == 1 and d.b.c == 2 and 'a' in dir(d)
+    assert dd.mapping(lambda x: x + 1)(d).b.c == 3
+    assert dd.leaves(d) == [1, 2]
+    with pytest.raises(AttributeError):
+        d.nope
+    x = ad.arrdict(p=torch.arange(6.).reshape(3, 2), q=torch.arange(3.))
+    assert x[1].p.tolist() == [2., 3.] and x[1].q.item() == 1.
+    assert (x + 1).q.tolist() == [1., 2., 3.] and (x * x).q.tolist() == [0., 1., 4.]
+    assert x.shape == ad.arrdict(p=torch.Size([3, 2]), q=torch.Size([3]))
+    y = x.clone()
+    y[0] = ad.arrdict(p=torch.tensor([9., 9.]), q=torch.tensor(9.))
+    assert y.p[0].tolist() == [9., 9.] and x.p[0].tolist() == [0., 1.]
+    with pytest.raises(ValueError):
+        x.z = 1
+    s = ad.stack([x, x])
+    assert s.p.shape == (2, 3, 2)
+    c = ad.cat([x, x])
+    assert c.q.shape == (6,)
+    n = ad.numpyify(x)
+    assert isinstance(n.p, np.ndarray)
+    t = ad.torchify(ad.arrdict(i=np.arange(3), f=np.ones(2), b=np.array([True])))
+    assert t.i.dtype == torch.int32 and t.f.dtype == torch.float32 and t.b.dtype == torch.bool
+    assert 'p' in str(x)
+
+
+def test_spaces():
+    assert spaces.MultiImage(2, 3, 1, 64).shape == (2, 3, 1, 64)
+    assert spaces.MultiVector(2, 3).shape == (2, 3)
+    assert spaces.MultiDiscrete(4, 7).shape == (4, 7)
+
+
+# ---- scene construction -------------------------------------------------------------------------------------------
+def test_agent_model_and_colors():
+    m = scene.agent_model()
+    assert m.shape == (8, 2, 2)
+    np.testing.assert_allclose(m[:, 1], np.roll(m[:, 0], -1, 0))           # a closed outline
+    assert np.abs(m).max() == pytest.approx(.075)
+    assert np.linalg.norm(m.reshape(-1, 2), axis=1).max() < common.AGENT_RADIUS   # inside the near plane
+    c = scene.agent_colors()
+    assert c.shape == (8, 3) and c[1].tolist() == [0., .5, 0.] and c[3].tolist() == [1., 0., 0.]
+    assert scene.to_rgb('#c185ae') == pytest.approx((0xc1 / 255, 0x85 / 255, 0xae / 255))
+
+
+def test_scene_arrays_layout():
+    gs = [toys.box(), toys.column()]
+    a = scene.scene_arrays(gs, 2, np.random.RandomState(0))
+    assert a['line_widths'].tolist() == [16 + 4, 16 + 4] and a['light_widths'].tolist() == [1, 4]
+    assert a['lines'].shape == (40, 2, 2) and a['lights'].shape == (5, 3)
+    assert a['tex_widths'].sum() == len(a['textures'])
+    # agent lines are 2 texels each; a 5 m wall is 100 texels (TEXTURE_RES = 5 cm)
+    assert (a['tex_widths'][:16] == 2).all() and (a['tex_widths'][16:20] == 100).all()
+    # agent texels keep their flat colours (pattern forced to 1), in linear space
+    np.testing.assert_allclose(a['textures'][2:4], np.tile(np.array([0., .5, 0.]) ** 2.2, (2, 1)), atol=1e-6)
+    assert ((a['lights'][:, 2] >= .5) & (a['lights'][:, 2] < 2.)).all()
+    b = scene.scene_arrays(gs, 2, np.random.RandomState(0))
+    np.testing.assert_array_equal(a['textures'], b['textures'])            # deterministic in the RandomState
+
+
+def test_box_geometry_matches_reference_docs():
+    g = toys.box(5)
+    # corners at 1..6 (toys.py:7-9 with MARGIN = 1), light in the centre
+    assert sorted(set(np.round(g.walls.reshape(-1), 6))) == [1., 6.]
+    assert g.lights.tolist() == [[3.5, 3.5]]
+    m = g.masks
+    assert m.shape == (36, 36) and set(np.unique(m)) == {-1, 0, 1}
+    i, j = geometry.indices(np.array([3.5, 3.5]), m.shape, g.res)
+    assert m[i, j] == 1                                                     # room interior
+    i, j = geometry.indices(np.array([6., 3.5]), m.shape, g.res)
+    assert m[i, j] == -1                                                    # the right wall
+    assert m[0, 0] == 0                                                     # outside
+    xy = geometry.centers(np.array([[i, j]]), m.shape, g.res)
+    assert np.abs(xy - [6., 3.5]).max() <= g.res
+
+
+def test_synthetic_floorplans_are_cubicasa_shaped_and_deterministic():
+    gs = synthetic.sample(64, seed=7)
+    W = np.array([len(g.walls) for g in gs])
+    I = np.array([len(g.lights) for g in gs])
+    assert 230 < W.mean() < 320 and W.min() >= 60 and W.max() <= 600
+    assert 17 < I.mean() < 25
+    assert min(g.walls.min() for g in gs) > 0                               # inside the +quadrant, with margin
+    again = synthetic.sample(64, seed=7)
+    np.testing.assert_array_equal(gs[13].walls, again[13].walls)
+    pos, ang = synthetic.spawns(gs, 4, np.random.RandomState(0))
+    assert pos.shape == (64, 4, 2) and ang.shape == (64, 4)
+    for g, p in zip(gs, pos):
+        inside = ((p[:, None, 0] > g.rooms[None, :, 0]) & (p[:, None, 0] < g.rooms[None, :, 2]) &
+                  (p[:, None, 1] > g.rooms[None, :, 1]) & (p[:, None, 1] < g.rooms[None, :, 3])).any(1)
+        assert inside.all()
+
+
+def test_tile_arrays_repeats_envs():
+    gs = synthetic.sample(3, seed=2)
+    a = scene.scene_arrays(gs, 1, np.random.RandomState(0))
+    b = synthetic.tile_arrays(a, 7)
+    assert b['line_widths'].tolist() == a['line_widths'][[0, 1, 2, 0, 1, 2, 0]].tolist()
+    assert b['tex_widths'].sum() == len(b['textures'])
+    L0 = a['line_widths'][0]
+    np.testing.assert_array_equal(b['lines'][-L0:], a['lines'][:L0])
+
+
+# ---- module maths ----------------------------------------------------------------------------------------------
+def test_frames_are_inverse_rotations():
+    ang = torch.tensor([[0., 90., -45.]])
+    p = torch.randn(1, 3, 2)
+    torch.testing.assert_close(modules.to_local_frame(ang, modules.to_global_frame(ang, p)), p, atol=1e-6, rtol=0)
+    g = modules.to_global_frame(torch.tensor([90.]), torch.tensor([[1., 0.]]))
+    torch.testing.assert_close(g, torch.tensor([[0., 1.]]), atol=1e-6, rtol=0)
+
+
+def test_downsample_and_observation_heads_on_a_fake_render():
+    class FakeCore:
+        res, n_agents, agent_radius = 8, 1, common.AGENT_RADIUS
+    r = ad.arrdict(distances=torch.tensor([.5, 1., 2., 4., 8., 16., float('inf'), common.AGENT_RADIUS]).reshape(1, 1, 1, 8),
+                   screen=torch.arange(24.).reshape(1, 1, 3, 1, 8))
+    assert modules.downsample(r.screen, 4).shape == (1, 1, 3, 1, 2, 4)
+    d = modules.Depth(FakeCore(), subsample=2)(r)
+    assert d.shape == (1, 1, 1, 1, 4)
+    full = 1 - ((r.distances - common.AGENT_RADIUS) / 10).clamp(0, 1)
+    torch.testing.assert_close(d.reshape(-1), full.reshape(4, 2).mean(-1))
+    assert full.reshape(-1)[6] == 0 and full.reshape(-1)[7] == 1              # infinity -> 0, near plane -> 1
+    rgb = modules.RGB(FakeCore(), subsample=4)(r)
+    assert rgb.shape == (1, 1, 3, 1, 2)
+    torch.testing.assert_close(rgb[0, 0, 0, 0], torch.tensor([1.5, 5.5]))
