@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py — agent-frames/s of the physics()+render() hot path on synthetic cubicasa-shaped scenes.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload deathmatch|explorer]
+
+A "step" is one whole environment tick over the batch: MomentumMovement (random actions) -> physics -> render (all
+five Render tensors materialised, as the reference's render() does) -> RGB/Depth/IMU observation heads.
+  * ours:      ONE launch of the fused sm_100a kernel (msb_step) through the C ABI.
+  * reference: the reference's OWN kernels.cu/wrappers.cpp built unmodified for sm_100a (oracle/_ref), driven through
+               its own API (megastepcuda.physics / .render) plus the PyTorch elementwise ops its modules.py runs around
+               them. megastep has no CPU step path (docs/faq.rst:23-27), so this — not a CPU run — is the reference arm;
+               if oracle/_ref is not loadable the arm falls back to timing the CPU oracle port on the host cores.
+
+Prints ONE JSON line (rank 0). See DESIGN.md §Measurement for what each key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+WORKLOADS = {
+    # BASELINE.json configs[2] (the configuration the metric is quoted on) and configs[1]
+    'deathmatch': dict(n_envs=4096, n_agents=4, res=128, fov=70., subsample=1),
+    'explorer': dict(n_envs=4096, n_agents=1, res=64, fov=130., subsample=1),
+    # the demo-faithful variants (render at 4x, subsample by 4: demo/envs/deathmatch.py:26-28, explorer.py:13-15)
+    'deathmatch-demo': dict(n_envs=4096, n_agents=4, res=512, fov=70., subsample=4),
+    'explorer-demo': dict(n_envs=4096, n_agents=1, res=256, fov=130., subsample=4),
+}
+AGENT_RADIUS = .15 / 2 ** .5
+FPS = 10.
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='deathmatch', choices=sorted(WORKLOADS))
+    ap.add_argument('--envs', type=int, default=None, help='envs per GPU (default: the workload\'s)')
+    ap.add_argument('--res', type=int, default=None)
+    ap.add_argument('--unique', type=int, default=256, help='distinct floorplans, tiled cyclically')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-raw', action='store_true', help='skip materialising the five Render tensors (obs heads only)')
+    ap.add_argument('--gather', action='store_true', help='all-gather the observations to every rank each step (NCCL)')
+    ap.add_argument('--dry-run', action='store_true', help='build the scene and the CPU baseline only (no GPU)')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# scene
+# ---------------------------------------------------------------------------------------------------------------
+def build_scene(cfg, n_envs, unique, rank):
+    from megastep_b200 import scene, synthetic
+    gs = synthetic.sample(n_envs, seed=1 + rank, n_unique=unique)
+    base = scene.scene_arrays(gs[:min(unique, n_envs)], cfg['n_agents'], np.random.RandomState(1 + rank))
+    arrays = synthetic.tile_arrays(base, n_envs)
+    pos, ang = synthetic.spawns(gs, cfg['n_agents'], np.random.RandomState(2 + rank))
+    return gs, arrays, pos, ang
+
+
+def algorithmic_bytes(cfg, arrays, fused, raw=True):
+    """Bytes one step must move, per SURVEY.md §8(d): B_env = 64A + 32AF + 32W + 68AR + 16 for the separate
+    physics + render calls (every Render output materialised, texel gathers counted per ray). The fused kernel
+    stages each env's segments once, so the second read of the static lines and of the agent state (16W + 12A + 8)
+    drops out; the observation heads add 16A*R/sub + 12A written."""
+    A, R, F = cfg['n_agents'], cfg['res'], 8
+    N = len(arrays['line_widths'])
+    W = float(arrays['line_widths'].mean()) - A * F
+    b_env = 64 * A + 32 * A * F + 32 * W + 68 * A * R + 16
+    if fused:
+        b_env -= 16 * W + 12 * A + 8
+    if not raw:
+        b_env -= 28 * A * R
+    b_env += 16 * A * R / cfg['subsample'] + 12 * A
+    return b_env * N, W
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip().split(', '))
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if v.strip().lower().startswith('active'):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on the host cores, bounded sample of the same workload
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_baseline(cfg, arrays, pos, ang, budget_s=12.):
+    from megastep_b200 import sharding
+    from oracle import oracle
+    A, R = cfg['n_agents'], cfg['res']
+    rng = np.random.RandomState(7)
+
+    def run(n):
+        sub = sharding.shard_arrays(arrays, 0, n)
+        sub['baked'] = np.ones(len(sub['textures']), np.float32) if 'baked' not in sub else sub['baked']
+        st = dict(angles=ang[:n].copy(), positions=pos[:n].copy(), angvelocity=np.zeros((n, A), np.float32),
+                  velocity=(2 * rng.normal(size=(n, A, 2))).astype(np.float32))
+        t = time.perf_counter()
+        oracle.physics(sub, st, fps=FPS)
+        oracle.render(sub, st, res=R, fov=cfg['fov'])
+        return time.perf_counter() - t
+
+    n = min(64, len(pos))
+    t = run(n)
+    n2 = int(min(len(pos), max(n, n * budget_s / max(t, 1e-3))))
+    if n2 > n:
+        t, n = run(n2), n2
+    return {'value': n * A / t, 'unit': 'agent-frames/s', 'cores': oracle.num_threads(), 'kind': 'port',
+            'sample': f'oracle/megastep_oracle.c physics+render, 1 step over the first {n} of {len(pos)} envs x {A} agents x {R} rays, '
+                      f'{oracle.num_threads()} OpenMP threads, {t:.2f} s'}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the two arms
+# ---------------------------------------------------------------------------------------------------------------
+class Ours:
+    name = 'ours'
+
+    def __init__(self, cfg, arrays, pos, ang, device, raw):
+        import torch
+        from megastep_b200 import core as core_, cuda, modules, scene
+        self.cuda = cuda
+        s = scene.upload(arrays, device)
+        cuda.bake(s, params=cuda.make_params(AGENT_RADIUS, cfg['res'], cfg['fov'], FPS))
+        self.core = core_.Core(s, res=cfg['res'], fov=cfg['fov'], fps=FPS)
+        self.core.agents.positions.copy_(torch.as_tensor(pos))
+        self.core.agents.angles.copy_(torch.as_tensor(ang))
+        self.stepper = modules.FusedStep(self.core, subsample=cfg['subsample'], raw=raw)
+        self.actions = self.stepper.actions
+        self.fused = True
+
+    def step(self):
+        self.stepper()                       # one launch: movement + physics + render + heads
+
+    def result(self):
+        return self.stepper._plan.progress
+
+    def obs(self):
+        p = self.stepper._plan
+        return {'rgb': p.rgb, 'd': p.depth, 'imu': p.imu}
+
+    def launches(self):
+        return self.cuda.launch_count()
+
+
+class Reference:
+    """The reference's own CUDA build through its own API, with the PyTorch ops of its modules.py around it
+    (modules.py:106-118 MomentumMovement, :126-136 render, :181-184 Depth, :222-224 RGB, :268-270 IMU)."""
+    name = 'reference'
+
+    def __init__(self, cfg, arrays, pos, ang, device, raw):
+        import torch
+        import common
+        self.torch = torch
+        self.ref = common.reference_module()
+        if self.ref is None:
+            raise RuntimeError('oracle/_ref is not built')
+        ref = self.ref
+        ref.initialize(AGENT_RADIUS, cfg['res'], cfg['fov'], FPS)
+        self.scenery = common.reference_scenery(ref, arrays, device)
+        ref.bake(self.scenery)
+        N, A = pos.shape[:2]
+        z = lambda *s: torch.zeros(s, device=device)
+        self.agents = ref.Agents(angles=torch.as_tensor(ang).to(device), positions=torch.as_tensor(pos).to(device),
+                                 angvelocity=z(N, A), velocity=z(N, A, 2))
+        self.actions = torch.zeros((N, A), dtype=torch.int32, device=device)
+        vel = torch.tensor([[0., 0.], [0., 1.], [0., -1.], [1., 0.], [-1., 0.], [0., 0.], [0., 0.]], device=device)
+        angv = torch.tensor([0., 0., 0., 0., 0., +1., -1.], device=device)
+        self.set_v, self.set_w = 5 / FPS * vel, 180 / FPS * angv
+        self.sub = cfg['subsample']
+        self.fused = False
+        self._p = self._obs = None
+
+    def step(self):
+        torch, ag = self.torch, self.agents
+        a = self.actions.long()
+        dv, dw = self.set_v[a], self.set_w[a]
+        ag.angvelocity[:] = (1 - .125) * ag.angvelocity + dw
+        rad = np.pi / 180 * ag.angles
+        c, s = torch.cos(rad), torch.sin(rad)
+        ag.velocity[:] = (1 - .125) * ag.velocity + torch.stack([c * dv[..., 0] - s * dv[..., 1], s * dv[..., 0] + c * dv[..., 1]], -1)
+        self._p = self.ref.physics(self.scenery, ag)
+        r = self.ref.render(self.scenery, ag)
+        screen = r.screen.unsqueeze(2).permute(0, 1, 4, 2, 3)
+        dist = r.distances.unsqueeze(2)
+        depth = 1 - ((dist - AGENT_RADIUS) / 10).clamp(0, 1)
+        ds = lambda x: x.view(*x.shape[:-1], x.shape[-1] // self.sub, self.sub).mean(-1)
+        rad = np.pi / 180 * ag.angles
+        c, s = torch.cos(rad), torch.sin(rad)
+        vx, vy = ag.velocity[..., 0], ag.velocity[..., 1]
+        imu = torch.cat([ag.angvelocity[..., None] / 360., torch.stack([c * vx + s * vy, -s * vx + c * vy], -1) / 10.], -1)
+        self._obs = {'rgb': ds(screen), 'd': ds(depth).unsqueeze(3), 'imu': imu}
+
+    def result(self):
+        return self._p.progress
+
+    def obs(self):
+        return self._obs
+
+    def launches(self):
+        return 0
+
+
+def run_gpu(args, cfg, arm_cls, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+    n_envs = args.envs or cfg['n_envs']
+    gs, arrays, pos, ang = build_scene(cfg, n_envs, args.unique, rank)
+    raw = not args.no_raw
+    arm = arm_cls(cfg, arrays, pos, ang, device, raw)
+    N, A = pos.shape[:2]
+    K, W = args.steps, args.warmup
+    rng = np.random.RandomState(3 + rank)
+    acts_host = torch.as_tensor(rng.randint(0, 7, (K + W, N, A)).astype(np.int32)).pin_memory()
+    acts_dev = acts_host.to(device)
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=device)
+    gather = None
+    if args.gather and world > 1:
+        from megastep_b200 import sharding
+        arm.actions.copy_(acts_dev[0])
+        arm.step()
+        gather = sharding.ObsGather(arm.obs())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM, L2 flushed between steps, device-timed per step -------------------------
+    for i in range(W):
+        arm.actions.copy_(acts_dev[i])
+        arm.step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = arm.launches()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    t0 = time.perf_counter()
+    for i in range(K):
+        arm.actions.copy_(acts_dev[W + i])
+        flush.fill_(0.)                       # evict the previous step's lines/outputs from the 126 MB L2
+        starts[i].record()
+        arm.step()
+        if gather is not None:
+            gather.start(arm.obs())
+            gather.wait()
+        stops[i].record()
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = arm.launches() - launches0
+    per_step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
+    step_ms = float(per_step_ms.sum())
+
+    # ---- e2e: host actions in pinned memory -> H2D -> step through the public API -> D2H of the step's result -----
+    result_host = torch.empty((N, A), dtype=torch.float32).pin_memory()
+    for i in range(W):
+        arm.actions.copy_(acts_host[i], non_blocking=True)
+        arm.step()
+        result_host.copy_(arm.result(), non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        arm.actions.copy_(acts_host[W + i], non_blocking=True)
+        arm.step()
+        result_host.copy_(arm.result(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the host consumes each step's result before the next
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+
+    # max over ranks
+    t = torch.tensor([step_ms, e2e_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms, e2e_ms = t.tolist()
+    total_bytes, mean_w = algorithmic_bytes(cfg, arrays, arm.fused, raw)
+    return dict(N=N, A=A, step_ms=step_ms, e2e_ms=e2e_ms, wall_s=wall, launches=launches, clocks=clocks,
+                bytes_per_step=total_bytes, mean_walls=mean_w, arrays=arrays, pos=pos, ang=ang,
+                per_step_ms=per_step_ms)
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650., 'fallback (B200_PROFILING.md)'
+
+
+def main():
+    args = parse()
+    cfg = dict(WORKLOADS[args.workload])
+    if args.res:
+        cfg['res'] = args.res
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    n_envs = args.envs or cfg['n_envs']
+
+    if args.dry_run:
+        gs, arrays, pos, ang = build_scene(cfg, n_envs, args.unique, 0)
+        b, w = algorithmic_bytes(cfg, arrays, True)
+        print(json.dumps({'envs': n_envs, 'mean_walls': w, 'bytes_per_step': b, 'cpu_baseline': cpu_baseline(cfg, arrays, pos, ang, 3.)}))
+        return
+
+    reference = args.impl == 'reference'
+    if reference and rank != 0:
+        return      # the reference is single-GPU: rank 0 alone runs it
+    if world > 1 and not reference:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=__import__('torch').device('cuda', local_rank))
+    eff_world = 1 if reference else world
+
+    arm_cls = Reference if reference else Ours
+    kind = 'reference'
+    try:
+        out = run_gpu(args, cfg, arm_cls, rank if not reference else 0, eff_world, local_rank)
+    except RuntimeError as e:
+        if not reference or 'oracle/_ref' not in str(e):
+            raise
+        out, kind = None, 'port'
+
+    if rank != 0:
+        if world > 1 and not reference:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    base_cfg = {'workload': f"{args.workload}: synthetic cubicasa-shaped floorplans, {n_envs} envs/GPU x {cfg['n_agents']} agents x "
+                            f"{cfg['res']} rays, fov {cfg['fov']:g}, MomentumMovement + physics + render + RGB/Depth/IMU (subsample {cfg['subsample']})",
+                'envs_per_gpu': n_envs, 'n_agents': cfg['n_agents'], 'res': cfg['res'], 'fov': cfg['fov'], 'subsample': cfg['subsample'],
+                'raw_render_outputs': not args.no_raw, 'parallelism': f'env-sharded x{eff_world}, no per-step collective' + (' + obs all-gather' if args.gather else ''),
+                'l2': f'flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write); per-step CUDA events'}
+
+    if out is None:
+        # reference arm without the reference build: the CPU oracle port on the host cores
+        gs, arrays, pos, ang = build_scene(cfg, n_envs, args.unique, 0)
+        cb = cpu_baseline(cfg, arrays, pos, ang)
+        line = {'metric': 'agent-frames/sec', 'value': cb['value'], 'unit': 'agent-frames/s', 'n_gpus': 0, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': None, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32', 'data': 'synthetic', 'config': base_cfg, 'impl': 'reference', 'cpu_baseline': cb,
+                'e2e': {'value': cb['value'], 'unit': 'agent-frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'gpu_launches': 0}
+        print(json.dumps(line))
+        return
+
+    K = args.steps
+    frames = out['N'] * out['A'] * eff_world
+    value = frames * K / (out['step_ms'] * 1e-3)
+    e2e = frames * K / (out['e2e_ms'] * 1e-3)
+    achieved = out['bytes_per_step'] / (out['step_ms'] / K * 1e-3) / 1e9
+    line = {
+        'metric': 'agent-frames/sec', 'value': value, 'unit': 'agent-frames/s', 'n_gpus': eff_world, 'steps': K, 'warmup': args.warmup,
+        'ms_per_step': out['step_ms'] / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': base_cfg, 'impl': args.impl,
+        'e2e': {'value': e2e, 'unit': 'agent-frames/s', 'h2d_bytes_per_step': out['N'] * out['A'] * 4,
+                'd2h_bytes_per_step': out['N'] * out['A'] * 4, 'ms_per_step': out['e2e_ms'] / K,
+                'what': 'pinned-host actions -> H2D -> step via the public API -> D2H of progress (the physics result) + stream sync, every step; observations stay on the device as in the reference'},
+        'gpu_launches': out['launches'],
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                     'kernel': 'env_kernel<MODE_STEP> (fused movement+physics+render+heads)' if args.impl == 'ours' else 'whole step (physics + render + ~40 ATen launches)',
+                     'algorithmic_bytes_per_step': out['bytes_per_step'], 'mean_walls_per_env': out['mean_walls'], 'peak_source': peak_src},
+        'clocks': out['clocks'],
+        'step_ms_percentiles': {p: float(np.percentile(out['per_step_ms'], p)) for p in (5, 50, 95)},
+    }
+    if reference:
+        line['cpu_baseline'] = {'value': value, 'unit': 'agent-frames/s', 'cores': 0, 'kind': 'reference',
+                                'sample': 'the reference\'s own CUDA build (oracle/_ref) on one B200 of this box: megastep has no CPU step path'}
+    elif not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline(cfg, out['arrays'], out['pos'], out['ang'])
+    print(json.dumps(line))
+    if world > 1 and not reference:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

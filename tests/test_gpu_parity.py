@@ -1,0 +1,328 @@
+"""Parity of the sm_100a kernels — called through the C ABI — on a real GPU.
+
+Three checkers, strongest first:
+  1. oracle/_ref: the reference's OWN kernels.cu/wrappers.cpp compiled unmodified for sm_100a. Bar: hit indices and
+     collision flags bit-exact, floats bit-exact too (the kernels restate its arithmetic op-for-op); the asserted
+     tolerance for positions/depth is the north-star's 1e-5 abs, and the exact-match fractions are printed.
+  2. oracle/megastep_oracle.c: the CPU restatement (always available). MUFU.RCP/SQRT are not reproducible on a
+     CPU, so floats are compared to 1e-4 relative and indices must agree except at near-ties.
+  3. size-independent properties at the benchmark's full size (BASELINE.json configs[2]).
+"""
+import numpy as np
+import pytest
+import torch
+
+import common
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, scene kind, n_envs, n_agents, res, fov
+    ('box-explorer', 'box', 3, 1, 64, 130.),
+    ('column', 'column', 2, 2, 32, 90.),
+    ('synthetic-explorer', 'synthetic', 24, 1, 64, 130.),
+    ('synthetic-deathmatch', 'synthetic', 16, 4, 128, 70.),
+    ('synthetic-ragged-res', 'synthetic', 5, 3, 48, 100.),     # res not a multiple of 32
+    ('synthetic-wide', 'synthetic', 4, 2, 512, 70.),
+]
+
+
+def make(kind, n_envs, n_agents, seed=11):
+    if kind == 'synthetic':
+        gs, arrays = common.synthetic_scene(n_envs, n_agents, seed=seed)
+    else:
+        gs, arrays = common.toy_scene(kind, n_envs, n_agents, seed=seed)
+    return gs, arrays, common.random_state(gs, n_agents, seed=seed + 1)
+
+
+@pytest.fixture(scope='module')
+def ref():
+    return common.reference_module()
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# 2. against the CPU oracle
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name,kind,N,A,res,fov', CASES)
+def test_render_against_oracle(name, kind, N, A, res, fov):
+    gs, arrays, st = make(kind, N, A)
+    c = common.to_device(arrays, st, res, fov)
+    r = c.render()
+    want = oracle.render(arrays, st, res=res, fov=fov)
+    torch.cuda.synchronize()
+    idx, dist = _np(r.indices), _np(r.distances)
+    differ, really = common.index_agreement(idx, want['indices'], dist, want['distances'])
+    assert really == 0., f'{name}: {really:.2%} of rays hit something at a different depth than the oracle'
+    assert differ < 2e-3, f'{name}: {differ:.2%} of hit indices differ from the oracle'
+    same = idx == want['indices']
+    hit = same & (idx >= 0)
+    np.testing.assert_allclose(dist[hit], want['distances'][hit], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(_np(r.locations)[hit], want['locations'][hit], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(_np(r.dots)[hit], want['dots'][hit], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(_np(r.screen)[same], want['screen'][same], rtol=0, atol=2e-3)
+    miss = same & (idx < 0)
+    assert np.isinf(dist[miss]).all() and np.isnan(_np(r.locations)[miss]).all() and (_np(r.screen)[miss] == 0).all()
+    # draw side effect: the agents' model lines now sit at the agents' poses
+    np.testing.assert_allclose(_np(c.scenery.lines.vals), want['lines'], rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize('name,kind,N,A,res,fov', CASES[:4])
+def test_physics_against_oracle(name, kind, N, A, res, fov):
+    gs, arrays, st = make(kind, N, A)
+    c = common.to_device(arrays, st, res, fov)
+    want_st = common.copy_state(st)
+    for _ in range(3):     # a few ticks so collisions, stops and re-accelerations all occur
+        p = c.physics()
+        want_p = oracle.physics(arrays, want_st, fps=10.)
+        got = common.read_state(c)
+        collided = _np(p.progress) < 1
+        assert (collided == (want_p < 1)).mean() > .995
+        agree = collided == (want_p < 1)
+        np.testing.assert_allclose(_np(p.progress)[agree], want_p[agree], rtol=0, atol=2e-4)
+        for k in ('positions', 'velocity'):
+            np.testing.assert_allclose(got[k][agree], want_st[k][agree], rtol=0, atol=2e-4, err_msg=k)
+        # angles wrap at +-180: compare on the circle
+        d = (got['angles'] - want_st['angles'] + 180.) % 360. - 180.
+        assert np.abs(d[agree]).max() < 1e-2
+        # resync so that one near-tie does not compound over the following ticks
+        common.load_state(c, want_st)
+        st_rand = np.random.RandomState(5)
+        want_st['velocity'] += st_rand.normal(size=want_st['velocity'].shape).astype(np.float32)
+        common.load_state(c, want_st)
+
+
+def test_bake_against_oracle():
+    gs, arrays = common.synthetic_scene(6, 2, seed=21, bake=True)
+    from megastep_b200 import cuda, scene
+    s = scene.upload(arrays)
+    cuda.bake(s, params=cuda.make_params(common.AGENT_RADIUS, 64, 130., 10.))
+    got = _np(s.baked.vals)
+    # a texel whose light ray grazes a wall end can flip between lit and unlit: allow a handful
+    bad = np.abs(got - arrays['baked']) > 1e-4
+    assert bad.mean() < 2e-3, f'{bad.mean():.3%} of baked texels differ from the oracle'
+
+
+def test_physics_known_answer_from_reference_docs():
+    # docs/tutorials/minimal-env/index.rst:140-145
+    gs, arrays = common.toy_scene('box', 4, 1)
+    st = dict(angles=np.zeros((4, 1), np.float32), positions=np.full((4, 1, 2), 3., np.float32),
+              angvelocity=np.zeros((4, 1), np.float32), velocity=np.tile(np.float32([1000., 0.]), (4, 1, 1)))
+    c = common.to_device(arrays, st, 64, 130.)
+    p = c.physics()
+    np.testing.assert_allclose(_np(c.agents.positions), np.tile(np.float32([5.8649, 3.]), (4, 1, 1)), atol=5e-5)
+    assert (_np(p.progress) < 1).all() and (_np(c.agents.velocity) == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# 1. against the reference's own CUDA build
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name,kind,N,A,res,fov', CASES)
+def test_render_bit_exact_against_reference_build(ref, name, kind, N, A, res, fov):
+    if ref is None:
+        pytest.skip('oracle/_ref not built (needs /root/reference at build time)')
+    gs, arrays, st = make(kind, N, A)
+    c = common.to_device(arrays, st, res, fov)
+    r = c.render()
+    ref.initialize(common.AGENT_RADIUS, res, fov, 10.)
+    rs, ra = common.reference_scenery(ref, arrays), common.reference_agents(ref, st)
+    rr = ref.render(rs, ra)
+    torch.cuda.synchronize()
+    assert torch.equal(r.indices, rr.indices), f'{name}: {(r.indices != rr.indices).float().mean():.3%} hit indices differ'
+    for k in ('locations', 'dots', 'distances', 'screen'):
+        a, b = getattr(r, k), getattr(rr, k)
+        same = (a == b) | (a.isnan() & b.isnan())
+        print(f'{name}: {k} bit-exact on {same.float().mean():.6%}')
+        torch.testing.assert_close(a, b, rtol=0, atol=1e-5, equal_nan=True)
+        assert same.all(), f'{name}: {k} is within 1e-5 but not bit-exact on {(~same).float().mean():.4%}'
+    assert torch.equal(c.scenery.lines.vals, rs.lines.vals)
+
+
+@pytest.mark.parametrize('name,kind,N,A,res,fov', CASES[:4])
+def test_physics_bit_exact_against_reference_build(ref, name, kind, N, A, res, fov):
+    if ref is None:
+        pytest.skip('oracle/_ref not built (needs /root/reference at build time)')
+    gs, arrays, st = make(kind, N, A)
+    c = common.to_device(arrays, st, res, fov)
+    ref.initialize(common.AGENT_RADIUS, res, fov, 10.)
+    rs, ra = common.reference_scenery(ref, arrays), common.reference_agents(ref, st)
+    rng = np.random.RandomState(9)
+    for tick in range(4):
+        p, rp = c.physics(), ref.physics(rs, ra)
+        assert torch.equal(p.progress < 1, rp.progress < 1), f'{name}: collision flags differ at tick {tick}'
+        for k, a, b in [('progress', p.progress, rp.progress)] + [(k, getattr(c.agents, k), getattr(ra, k)) for k in
+                                                                   ('positions', 'angles', 'velocity', 'angvelocity')]:
+            torch.testing.assert_close(a, b, rtol=0, atol=1e-5, msg=lambda m: f'{name} tick {tick} {k}: {m}')
+            assert torch.equal(a, b), f'{name} tick {tick}: {k} within 1e-5 but not bit-exact'
+        kick = torch.as_tensor(rng.normal(size=st['velocity'].shape).astype(np.float32) * 2).cuda()
+        c.agents.velocity.add_(kick)
+        ra.velocity.add_(kick)
+
+
+def test_bake_bit_exact_against_reference_build(ref):
+    if ref is None:
+        pytest.skip('oracle/_ref not built (needs /root/reference at build time)')
+    gs, arrays = common.synthetic_scene(6, 2, seed=21, bake=False)
+    from megastep_b200 import cuda, scene
+    s = scene.upload(arrays)
+    cuda.bake(s, params=cuda.make_params(common.AGENT_RADIUS, 64, 130., 10.))
+    ref.initialize(common.AGENT_RADIUS, 64, 130., 10.)
+    rs = common.reference_scenery(ref, arrays)
+    ref.bake(rs)
+    torch.cuda.synchronize()
+    same = s.baked.vals == rs.baked.vals
+    assert same.all(), f'{(~same).float().mean():.4%} of baked texels differ from the reference build'
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused paths against the unfused ones
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('A,res,fov,sub', [(4, 128, 70., 1), (4, 512, 70., 4), (1, 256, 130., 4)])
+def test_fused_step_equals_modules_pipeline(A, res, fov, sub):
+    from megastep_b200 import modules
+    from megastep_b200.arrdict import arrdict
+    gs, arrays, st = make('synthetic', 12, A, seed=31)
+    c1, c2 = common.to_device(arrays, st, res, fov), common.to_device(arrays, st, res, fov)
+    mover, rgb, depth, imu = modules.MomentumMovement(c1), modules.RGB(c1, subsample=sub), modules.Depth(c1, subsample=sub), modules.IMU(c1)
+    fused = modules.FusedStep(c2, subsample=sub, raw=True)
+    rng = np.random.RandomState(3)
+    for tick in range(5):
+        actions = torch.as_tensor(rng.randint(0, 7, (12, A))).int().cuda()
+        p = mover(arrdict(actions=actions))
+        r = modules.render(c1)
+        want = arrdict(rgb=rgb(r), d=depth(r), imu=imu())
+        out = fused(actions)
+        torch.cuda.synchronize()
+        assert torch.equal(out.progress < 1, p.progress < 1)
+        torch.testing.assert_close(out.progress, p.progress, rtol=0, atol=1e-6)
+        for k in ('positions', 'angles', 'velocity', 'angvelocity'):
+            torch.testing.assert_close(getattr(c2.agents, k), getattr(c1.agents, k), rtol=0, atol=1e-5, msg=lambda m: f'tick {tick} {k}: {m}')
+        same = out.render.indices == r.indices.squeeze(2)
+        assert same.float().mean() > .999
+        torch.testing.assert_close(out.obs.imu, want.imu, rtol=0, atol=1e-6)
+        ok = downsampled_all(same, sub)
+        torch.testing.assert_close(out.obs.d.squeeze(2).squeeze(2)[ok], want.d.squeeze(2).squeeze(2)[ok], rtol=0, atol=1e-5)
+        okc = ok[:, :, None, :].expand(-1, -1, 3, -1)
+        torch.testing.assert_close(out.obs.rgb.squeeze(3)[okc], want.rgb.squeeze(3)[okc], rtol=0, atol=1e-5)
+        # keep the two cores in lock step even if a near-tie made them diverge by an ulp
+        common.load_state(c2, common.read_state(c1))
+
+
+def downsampled_all(mask, sub):
+    return mask.reshape(*mask.shape[:-1], mask.shape[-1] // sub, sub).all(-1)
+
+
+def test_rgbd_head_equals_rgb_and_depth_modules():
+    from megastep_b200 import modules
+    gs, arrays, st = make('synthetic', 8, 4, seed=41)
+    c = common.to_device(arrays, st, 512, 70.)
+    r = modules.render(c)
+    want_rgb, want_d, want_imu = modules.RGB(c, subsample=4)(r), modules.Depth(c, subsample=4)(r), modules.IMU(c)()
+    obs = modules.RGBD(c, subsample=4)()
+    torch.cuda.synchronize()
+    assert obs.rgb.shape == want_rgb.shape and obs.d.shape == want_d.shape
+    torch.testing.assert_close(obs.rgb, want_rgb, rtol=0, atol=1e-6)
+    torch.testing.assert_close(obs.d, want_d, rtol=0, atol=1e-6)
+    torch.testing.assert_close(obs.imu, want_imu, rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize('res', [64, 128, 512])
+def test_every_kernel_variant_gives_identical_results(res):
+    """The chunking / thread-count options change which exact tests are skipped and who runs them, never results."""
+    from megastep_b200 import cuda
+    gs, arrays, st = make('synthetic', 10, 4, seed=51)
+    c = common.to_device(arrays, st, res, 70.)
+    base = c.render()
+    try:
+        for nch in (1, 2, 4):
+            for threads in (64, 128, 256):
+                cuda.set_option('nch', nch)
+                cuda.set_option('threads', threads)
+                r = c.render()
+                for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
+                    a, b = getattr(r, k), getattr(base, k)
+                    assert ((a == b) | (a != a) & (b != b)).all(), f'nch={nch} threads={threads}: {k} differs'
+    finally:
+        cuda.set_option('nch', 0)
+        cuda.set_option('threads', 0)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# 3. properties at the benchmark's full size (Deathmatch 4096 x 4 x 128)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def full():
+    from megastep_b200 import scene, synthetic, cuda, core as core_
+    N, A = 4096, 4
+    gs = synthetic.sample(N, seed=1, n_unique=256)
+    arrays = synthetic.tile_arrays(scene.scene_arrays(gs[:256], A, np.random.RandomState(1)), N)
+    s = scene.upload(arrays)
+    cuda.bake(s, params=cuda.make_params(common.AGENT_RADIUS, 128, 70., 10.))
+    c = core_.Core(s, res=128, fov=70., fps=10.)
+    pos, ang = synthetic.spawns(gs, A, np.random.RandomState(2))
+    c.agents.positions.copy_(torch.as_tensor(pos))
+    c.agents.angles.copy_(torch.as_tensor(ang))
+    return c, gs, arrays
+
+
+def test_full_size_render_properties(full):
+    c, gs, arrays = full
+    r1, r2 = c.render(), c.render()
+    torch.cuda.synchronize()
+    # idempotent and deterministic
+    for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
+        a, b = getattr(r1, k), getattr(r2, k)
+        assert ((a == b) | (a != a) & (b != b)).all()
+    idx = r1.indices
+    widths = c.scenery.lines.widths[:, None, None]
+    assert (idx >= -1).all() and (idx < widths).all()
+    hit = idx >= 0
+    assert hit.float().mean() > .95                                        # indoors, nearly every ray hits a wall
+    assert (r1.distances[hit] > common.AGENT_RADIUS * .999).all() and r1.distances[~hit].isinf().all()
+    assert ((r1.locations[hit] >= 0) & (r1.locations[hit] <= 1)).all()
+    assert (r1.screen >= 0).all() and (r1.screen <= 1.0001).all() and (r1.screen[~hit] == 0).all()
+    # a sampled slice of envs against the CPU oracle (a checksum of the whole against a checksum of the sample's kin)
+    pick = np.arange(0, 4096, 512)
+    st = common.read_state(c)
+    for n in pick:
+        sub = {k: v[n:n + 1] for k, v in st.items()}
+        lo, hi = int(c.scenery.lines.starts[n]), int(c.scenery.lines.ends[n])
+        tl, th = int(c.scenery.textures._long_starts()[lo]), int(c.scenery.textures._long_starts()[hi - 1] + c.scenery.textures.widths[hi - 1])
+        one = dict(n_agents=4, model=arrays['model'], lines=_np(c.scenery.lines.vals[lo:hi]), line_widths=np.int32([hi - lo]),
+                   lights=_np(c.scenery.lights[int(n)]), light_widths=np.int32([len(c.scenery.lights[int(n)])]),
+                   textures=_np(c.scenery.textures.vals[tl:th]), tex_widths=_np(c.scenery.textures.widths[lo:hi]),
+                   baked=_np(c.scenery.baked.vals[tl:th]))
+        want = oracle.render(one, sub, res=128, fov=70.)
+        differ, really = common.index_agreement(_np(r1.indices[n:n + 1]), want['indices'], _np(r1.distances[n:n + 1]), want['distances'])
+        assert really == 0. and differ < 5e-3
+
+
+def test_full_size_physics_properties(full):
+    c, gs, arrays = full
+    before = common.read_state(c)
+    # at rest nothing moves and nothing collides
+    c.agents.velocity.zero_()
+    c.agents.angvelocity.zero_()
+    p = c.physics()
+    assert (p.progress == 1).all()
+    assert torch.equal(c.agents.positions.cpu(), torch.as_tensor(before['positions']))
+    # with random velocities: progress in [0, 1]; collided agents are stopped; nobody tunnels out of the building
+    rng = np.random.RandomState(3)
+    c.agents.velocity.copy_(torch.as_tensor((4 * rng.normal(size=before['velocity'].shape)).astype(np.float32)))
+    c.agents.angvelocity.copy_(torch.as_tensor(rng.uniform(-300, 300, before['angvelocity'].shape).astype(np.float32)))
+    v0 = c.agents.velocity.clone()
+    for _ in range(10):
+        p = c.physics()
+        assert ((p.progress >= 0) & (p.progress <= 1)).all()
+        stopped = p.progress < 1
+        assert (c.agents.velocity[stopped] == 0).all() and (c.agents.angvelocity[stopped] == 0).all()
+        assert ((c.agents.angles >= -180) & (c.agents.angles < 180)).all()
+        c.agents.velocity.copy_(v0)
+    pos = c.agents.positions.cpu().numpy()
+    hi = np.array([[g.rooms[:, 2].max(), g.rooms[:, 3].max()] for g in gs])[:, None]
+    assert (pos > .5).all() and (pos < hi + .5).all()
+    common.load_state(c, before)
