@@ -50,6 +50,7 @@ struct KArgs {
     float inv_fps;          // IEEE 1/fps (ATen's tensor/scalar == tensor*(1/scalar), kernels.cu:224,226)
     float mv_keep, mv_dv, mv_dw;   // 1-decay, accel/fps, ang_accel/fps evaluated in double like the Python does
     float inv_max_depth, inv_speed, inv_ang, inv_sub;   // reciprocals ATen would multiply by
+    float bin_kappa, bin_rmid, bin_xclip;               // screen-space binning constants (culling only)
     unsigned long long* stats;  // optional diagnostics counters (may be null)
 };
 
@@ -304,10 +305,9 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
     }
 
     // ---- conservative screen-space binning constants (never affect results, only which exact tests are skipped)
-    const float hs = k.p.half_screen;
-    const float kappa = Rf / (2.f * hs);                 // rays per unit of screen coordinate
-    const float rmid = 0.5f * (Rf - 1.f);
-    const float xclip = 0.5f * k.p.agent_radius * rsqrtf(1.f + hs * hs);   // well inside every ray's near plane
+    const float kappa = k.bin_kappa;     // rays per unit of screen coordinate, R / (2 tan(fov/2))
+    const float rmid = k.bin_rmid;       // (R - 1) / 2
+    const float xclip = k.bin_xclip;     // well inside every ray's near plane
     const float delta = 0.05f;
     const float lo_chunk = (float)r0, hi_chunk = (float)(r0 + 32 * NCH - 1);
     unsigned tests = 0, groups = 0;
@@ -328,9 +328,9 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
             float xb = bxr * cs + byr * sn, yb = byr * cs - bxr * sn;
             const bool behind = (xa < xclip) && (xb < xclip);
             if (!behind) {
-                if (xa < xclip) { const float tt = (xclip - xa) / (xb - xa); ya = ya + tt * (yb - ya); xa = xclip; }
-                if (xb < xclip) { const float tt = (xclip - xb) / (xa - xb); yb = yb + tt * (ya - yb); xb = xclip; }
-                const float sa = ya / xa, sb = yb / xb;
+                if (xa < xclip) { const float tt = __fdividef(xclip - xa, xb - xa); ya = ya + tt * (yb - ya); xa = xclip; }
+                if (xb < xclip) { const float tt = __fdividef(xclip - xb, xa - xb); yb = yb + tt * (ya - yb); xb = xclip; }
+                const float sa = __fdividef(ya, xa), sb = __fdividef(yb, xb);
                 const float rf_first = rmid - fmaxf(sa, sb) * kappa - delta;
                 const float rf_last = rmid - fminf(sa, sb) * kappa + delta;
                 // NaN-safe: any comparison failing leaves the full range, i.e. the exact test still runs
@@ -700,6 +700,9 @@ static void fill(KArgs& k, const msb_params* p, const msb_scenery* s, const msb_
     k.inv_fps = 1.0f / p->fps;
     k.ray_blocks = 1;
     k.stats = g_stats;
+    k.bin_kappa = (float)p->res / (2.f * p->half_screen);
+    k.bin_rmid = 0.5f * ((float)p->res - 1.f);
+    k.bin_xclip = 0.5f * p->agent_radius / sqrtf(1.f + p->half_screen * p->half_screen);
 }
 
 extern "C" int msb_physics(const msb_params* p, const msb_scenery* s, const msb_agents* a, float* progress,
