@@ -211,30 +211,80 @@ __device__ __forceinline__ void physics_stage(const KArgs& k, const Smem& m, int
 // render
 // ---------------------------------------------------------------------------------------------------------------
 
-// light_intensity() (kernels.cu:238-268) at point C, evaluated by a whole warp: lanes stride the static lines,
-// the first occluder found ends that light. Returns the same value in every lane.
-__device__ __forceinline__ float light_intensity_warp(const KArgs& k, const Smem& m, int n, int L, int AF, float Cx,
-                                                      float Cy, int lane, unsigned& iters) {
-    const int I = k.s.light_widths[n];
-    const float* lt = k.s.lights + 3 * (int64_t)k.s.light_starts[n];
+// light_intensity() (kernels.cu:238-268) for a ray that hit an agent, evaluated by a whole warp with the first 32
+// lights resident one per lane. Each lane remembers the static line that last occluded its light: consecutive
+// agent-hit rays land centimetres apart, so one test per light (all lights in parallel) settles almost every
+// occluded light; only the remaining lights are scanned against all static lines (lanes stride the lines, stop at
+// the first occluder). Unoccluded lights are then accumulated in light order, exactly as the reference sums them.
+// Which lines get tested varies; the occluded/unoccluded answer per light — hence the result — does not.
+struct LaneLight { float x, y, i; int occ; };
+
+template <bool STATS>
+__device__ __forceinline__ float light_intensity_cached(const Smem& m, int L, int AF, int I, const float* lt, float Cx,
+                                                        float Cy, int lane, LaneLight& ll, unsigned& iters) {
+    const int nres = I < 32 ? I : 32;
+    // phase 1: the remembered occluder of each resident light
+    bool ob = false;
+    if (lane < nres && ll.occ >= 0) {
+        const Hit h = intersect(ll.x, ll.y, fsub(Cx, ll.x), fsub(Cy, ll.y), m.seg[ll.occ]);
+        ob = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
+    }
+    const unsigned resident = nres == 32 ? 0xffffffffu : ((1u << nres) - 1u);
+    unsigned todo = resident & ~__ballot_sync(0xffffffffu, ob);
+    unsigned lit = 0;
+    if (STATS) iters++;
+    // phase 2: full scans for the lights the cache did not settle
+    while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float Ix = __shfl_sync(0xffffffffu, ll.x, i), Iy = __shfl_sync(0xffffffffu, ll.y, i);
+        const float Ux = fsub(Cx, Ix), Uy = fsub(Cy, Iy);
+        int found = -1;
+        for (int base = AF; base < L; base += 64) {
+            const int l0 = base + lane, l1 = base + 32 + lane;
+            bool o0 = false, o1 = false;
+            if (l0 < L) {
+                const Hit h = intersect(Ix, Iy, Ux, Uy, m.seg[l0]);
+                o0 = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
+            }
+            if (l1 < L) {
+                const Hit h = intersect(Ix, Iy, Ux, Uy, m.seg[l1]);
+                o1 = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
+            }
+            if (STATS) iters++;
+            const unsigned b0 = __ballot_sync(0xffffffffu, o0), b1 = __ballot_sync(0xffffffffu, o1);
+            if (b0 | b1) { found = b0 ? base + __ffs(b0) - 1 : base + 32 + __ffs(b1) - 1; break; }
+        }
+        if (found < 0) lit |= 1u << i;
+        else if (lane == i) ll.occ = found;
+    }
+    // phase 3: sum the unoccluded lights in light order (:261-264)
     float acc = 0.1f;   // AMBIENT (kernels.cu:9)
-    for (int i = 0; i < I; i++) {
+    while (lit) {
+        const int i = __ffs(lit) - 1;
+        lit &= lit - 1;
+        const float Ix = __shfl_sync(0xffffffffu, ll.x, i), Iy = __shfl_sync(0xffffffffu, ll.y, i);
+        const float Ii = __shfl_sync(0xffffffffu, ll.i, i);
+        const float dx = fsub(Ix, Cx), dy = fsub(Iy, Cy);
+        acc = ffma(fadd(Ii, Ii), rcp(fmaxf(ffma(dx, dx, fmul(dy, dy)), 1.f)), acc);   // LUMINANCE = 2 (:240)
+    }
+    // lights beyond the first 32 (rare): the plain cooperative scan, still in light order
+    for (int i = 32; i < I; i++) {
         const float Ix = __ldg(lt + 3 * i), Iy = __ldg(lt + 3 * i + 1), Ii = __ldg(lt + 3 * i + 2);
         const float Ux = fsub(Cx, Ix), Uy = fsub(Cy, Iy);
         bool occluded = false;
         for (int base = AF; base < L; base += 32) {
             const int l = base + lane;
-            bool ob = false;
+            bool o = false;
             if (l < L) {
                 const Hit h = intersect(Ix, Iy, Ux, Uy, m.seg[l]);
-                ob = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
+                o = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
             }
-            iters++;
-            if (__any_sync(0xffffffffu, ob)) { occluded = true; break; }
+            if (__any_sync(0xffffffffu, o)) { occluded = true; break; }
         }
         if (!occluded) {
             const float dx = fsub(Ix, Cx), dy = fsub(Iy, Cy);
-            acc = ffma(fadd(Ii, Ii), rcp(fmaxf(ffma(dx, dx, fmul(dy, dy)), 1.f)), acc);   // LUMINANCE = 2 (:240)
+            acc = ffma(fadd(Ii, Ii), rcp(fmaxf(ffma(dx, dx, fmul(dy, dy)), 1.f)), acc);
         }
     }
     return fminf(acc, 1.f);
@@ -289,7 +339,7 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
     const float Rf = (float)R;
     const float rcpR = rcp(Rf);
     const int r0 = rb * (32 * NCH);
-    float rux[NCH], ruy[NCH], rlen[NCH], nearp[NCH], best[NCH], loc[NCH];
+    float rux[NCH], ruy[NCH], rlen[NCH], nearp[NCH], best[NCH], bestm[NCH], loc[NCH];
     int idx[NCH];
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
@@ -300,6 +350,7 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
         rlen[c] = sqrt_(ffma(rux[c], rux[c], fmul(ruy[c], ruy[c])));
         nearp[c] = fmul(rcp(rlen[c]), k.p.agent_radius);
         best[c] = CUDART_INF_F;
+        bestm[c] = CUDART_INF_F;   // best + -1e-4f, kept alongside (inf - 1e-4 = inf)
         loc[c] = __int_as_float(0x7fffffff);
         idx[c] = -1;
     }
@@ -348,11 +399,14 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
                 mask &= mask - 1;
                 const float4 q = scr[j];
                 const float snum = scr[32 + j].x;
-                // raycast_kernel inner loop (kernels.cu:353-376)
-                const Hit h = intersect_pre(rux[c], ruy[c], q.x, q.y, q.z, q.w, snum);
-                const bool hit = (h.t >= 0.f) && (h.t <= 1.f);
-                const bool better = (nearp[c] < h.s) && (h.s < fadd(best[c], -1.e-4f));
-                if (hit && better) { best[c] = h.s; loc[c] = h.t; idx[c] = gbase + j; }
+                // raycast_kernel inner loop (kernels.cu:353-376), branch-free. A near-parallel line (|UxV| < 1e-3,
+                // s = t = inf in the reference) can never be accepted, so its s/t need not be forced to inf.
+                const float UxV = cross2(rux[c], q.y, ruy[c], q.x);
+                const float rc = rcp(UxV);
+                const float hs_ = fmul(snum, rc);
+                const float ht_ = fmul(cross2(ruy[c], q.z, rux[c], q.w), rc);
+                const bool take = !(fabsf(UxV) < PARALLEL_EPS) && (ht_ >= 0.f) && (ht_ <= 1.f) && (nearp[c] < hs_) && (hs_ < bestm[c]);
+                if (take) { best[c] = hs_; bestm[c] = fadd(hs_, -1.e-4f); loc[c] = ht_; idx[c] = gbase + j; }
                 if (STATS) tests++;
             }
         }
@@ -363,6 +417,12 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
     // ---- shade + store (shader_kernel, kernels.cu:407-450)
     unsigned dyn_rays = 0, dyn_iters = 0;
     const int sub_ = k.has_obs ? k.obs.subsample : 1;
+    const int nlights = __ldg(k.s.light_widths + n);
+    const float* lt = k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n);
+    LaneLight ll;
+    ll.occ = -1;
+    if (lane < nlights) { ll.x = __ldg(lt + 3 * lane); ll.y = __ldg(lt + 3 * lane + 1); ll.i = __ldg(lt + 3 * lane + 2); }
+    else { ll.x = 0.f; ll.y = 0.f; ll.i = 0.f; }
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
         const int r = r0 + 32 * c + lane;
@@ -395,7 +455,7 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
             tl0 = __ldg(tl); tl1 = __ldg(tl + 1); tl2 = __ldg(tl + 2);
             tr0 = __ldg(tr); tr1 = __ldg(tr + 1); tr2 = __ldg(tr + 2);
             if (l0 >= AF) {
-                intensity = ffma(rw, __ldg(k.s.baked + ts + fr), fmul(lw, __ldg(k.s.baked + ts + fl)));   // :438
+                intensity = ffma(lw, __ldg(k.s.baked + ts + fl), fmul(rw, __ldg(k.s.baked + ts + fr)));   // :438
             } else {
                 const float om = fsub(1.f, loc[c]);                                                       // :435
                 Cx = ffma(s4.x, om, fmul(loc[c], s4.z));
@@ -408,15 +468,15 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
             const int j = __ffs(dm) - 1;
             dm &= dm - 1;
             const float cx = __shfl_sync(0xffffffffu, Cx, j), cy = __shfl_sync(0xffffffffu, Cy, j);
-            const float v = light_intensity_warp(k, m, n, L, AF, cx, cy, lane, dyn_iters);
+            const float v = light_intensity_cached<STATS>(m, L, AF, nlights, lt, cx, cy, lane, ll, dyn_iters);
             if (lane == j) intensity = v;
-            dyn_rays++;
+            if (STATS) dyn_rays++;
         }
         if (hitany) {
             const float kk = fmul(ffma(-dotv, dotv, 1.f), intensity);                                       // :442-445
-            s0 = fmul(kk, ffma(rw, tr0, fmul(lw, tl0)));
-            s1 = fmul(kk, ffma(rw, tr1, fmul(lw, tl1)));
-            s2 = fmul(kk, ffma(rw, tr2, fmul(lw, tl2)));
+            s0 = fmul(kk, ffma(lw, tl0, fmul(rw, tr0)));
+            s1 = fmul(kk, ffma(lw, tl1, fmul(rw, tr1)));
+            s2 = fmul(kk, ffma(lw, tl2, fmul(rw, tr2)));
         }
         const float dist = fmul(rlen[c], best[c]);
         if (live) {
