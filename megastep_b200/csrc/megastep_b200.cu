@@ -52,6 +52,7 @@ struct KArgs {
     float inv_max_depth, inv_speed, inv_ang, inv_sub;   // reciprocals ATen would multiply by
     float bin_kappa, bin_rmid, bin_xclip;               // screen-space binning constants (culling only)
     unsigned long long* stats;  // optional diagnostics counters (may be null)
+    int32_t debug_skip_dyn;     // timing experiments only: leave agent-hit rays unlit
 };
 
 enum { MODE_PHYSICS = 1, MODE_RENDER = 2, MODE_STEP = 3 };
@@ -464,6 +465,7 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
         }
         // dynamic lighting for rays that hit an agent's model (:434-436), one ray at a time, whole warp
         unsigned dm = __ballot_sync(0xffffffffu, hitany && (l0 < AF));
+        if (k.debug_skip_dyn) dm = 0;
         while (dm) {
             const int j = __ffs(dm) - 1;
             dm &= dm - 1;
@@ -643,6 +645,7 @@ static thread_local char g_err[512] = "";
 static long long g_launches = 0;
 static long long g_opt_nch = 0;          // 0 = auto
 static long long g_opt_threads = 0;      // 0 = auto
+static long long g_opt_skip_dyn = 0;     // debug
 static unsigned long long* g_stats = nullptr;   // device counters, enabled by option "stats"
 
 static int fail(const char* fmt, const char* detail) {
@@ -676,6 +679,7 @@ extern "C" int msb_params_init(msb_params* p, float agent_radius, int32_t res, f
 extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "nch")) { g_opt_nch = value; return 0; }
     if (!strcmp(name, "threads")) { g_opt_threads = value; return 0; }
+    if (!strcmp(name, "debug_skip_dyn")) { g_opt_skip_dyn = value; return 0; }
     if (!strcmp(name, "stats")) {
         if (value && !g_stats) {
             if (check(cudaMalloc(&g_stats, 8 * sizeof(unsigned long long)), "cudaMalloc(stats)")) return 1;
@@ -760,6 +764,7 @@ static void fill(KArgs& k, const msb_params* p, const msb_scenery* s, const msb_
     k.inv_fps = 1.0f / p->fps;
     k.ray_blocks = 1;
     k.stats = g_stats;
+    k.debug_skip_dyn = (int32_t)g_opt_skip_dyn;
     k.bin_kappa = (float)p->res / (2.f * p->half_screen);
     k.bin_rmid = 0.5f * ((float)p->res - 1.f);
     k.bin_xclip = 0.5f * p->agent_radius / sqrtf(1.f + p->half_screen * p->half_screen);

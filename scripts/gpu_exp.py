@@ -1,0 +1,42 @@
+"""Timing experiments (not a benchmark): render/step on Deathmatch 4096x4x128 under debug switches."""
+import json, os, sys, time
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import common
+from megastep_b200 import cuda, modules, scene, synthetic, core as core_
+
+def timeit(fn, iters=50, warm=5):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+def setup(N=4096, A=4, res=128, fov=70.):
+    gs = synthetic.sample(N, seed=1, n_unique=256)
+    arrays = synthetic.tile_arrays(scene.scene_arrays(gs[:256], A, np.random.RandomState(1)), N)
+    pos, ang = synthetic.spawns(gs, A, np.random.RandomState(2))
+    s = scene.upload(arrays)
+    cuda.bake(s, params=cuda.make_params(common.AGENT_RADIUS, res, fov, 10.))
+    c = core_.Core(s, res=res, fov=fov, fps=10.)
+    c.agents.positions.copy_(torch.as_tensor(pos)); c.agents.angles.copy_(torch.as_tensor(ang))
+    return c
+
+if __name__ == '__main__':
+    mode = sys.argv[1] if len(sys.argv) > 1 else 'exp'
+    c = setup()
+    if mode == 'ncu':
+        for _ in range(3): c.render()
+        torch.cuda.synchronize()
+        sys.exit(0)
+    out = {}
+    for skip in (0, 1):
+        cuda.set_option('debug_skip_dyn', skip)
+        for nch in (1, 2, 4):
+            cuda.set_option('nch', nch)
+            out[f'render_us/skip_dyn{skip}/nch{nch}'] = timeit(lambda: c.render())
+    cuda.set_option('nch', 0); cuda.set_option('debug_skip_dyn', 0)
+    print(json.dumps(out))
