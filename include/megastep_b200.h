@@ -4,7 +4,7 @@
  * pybind11/ATen extension (`megastepcuda`, megastep/src/wrappers.cpp:30-172); the entry points below are what a
  * binding for it binds, with every at::Tensor flattened to a raw DEVICE pointer plus sizes, and the reference's
  * process-global `initialize()` constants (megastep/src/kernels.cu:12-27) turned into an explicit per-call params
- * struct. No torch types, no globals, no allocation: the caller owns every buffer; kernels are enqueued on the
+ * struct. No torch types, no globals, no allocation: the caller owns every buffer (scratch included); kernels are enqueued on the
  * caller's stream and return without synchronising (as the reference: kernels.cu:30-32, no device sync anywhere).
  *
  * All functions return 0 on success, non-zero on failure (msb_last_error() describes it). Pointer arguments are
@@ -102,6 +102,15 @@ typedef struct msb_movement {
     float decay;            /* default 0.125 */
 } msb_movement;
 
+/* Scratch for the second pass that lights the rays which hit agents (their light is dynamic: kernels.cu:434-436).
+ * Caller-owned device memory, 16-byte aligned, zero-filled once before first use; sized by msb_workspace_bytes
+ * (any size works — what does not fit is resolved inline by the first pass, same results, longer tail). One
+ * workspace per concurrent stream. NULL disables the second pass. */
+typedef struct msb_workspace {
+    void* ptr;
+    int64_t bytes;
+} msb_workspace;
+
 int msb_abi_version(void);
 const char* msb_last_error(void);
 
@@ -118,12 +127,17 @@ int msb_physics(const msb_params* p, const msb_scenery* s, const msb_agents* a, 
 /* render(scenery, agents) -> Render — wrappers.cpp:82, kernels.cu:297-475. Also rewrites the agents' model
  * lines inside s->lines (the reference's draw_kernel side effect). obs may be NULL. */
 int msb_render(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_render_out* out,
-               const msb_obs_out* obs, void* cuda_stream);
+               const msb_obs_out* obs, const msb_workspace* ws, void* cuda_stream);
 
-/* One whole environment tick in a single launch: MomentumMovement -> physics -> render -> observation heads.
+/* One whole environment tick: MomentumMovement -> physics -> render -> observation heads in ONE kernel, followed —
+ * when a workspace is given — by the small second pass that lights agent-hit rays.
  * mv may be NULL (velocities are then taken as already set, i.e. plain physics+render). out/obs as msb_render. */
 int msb_step(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_movement* mv,
-             float* progress, const msb_render_out* out, const msb_obs_out* obs, void* cuda_stream);
+             float* progress, const msb_render_out* out, const msb_obs_out* obs, const msb_workspace* ws,
+             void* cuda_stream);
+
+/* [host] Recommended workspace size in bytes for this scene and observation subsample (1 when obs is NULL). */
+int64_t msb_workspace_bytes(const msb_params* p, const msb_scenery* s, int32_t subsample);
 
 /* Tuning/diagnostics: selects kernel variants (0 = default). Affects speed only, never results. */
 int msb_set_option(const char* name, int64_t value);

@@ -53,6 +53,11 @@ struct KArgs {
     float bin_kappa, bin_rmid, bin_xclip;               // screen-space binning constants (culling only)
     unsigned long long* stats;  // optional diagnostics counters (may be null)
     int32_t debug_skip_dyn;     // timing experiments only: leave agent-hit rays unlit
+    // queue of pixel groups whose dynamic lighting is resolved by dyn_kernel (load-balanced second pass)
+    int* dyn_ctrl;              // [0] entries reserved, [1] CTAs of dyn_kernel done
+    unsigned char* dyn_entries; // null -> dynamic lights are resolved inline by the ray's own warp
+    int32_t dyn_cap;            // entries that fit
+    int32_t dyn_stride;         // bytes per entry = 16 + 32 * subsample
 };
 
 enum { MODE_PHYSICS = 1, MODE_RENDER = 2, MODE_STEP = 3 };
@@ -221,13 +226,14 @@ __device__ __forceinline__ void physics_stage(const KArgs& k, const Smem& m, int
 struct LaneLight { float x, y, i; int occ; };
 
 template <bool STATS>
-__device__ __forceinline__ float light_intensity_cached(const Smem& m, int L, int AF, int I, const float* lt, float Cx,
-                                                        float Cy, int lane, LaneLight& ll, unsigned& iters) {
+__device__ __forceinline__ float light_intensity_cached(const float4* __restrict__ seg, int L, int AF, int I,
+                                                        const float* lt, float Cx, float Cy, int lane, LaneLight& ll,
+                                                        unsigned& iters) {
     const int nres = I < 32 ? I : 32;
     // phase 1: the remembered occluder of each resident light
     bool ob = false;
     if (lane < nres && ll.occ >= 0) {
-        const Hit h = intersect(ll.x, ll.y, fsub(Cx, ll.x), fsub(Cy, ll.y), m.seg[ll.occ]);
+        const Hit h = intersect(ll.x, ll.y, fsub(Cx, ll.x), fsub(Cy, ll.y), seg[ll.occ]);
         ob = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
     }
     const unsigned resident = nres == 32 ? 0xffffffffu : ((1u << nres) - 1u);
@@ -245,11 +251,11 @@ __device__ __forceinline__ float light_intensity_cached(const Smem& m, int L, in
             const int l0 = base + lane, l1 = base + 32 + lane;
             bool o0 = false, o1 = false;
             if (l0 < L) {
-                const Hit h = intersect(Ix, Iy, Ux, Uy, m.seg[l0]);
+                const Hit h = intersect(Ix, Iy, Ux, Uy, seg[l0]);
                 o0 = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
             }
             if (l1 < L) {
-                const Hit h = intersect(Ix, Iy, Ux, Uy, m.seg[l1]);
+                const Hit h = intersect(Ix, Iy, Ux, Uy, seg[l1]);
                 o1 = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
             }
             if (STATS) iters++;
@@ -278,7 +284,7 @@ __device__ __forceinline__ float light_intensity_cached(const Smem& m, int L, in
             const int l = base + lane;
             bool o = false;
             if (l < L) {
-                const Hit h = intersect(Ix, Iy, Ux, Uy, m.seg[l]);
+                const Hit h = intersect(Ix, Iy, Ux, Uy, seg[l]);
                 o = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
             }
             if (__any_sync(0xffffffffu, o)) { occluded = true; break; }
@@ -463,23 +469,64 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
                 Cy = ffma(s4.y, om, fmul(loc[c], s4.w));
             }
         }
-        // dynamic lighting for rays that hit an agent's model (:434-436), one ray at a time, whole warp
-        unsigned dm = __ballot_sync(0xffffffffu, hitany && (l0 < AF));
+        // (1 - dot^2) and the filtered texel, common to static and dynamic lighting (:442-445)
+        const bool isdyn = hitany && (l0 < AF);
+        float kk0 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        if (hitany) {
+            kk0 = ffma(-dotv, dotv, 1.f);
+            b0 = ffma(lw, tl0, fmul(rw, tr0));
+            b1 = ffma(lw, tl1, fmul(rw, tr1));
+            b2 = ffma(lw, tl2, fmul(rw, tr2));
+        }
+        // dynamic lighting for rays that hit an agent's model (:434-436). Preferred: queue the pixel group for the
+        // load-balanced second pass (dyn_kernel). Fallback (no workspace / queue full): this warp resolves them
+        // one ray at a time.
+        unsigned dm = __ballot_sync(0xffffffffu, isdyn);
         if (k.debug_skip_dyn) dm = 0;
-        while (dm) {
-            const int j = __ffs(dm) - 1;
-            dm &= dm - 1;
-            const float cx = __shfl_sync(0xffffffffu, Cx, j), cy = __shfl_sync(0xffffffffu, Cy, j);
-            const float v = light_intensity_cached<STATS>(m, L, AF, nlights, lt, cx, cy, lane, ll, dyn_iters);
-            if (lane == j) intensity = v;
-            if (STATS) dyn_rays++;
+        const int gl = lane & ~(sub_ - 1);                                    // first lane of my pixel group
+        const unsigned subm = sub_ == 32 ? 0xffffffffu : ((1u << sub_) - 1u);
+        const unsigned gmask = (dm >> gl) & subm;                             // my group's agent-hit pixels
+        bool queued = false;
+        if (dm && k.dyn_entries) {
+            const unsigned leaders = __ballot_sync(0xffffffffu, gmask != 0 && lane == gl);
+            const int cnt = __popc(leaders);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(k.dyn_ctrl, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            queued = base + cnt <= k.dyn_cap;
+            if (gmask) {
+                const int slot = base + __popc(leaders & ((1u << gl) - 1u));
+                if (slot < k.dyn_cap) {
+                    unsigned char* e = k.dyn_entries + (size_t)slot * k.dyn_stride;
+                    if (lane == gl) {
+                        const int64_t o0 = ((int64_t)n * A + a) * R + (r0 + 32 * c + gl);
+                        *reinterpret_cast<int4*>(e) = make_int4((int)(o0 & 0xffffffffll), (int)(o0 >> 32), queued ? (int)gmask : 0, sub_);
+                    }
+                    if (queued) {
+                        float4* rec = reinterpret_cast<float4*>(e + 16) + 2 * (lane - gl);
+                        rec[0] = make_float4(b0, b1, b2, kk0);
+                        rec[1] = make_float4(Cx, Cy, intensity, isdyn ? 1.f : 0.f);
+                    }
+                }
+            }
+        }
+        if (!queued) {
+            while (dm) {
+                const int j = __ffs(dm) - 1;
+                dm &= dm - 1;
+                const float cx = __shfl_sync(0xffffffffu, Cx, j), cy = __shfl_sync(0xffffffffu, Cy, j);
+                const float v = light_intensity_cached<STATS>(m.seg, L, AF, nlights, lt, cx, cy, lane, ll, dyn_iters);
+                if (lane == j) intensity = v;
+                if (STATS) dyn_rays++;
+            }
         }
         if (hitany) {
-            const float kk = fmul(ffma(-dotv, dotv, 1.f), intensity);                                       // :442-445
-            s0 = fmul(kk, ffma(lw, tl0, fmul(rw, tr0)));
-            s1 = fmul(kk, ffma(lw, tl1, fmul(rw, tr1)));
-            s2 = fmul(kk, ffma(lw, tl2, fmul(rw, tr2)));
+            const float kk = fmul(kk0, intensity);
+            s0 = fmul(kk, b0);
+            s1 = fmul(kk, b1);
+            s2 = fmul(kk, b2);
         }
+        const bool deferred = queued && gmask != 0;      // dyn_kernel writes this group's screen / rgb
         const float dist = fmul(rlen[c], best[c]);
         if (live) {
             const int64_t o = ((int64_t)n * A + a) * R + r;
@@ -487,7 +534,7 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
             if (k.out.locations) k.out.locations[o] = loc[c];
             if (k.out.dots) k.out.dots[o] = dotv;
             if (k.out.distances) k.out.distances[o] = dist;
-            if (k.out.screen) { float* sc = k.out.screen + 3 * o; sc[0] = s0; sc[1] = s1; sc[2] = s2; }
+            if (k.out.screen && !(queued && isdyn)) { float* sc = k.out.screen + 3 * o; sc[0] = s0; sc[1] = s1; sc[2] = s2; }
         }
         // fused observation heads: Depth (modules.py:181-183) and RGB (:222-223), mean over `subsample` pixels
         if (k.has_obs) {
@@ -503,15 +550,15 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
                 v2 = __fadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
                 v3 = __fadd_rn(v3, __shfl_xor_sync(0xffffffffu, v3, o));
             }
-            if (live && (lane % sub_) == 0) {
+            if (live && lane == gl) {
                 const int Ro = R / sub_, ro = r / sub_;
                 const float inv = k.inv_sub;
                 const int64_t ag = (int64_t)n * A + a;
-                if (k.obs.rgb) {
+                if (k.obs.rgb && !deferred) {
                     float* q = k.obs.rgb + ag * 3 * Ro + ro;
-                    q[0] = v0 * inv; q[Ro] = v1 * inv; q[2 * Ro] = v2 * inv;
+                    q[0] = __fmul_rn(v0, inv); q[Ro] = __fmul_rn(v1, inv); q[2 * Ro] = __fmul_rn(v2, inv);
                 }
-                if (k.obs.depth) k.obs.depth[ag * Ro + ro] = v3 * inv;
+                if (k.obs.depth) k.obs.depth[ag * Ro + ro] = __fmul_rn(v3, inv);
             }
         }
     }
@@ -599,6 +646,100 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ KArgs 
             render_agent<NCH, STATS>(k, m, n, g0, L, w / RB, w % RB, m.scratch + warp * 64, lane);
         }
         if (k.has_obs && k.obs.imu) imu_stage(k, m, n);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dyn_kernel: the load-balanced second pass over pixel groups that contain agent-hit rays.
+// Entry = 16-byte header {o0 lo, o0 hi, mask of agent-hit pixels, subsample} + per pixel two float4:
+//   {texel rgb, 1-dot^2} and {hit point x, hit point y, static intensity, is-agent-hit}.
+// A warp takes DYN_BLOCK consecutive entries (neighbouring pixels of one agent's view, so the per-light occluder
+// cache keeps working), reads the env's segments straight from HBM/L2, and writes the final screen pixels and the
+// pooled RGB observation of the group.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int DYN_BLOCK = 8;
+
+template <bool STATS>
+__global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs k) {
+    const int lane = threadIdx.x & 31;
+    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
+    const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
+    const int reserved = *reinterpret_cast<volatile int*>(k.dyn_ctrl);
+    const int count = reserved < k.dyn_cap ? reserved : k.dyn_cap;
+    unsigned dyn_rays = 0, dyn_iters = 0;
+    int64_t cur_n = -1;
+    int L = 0, nlights = 0;
+    const float4* seg = nullptr;
+    const float* lt = nullptr;
+    LaneLight ll;
+    ll.occ = -1; ll.x = ll.y = ll.i = 0.f;
+    for (int blk = wg; blk * DYN_BLOCK < count; blk += tw) {
+        const int e_end = min(count, (blk + 1) * DYN_BLOCK);
+        for (int ei = blk * DYN_BLOCK; ei < e_end; ei++) {
+            const unsigned char* e = k.dyn_entries + (size_t)ei * k.dyn_stride;
+            const int4 hdr = *reinterpret_cast<const int4*>(e);
+            const unsigned mask = (unsigned)hdr.z;
+            if (!mask) continue;                                   // slot reserved by a chunk that fell back inline
+            const int sub = hdr.w;
+            const int64_t o0 = ((int64_t)hdr.y << 32) | (unsigned)hdr.x;
+            const int64_t ag = o0 / R;
+            const int r = (int)(o0 - ag * R);
+            const int64_t n = ag / A;
+            if (n != cur_n) {
+                cur_n = n;
+                L = __ldg(k.s.line_widths + n);
+                seg = reinterpret_cast<const float4*>(k.s.lines) + __ldg(k.s.line_starts + n);
+                nlights = __ldg(k.s.light_widths + n);
+                lt = k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n);
+                ll.occ = -1;
+                if (lane < nlights) { ll.x = __ldg(lt + 3 * lane); ll.y = __ldg(lt + 3 * lane + 1); ll.i = __ldg(lt + 3 * lane + 2); }
+            }
+            float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < sub) {
+                const float4* rec = reinterpret_cast<const float4*>(e + 16) + 2 * lane;
+                ra = rec[0];
+                rb = rec[1];
+            }
+            float intensity = rb.z;
+            unsigned m = mask;
+            while (m) {
+                const int p = __ffs(m) - 1;
+                m &= m - 1;
+                const float cx = __shfl_sync(0xffffffffu, rb.x, p), cy = __shfl_sync(0xffffffffu, rb.y, p);
+                const float v = light_intensity_cached<STATS>(seg, L, AF, nlights, lt, cx, cy, lane, ll, dyn_iters);
+                if (lane == p) intensity = v;
+                if (STATS) dyn_rays++;
+            }
+            const float kk = fmul(ra.w, intensity);
+            const float s0 = fmul(kk, ra.x), s1 = fmul(kk, ra.y), s2 = fmul(kk, ra.z);
+            if (k.out.screen && lane < sub && ((mask >> lane) & 1u)) {
+                float* sc = k.out.screen + 3 * (o0 + lane);
+                sc[0] = s0; sc[1] = s1; sc[2] = s2;
+            }
+            if (k.has_obs && k.obs.rgb) {
+                float v0 = lane < sub ? s0 : 0.f, v1 = lane < sub ? s1 : 0.f, v2 = lane < sub ? s2 : 0.f;
+                for (int o = 1; o < sub; o <<= 1) {
+                    v0 = __fadd_rn(v0, __shfl_xor_sync(0xffffffffu, v0, o));
+                    v1 = __fadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+                    v2 = __fadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
+                }
+                if (lane == 0) {
+                    const int Ro = R / sub, ro = r / sub;
+                    float* q = k.obs.rgb + ag * 3 * Ro + ro;
+                    q[0] = __fmul_rn(v0, k.inv_sub); q[Ro] = __fmul_rn(v1, k.inv_sub); q[2 * Ro] = __fmul_rn(v2, k.inv_sub);
+                }
+            }
+        }
+    }
+    if (STATS && k.stats && lane == 0) {
+        atomicAdd(k.stats + STAT_DYN_RAYS, (unsigned long long)dyn_rays);
+        atomicAdd(k.stats + STAT_DYN_ITERS, (unsigned long long)dyn_iters);
+    }
+    // the last CTA out re-arms the queue for the next step
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(k.dyn_ctrl + 1, 1) == (int)gridDim.x - 1) { k.dyn_ctrl[0] = 0; k.dyn_ctrl[1] = 0; }
     }
 }
 
@@ -783,6 +924,45 @@ extern "C" int msb_physics(const msb_params* p, const msb_scenery* s, const msb_
     return launch_env<MODE_PHYSICS>(k, 1, threads, (cudaStream_t)cuda_stream);
 }
 
+// workspace layout: int ctrl[4] (16 bytes), then entries of (16 + 32*subsample) bytes
+static int set_workspace(KArgs& k, const msb_workspace* ws) {
+    k.dyn_ctrl = nullptr;
+    k.dyn_entries = nullptr;
+    k.dyn_cap = 0;
+    const int sub = k.has_obs ? k.obs.subsample : 1;
+    k.dyn_stride = 16 + 32 * sub;
+    if (!ws || !ws->ptr) return 0;
+    if (((uintptr_t)ws->ptr & 15) != 0) return fail("%s", "workspace must be 16-byte aligned");
+    const int64_t cap = (ws->bytes - 16) / k.dyn_stride;
+    if (cap < 1) return 0;
+    k.dyn_ctrl = reinterpret_cast<int*>(ws->ptr);
+    k.dyn_entries = reinterpret_cast<unsigned char*>(ws->ptr) + 16;
+    k.dyn_cap = cap > 0x7fffffff ? 0x7fffffff : (int32_t)cap;
+    return 0;
+}
+
+static int launch_dyn(const KArgs& k, cudaStream_t st) {
+    if (!k.dyn_entries) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = sms * 8;
+    if (k.stats) dyn_kernel<true><<<grid, 128, 0, st>>>(k);
+    else dyn_kernel<false><<<grid, 128, 0, st>>>(k);
+    g_launches++;
+    return check(cudaGetLastError(), "dyn_kernel launch");
+}
+
+extern "C" int64_t msb_workspace_bytes(const msb_params* p, const msb_scenery* s, int32_t subsample) {
+    if (!p || !s || subsample < 1) return 0;
+    const int64_t rays = (int64_t)s->n_envs * s->n_agents * p->res;
+    const int64_t groups = rays / subsample;
+    // room for a quarter of all pixel groups to contain an agent-hit ray (overflow falls back to inline, still exact)
+    int64_t cap = groups / 4;
+    if (cap < 65536) cap = groups < 65536 ? groups : 65536;
+    return 16 + cap * (16 + 32 * (int64_t)subsample);
+}
+
 static void set_obs(KArgs& k, const msb_obs_out* obs) {
     if (!obs) return;
     k.obs = *obs;
@@ -801,7 +981,7 @@ static int check_obs(const msb_params* p, const msb_obs_out* obs) {
 }
 
 extern "C" int msb_render(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_render_out* out,
-                          const msb_obs_out* obs, void* cuda_stream) {
+                          const msb_obs_out* obs, const msb_workspace* ws, void* cuda_stream) {
     if (validate(p, s) || check_obs(p, obs)) return 1;
     if (!a || !a->angles || !a->positions) return fail("%s", "msb_render: null agents");
     if (s->n_envs == 0) return 0;
@@ -809,14 +989,17 @@ extern "C" int msb_render(const msb_params* p, const msb_scenery* s, const msb_a
     fill(k, p, s, a);
     if (out) k.out = *out;
     set_obs(k, obs);
+    if (set_workspace(k, ws)) return 1;
     int nch, rb, threads;
     plan_render(p, s, &nch, &rb, &threads);
     k.ray_blocks = rb;
-    return launch_env<MODE_RENDER>(k, nch, threads, (cudaStream_t)cuda_stream);
+    if (launch_env<MODE_RENDER>(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
+    return launch_dyn(k, (cudaStream_t)cuda_stream);
 }
 
 extern "C" int msb_step(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_movement* mv,
-                        float* progress, const msb_render_out* out, const msb_obs_out* obs, void* cuda_stream) {
+                        float* progress, const msb_render_out* out, const msb_obs_out* obs, const msb_workspace* ws,
+                        void* cuda_stream) {
     if (validate(p, s) || check_obs(p, obs)) return 1;
     if (!a || !a->angles || !a->positions || !a->angvelocity || !a->velocity) return fail("%s", "msb_step: null agents");
     if (mv && !mv->actions) return fail("%s", "msb_step: movement without actions");
@@ -833,10 +1016,12 @@ extern "C" int msb_step(const msb_params* p, const msb_scenery* s, const msb_age
         k.mv_dv = (float)((double)mv->accel / (double)p->fps);
         k.mv_dw = (float)((double)mv->ang_accel / (double)p->fps);
     }
+    if (set_workspace(k, ws)) return 1;
     int nch, rb, threads;
     plan_render(p, s, &nch, &rb, &threads);
     k.ray_blocks = rb;
-    return launch_env<MODE_STEP>(k, nch, threads, (cudaStream_t)cuda_stream);
+    if (launch_env<MODE_STEP>(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
+    return launch_dyn(k, (cudaStream_t)cuda_stream);
 }
 
 extern "C" int msb_bake(const msb_params* p, const msb_scenery* s, void* cuda_stream) {

@@ -60,6 +60,10 @@ class _ObsOut(ctypes.Structure):
                 ('ang_scale', ctypes.c_float)]
 
 
+class _Workspace(ctypes.Structure):
+    _fields_ = [('ptr', ctypes.c_void_p), ('bytes', ctypes.c_int64)]
+
+
 class _Movement(ctypes.Structure):
     _fields_ = [('actions', ctypes.c_void_p), ('accel', ctypes.c_float), ('ang_accel', ctypes.c_float),
                 ('decay', ctypes.c_float)]
@@ -78,9 +82,11 @@ def _load():
     lib.msb_params_init.argtypes = [P(Params), ctypes.c_float, ctypes.c_int32, ctypes.c_float, ctypes.c_float]
     lib.msb_bake.argtypes = [P(Params), P(_Scenery), ctypes.c_void_p]
     lib.msb_physics.argtypes = [P(Params), P(_Scenery), P(_Agents), ctypes.c_void_p, ctypes.c_void_p]
-    lib.msb_render.argtypes = [P(Params), P(_Scenery), P(_Agents), P(_RenderOut), P(_ObsOut), ctypes.c_void_p]
+    lib.msb_render.argtypes = [P(Params), P(_Scenery), P(_Agents), P(_RenderOut), P(_ObsOut), P(_Workspace), ctypes.c_void_p]
     lib.msb_step.argtypes = [P(Params), P(_Scenery), P(_Agents), P(_Movement), ctypes.c_void_p, P(_RenderOut),
-                             P(_ObsOut), ctypes.c_void_p]
+                             P(_ObsOut), P(_Workspace), ctypes.c_void_p]
+    lib.msb_workspace_bytes.argtypes = [P(Params), P(_Scenery), ctypes.c_int32]
+    lib.msb_workspace_bytes.restype = ctypes.c_int64
     lib.msb_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
     lib.msb_get_option.argtypes = [ctypes.c_char_p]
     lib.msb_get_option.restype = ctypes.c_int64
@@ -234,6 +240,7 @@ class Scenery:
         self._baked = Ragged1D(torch.ones_like(textures.vals[:, 0]).contiguous(), textures.widths)
         self._params = None   # set by core.Core so that several Cores can coexist
         self._c = None
+        self._ws = {}
 
     n_agents = property(lambda self: self._n_agents)
     lights = property(lambda self: self._lights)
@@ -267,6 +274,22 @@ class Scenery:
         return self._c
 
 
+def make_workspace(scenery, params, subsample=1):
+    """Zeroed scratch for the second (dynamic-light) pass; returns (tensor, _Workspace struct)."""
+    s = scenery._struct()
+    nbytes = int(_lib.msb_workspace_bytes(ctypes.byref(params), ctypes.byref(s), int(subsample)))
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device=scenery.model.device)
+    return buf, _Workspace(buf.data_ptr(), nbytes)
+
+
+def _shared_workspace(scenery, params):
+    """The per-(scenery, res) scratch used by plain render() calls on the default stream."""
+    key = (params.res, torch.cuda.current_stream(scenery.model.device).cuda_stream)
+    if key not in scenery._ws:
+        scenery._ws[key] = make_workspace(scenery, params, 1)
+    return scenery._ws[key][1]
+
+
 class Render:
     """The result of a render() call. Exactly five public attributes (modules.unpack walks dir())."""
     __slots__ = ('screen', 'indices', 'locations', 'dots', 'distances')
@@ -286,6 +309,7 @@ class Physics:
 # functions
 # --------------------------------------------------------------------------------------------------------------
 _PARAMS = None
+USE_WORKSPACE = True   # False: agent-hit rays are lit inline by the first pass (same results; used by tests)
 
 
 def make_params(agent_radius, res, fov, fps):
@@ -369,7 +393,9 @@ def render(scenery, agents, params=None):
     out = _alloc_render(n, a, p.res, agents._angles.device)
     c = _render_struct(out)
     with _on_device(agents._angles) as stream:
-        _check(_lib.msb_render(ctypes.byref(p), ctypes.byref(s), ctypes.byref(agents._c), ctypes.byref(c), None, stream))
+        ws = _shared_workspace(scenery, p) if USE_WORKSPACE else None
+        _check(_lib.msb_render(ctypes.byref(p), ctypes.byref(s), ctypes.byref(agents._c), ctypes.byref(c), None,
+                               ctypes.byref(ws) if ws is not None else None, stream))
     return out
 
 
@@ -403,6 +429,7 @@ class StepPlan:
             self._obs = _ObsOut(self.rgb.data_ptr(), self.depth.data_ptr(), self.imu.data_ptr(), subsample,
                                 max_depth, speed_scale, ang_scale)
         self._s = scenery._struct()
+        self._wsbuf, self._ws = make_workspace(scenery, params, subsample or 1) if USE_WORKSPACE else (None, None)
 
     def step(self):
         """movement (if actions were bound) + physics + render + heads, one launch"""
@@ -410,7 +437,8 @@ class StepPlan:
             _check(_lib.msb_step(ctypes.byref(self.params), ctypes.byref(self._s), ctypes.byref(self.agents._c),
                                  ctypes.byref(self._mv) if self._mv is not None else None, self.progress.data_ptr(),
                                  ctypes.byref(self._out) if self._out is not None else None,
-                                 ctypes.byref(self._obs) if self._obs is not None else None, stream))
+                                 ctypes.byref(self._obs) if self._obs is not None else None,
+                                 ctypes.byref(self._ws) if self._ws is not None else None, stream))
 
     __call__ = step
 
@@ -419,7 +447,8 @@ class StepPlan:
         with _on_device(self.progress) as stream:
             _check(_lib.msb_render(ctypes.byref(self.params), ctypes.byref(self._s), ctypes.byref(self.agents._c),
                                    ctypes.byref(self._out) if self._out is not None else None,
-                                   ctypes.byref(self._obs) if self._obs is not None else None, stream))
+                                   ctypes.byref(self._obs) if self._obs is not None else None,
+                                   ctypes.byref(self._ws) if self._ws is not None else None, stream))
 
 
 def set_option(name, value):

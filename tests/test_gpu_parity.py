@@ -251,6 +251,42 @@ def test_every_kernel_variant_gives_identical_results(res):
         cuda.set_option('threads', 0)
 
 
+def _same(a, b):
+    return bool(((a == b) | (a != a) & (b != b)).all())
+
+
+@pytest.mark.parametrize('sub', [1, 4])
+def test_second_pass_inline_and_overflow_paths_agree(sub):
+    """Agent-hit rays are lit by dyn_kernel (workspace), inline (no workspace) or a mix (workspace too small):
+    all three must give identical screens and observations. Agents are packed close so many rays hit agents."""
+    import ctypes
+    from megastep_b200 import cuda, modules
+    gs, arrays, st = make('box', 6, 4, seed=61)
+    rng = np.random.RandomState(0)
+    st['positions'] = (3.5 + rng.uniform(-.6, .6, st['positions'].shape)).astype(np.float32)
+    res = 128
+    outs = []
+    for mode in ('workspace', 'inline', 'overflow'):
+        c = common.to_device(arrays, st, res, 100.)
+        cuda.USE_WORKSPACE = mode != 'inline'
+        try:
+            plan = cuda.StepPlan(c.scenery, c.agents, c.params, actions=None, raw=True, subsample=sub)
+        finally:
+            cuda.USE_WORKSPACE = True
+        if mode == 'overflow':
+            small = 16 + 3 * (16 + 32 * sub)                       # room for three pixel groups only
+            plan._wsbuf = torch.zeros(small, dtype=torch.uint8, device='cuda')
+            plan._ws = cuda._Workspace(plan._wsbuf.data_ptr(), small)
+        for _ in range(2):                                          # twice: the queue must re-arm itself
+            plan.render_only()
+        torch.cuda.synchronize()
+        outs.append((plan.render.screen.clone(), plan.rgb.clone(), plan.render.indices.clone()))
+    n_dyn = int(((outs[0][2] >= 0) & (outs[0][2] < 32)).sum())
+    assert n_dyn > 50, 'the scene should have plenty of agent-hit rays'
+    for other in outs[1:]:
+        assert _same(outs[0][0], other[0]) and _same(outs[0][1], other[1])
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # 3. properties at the benchmark's full size (Deathmatch 4096 x 4 x 128)
 # ------------------------------------------------------------------------------------------------------------------
