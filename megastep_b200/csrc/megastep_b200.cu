@@ -70,6 +70,8 @@ struct Smem {
     float* st_in;       // [A][8] start-of-step agent state
     float* st_out;      // [A][8] post-physics agent state
     int* xmin;          // [A] progress, as ordered int bits
+    int* ncand;         // [A] physics: segments that survived the bounding-box cull
+    unsigned short* cand;   // [A][seg_cap] their indices
     uint64_t* bar;
 };
 
@@ -80,14 +82,17 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int seg_cap, int nwar
     m.st_in = reinterpret_cast<float*>(m.scratch + nwarps * 64);
     m.st_out = m.st_in + A * ST_STRIDE;
     m.xmin = reinterpret_cast<int*>(m.st_out + A * ST_STRIDE);
-    uintptr_t p = reinterpret_cast<uintptr_t>(m.xmin + A);
+    m.ncand = m.xmin + A;
+    m.cand = reinterpret_cast<unsigned short*>(m.ncand + A);
+    uintptr_t p = reinterpret_cast<uintptr_t>(m.cand + (size_t)A * seg_cap);
     p = (p + 15) & ~uintptr_t(15);
     m.bar = reinterpret_cast<uint64_t*>(p);
     return m;
 }
 
 static size_t smem_bytes(int seg_cap, int nwarps, int A) {
-    size_t b = (size_t)seg_cap * 16 + (size_t)nwarps * 64 * 16 + (size_t)A * ST_STRIDE * 4 * 2 + (size_t)A * 4;
+    size_t b = (size_t)seg_cap * 16 + (size_t)nwarps * 64 * 16 + (size_t)A * ST_STRIDE * 4 * 2 + (size_t)A * 8 +
+               (size_t)A * seg_cap * 2;
     b = (b + 15) & ~size_t(15);
     return b + 16;
 }
@@ -169,6 +174,38 @@ __device__ __forceinline__ void physics_stage(const KArgs& k, const Smem& m, int
     const float r1 = fmul(k.p.agent_radius, 1.0010000467300415039f);
     const float r1sq = fmul(r1, r1);
 
+    // pass 1: which static segments can possibly matter to each agent this tick? A segment farther from the agent
+    // than rho = 1.05|v| + 2.2 r + 0.02 cannot trigger any branch of collision() with a result below 1 (see
+    // DESIGN.md "physics cull"), so dropping it leaves progress bit-identical. Survivors are compacted (ballot +
+    // prefix popcount) so that pass 2 runs the ~100-instruction test on dense lanes.
+    const int cap = k.seg_cap;
+    for (int a = 0; a < A; a++) {
+        const float* me = m.st_in + a * ST_STRIDE;
+        const float px = me[ST_PX], py = me[ST_PY];
+        const float vx = fmul(me[ST_VX], rF), vy = fmul(me[ST_VY], rF);
+        const float vlen = sqrt_(ffma(vx, vx, fmul(vy, vy)));
+        const bool can_cull = vlen >= 1e-3f;          // for slower agents project()'s +1e-6 distorts distances: test all
+        const float rho = 1.05f * vlen + 2.2f * r1 + 0.02f;
+        for (int base = AF; base < L; base += blockDim.x) {
+            const int l = base + tid;
+            bool keep = false;
+            if (l < L) {
+                const float4 s4 = m.seg[l];
+                const bool outside = (fminf(s4.x, s4.z) > px + rho) || (fmaxf(s4.x, s4.z) < px - rho) ||
+                                     (fminf(s4.y, s4.w) > py + rho) || (fmaxf(s4.y, s4.w) < py - rho);
+                keep = !(can_cull && outside);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (bal) {
+                int off = 0;
+                if (lane == 0) off = atomicAdd(m.ncand + a, __popc(bal));
+                off = __shfl_sync(0xffffffffu, off, 0);
+                if (keep) m.cand[a * cap + off + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)l;
+            }
+        }
+    }
+    __syncthreads();
+    // pass 2: exact tests
     for (int a = 0; a < A; a++) {
         const float* me = m.st_in + a * ST_STRIDE;
         const float px = me[ST_PX], py = me[ST_PY], mx = me[ST_VX], my = me[ST_VY];
@@ -184,11 +221,12 @@ __device__ __forceinline__ void physics_stage(const KArgs& k, const Smem& m, int
         const float vx = fmul(mx, rF), vy = fmul(my, rF);
         const float vlen = sqrt_(ffma(vx, vx, fmul(vy, vy)));
         const float u = fadd(vlen, 1e-6f), uu = fmul(u, u);
-        for (int l = AF + tid; l < L; l += blockDim.x) {
-            x = fminf(x, collide_line(px, py, vx, vy, vlen, u, uu, m.seg[l], r1, r1sq));
+        const int nc = m.ncand[a];
+        for (int i = tid; i < nc; i += blockDim.x) {
+            x = fminf(x, collide_line(px, py, vx, vy, vlen, u, uu, m.seg[m.cand[a * cap + i]], r1, r1sq));
         }
         x = warp_min(x);
-        if (lane == 0) atomicMin(m.xmin + a, __float_as_int(x));   // x in [0, 1]: int order == float order
+        if (lane == 0 && x < 1.f) atomicMin(m.xmin + a, __float_as_int(x));   // x in [0, 1]: int order == float order
     }
     __syncthreads();
 
@@ -247,20 +285,24 @@ __device__ __forceinline__ float light_intensity_cached(const float4* __restrict
         const float Ix = __shfl_sync(0xffffffffu, ll.x, i), Iy = __shfl_sync(0xffffffffu, ll.y, i);
         const float Ux = fsub(Cx, Ix), Uy = fsub(Cy, Iy);
         int found = -1;
-        for (int base = AF; base < L; base += 64) {
-            const int l0 = base + lane, l1 = base + 32 + lane;
-            bool o0 = false, o1 = false;
-            if (l0 < L) {
-                const Hit h = intersect(Ix, Iy, Ux, Uy, seg[l0]);
-                o0 = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
-            }
-            if (l1 < L) {
-                const Hit h = intersect(Ix, Iy, Ux, Uy, seg[l1]);
-                o1 = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
+        for (int base = AF; base < L; base += 128) {
+            unsigned bal[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int l = base + 32 * u + lane;
+                bool o = false;
+                if (l < L) {
+                    const Hit h = intersect(Ix, Iy, Ux, Uy, seg[l]);
+                    o = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
+                }
+                bal[u] = __ballot_sync(0xffffffffu, o);
             }
             if (STATS) iters++;
-            const unsigned b0 = __ballot_sync(0xffffffffu, o0), b1 = __ballot_sync(0xffffffffu, o1);
-            if (b0 | b1) { found = b0 ? base + __ffs(b0) - 1 : base + 32 + __ffs(b1) - 1; break; }
+            if (bal[0] | bal[1] | bal[2] | bal[3]) {
+#pragma unroll
+                for (int u = 3; u >= 0; u--) if (bal[u]) found = base + 32 * u + __ffs(bal[u]) - 1;
+                break;
+            }
         }
         if (found < 0) lit |= 1u << i;
         else if (lane == i) ll.occ = found;
@@ -401,20 +443,30 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
         for (int c = 0; c < NCH; c++) {
             const int c_lo = r0 + 32 * c, c_hi = c_lo + 31;
             unsigned mask = __ballot_sync(0xffffffffu, (rlo <= c_hi) && (rhi >= c_lo) && (rlo <= rhi));
-            while (mask) {
-                const int j = __ffs(mask) - 1;
+            if (mask) {
+                int j = __ffs(mask) - 1;
                 mask &= mask - 1;
-                const float4 q = scr[j];
-                const float snum = scr[32 + j].x;
-                // raycast_kernel inner loop (kernels.cu:353-376), branch-free. A near-parallel line (|UxV| < 1e-3,
-                // s = t = inf in the reference) can never be accepted, so its s/t need not be forced to inf.
-                const float UxV = cross2(rux[c], q.y, ruy[c], q.x);
-                const float rc = rcp(UxV);
-                const float hs_ = fmul(snum, rc);
-                const float ht_ = fmul(cross2(ruy[c], q.z, rux[c], q.w), rc);
-                const bool take = !(fabsf(UxV) < PARALLEL_EPS) && (ht_ >= 0.f) && (ht_ <= 1.f) && (nearp[c] < hs_) && (hs_ < bestm[c]);
-                if (take) { best[c] = hs_; bestm[c] = fadd(hs_, -1.e-4f); loc[c] = ht_; idx[c] = gbase + j; }
-                if (STATS) tests++;
+                float4 q = scr[j];
+                float snum = scr[32 + j].x;
+                while (true) {
+                    // fetch the next candidate's terms before the arithmetic of this one (hides the LDS latency)
+                    const bool more = mask != 0;
+                    const int jn = more ? __ffs(mask) - 1 : j;
+                    mask &= mask - 1;
+                    const float4 qn = scr[jn];
+                    const float snn = scr[32 + jn].x;
+                    // raycast_kernel inner loop (kernels.cu:353-376), branch-free. A near-parallel line
+                    // (|UxV| < 1e-3: s = t = inf in the reference) can never be accepted, so its s/t need no forcing.
+                    const float UxV = cross2(rux[c], q.y, ruy[c], q.x);
+                    const float rc = rcp(UxV);
+                    const float hs_ = fmul(snum, rc);
+                    const float ht_ = fmul(cross2(ruy[c], q.z, rux[c], q.w), rc);
+                    const bool take = !(fabsf(UxV) < PARALLEL_EPS) && (ht_ >= 0.f) && (ht_ <= 1.f) && (nearp[c] < hs_) && (hs_ < bestm[c]);
+                    if (take) { best[c] = hs_; bestm[c] = fadd(hs_, -1.e-4f); loc[c] = ht_; idx[c] = gbase + j; }
+                    if (STATS) tests++;
+                    if (!more) break;
+                    j = jn; q = qn; snum = snn;
+                }
             }
         }
         if (STATS) groups++;
@@ -630,6 +682,7 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ KArgs 
         float* st = ((MODE & MODE_PHYSICS) ? m.st_in : m.st_out) + a * ST_STRIDE;
         st[ST_ANG] = ang; st[ST_PX] = pos.x; st[ST_PY] = pos.y; st[ST_AV] = av; st[ST_VX] = vel.x; st[ST_VY] = vel.y;
         m.xmin[a] = __float_as_int(1.f);
+        m.ncand[a] = 0;
     }
     __syncthreads();
     if (W > 0) mbar_wait(m.bar, 0);
@@ -657,10 +710,12 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ KArgs 
 // cache keeps working), reads the env's segments straight from HBM/L2, and writes the final screen pixels and the
 // pooled RGB observation of the group.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int DYN_BLOCK = 8;
+constexpr int DYN_BLOCK = 4;
 
 template <bool STATS>
 __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* wseg = reinterpret_cast<float4*>(smem_raw) + (size_t)(threadIdx.x >> 5) * k.seg_cap;   // this warp's copy
     const int lane = threadIdx.x & 31;
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
     const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
@@ -688,7 +743,11 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
             if (n != cur_n) {
                 cur_n = n;
                 L = __ldg(k.s.line_widths + n);
-                seg = reinterpret_cast<const float4*>(k.s.lines) + __ldg(k.s.line_starts + n);
+                const float4* gseg = reinterpret_cast<const float4*>(k.s.lines) + __ldg(k.s.line_starts + n);
+                __syncwarp();
+                for (int l = AF + lane; l < L; l += 32) wseg[l] = __ldg(gseg + l);   // coalesced, all loads in flight at once
+                __syncwarp();
+                seg = wseg;
                 nlights = __ldg(k.s.light_widths + n);
                 lt = k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n);
                 ll.occ = -1;
@@ -854,6 +913,7 @@ static int validate(const msb_params* p, const msb_scenery* s) {
     if (!p || !s) return fail("%s", "null params/scenery");
     if (s->n_envs < 0 || s->n_agents < 1 || s->n_model < 0) return fail("%s", "bad scenery dimensions");
     if (s->max_lines < s->n_agents * s->n_model) return fail("%s", "scenery.max_lines is smaller than n_agents*n_model");
+    if (s->max_lines > 14000) return fail("%s", "scene too large: more than 14000 segments in one environment");
     return 0;
 }
 
@@ -946,9 +1006,16 @@ static int launch_dyn(const KArgs& k, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = sms * 8;
-    if (k.stats) dyn_kernel<true><<<grid, 128, 0, st>>>(k);
-    else dyn_kernel<false><<<grid, 128, 0, st>>>(k);
+    const size_t sm = (size_t)4 * k.seg_cap * 16;
+    if (sm > 227 * 1024) return fail("%s", "scene too large for dyn_kernel's shared memory");
+    int per_sm = sm ? (int)((200 * 1024) / sm) : 8;
+    if (per_sm > 12) per_sm = 12;
+    if (per_sm < 1) per_sm = 1;
+    const int grid = sms * per_sm;
+    auto fn = k.stats ? dyn_kernel<true> : dyn_kernel<false>;
+    if (sm > 48 * 1024 && check(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "cudaFuncSetAttribute"))
+        return 1;
+    fn<<<grid, 128, sm, st>>>(k);
     g_launches++;
     return check(cudaGetLastError(), "dyn_kernel launch");
 }
