@@ -63,6 +63,12 @@ typedef struct msb_scenery {
     const float* model;         /* (F, 4) */
     int64_t n_lines;            /* sum L */
     int64_t n_texels;           /* sum T */
+    /* Optional occluder table (all NULL to disable): a spatially sorted copy of every env's STATIC segments, used
+     * only for shadow tests (whose any-of-the-lines answer does not depend on order). Built once per scenery. */
+    const float* occ_lines;     /* (sum W, 4) static segments, sorted by Morton code of their midpoint within each env */
+    const int32_t* occ_starts;  /* (N) start of env n's rows in occ_lines; it has line_widths[n] - A*F rows */
+    const float* occ_boxes;     /* (sum ceil(W/32), 4) {xmin, ymin, xmax, ymax} of each run of 32 sorted segments */
+    const int32_t* box_starts;  /* (N) start of env n's rows in occ_boxes */
 } msb_scenery;
 
 /* The Agents struct of megastep/src/common.h:162-177. Updated in place by msb_physics. */

@@ -285,24 +285,20 @@ __device__ __forceinline__ float light_intensity_cached(const float4* __restrict
         const float Ix = __shfl_sync(0xffffffffu, ll.x, i), Iy = __shfl_sync(0xffffffffu, ll.y, i);
         const float Ux = fsub(Cx, Ix), Uy = fsub(Cy, Iy);
         int found = -1;
-        for (int base = AF; base < L; base += 128) {
-            unsigned bal[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int l = base + 32 * u + lane;
-                bool o = false;
-                if (l < L) {
-                    const Hit h = intersect(Ix, Iy, Ux, Uy, seg[l]);
-                    o = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
-                }
-                bal[u] = __ballot_sync(0xffffffffu, o);
+        for (int base = AF; base < L; base += 64) {
+            const int l0 = base + lane, l1 = base + 32 + lane;
+            bool o0 = false, o1 = false;
+            if (l0 < L) {
+                const Hit h = intersect(Ix, Iy, Ux, Uy, seg[l0]);
+                o0 = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
+            }
+            if (l1 < L) {
+                const Hit h = intersect(Ix, Iy, Ux, Uy, seg[l1]);
+                o1 = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
             }
             if (STATS) iters++;
-            if (bal[0] | bal[1] | bal[2] | bal[3]) {
-#pragma unroll
-                for (int u = 3; u >= 0; u--) if (bal[u]) found = base + 32 * u + __ffs(bal[u]) - 1;
-                break;
-            }
+            const unsigned b0 = __ballot_sync(0xffffffffu, o0), b1 = __ballot_sync(0xffffffffu, o1);
+            if (b0 | b1) { found = b0 ? base + __ffs(b0) - 1 : base + 32 + __ffs(b1) - 1; break; }
         }
         if (found < 0) lit |= 1u << i;
         else if (lane == i) ll.occ = found;
@@ -335,6 +331,74 @@ __device__ __forceinline__ float light_intensity_cached(const float4* __restrict
             const float dx = fsub(Ix, Cx), dy = fsub(Iy, Cy);
             acc = ffma(fadd(Ii, Ii), rcp(fmaxf(ffma(dx, dx, fmul(dy, dy)), 1.f)), acc);
         }
+    }
+    return fminf(acc, 1.f);
+}
+
+// The same, over the occluder table: `occ` holds this env's W static segments sorted along a Morton curve, `boxes`
+// the bounding box of each run of 32. A run can only contain an occluder of the light ray I->C if its box, grown by
+// a margin covering the worst-case rounding of intersect() (near-parallel lines: |UxV| >= 1e-3 bounds the
+// amplification), overlaps the ray's box; all other runs are skipped. Lane b tests run b's box, a ballot gives the
+// runs to visit. Up to 32 lights resident one per lane (more: the caller falls back to the unsorted scan).
+struct OccEnv { const float4* occ; const float4* boxes; int W, nb; float vmax, diam; };
+
+template <bool STATS>
+__device__ __forceinline__ float light_intensity_boxed(const OccEnv& oe, int I, float Cx, float Cy, int lane,
+                                                       LaneLight& ll, unsigned& iters) {
+    const int nres = I < 32 ? I : 32;
+    bool ob = false;
+    if (lane < nres && ll.occ >= 0) {
+        const Hit h = intersect(ll.x, ll.y, fsub(Cx, ll.x), fsub(Cy, ll.y), oe.occ[ll.occ]);
+        ob = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
+    }
+    const unsigned resident = nres == 32 ? 0xffffffffu : ((1u << nres) - 1u);
+    unsigned todo = resident & ~__ballot_sync(0xffffffffu, ob);
+    unsigned lit = 0;
+    if (STATS) iters++;
+    while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float Ix = __shfl_sync(0xffffffffu, ll.x, i), Iy = __shfl_sync(0xffffffffu, ll.y, i);
+        const float Ux = fsub(Cx, Ix), Uy = fsub(Cy, Iy);
+        // conservative query box (see DESIGN.md "shadow cull"): rounding can move the computed crossing by at most
+        // delta (a fraction of each segment's length) along either segment
+        const float ulen = fmaxf(fabsf(Ux), fabsf(Uy));
+        const float delta = 4e-4f * oe.vmax * (oe.diam + ulen);
+        const float mg = delta * (ulen + oe.vmax) + 0.01f;
+        const float qx0 = fminf(Ix, Cx) - mg, qx1 = fmaxf(Ix, Cx) + mg, qy0 = fminf(Iy, Cy) - mg, qy1 = fmaxf(Iy, Cy) + mg;
+        int found = -1;
+        for (int b0 = 0; b0 < oe.nb && found < 0; b0 += 32) {
+            bool visit = false;
+            if (b0 + lane < oe.nb) {
+                const float4 bx = oe.boxes[b0 + lane];
+                visit = !(bx.x > qx1 || bx.z < qx0 || bx.y > qy1 || bx.w < qy0);
+            }
+            unsigned runs = __ballot_sync(0xffffffffu, visit);
+            while (runs) {
+                const int b = b0 + __ffs(runs) - 1;
+                runs &= runs - 1;
+                const int l = 32 * b + lane;
+                bool o = false;
+                if (l < oe.W) {
+                    const Hit h = intersect(Ix, Iy, Ux, Uy, oe.occ[l]);
+                    o = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
+                }
+                if (STATS) iters++;
+                const unsigned bal = __ballot_sync(0xffffffffu, o);
+                if (bal) { found = 32 * b + __ffs(bal) - 1; break; }
+            }
+        }
+        if (found < 0) lit |= 1u << i;
+        else if (lane == i) ll.occ = found;
+    }
+    float acc = 0.1f;   // AMBIENT (kernels.cu:9)
+    while (lit) {
+        const int i = __ffs(lit) - 1;
+        lit &= lit - 1;
+        const float Ix = __shfl_sync(0xffffffffu, ll.x, i), Iy = __shfl_sync(0xffffffffu, ll.y, i);
+        const float Ii = __shfl_sync(0xffffffffu, ll.i, i);
+        const float dx = fsub(Ix, Cx), dy = fsub(Iy, Cy);
+        acc = ffma(fadd(Ii, Ii), rcp(fmaxf(ffma(dx, dx, fmul(dy, dy)), 1.f)), acc);   // LUMINANCE = 2 (:240)
     }
     return fminf(acc, 1.f);
 }
@@ -715,7 +779,12 @@ constexpr int DYN_BLOCK = 4;
 template <bool STATS>
 __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* wseg = reinterpret_cast<float4*>(smem_raw) + (size_t)(threadIdx.x >> 5) * k.seg_cap;   // this warp's copy
+    const int wcap = k.seg_cap + ((k.seg_cap + 31) >> 5);                                      // segments + run boxes
+    float4* wseg = reinterpret_cast<float4*>(smem_raw) + (size_t)(threadIdx.x >> 5) * wcap;     // this warp's copy
+    float4* wbox = wseg + k.seg_cap;
+    const bool sorted = k.s.occ_lines != nullptr;
+    OccEnv oe;
+    oe.occ = wseg; oe.boxes = wbox; oe.W = 0; oe.nb = 0; oe.vmax = 0.f; oe.diam = 0.f;
     const int lane = threadIdx.x & 31;
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
     const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
@@ -728,6 +797,7 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
     const float* lt = nullptr;
     LaneLight ll;
     ll.occ = -1; ll.x = ll.y = ll.i = 0.f;
+    bool use_sorted = false;
     for (int blk = wg; blk * DYN_BLOCK < count; blk += tw) {
         const int e_end = min(count, (blk + 1) * DYN_BLOCK);
         for (int ei = blk * DYN_BLOCK; ei < e_end; ei++) {
@@ -743,12 +813,40 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
             if (n != cur_n) {
                 cur_n = n;
                 L = __ldg(k.s.line_widths + n);
-                const float4* gseg = reinterpret_cast<const float4*>(k.s.lines) + __ldg(k.s.line_starts + n);
+                nlights = __ldg(k.s.light_widths + n);
                 __syncwarp();
-                for (int l = AF + lane; l < L; l += 32) wseg[l] = __ldg(gseg + l);   // coalesced, all loads in flight at once
+                if (sorted && nlights <= 32) {
+                    // this env's sorted occluders and run boxes -> this warp's shared memory (coalesced, all in flight)
+                    const int W = L - AF;
+                    const float4* gocc = reinterpret_cast<const float4*>(k.s.occ_lines) + __ldg(k.s.occ_starts + n);
+                    const float4* gbox = reinterpret_cast<const float4*>(k.s.occ_boxes) + __ldg(k.s.box_starts + n);
+                    const int nb = (W + 31) >> 5;
+                    float vmax = 0.f, x0 = CUDART_INF_F, y0 = CUDART_INF_F, x1 = -CUDART_INF_F, y1 = -CUDART_INF_F;
+                    for (int l = lane; l < W; l += 32) {
+                        const float4 v = __ldg(gocc + l);
+                        wseg[l] = v;
+                        vmax = fmaxf(vmax, fmaxf(fabsf(v.z - v.x), fabsf(v.w - v.y)));
+                    }
+                    for (int b = lane; b < nb; b += 32) {
+                        const float4 v = __ldg(gbox + b);
+                        wbox[b] = v;
+                        x0 = fminf(x0, v.x); y0 = fminf(y0, v.y); x1 = fmaxf(x1, v.z); y1 = fmaxf(y1, v.w);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+                        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+                        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+                    }
+                    oe.W = W; oe.nb = nb; oe.vmax = vmax; oe.diam = nb ? fmaxf(x1 - x0, y1 - y0) : 0.f;
+                    use_sorted = true;
+                } else {
+                    const float4* gseg = reinterpret_cast<const float4*>(k.s.lines) + __ldg(k.s.line_starts + n);
+                    for (int l = AF + lane; l < L; l += 32) wseg[l] = __ldg(gseg + l);
+                    use_sorted = false;
+                }
                 __syncwarp();
                 seg = wseg;
-                nlights = __ldg(k.s.light_widths + n);
                 lt = k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n);
                 ll.occ = -1;
                 if (lane < nlights) { ll.x = __ldg(lt + 3 * lane); ll.y = __ldg(lt + 3 * lane + 1); ll.i = __ldg(lt + 3 * lane + 2); }
@@ -765,7 +863,8 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
                 const int p = __ffs(m) - 1;
                 m &= m - 1;
                 const float cx = __shfl_sync(0xffffffffu, rb.x, p), cy = __shfl_sync(0xffffffffu, rb.y, p);
-                const float v = light_intensity_cached<STATS>(seg, L, AF, nlights, lt, cx, cy, lane, ll, dyn_iters);
+                const float v = use_sorted ? light_intensity_boxed<STATS>(oe, nlights, cx, cy, lane, ll, dyn_iters)
+                                           : light_intensity_cached<STATS>(seg, L, AF, nlights, lt, cx, cy, lane, ll, dyn_iters);
                 if (lane == p) intensity = v;
                 if (STATS) dyn_rays++;
             }
@@ -1006,7 +1105,7 @@ static int launch_dyn(const KArgs& k, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t sm = (size_t)4 * k.seg_cap * 16;
+    const size_t sm = (size_t)4 * (k.seg_cap + ((k.seg_cap + 31) >> 5)) * 16;
     if (sm > 227 * 1024) return fail("%s", "scene too large for dyn_kernel's shared memory");
     int per_sm = sm ? (int)((200 * 1024) / sm) : 8;
     if (per_sm > 12) per_sm = 12;

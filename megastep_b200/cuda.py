@@ -41,7 +41,9 @@ class _Scenery(ctypes.Structure):
                 ('lights', ctypes.c_void_p), ('light_widths', ctypes.c_void_p), ('light_starts', ctypes.c_void_p),
                 ('textures', ctypes.c_void_p), ('tex_widths', ctypes.c_void_p), ('tex_starts', ctypes.c_void_p),
                 ('baked', ctypes.c_void_p), ('model', ctypes.c_void_p),
-                ('n_lines', ctypes.c_int64), ('n_texels', ctypes.c_int64)]
+                ('n_lines', ctypes.c_int64), ('n_texels', ctypes.c_int64),
+                ('occ_lines', ctypes.c_void_p), ('occ_starts', ctypes.c_void_p), ('occ_boxes', ctypes.c_void_p),
+                ('box_starts', ctypes.c_void_p)]
 
 
 class _Agents(ctypes.Structure):
@@ -271,6 +273,9 @@ class Scenery:
                 textures=self._textures.vals.data_ptr(), tex_widths=self._textures.widths.data_ptr(),
                 tex_starts=self._tex_starts.data_ptr(), baked=self._baked.vals.data_ptr(), model=self._model.data_ptr(),
                 n_lines=self._lines.vals.size(0), n_texels=self._textures.vals.size(0))
+            if BUILD_OCCLUDERS and self._lines.vals.size(0) > 0:
+                self._occ = _occluder_table(self._lines, self._n_agents * self._model.size(0))
+                self._c.occ_lines, self._c.occ_starts, self._c.occ_boxes, self._c.box_starts = (t.data_ptr() for t in self._occ)
         return self._c
 
 
@@ -288,6 +293,52 @@ def _shared_workspace(scenery, params):
     if key not in scenery._ws:
         scenery._ws[key] = make_workspace(scenery, params, 1)
     return scenery._ws[key][1]
+
+
+def _morton16(x, y):
+    """Interleave the low 16 bits of two int64 tensors."""
+    def spread(v):
+        v = v & 0xFFFF
+        v = (v | (v << 8)) & 0x00FF00FF
+        v = (v | (v << 4)) & 0x0F0F0F0F
+        v = (v | (v << 2)) & 0x33333333
+        v = (v | (v << 1)) & 0x55555555
+        return v
+    return spread(x) | (spread(y) << 1)
+
+
+@torch.no_grad()
+def _occluder_table(lines, n_dynamic):
+    """(occ_lines, occ_starts, occ_boxes, box_starts) of include/megastep_b200.h: every env's static segments sorted
+    along a Morton curve, plus the bounding box of each run of 32. Shadow tests ask "does ANY static segment cross
+    this light ray", which no ordering can change; the sort only lets the kernel skip runs that are nowhere near."""
+    vals, widths = lines.vals.reshape(-1, 4), lines.widths.long()
+    dev = vals.device
+    env = lines.inverse.long()
+    local = torch.arange(vals.size(0), device=dev) - lines.starts.long()[env]
+    static = local >= n_dynamic
+    sv, senv = vals[static], env[static]
+    mid = (sv[:, :2] + sv[:, 2:]) * .5
+    lo = mid.min(0).values if len(mid) else torch.zeros(2, device=dev)
+    cell = ((mid - lo) / .25).clamp(0, 65535).long()
+    key = (senv << 32) | _morton16(cell[:, 0], cell[:, 1])
+    order = torch.argsort(key)
+    occ = sv[order].contiguous()
+    W = (widths - n_dynamic).clamp(min=0)
+    occ_starts = (W.cumsum(0) - W)
+    nb = (W + 31) // 32
+    box_starts = nb.cumsum(0) - nb
+    oenv = senv[order]
+    rank = torch.arange(occ.size(0), device=dev) - occ_starts[oenv]
+    box = box_starts[oenv] + rank // 32
+    nbox = int(nb.sum().item())
+    big = torch.finfo(torch.float32).max
+    xmin = torch.full((nbox,), big, device=dev).scatter_reduce(0, box, torch.minimum(occ[:, 0], occ[:, 2]), 'amin')
+    ymin = torch.full((nbox,), big, device=dev).scatter_reduce(0, box, torch.minimum(occ[:, 1], occ[:, 3]), 'amin')
+    xmax = torch.full((nbox,), -big, device=dev).scatter_reduce(0, box, torch.maximum(occ[:, 0], occ[:, 2]), 'amax')
+    ymax = torch.full((nbox,), -big, device=dev).scatter_reduce(0, box, torch.maximum(occ[:, 1], occ[:, 3]), 'amax')
+    boxes = torch.stack([xmin, ymin, xmax, ymax], -1).contiguous()
+    return occ, occ_starts.int().contiguous(), boxes, box_starts.int().contiguous()
 
 
 class Render:
@@ -309,6 +360,7 @@ class Physics:
 # functions
 # --------------------------------------------------------------------------------------------------------------
 _PARAMS = None
+BUILD_OCCLUDERS = True  # False: the second pass scans the segments in their original order (same results, slower)
 USE_WORKSPACE = True   # False: agent-hit rays are lit inline by the first pass (same results; used by tests)
 
 

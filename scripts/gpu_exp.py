@@ -32,6 +32,13 @@ if __name__ == '__main__':
         for _ in range(3): c.render()
         torch.cuda.synchronize()
         sys.exit(0)
+    if mode == 'launches':
+        step = modules.FusedStep(c, subsample=1, raw=True)
+        acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')
+        for _ in range(3):
+            c.physics(); c.render(); step(acts)
+        torch.cuda.synchronize()
+        sys.exit(0)
     out = {}
     for skip in (0, 1):
         cuda.set_option('debug_skip_dyn', skip)

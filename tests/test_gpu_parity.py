@@ -257,8 +257,9 @@ def _same(a, b):
 
 @pytest.mark.parametrize('sub', [1, 4])
 def test_second_pass_inline_and_overflow_paths_agree(sub):
-    """Agent-hit rays are lit by dyn_kernel (workspace), inline (no workspace) or a mix (workspace too small):
-    all three must give identical screens and observations. Agents are packed close so many rays hit agents."""
+    """Agent-hit rays are lit by dyn_kernel over the sorted occluder table (workspace), inline by the first pass (no
+    workspace), by a mix (workspace too small), or by dyn_kernel over the unsorted segments: all must give identical
+    screens and observations. Agents are packed close so many rays hit agents."""
     import ctypes
     from megastep_b200 import cuda, modules
     gs, arrays, st = make('box', 6, 4, seed=61)
@@ -266,13 +267,15 @@ def test_second_pass_inline_and_overflow_paths_agree(sub):
     st['positions'] = (3.5 + rng.uniform(-.6, .6, st['positions'].shape)).astype(np.float32)
     res = 128
     outs = []
-    for mode in ('workspace', 'inline', 'overflow'):
-        c = common.to_device(arrays, st, res, 100.)
+    for mode in ('workspace', 'inline', 'overflow', 'unsorted'):
         cuda.USE_WORKSPACE = mode != 'inline'
+        cuda.BUILD_OCCLUDERS = mode != 'unsorted'
         try:
+            c = common.to_device(arrays, st, res, 100.)
             plan = cuda.StepPlan(c.scenery, c.agents, c.params, actions=None, raw=True, subsample=sub)
         finally:
             cuda.USE_WORKSPACE = True
+            cuda.BUILD_OCCLUDERS = True
         if mode == 'overflow':
             small = 16 + 3 * (16 + 32 * sub)                       # room for three pixel groups only
             plan._wsbuf = torch.zeros(small, dtype=torch.uint8, device='cuda')
