@@ -104,14 +104,28 @@ def test_params_init_matches_reference_formula_and_validates():
         cuda.make_params(.1, 0, 90., 10.)
 
 
-def test_struct_layouts_match_the_header():
-    # sizes the C compiler gives the structs (LP64): guards the ctypes mirrors against drift
-    assert ctypes.sizeof(cuda.Params) == 32
-    assert ctypes.sizeof(cuda._Scenery) == 24 + 11 * 8 + 16
-    assert ctypes.sizeof(cuda._Agents) == 32
-    assert ctypes.sizeof(cuda._RenderOut) == 40
-    assert ctypes.sizeof(cuda._ObsOut) == 40
-    assert ctypes.sizeof(cuda._Movement) == 24
+def test_struct_layouts_match_the_header(tmp_path):
+    """Compile the header with the C compiler and compare every struct's size and field offsets with the ctypes
+    mirrors in megastep_b200/cuda.py."""
+    import subprocess
+    structs = {'msb_params': cuda.Params, 'msb_scenery': cuda._Scenery, 'msb_agents': cuda._Agents,
+               'msb_render_out': cuda._RenderOut, 'msb_obs_out': cuda._ObsOut, 'msb_movement': cuda._Movement,
+               'msb_workspace': cuda._Workspace}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "megastep_b200.h"', 'int main(void) {']
+    for cname, mirror in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, *_ in mirror._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['return 0; }']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-I', os.path.join(common.ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, mirror in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(mirror), cname
+        for fname, *_ in mirror._fields_:
+            assert int(got[f'{cname}.{fname}']) == getattr(mirror, fname).offset, f'{cname}.{fname}'
 
 
 # ---- containers --------------------------------------------------------------------------------------------------
