@@ -49,7 +49,7 @@ typedef struct msb_scenery {
     int32_t n_model;            /* F: lines in the agent model */
     int32_t max_lines;          /* max over envs of line_widths (shared-memory sizing) */
     int32_t max_lights;         /* max over envs of light_widths */
-    int32_t reserved;
+    int32_t occ_run;            /* segments per occluder box: 8, 16 or 32 (only read when occ_lines is set) */
     float* lines;               /* (sum L, 4) — render()/step() write the agents' lines in place */
     const int32_t* line_widths; /* (N) */
     const int32_t* line_starts; /* (N) exclusive prefix sum of line_widths */
@@ -67,7 +67,7 @@ typedef struct msb_scenery {
      * only for shadow tests (whose any-of-the-lines answer does not depend on order). Built once per scenery. */
     const float* occ_lines;     /* (sum W, 4) static segments, sorted by Morton code of their midpoint within each env */
     const int32_t* occ_starts;  /* (N) start of env n's rows in occ_lines; it has line_widths[n] - A*F rows */
-    const float* occ_boxes;     /* (sum ceil(W/32), 4) {xmin, ymin, xmax, ymax} of each run of 32 sorted segments */
+    const float* occ_boxes;     /* (sum ceil(W/occ_run), 4) {xmin, ymin, xmax, ymax} of each run of occ_run sorted segments */
     const int32_t* box_starts;  /* (N) start of env n's rows in occ_boxes */
 } msb_scenery;
 

@@ -340,7 +340,7 @@ __device__ __forceinline__ float light_intensity_cached(const float4* __restrict
 // a margin covering the worst-case rounding of intersect() (near-parallel lines: |UxV| >= 1e-3 bounds the
 // amplification), overlaps the ray's box; all other runs are skipped. Lane b tests run b's box, a ballot gives the
 // runs to visit. Up to 32 lights resident one per lane (more: the caller falls back to the unsorted scan).
-struct OccEnv { const float4* occ; const float4* boxes; int W, nb; float vmax, diam; };
+struct OccEnv { const float4* occ; const float4* boxes; int W, nb, run; float vmax, diam; };
 
 template <bool STATS>
 __device__ __forceinline__ float light_intensity_boxed(const OccEnv& oe, int I, float Cx, float Cy, int lane,
@@ -355,6 +355,8 @@ __device__ __forceinline__ float light_intensity_boxed(const OccEnv& oe, int I, 
     unsigned todo = resident & ~__ballot_sync(0xffffffffu, ob);
     unsigned lit = 0;
     if (STATS) iters++;
+    const int run = oe.run, per = 32 / run;          // segments per box; boxes scanned per warp iteration
+    const int slot = lane / run, within = lane - slot * run;
     while (todo) {
         const int i = __ffs(todo) - 1;
         todo &= todo - 1;
@@ -375,9 +377,9 @@ __device__ __forceinline__ float light_intensity_boxed(const OccEnv& oe, int I, 
             }
             unsigned runs = __ballot_sync(0xffffffffu, visit);
             while (runs) {
-                const int b = b0 + __ffs(runs) - 1;
-                runs &= runs - 1;
-                const int l = 32 * b + lane;
+                // lanes [slot*run, (slot+1)*run) take the slot-th box still to visit
+                const unsigned nth = __fns(runs, 0, slot + 1);          // 0xffffffff when fewer boxes remain
+                const int l = nth < 32u ? run * (b0 + (int)nth) + within : oe.W;
                 bool o = false;
                 if (l < oe.W) {
                     const Hit h = intersect(Ix, Iy, Ux, Uy, oe.occ[l]);
@@ -385,7 +387,8 @@ __device__ __forceinline__ float light_intensity_boxed(const OccEnv& oe, int I, 
                 }
                 if (STATS) iters++;
                 const unsigned bal = __ballot_sync(0xffffffffu, o);
-                if (bal) { found = 32 * b + __ffs(bal) - 1; break; }
+                if (bal) { found = __shfl_sync(0xffffffffu, l, __ffs(bal) - 1); break; }
+                for (int d = 0; d < per && runs; d++) runs &= runs - 1;    // drop the boxes just scanned
             }
         }
         if (found < 0) lit |= 1u << i;
@@ -779,12 +782,12 @@ constexpr int DYN_BLOCK = 4;
 template <bool STATS>
 __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int wcap = k.seg_cap + ((k.seg_cap + 31) >> 5);                                      // segments + run boxes
+    const int wcap = k.seg_cap + (k.seg_cap + k.s.occ_run - 1) / k.s.occ_run;                 // segments + run boxes
     float4* wseg = reinterpret_cast<float4*>(smem_raw) + (size_t)(threadIdx.x >> 5) * wcap;     // this warp's copy
     float4* wbox = wseg + k.seg_cap;
     const bool sorted = k.s.occ_lines != nullptr;
     OccEnv oe;
-    oe.occ = wseg; oe.boxes = wbox; oe.W = 0; oe.nb = 0; oe.vmax = 0.f; oe.diam = 0.f;
+    oe.occ = wseg; oe.boxes = wbox; oe.W = 0; oe.nb = 0; oe.vmax = 0.f; oe.diam = 0.f; oe.run = k.s.occ_run;
     const int lane = threadIdx.x & 31;
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
     const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
@@ -820,7 +823,7 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
                     const int W = L - AF;
                     const float4* gocc = reinterpret_cast<const float4*>(k.s.occ_lines) + __ldg(k.s.occ_starts + n);
                     const float4* gbox = reinterpret_cast<const float4*>(k.s.occ_boxes) + __ldg(k.s.box_starts + n);
-                    const int nb = (W + 31) >> 5;
+                    const int nb = (W + k.s.occ_run - 1) / k.s.occ_run;
                     float vmax = 0.f, x0 = CUDART_INF_F, y0 = CUDART_INF_F, x1 = -CUDART_INF_F, y1 = -CUDART_INF_F;
                     for (int l = lane; l < W; l += 32) {
                         const float4 v = __ldg(gocc + l);
@@ -1061,6 +1064,7 @@ static void fill(KArgs& k, const msb_params* p, const msb_scenery* s, const msb_
     k.s = *s;
     if (a) k.a = *a;
     k.seg_cap = s->max_lines > 0 ? s->max_lines : 1;
+    if (k.s.occ_run != 8 && k.s.occ_run != 16 && k.s.occ_run != 32) { k.s.occ_run = 32; if (k.s.occ_lines) k.s.occ_lines = nullptr; }
     k.inv_fps = 1.0f / p->fps;
     k.ray_blocks = 1;
     k.stats = g_stats;
@@ -1105,7 +1109,8 @@ static int launch_dyn(const KArgs& k, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t sm = (size_t)4 * (k.seg_cap + ((k.seg_cap + 31) >> 5)) * 16;
+    const int run = k.s.occ_run > 0 ? k.s.occ_run : 32;
+    const size_t sm = (size_t)4 * (k.seg_cap + (k.seg_cap + run - 1) / run) * 16;
     if (sm > 227 * 1024) return fail("%s", "scene too large for dyn_kernel's shared memory");
     int per_sm = sm ? (int)((200 * 1024) / sm) : 8;
     if (per_sm > 12) per_sm = 12;

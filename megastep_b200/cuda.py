@@ -36,7 +36,7 @@ class Params(ctypes.Structure):
 
 class _Scenery(ctypes.Structure):
     _fields_ = [('n_envs', ctypes.c_int32), ('n_agents', ctypes.c_int32), ('n_model', ctypes.c_int32),
-                ('max_lines', ctypes.c_int32), ('max_lights', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('max_lines', ctypes.c_int32), ('max_lights', ctypes.c_int32), ('occ_run', ctypes.c_int32),
                 ('lines', ctypes.c_void_p), ('line_widths', ctypes.c_void_p), ('line_starts', ctypes.c_void_p),
                 ('lights', ctypes.c_void_p), ('light_widths', ctypes.c_void_p), ('light_starts', ctypes.c_void_p),
                 ('textures', ctypes.c_void_p), ('tex_widths', ctypes.c_void_p), ('tex_starts', ctypes.c_void_p),
@@ -267,14 +267,14 @@ class Scenery:
             self._c = _Scenery(
                 n_envs=len(self._lines), n_agents=self._n_agents, n_model=self._model.size(0),
                 max_lines=int(lw.max().item()) if lw.numel() else 0,
-                max_lights=int(iw.max().item()) if iw.numel() else 0, reserved=0,
+                max_lights=int(iw.max().item()) if iw.numel() else 0, occ_run=OCCLUDER_RUN,
                 lines=self._lines.vals.data_ptr(), line_widths=lw.data_ptr(), line_starts=self._lines.starts.data_ptr(),
                 lights=self._lights.vals.data_ptr(), light_widths=iw.data_ptr(), light_starts=self._lights.starts.data_ptr(),
                 textures=self._textures.vals.data_ptr(), tex_widths=self._textures.widths.data_ptr(),
                 tex_starts=self._tex_starts.data_ptr(), baked=self._baked.vals.data_ptr(), model=self._model.data_ptr(),
                 n_lines=self._lines.vals.size(0), n_texels=self._textures.vals.size(0))
             if BUILD_OCCLUDERS and self._lines.vals.size(0) > 0:
-                self._occ = _occluder_table(self._lines, self._n_agents * self._model.size(0))
+                self._occ = _occluder_table(self._lines, self._n_agents * self._model.size(0), OCCLUDER_RUN)
                 self._c.occ_lines, self._c.occ_starts, self._c.occ_boxes, self._c.box_starts = (t.data_ptr() for t in self._occ)
         return self._c
 
@@ -308,7 +308,7 @@ def _morton16(x, y):
 
 
 @torch.no_grad()
-def _occluder_table(lines, n_dynamic):
+def _occluder_table(lines, n_dynamic, run=32):
     """(occ_lines, occ_starts, occ_boxes, box_starts) of include/megastep_b200.h: every env's static segments sorted
     along a Morton curve, plus the bounding box of each run of 32. Shadow tests ask "does ANY static segment cross
     this light ray", which no ordering can change; the sort only lets the kernel skip runs that are nowhere near."""
@@ -326,11 +326,11 @@ def _occluder_table(lines, n_dynamic):
     occ = sv[order].contiguous()
     W = (widths - n_dynamic).clamp(min=0)
     occ_starts = (W.cumsum(0) - W)
-    nb = (W + 31) // 32
+    nb = (W + run - 1) // run
     box_starts = nb.cumsum(0) - nb
     oenv = senv[order]
     rank = torch.arange(occ.size(0), device=dev) - occ_starts[oenv]
-    box = box_starts[oenv] + rank // 32
+    box = box_starts[oenv] + rank // run
     nbox = int(nb.sum().item())
     big = torch.finfo(torch.float32).max
     xmin = torch.full((nbox,), big, device=dev).scatter_reduce(0, box, torch.minimum(occ[:, 0], occ[:, 2]), 'amin')
@@ -360,6 +360,7 @@ class Physics:
 # functions
 # --------------------------------------------------------------------------------------------------------------
 _PARAMS = None
+OCCLUDER_RUN = 16        # segments per bounding box in the occluder table (8, 16 or 32)
 BUILD_OCCLUDERS = True  # False: the second pass scans the segments in their original order (same results, slower)
 USE_WORKSPACE = True   # False: agent-hit rays are lit inline by the first pass (same results; used by tests)
 

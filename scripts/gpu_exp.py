@@ -27,6 +27,7 @@ def setup(N=4096, A=4, res=128, fov=70.):
 
 if __name__ == '__main__':
     mode = sys.argv[1] if len(sys.argv) > 1 else 'exp'
+    if len(sys.argv) > 2: cuda.OCCLUDER_RUN = int(sys.argv[2])
     c = setup()
     if mode == 'ncu':
         for _ in range(3): c.render()
@@ -38,6 +39,12 @@ if __name__ == '__main__':
         for _ in range(3):
             c.physics(); c.render(); step(acts)
         torch.cuda.synchronize()
+        sys.exit(0)
+    if mode == 'run':
+        step = modules.FusedStep(c, subsample=1, raw=True)
+        acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')
+        print(json.dumps({'run': cuda.OCCLUDER_RUN, 'render_us': timeit(lambda: c.render()), 'step_us': timeit(lambda: step(acts)),
+                          'phys_then_render_us': timeit(lambda: (c.physics(), c.render()))}))
         sys.exit(0)
     out = {}
     for skip in (0, 1):
