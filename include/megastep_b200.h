@@ -69,6 +69,7 @@ typedef struct msb_scenery {
     const int32_t* occ_starts;  /* (N) start of env n's rows in occ_lines; it has line_widths[n] - A*F rows */
     const float* occ_boxes;     /* (sum ceil(W/occ_run), 4) {xmin, ymin, xmax, ymax} of each run of occ_run sorted segments */
     const int32_t* box_starts;  /* (N) start of env n's rows in occ_boxes */
+    const float* occ_meta;      /* (N, 2) per env: longest static segment extent (max |dx|,|dy|), extent of the env */
 } msb_scenery;
 
 /* The Agents struct of megastep/src/common.h:162-177. Updated in place by msb_physics. */

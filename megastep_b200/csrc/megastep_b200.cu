@@ -58,6 +58,7 @@ struct KArgs {
     unsigned char* dyn_entries; // null -> dynamic lights are resolved inline by the ray's own warp
     int32_t dyn_cap;            // entries that fit
     int32_t dyn_stride;         // bytes per entry = 16 + 32 * subsample
+    int* dyn_cache;             // [N][A][32] last occluder of each light as seen from (around) each agent; a hint
 };
 
 enum { MODE_PHYSICS = 1, MODE_RENDER = 2, MODE_STEP = 3 };
@@ -335,11 +336,11 @@ __device__ __forceinline__ float light_intensity_cached(const float4* __restrict
     return fminf(acc, 1.f);
 }
 
-// The same, over the occluder table: `occ` holds this env's W static segments sorted along a Morton curve, `boxes`
-// the bounding box of each run of 32. A run can only contain an occluder of the light ray I->C if its box, grown by
-// a margin covering the worst-case rounding of intersect() (near-parallel lines: |UxV| >= 1e-3 bounds the
-// amplification), overlaps the ray's box; all other runs are skipped. Lane b tests run b's box, a ballot gives the
-// runs to visit. Up to 32 lights resident one per lane (more: the caller falls back to the unsorted scan).
+// The same, over the occluder table, reading straight from HBM/L2: `occ` holds this env's W static segments sorted
+// along a Morton curve, `boxes` the bounding box of each run of `run` of them. A run can only contain an occluder of
+// the light ray I->C if its box, grown by a margin covering the worst-case rounding of intersect() (near-parallel
+// lines: |UxV| >= 1e-3 bounds the amplification), overlaps the ray's box; all other runs are skipped. Lane b tests
+// box b, a ballot gives the runs to visit, 32/run of them per warp iteration. Up to 32 lights, one per lane.
 struct OccEnv { const float4* occ; const float4* boxes; int W, nb, run; float vmax, diam; };
 
 template <bool STATS>
@@ -347,8 +348,8 @@ __device__ __forceinline__ float light_intensity_boxed(const OccEnv& oe, int I, 
                                                        LaneLight& ll, unsigned& iters) {
     const int nres = I < 32 ? I : 32;
     bool ob = false;
-    if (lane < nres && ll.occ >= 0) {
-        const Hit h = intersect(ll.x, ll.y, fsub(Cx, ll.x), fsub(Cy, ll.y), oe.occ[ll.occ]);
+    if (lane < nres && ll.occ >= 0 && ll.occ < oe.W) {
+        const Hit h = intersect(ll.x, ll.y, fsub(Cx, ll.x), fsub(Cy, ll.y), __ldg(oe.occ + ll.occ));
         ob = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
     }
     const unsigned resident = nres == 32 ? 0xffffffffu : ((1u << nres) - 1u);
@@ -357,6 +358,9 @@ __device__ __forceinline__ float light_intensity_boxed(const OccEnv& oe, int I, 
     if (STATS) iters++;
     const int run = oe.run, per = 32 / run;          // segments per box; boxes scanned per warp iteration
     const int slot = lane / run, within = lane - slot * run;
+    // this lane's boxes (box b0+lane of each 32-box round) do not depend on the light: load the first round once
+    float4 bx0 = make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+    if (todo && lane < oe.nb) bx0 = __ldg(oe.boxes + lane);
     while (todo) {
         const int i = __ffs(todo) - 1;
         todo &= todo - 1;
@@ -370,11 +374,9 @@ __device__ __forceinline__ float light_intensity_boxed(const OccEnv& oe, int I, 
         const float qx0 = fminf(Ix, Cx) - mg, qx1 = fmaxf(Ix, Cx) + mg, qy0 = fminf(Iy, Cy) - mg, qy1 = fmaxf(Iy, Cy) + mg;
         int found = -1;
         for (int b0 = 0; b0 < oe.nb && found < 0; b0 += 32) {
-            bool visit = false;
-            if (b0 + lane < oe.nb) {
-                const float4 bx = oe.boxes[b0 + lane];
-                visit = !(bx.x > qx1 || bx.z < qx0 || bx.y > qy1 || bx.w < qy0);
-            }
+            float4 bx = bx0;
+            if (b0) bx = (b0 + lane < oe.nb) ? __ldg(oe.boxes + b0 + lane) : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+            const bool visit = !(bx.x > qx1 || bx.z < qx0 || bx.y > qy1 || bx.w < qy0);
             unsigned runs = __ballot_sync(0xffffffffu, visit);
             while (runs) {
                 // lanes [slot*run, (slot+1)*run) take the slot-th box still to visit
@@ -382,7 +384,7 @@ __device__ __forceinline__ float light_intensity_boxed(const OccEnv& oe, int I, 
                 const int l = nth < 32u ? run * (b0 + (int)nth) + within : oe.W;
                 bool o = false;
                 if (l < oe.W) {
-                    const Hit h = intersect(Ix, Iy, Ux, Uy, oe.occ[l]);
+                    const Hit h = intersect(Ix, Iy, Ux, Uy, __ldg(oe.occ + l));
                     o = (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f);
                 }
                 if (STATS) iters++;
@@ -613,13 +615,16 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
             if (lane == 0) base = atomicAdd(k.dyn_ctrl, cnt);
             base = __shfl_sync(0xffffffffu, base, 0);
             queued = base + cnt <= k.dyn_cap;
+            // which agent the group's first agent-hit pixel landed on: keys the persistent occluder cache
+            const int tgt = __shfl_sync(0xffffffffu, l0, gl + (gmask ? __ffs(gmask) - 1 : 0)) / k.s.n_model;
             if (gmask) {
                 const int slot = base + __popc(leaders & ((1u << gl) - 1u));
                 if (slot < k.dyn_cap) {
                     unsigned char* e = k.dyn_entries + (size_t)slot * k.dyn_stride;
                     if (lane == gl) {
                         const int64_t o0 = ((int64_t)n * A + a) * R + (r0 + 32 * c + gl);
-                        *reinterpret_cast<int4*>(e) = make_int4((int)(o0 & 0xffffffffll), (int)(o0 >> 32), queued ? (int)gmask : 0, sub_);
+                        *reinterpret_cast<int4*>(e) = make_int4((int)(o0 & 0xffffffffll), (int)(o0 >> 32), queued ? (int)gmask : 0,
+                                                                sub_ | (tgt << 8));
                     }
                     if (queued) {
                         float4* rec = reinterpret_cast<float4*>(e + 16) + 2 * (lane - gl);
@@ -773,122 +778,86 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ KArgs 
 // dyn_kernel: the load-balanced second pass over pixel groups that contain agent-hit rays.
 // Entry = 16-byte header {o0 lo, o0 hi, mask of agent-hit pixels, subsample} + per pixel two float4:
 //   {texel rgb, 1-dot^2} and {hit point x, hit point y, static intensity, is-agent-hit}.
-// A warp takes DYN_BLOCK consecutive entries (neighbouring pixels of one agent's view, so the per-light occluder
-// cache keeps working), reads the env's segments straight from HBM/L2, and writes the final screen pixels and the
-// pooled RGB observation of the group.
+// One warp per entry (every agent-hit pixel group is an independent unit of work, so the whole machine is busy).
+// The warp keeps the env's first 32 lights one per lane, each with the occluder last found for that light from
+// around the agent that was hit (persistent across entries and steps in the workspace: a hint, re-verified by the
+// exact test), reads only the occluder runs it visits straight from HBM/L2, and writes the final screen pixels and
+// the pooled RGB observation of the group.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int DYN_BLOCK = 4;
-
 template <bool STATS>
 __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs k) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int wcap = k.seg_cap + (k.seg_cap + k.s.occ_run - 1) / k.s.occ_run;                 // segments + run boxes
-    float4* wseg = reinterpret_cast<float4*>(smem_raw) + (size_t)(threadIdx.x >> 5) * wcap;     // this warp's copy
-    float4* wbox = wseg + k.seg_cap;
-    const bool sorted = k.s.occ_lines != nullptr;
-    OccEnv oe;
-    oe.occ = wseg; oe.boxes = wbox; oe.W = 0; oe.nb = 0; oe.vmax = 0.f; oe.diam = 0.f; oe.run = k.s.occ_run;
     const int lane = threadIdx.x & 31;
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
     const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
     const int reserved = *reinterpret_cast<volatile int*>(k.dyn_ctrl);
     const int count = reserved < k.dyn_cap ? reserved : k.dyn_cap;
+    const bool sorted = k.s.occ_lines != nullptr;
     unsigned dyn_rays = 0, dyn_iters = 0;
-    int64_t cur_n = -1;
-    int L = 0, nlights = 0;
-    const float4* seg = nullptr;
-    const float* lt = nullptr;
-    LaneLight ll;
-    ll.occ = -1; ll.x = ll.y = ll.i = 0.f;
-    bool use_sorted = false;
-    for (int blk = wg; blk * DYN_BLOCK < count; blk += tw) {
-        const int e_end = min(count, (blk + 1) * DYN_BLOCK);
-        for (int ei = blk * DYN_BLOCK; ei < e_end; ei++) {
-            const unsigned char* e = k.dyn_entries + (size_t)ei * k.dyn_stride;
-            const int4 hdr = *reinterpret_cast<const int4*>(e);
-            const unsigned mask = (unsigned)hdr.z;
-            if (!mask) continue;                                   // slot reserved by a chunk that fell back inline
-            const int sub = hdr.w;
-            const int64_t o0 = ((int64_t)hdr.y << 32) | (unsigned)hdr.x;
-            const int64_t ag = o0 / R;
-            const int r = (int)(o0 - ag * R);
-            const int64_t n = ag / A;
-            if (n != cur_n) {
-                cur_n = n;
-                L = __ldg(k.s.line_widths + n);
-                nlights = __ldg(k.s.light_widths + n);
-                __syncwarp();
-                if (sorted && nlights <= 32) {
-                    // this env's sorted occluders and run boxes -> this warp's shared memory (coalesced, all in flight)
-                    const int W = L - AF;
-                    const float4* gocc = reinterpret_cast<const float4*>(k.s.occ_lines) + __ldg(k.s.occ_starts + n);
-                    const float4* gbox = reinterpret_cast<const float4*>(k.s.occ_boxes) + __ldg(k.s.box_starts + n);
-                    const int nb = (W + k.s.occ_run - 1) / k.s.occ_run;
-                    float vmax = 0.f, x0 = CUDART_INF_F, y0 = CUDART_INF_F, x1 = -CUDART_INF_F, y1 = -CUDART_INF_F;
-                    for (int l = lane; l < W; l += 32) {
-                        const float4 v = __ldg(gocc + l);
-                        wseg[l] = v;
-                        vmax = fmaxf(vmax, fmaxf(fabsf(v.z - v.x), fabsf(v.w - v.y)));
-                    }
-                    for (int b = lane; b < nb; b += 32) {
-                        const float4 v = __ldg(gbox + b);
-                        wbox[b] = v;
-                        x0 = fminf(x0, v.x); y0 = fminf(y0, v.y); x1 = fmaxf(x1, v.z); y1 = fmaxf(y1, v.w);
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-                        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
-                        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-                    }
-                    oe.W = W; oe.nb = nb; oe.vmax = vmax; oe.diam = nb ? fmaxf(x1 - x0, y1 - y0) : 0.f;
-                    use_sorted = true;
-                } else {
-                    const float4* gseg = reinterpret_cast<const float4*>(k.s.lines) + __ldg(k.s.line_starts + n);
-                    for (int l = AF + lane; l < L; l += 32) wseg[l] = __ldg(gseg + l);
-                    use_sorted = false;
-                }
-                __syncwarp();
-                seg = wseg;
-                lt = k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n);
-                ll.occ = -1;
-                if (lane < nlights) { ll.x = __ldg(lt + 3 * lane); ll.y = __ldg(lt + 3 * lane + 1); ll.i = __ldg(lt + 3 * lane + 2); }
+    for (int ei = wg; ei < count; ei += tw) {
+        const unsigned char* e = k.dyn_entries + (size_t)ei * k.dyn_stride;
+        const int4 hdr = *reinterpret_cast<const int4*>(e);
+        const unsigned mask = (unsigned)hdr.z;
+        if (!mask) continue;                                   // slot reserved by a chunk that fell back inline
+        const int sub = hdr.w & 0xff, tgt = hdr.w >> 8;
+        const int64_t o0 = ((int64_t)hdr.y << 32) | (unsigned)hdr.x;
+        const int64_t ag = o0 / R;
+        const int r = (int)(o0 - ag * R);
+        const int64_t n = ag / A;
+        const int L = __ldg(k.s.line_widths + n);
+        const int nlights = __ldg(k.s.light_widths + n);
+        const float* lt = k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n);
+        // lights one per lane, each with the occluder remembered for this (env, agent that was hit)
+        int* cache = k.dyn_cache + ((size_t)n * A + (tgt < A ? tgt : 0)) * 32;
+        LaneLight ll;
+        ll.x = ll.y = ll.i = 0.f;
+        ll.occ = cache[lane];
+        if (lane < nlights) { ll.x = __ldg(lt + 3 * lane); ll.y = __ldg(lt + 3 * lane + 1); ll.i = __ldg(lt + 3 * lane + 2); }
+        const int occ_before = ll.occ;
+        const bool use_sorted = sorted && nlights <= 32;
+        OccEnv oe;
+        const float4* seg = reinterpret_cast<const float4*>(k.s.lines) + __ldg(k.s.line_starts + n);
+        if (use_sorted) {
+            const int W = L - AF;
+            oe.occ = reinterpret_cast<const float4*>(k.s.occ_lines) + __ldg(k.s.occ_starts + n);
+            oe.boxes = reinterpret_cast<const float4*>(k.s.occ_boxes) + __ldg(k.s.box_starts + n);
+            oe.W = W; oe.run = k.s.occ_run; oe.nb = (W + oe.run - 1) / oe.run;
+            oe.vmax = __ldg(k.s.occ_meta + 2 * n); oe.diam = __ldg(k.s.occ_meta + 2 * n + 1);
+        } else if (ll.occ < AF || ll.occ >= L) ll.occ = -1;
+        float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < sub) {
+            const float4* rec = reinterpret_cast<const float4*>(e + 16) + 2 * lane;
+            ra = rec[0];
+            rb = rec[1];
+        }
+        float intensity = rb.z;
+        unsigned m = mask;
+        while (m) {
+            const int p = __ffs(m) - 1;
+            m &= m - 1;
+            const float cx = __shfl_sync(0xffffffffu, rb.x, p), cy = __shfl_sync(0xffffffffu, rb.y, p);
+            const float v = use_sorted ? light_intensity_boxed<STATS>(oe, nlights, cx, cy, lane, ll, dyn_iters)
+                                       : light_intensity_cached<STATS>(seg, L, AF, nlights, lt, cx, cy, lane, ll, dyn_iters);
+            if (lane == p) intensity = v;
+            if (STATS) dyn_rays++;
+        }
+        if (ll.occ != occ_before) cache[lane] = ll.occ;        // racy on purpose: any stored value is only a hint
+        const float kk = fmul(ra.w, intensity);
+        const float s0 = fmul(kk, ra.x), s1 = fmul(kk, ra.y), s2 = fmul(kk, ra.z);
+        if (k.out.screen && lane < sub && ((mask >> lane) & 1u)) {
+            float* sc = k.out.screen + 3 * (o0 + lane);
+            sc[0] = s0; sc[1] = s1; sc[2] = s2;
+        }
+        if (k.has_obs && k.obs.rgb) {
+            float v0 = lane < sub ? s0 : 0.f, v1 = lane < sub ? s1 : 0.f, v2 = lane < sub ? s2 : 0.f;
+            for (int o = 1; o < sub; o <<= 1) {
+                v0 = __fadd_rn(v0, __shfl_xor_sync(0xffffffffu, v0, o));
+                v1 = __fadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+                v2 = __fadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
             }
-            float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane < sub) {
-                const float4* rec = reinterpret_cast<const float4*>(e + 16) + 2 * lane;
-                ra = rec[0];
-                rb = rec[1];
-            }
-            float intensity = rb.z;
-            unsigned m = mask;
-            while (m) {
-                const int p = __ffs(m) - 1;
-                m &= m - 1;
-                const float cx = __shfl_sync(0xffffffffu, rb.x, p), cy = __shfl_sync(0xffffffffu, rb.y, p);
-                const float v = use_sorted ? light_intensity_boxed<STATS>(oe, nlights, cx, cy, lane, ll, dyn_iters)
-                                           : light_intensity_cached<STATS>(seg, L, AF, nlights, lt, cx, cy, lane, ll, dyn_iters);
-                if (lane == p) intensity = v;
-                if (STATS) dyn_rays++;
-            }
-            const float kk = fmul(ra.w, intensity);
-            const float s0 = fmul(kk, ra.x), s1 = fmul(kk, ra.y), s2 = fmul(kk, ra.z);
-            if (k.out.screen && lane < sub && ((mask >> lane) & 1u)) {
-                float* sc = k.out.screen + 3 * (o0 + lane);
-                sc[0] = s0; sc[1] = s1; sc[2] = s2;
-            }
-            if (k.has_obs && k.obs.rgb) {
-                float v0 = lane < sub ? s0 : 0.f, v1 = lane < sub ? s1 : 0.f, v2 = lane < sub ? s2 : 0.f;
-                for (int o = 1; o < sub; o <<= 1) {
-                    v0 = __fadd_rn(v0, __shfl_xor_sync(0xffffffffu, v0, o));
-                    v1 = __fadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, o));
-                    v2 = __fadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
-                }
-                if (lane == 0) {
-                    const int Ro = R / sub, ro = r / sub;
-                    float* q = k.obs.rgb + ag * 3 * Ro + ro;
-                    q[0] = __fmul_rn(v0, k.inv_sub); q[Ro] = __fmul_rn(v1, k.inv_sub); q[2 * Ro] = __fmul_rn(v2, k.inv_sub);
-                }
+            if (lane == 0) {
+                const int Ro = R / sub, ro = r / sub;
+                float* q = k.obs.rgb + ag * 3 * Ro + ro;
+                q[0] = __fmul_rn(v0, k.inv_sub); q[Ro] = __fmul_rn(v1, k.inv_sub); q[2 * Ro] = __fmul_rn(v2, k.inv_sub);
             }
         }
     }
@@ -1087,19 +1056,24 @@ extern "C" int msb_physics(const msb_params* p, const msb_scenery* s, const msb_
     return launch_env<MODE_PHYSICS>(k, 1, threads, (cudaStream_t)cuda_stream);
 }
 
-// workspace layout: int ctrl[4] (16 bytes), then entries of (16 + 32*subsample) bytes
+// workspace layout: int ctrl[4] (16 bytes) | occluder cache int[N][A][32] | entries of (16 + 32*subsample) bytes
+static int64_t cache_bytes(const msb_scenery* s) { return (int64_t)s->n_envs * s->n_agents * 32 * 4; }
+
 static int set_workspace(KArgs& k, const msb_workspace* ws) {
     k.dyn_ctrl = nullptr;
     k.dyn_entries = nullptr;
+    k.dyn_cache = nullptr;
     k.dyn_cap = 0;
     const int sub = k.has_obs ? k.obs.subsample : 1;
     k.dyn_stride = 16 + 32 * sub;
     if (!ws || !ws->ptr) return 0;
     if (((uintptr_t)ws->ptr & 15) != 0) return fail("%s", "workspace must be 16-byte aligned");
-    const int64_t cap = (ws->bytes - 16) / k.dyn_stride;
+    const int64_t head = 16 + cache_bytes(&k.s);
+    const int64_t cap = (ws->bytes - head) / k.dyn_stride;
     if (cap < 1) return 0;
     k.dyn_ctrl = reinterpret_cast<int*>(ws->ptr);
-    k.dyn_entries = reinterpret_cast<unsigned char*>(ws->ptr) + 16;
+    k.dyn_cache = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws->ptr) + 16);
+    k.dyn_entries = reinterpret_cast<unsigned char*>(ws->ptr) + head;
     k.dyn_cap = cap > 0x7fffffff ? 0x7fffffff : (int32_t)cap;
     return 0;
 }
@@ -1109,17 +1083,9 @@ static int launch_dyn(const KArgs& k, cudaStream_t st) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int run = k.s.occ_run > 0 ? k.s.occ_run : 32;
-    const size_t sm = (size_t)4 * (k.seg_cap + (k.seg_cap + run - 1) / run) * 16;
-    if (sm > 227 * 1024) return fail("%s", "scene too large for dyn_kernel's shared memory");
-    int per_sm = sm ? (int)((200 * 1024) / sm) : 8;
-    if (per_sm > 12) per_sm = 12;
-    if (per_sm < 1) per_sm = 1;
-    const int grid = sms * per_sm;
-    auto fn = k.stats ? dyn_kernel<true> : dyn_kernel<false>;
-    if (sm > 48 * 1024 && check(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "cudaFuncSetAttribute"))
-        return 1;
-    fn<<<grid, 128, sm, st>>>(k);
+    const int grid = sms * 12;                      // 48 warps per SM, each striding over the queue
+    if (k.stats) dyn_kernel<true><<<grid, 128, 0, st>>>(k);
+    else dyn_kernel<false><<<grid, 128, 0, st>>>(k);
     g_launches++;
     return check(cudaGetLastError(), "dyn_kernel launch");
 }
@@ -1131,7 +1097,7 @@ extern "C" int64_t msb_workspace_bytes(const msb_params* p, const msb_scenery* s
     // room for a quarter of all pixel groups to contain an agent-hit ray (overflow falls back to inline, still exact)
     int64_t cap = groups / 4;
     if (cap < 65536) cap = groups < 65536 ? groups : 65536;
-    return 16 + cap * (16 + 32 * (int64_t)subsample);
+    return 16 + cache_bytes(s) + cap * (16 + 32 * (int64_t)subsample);
 }
 
 static void set_obs(KArgs& k, const msb_obs_out* obs) {

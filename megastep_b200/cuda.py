@@ -43,7 +43,7 @@ class _Scenery(ctypes.Structure):
                 ('baked', ctypes.c_void_p), ('model', ctypes.c_void_p),
                 ('n_lines', ctypes.c_int64), ('n_texels', ctypes.c_int64),
                 ('occ_lines', ctypes.c_void_p), ('occ_starts', ctypes.c_void_p), ('occ_boxes', ctypes.c_void_p),
-                ('box_starts', ctypes.c_void_p)]
+                ('box_starts', ctypes.c_void_p), ('occ_meta', ctypes.c_void_p)]
 
 
 class _Agents(ctypes.Structure):
@@ -275,7 +275,8 @@ class Scenery:
                 n_lines=self._lines.vals.size(0), n_texels=self._textures.vals.size(0))
             if BUILD_OCCLUDERS and self._lines.vals.size(0) > 0:
                 self._occ = _occluder_table(self._lines, self._n_agents * self._model.size(0), OCCLUDER_RUN)
-                self._c.occ_lines, self._c.occ_starts, self._c.occ_boxes, self._c.box_starts = (t.data_ptr() for t in self._occ)
+                (self._c.occ_lines, self._c.occ_starts, self._c.occ_boxes, self._c.box_starts,
+                 self._c.occ_meta) = (t.data_ptr() for t in self._occ)
         return self._c
 
 
@@ -338,7 +339,17 @@ def _occluder_table(lines, n_dynamic, run=32):
     xmax = torch.full((nbox,), -big, device=dev).scatter_reduce(0, box, torch.maximum(occ[:, 0], occ[:, 2]), 'amax')
     ymax = torch.full((nbox,), -big, device=dev).scatter_reduce(0, box, torch.maximum(occ[:, 1], occ[:, 3]), 'amax')
     boxes = torch.stack([xmin, ymin, xmax, ymax], -1).contiguous()
-    return occ, occ_starts.int().contiguous(), boxes, box_starts.int().contiguous()
+    # per env: the longest segment extent and the extent of the env (they size the shadow cull's safety margin)
+    n = widths.size(0)
+    ext = torch.maximum((occ[:, 2] - occ[:, 0]).abs(), (occ[:, 3] - occ[:, 1]).abs())
+    vmax = torch.zeros(n, device=dev).scatter_reduce(0, oenv, ext, 'amax')
+    lo_x = torch.full((n,), big, device=dev).scatter_reduce(0, oenv, torch.minimum(occ[:, 0], occ[:, 2]), 'amin')
+    lo_y = torch.full((n,), big, device=dev).scatter_reduce(0, oenv, torch.minimum(occ[:, 1], occ[:, 3]), 'amin')
+    hi_x = torch.full((n,), -big, device=dev).scatter_reduce(0, oenv, torch.maximum(occ[:, 0], occ[:, 2]), 'amax')
+    hi_y = torch.full((n,), -big, device=dev).scatter_reduce(0, oenv, torch.maximum(occ[:, 1], occ[:, 3]), 'amax')
+    diam = torch.where(W > 0, torch.maximum(hi_x - lo_x, hi_y - lo_y), torch.zeros_like(vmax))
+    meta = torch.stack([vmax, diam], -1).contiguous()
+    return occ, occ_starts.int().contiguous(), boxes, box_starts.int().contiguous(), meta
 
 
 class Render:

@@ -277,7 +277,7 @@ def test_second_pass_inline_and_overflow_paths_agree(sub):
             cuda.USE_WORKSPACE = True
             cuda.BUILD_OCCLUDERS = True
         if mode == 'overflow':
-            small = 16 + 3 * (16 + 32 * sub)                       # room for three pixel groups only
+            small = 16 + 6 * 4 * 32 * 4 + 3 * (16 + 32 * sub)      # ctrl + occluder cache + room for three pixel groups only
             plan._wsbuf = torch.zeros(small, dtype=torch.uint8, device='cuda')
             plan._ws = cuda._Workspace(plan._wsbuf.data_ptr(), small)
         for _ in range(2):                                          # twice: the queue must re-arm itself
