@@ -49,7 +49,7 @@ typedef struct msb_scenery {
     int32_t n_model;            /* F: lines in the agent model */
     int32_t max_lines;          /* max over envs of line_widths (shared-memory sizing) */
     int32_t max_lights;         /* max over envs of light_widths */
-    int32_t occ_run;            /* segments per occluder box: 8, 16 or 32 (only read when occ_lines is set) */
+    int32_t occ_run;            /* segments per occluder box: 16 or 32 (only read when occ_lines is set) */
     float* lines;               /* (sum L, 4) — render()/step() write the agents' lines in place */
     const int32_t* line_widths; /* (N) */
     const int32_t* line_starts; /* (N) exclusive prefix sum of line_widths */

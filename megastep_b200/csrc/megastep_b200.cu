@@ -175,20 +175,24 @@ __device__ __forceinline__ void physics_stage(const KArgs& k, const Smem& m, int
     const float r1 = fmul(k.p.agent_radius, 1.0010000467300415039f);
     const float r1sq = fmul(r1, r1);
 
-    // pass 1: which static segments can possibly matter to each agent this tick? A segment farther from the agent
+    // One warp per agent, no block-level synchronisation.
+    // pass 1: which static segments can possibly matter to this agent this tick? A segment farther from the agent
     // than rho = 1.05|v| + 2.2 r + 0.02 cannot trigger any branch of collision() with a result below 1 (see
     // DESIGN.md "physics cull"), so dropping it leaves progress bit-identical. Survivors are compacted (ballot +
     // prefix popcount) so that pass 2 runs the ~100-instruction test on dense lanes.
     const int cap = k.seg_cap;
-    for (int a = 0; a < A; a++) {
+    const int warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int a = warp; a < A; a += nwarps) {
         const float* me = m.st_in + a * ST_STRIDE;
-        const float px = me[ST_PX], py = me[ST_PY];
-        const float vx = fmul(me[ST_VX], rF), vy = fmul(me[ST_VY], rF);
+        const float px = me[ST_PX], py = me[ST_PY], mx = me[ST_VX], my = me[ST_VY];
+        const float vx = fmul(mx, rF), vy = fmul(my, rF);
         const float vlen = sqrt_(ffma(vx, vx, fmul(vy, vy)));
         const bool can_cull = vlen >= 1e-3f;          // for slower agents project()'s +1e-6 distorts distances: test all
         const float rho = 1.05f * vlen + 2.2f * r1 + 0.02f;
-        for (int base = AF; base < L; base += blockDim.x) {
-            const int l = base + tid;
+        unsigned short* mine = m.cand + a * cap;
+        int nc = 0;
+        for (int base = AF; base < L; base += 32) {
+            const int l = base + lane;
             bool keep = false;
             if (l < L) {
                 const float4 s4 = m.seg[l];
@@ -197,37 +201,26 @@ __device__ __forceinline__ void physics_stage(const KArgs& k, const Smem& m, int
                 keep = !(can_cull && outside);
             }
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (bal) {
-                int off = 0;
-                if (lane == 0) off = atomicAdd(m.ncand + a, __popc(bal));
-                off = __shfl_sync(0xffffffffu, off, 0);
-                if (keep) m.cand[a * cap + off + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)l;
-            }
+            if (keep) mine[nc + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)l;
+            nc += __popc(bal);
         }
-    }
-    __syncthreads();
-    // pass 2: exact tests
-    for (int a = 0; a < A; a++) {
-        const float* me = m.st_in + a * ST_STRIDE;
-        const float px = me[ST_PX], py = me[ST_PY], mx = me[ST_VX], my = me[ST_VY];
+        __syncwarp();
+        // pass 2: exact tests
         float x = 1.f;
         // other agents (:193-200): start-of-step state, no sequential resolution
-        for (int d1 = tid; d1 < A; d1 += blockDim.x) {
+        for (int d1 = lane; d1 < A; d1 += 32) {
             if (d1 != a) {
                 const float* o = m.st_in + d1 * ST_STRIDE;
                 x = fminf(x, collide_agents(px, py, mx, my, o[ST_PX], o[ST_PY], o[ST_VX], o[ST_VY], rF, r2));
             }
         }
         // static lines (:203-205); the agents' own model lines [0, AF) are skipped
-        const float vx = fmul(mx, rF), vy = fmul(my, rF);
-        const float vlen = sqrt_(ffma(vx, vx, fmul(vy, vy)));
         const float u = fadd(vlen, 1e-6f), uu = fmul(u, u);
-        const int nc = m.ncand[a];
-        for (int i = tid; i < nc; i += blockDim.x) {
-            x = fminf(x, collide_line(px, py, vx, vy, vlen, u, uu, m.seg[m.cand[a * cap + i]], r1, r1sq));
+        for (int i = lane; i < nc; i += 32) {
+            x = fminf(x, collide_line(px, py, vx, vy, vlen, u, uu, m.seg[mine[i]], r1, r1sq));
         }
         x = warp_min(x);
-        if (lane == 0 && x < 1.f) atomicMin(m.xmin + a, __float_as_int(x));   // x in [0, 1]: int order == float order
+        if (lane == 0) m.xmin[a] = __float_as_int(x);
     }
     __syncthreads();
 
@@ -380,8 +373,10 @@ __device__ __forceinline__ float light_intensity_boxed(const OccEnv& oe, int I, 
             unsigned runs = __ballot_sync(0xffffffffu, visit);
             while (runs) {
                 // lanes [slot*run, (slot+1)*run) take the slot-th box still to visit
-                const unsigned nth = __fns(runs, 0, slot + 1);          // 0xffffffff when fewer boxes remain
-                const int l = nth < 32u ? run * (b0 + (int)nth) + within : oe.W;
+                const unsigned rest = runs & (runs - 1);
+                const int n0 = __ffs(runs) - 1, n1 = rest ? __ffs(rest) - 1 : -1;
+                const int nth = (per == 1 || slot == 0) ? n0 : ((slot == 1) ? n1 : -1);
+                const int l = nth >= 0 ? run * (b0 + nth) + within : oe.W;
                 bool o = false;
                 if (l < oe.W) {
                     const Hit h = intersect(Ix, Iy, Ux, Uy, __ldg(oe.occ + l));
@@ -622,9 +617,7 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
                 if (slot < k.dyn_cap) {
                     unsigned char* e = k.dyn_entries + (size_t)slot * k.dyn_stride;
                     if (lane == gl) {
-                        const int64_t o0 = ((int64_t)n * A + a) * R + (r0 + 32 * c + gl);
-                        *reinterpret_cast<int4*>(e) = make_int4((int)(o0 & 0xffffffffll), (int)(o0 >> 32), queued ? (int)gmask : 0,
-                                                                sub_ | (tgt << 8));
+                        *reinterpret_cast<int4*>(e) = make_int4(n, a * R + (r0 + 32 * c + gl), queued ? (int)gmask : 0, sub_ | (tgt << 8));
                     }
                     if (queued) {
                         float4* rec = reinterpret_cast<float4*>(e + 16) + 2 * (lane - gl);
@@ -776,7 +769,7 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ KArgs 
 
 // ---------------------------------------------------------------------------------------------------------------
 // dyn_kernel: the load-balanced second pass over pixel groups that contain agent-hit rays.
-// Entry = 16-byte header {o0 lo, o0 hi, mask of agent-hit pixels, subsample} + per pixel two float4:
+// Entry = 16-byte header {env, agent*R + first ray, mask of agent-hit pixels, subsample | hit agent << 8} + per pixel two float4:
 //   {texel rgb, 1-dot^2} and {hit point x, hit point y, static intensity, is-agent-hit}.
 // One warp per entry (every agent-hit pixel group is an independent unit of work, so the whole machine is busy).
 // The warp keeps the env's first 32 lights one per lane, each with the occluder last found for that light from
@@ -785,7 +778,7 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ KArgs 
 // the pooled RGB observation of the group.
 // ---------------------------------------------------------------------------------------------------------------
 template <bool STATS>
-__global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs k) {
+__global__ void __launch_bounds__(128, 6) dyn_kernel(const __grid_constant__ KArgs k) {
     const int lane = threadIdx.x & 31;
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
     const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
@@ -799,10 +792,10 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
         const unsigned mask = (unsigned)hdr.z;
         if (!mask) continue;                                   // slot reserved by a chunk that fell back inline
         const int sub = hdr.w & 0xff, tgt = hdr.w >> 8;
-        const int64_t o0 = ((int64_t)hdr.y << 32) | (unsigned)hdr.x;
-        const int64_t ag = o0 / R;
-        const int r = (int)(o0 - ag * R);
-        const int64_t n = ag / A;
+        const int n = hdr.x, ar = hdr.y;                       // env; agent * R + first ray of the group
+        const int av = ar / R, r = ar - av * R;
+        const int64_t ag = (int64_t)n * A + av;
+        const int64_t o0 = ag * R + r;
         const int L = __ldg(k.s.line_widths + n);
         const int nlights = __ldg(k.s.light_widths + n);
         const float* lt = k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n);
@@ -1033,7 +1026,7 @@ static void fill(KArgs& k, const msb_params* p, const msb_scenery* s, const msb_
     k.s = *s;
     if (a) k.a = *a;
     k.seg_cap = s->max_lines > 0 ? s->max_lines : 1;
-    if (k.s.occ_run != 8 && k.s.occ_run != 16 && k.s.occ_run != 32) { k.s.occ_run = 32; if (k.s.occ_lines) k.s.occ_lines = nullptr; }
+    if (k.s.occ_run != 16 && k.s.occ_run != 32) { k.s.occ_run = 32; if (k.s.occ_lines) k.s.occ_lines = nullptr; }
     k.inv_fps = 1.0f / p->fps;
     k.ray_blocks = 1;
     k.stats = g_stats;

@@ -371,7 +371,7 @@ class Physics:
 # functions
 # --------------------------------------------------------------------------------------------------------------
 _PARAMS = None
-OCCLUDER_RUN = 16        # segments per bounding box in the occluder table (8, 16 or 32)
+OCCLUDER_RUN = 16        # segments per bounding box in the occluder table (16 or 32)
 BUILD_OCCLUDERS = True  # False: the second pass scans the segments in their original order (same results, slower)
 USE_WORKSPACE = True   # False: agent-hit rays are lit inline by the first pass (same results; used by tests)
 

@@ -43,8 +43,13 @@ if __name__ == '__main__':
     if mode == 'run':
         step = modules.FusedStep(c, subsample=1, raw=True)
         acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')
-        print(json.dumps({'run': cuda.OCCLUDER_RUN, 'render_us': timeit(lambda: c.render()), 'step_us': timeit(lambda: step(acts)),
-                          'phys_then_render_us': timeit(lambda: (c.physics(), c.render()))}))
+        res = {'run': cuda.OCCLUDER_RUN, 'render_us': timeit(lambda: c.render()), 'step_us': timeit(lambda: step(acts)),
+               'phys_then_render_us': timeit(lambda: (c.physics(), c.render())), 'physics_us': timeit(lambda: c.physics())}
+        cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0)
+        c.render(); torch.cuda.synchronize()
+        for k in ('stat_tests', 'stat_groups', 'stat_dyn_rays', 'stat_dyn_iters'): res[k] = cuda.get_option(k)
+        cuda.set_option('stats', 0)
+        print(json.dumps(res))
         sys.exit(0)
     out = {}
     for skip in (0, 1):
