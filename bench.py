@@ -43,8 +43,8 @@ L2_FLUSH_BYTES = 256 << 20
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=1000)
+    ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='deathmatch', choices=sorted(WORKLOADS))
     ap.add_argument('--envs', type=int, default=None, help='envs per GPU (default: the workload\'s)')
@@ -96,7 +96,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -175,10 +175,10 @@ class Ours:
         self.core.agents.angles.copy_(torch.as_tensor(ang))
         self.stepper = modules.FusedStep(self.core, subsample=cfg['subsample'], raw=raw)
         self.actions = self.stepper.actions
-        self.fused = True
+        self.fused = False                   # physics and render are separate launches: each stages the segments
 
     def step(self):
-        self.stepper()                       # one launch: movement + physics + render + heads
+        self.stepper()                       # movement+physics | render+heads | agent-hit lighting: 3 launches, no host sync
 
     def result(self):
         return self.stepper._plan.progress
@@ -409,7 +409,7 @@ def main():
                 'what': 'pinned-host actions -> H2D -> step via the public API -> D2H of progress (the physics result) + stream sync, every step; observations stay on the device as in the reference'},
         'gpu_launches': out['launches'],
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
-                     'kernel': 'env_kernel<MODE_STEP> (fused movement+physics+render+heads)' if args.impl == 'ours' else 'whole step (physics + render + ~40 ATen launches)',
+                     'kernel': 'whole step = env_kernel<PHYSICS> (movement+physics) + env_kernel<RENDER> (draw+raycast+shade+heads) + dyn_kernel; env_kernel<RENDER> dominates (~65%)' if args.impl == 'ours' else 'whole step (physics + render + ~40 ATen launches)',
                      'algorithmic_bytes_per_step': out['bytes_per_step'], 'mean_walls_per_env': out['mean_walls'], 'peak_source': peak_src},
         'clocks': out['clocks'],
         'step_ms_percentiles': {p: float(np.percentile(out['per_step_ms'], p)) for p in (5, 50, 95)},

@@ -136,8 +136,8 @@ int msb_physics(const msb_params* p, const msb_scenery* s, const msb_agents* a, 
 int msb_render(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_render_out* out,
                const msb_obs_out* obs, const msb_workspace* ws, void* cuda_stream);
 
-/* One whole environment tick: MomentumMovement -> physics -> render -> observation heads in ONE kernel, followed —
- * when a workspace is given — by the small second pass that lights agent-hit rays.
+/* One whole environment tick: MomentumMovement + physics (one kernel), render + observation heads (one kernel) and —
+ * when a workspace is given — the small second pass that lights agent-hit rays. No host round trip in between.
  * mv may be NULL (velocities are then taken as already set, i.e. plain physics+render). out/obs as msb_render. */
 int msb_step(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_movement* mv,
              float* progress, const msb_render_out* out, const msb_obs_out* obs, const msb_workspace* ws,
