@@ -53,6 +53,7 @@ struct KArgs {
     float bin_kappa, bin_rmid, bin_xclip;               // screen-space binning constants (culling only)
     unsigned long long* stats;  // optional diagnostics counters (may be null)
     int32_t debug_skip_dyn;     // timing experiments only: leave agent-hit rays unlit
+    int32_t variant;            // bit 0: depth culling off; bit 1: software-pipelined candidate loop
     // queue of pixel groups whose dynamic lighting is resolved by dyn_kernel (load-balanced second pass)
     int* dyn_ctrl;              // [0] entries reserved, [1] CTAs of dyn_kernel done
     unsigned char* dyn_entries; // null -> dynamic lights are resolved inline by the ray's own warp
@@ -479,6 +480,7 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
     for (int gbase = 0; gbase < L; gbase += 32) {
         const int l = gbase + lane;
         int rlo = 1, rhi = 0;
+        float smin = CUDART_INF_F;          // conservative lower bound of s (= forward distance) over the segment
         if (l < L) {
             const float4 s4 = m.seg[l];
             // exact per-(agent, line) terms of intersect() (kernels.cu:83-85), hoisted out of the per-ray loop
@@ -497,28 +499,55 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
                 const float sa = __fdividef(ya, xa), sb = __fdividef(yb, xb);
                 const float rf_first = rmid - fmaxf(sa, sb) * kappa - delta;
                 const float rf_last = rmid - fminf(sa, sb) * kappa + delta;
-                // NaN-safe: any comparison failing leaves the full range, i.e. the exact test still runs
-                rlo = (rf_first > lo_chunk) ? ((rf_first < hi_chunk + 1.f) ? (int)ceilf(rf_first) : (int)hi_chunk + 1) : (int)lo_chunk;
-                rhi = (rf_last < hi_chunk) ? ((rf_last > lo_chunk - 1.f) ? (int)floorf(rf_last) : (int)lo_chunk - 1) : (int)hi_chunk;
+                // fmaxf/fminf return the non-NaN operand, so a NaN leaves the full range and the exact test still runs
+                rlo = (int)fminf(fmaxf(ceilf(rf_first), lo_chunk), hi_chunk + 1.f);
+                rhi = (int)fmaxf(fminf(floorf(rf_last), hi_chunk), lo_chunk - 1.f);
+                smin = fminf(xa, xb) - 1e-3f - 1e-4f * fmaxf(fabsf(xa), fabsf(xb));
             }
         }
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
             const int c_lo = r0 + 32 * c, c_hi = c_lo + 31;
-            unsigned mask = __ballot_sync(0xffffffffu, (rlo <= c_hi) && (rhi >= c_lo) && (rlo <= rhi));
-            if (mask) {
-                int j = __ffs(mask) - 1;
-                mask &= mask - 1;
-                float4 q = scr[j];
-                float snum = scr[32 + j].x;
-                while (true) {
-                    // fetch the next candidate's terms before the arithmetic of this one (hides the LDS latency)
-                    const bool more = mask != 0;
-                    const int jn = more ? __ffs(mask) - 1 : j;
+            // depth cull (exact): a hit on this segment has s >= smin; if that is beyond the current hit of EVERY ray
+            // of the chunk it cannot satisfy s < best - 1e-4 for any of them
+            float cmax = CUDART_INF_F;
+            if (!(k.variant & 1)) {
+                cmax = best[c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, (rlo <= c_hi) && (rhi >= c_lo) && (rlo <= rhi) && !(smin > cmax));
+            if (k.variant & 2) {
+                if (mask) {
+                    int j = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    const float4 qn = scr[jn];
-                    const float snn = scr[32 + jn].x;
+                    float4 q = scr[j];
+                    float snum = scr[32 + j].x;
+                    while (true) {
+                        // fetch the next candidate's terms before the arithmetic of this one (hides the LDS latency)
+                        const bool more = mask != 0;
+                        const int jn = more ? __ffs(mask) - 1 : j;
+                        mask &= mask - 1;
+                        const float4 qn = scr[jn];
+                        const float snn = scr[32 + jn].x;
+                        const float UxV = cross2(rux[c], q.y, ruy[c], q.x);
+                        const float rc = rcp(UxV);
+                        const float hs_ = fmul(snum, rc);
+                        const float ht_ = fmul(cross2(ruy[c], q.z, rux[c], q.w), rc);
+                        const bool take = !(fabsf(UxV) < PARALLEL_EPS) && (ht_ >= 0.f) && (ht_ <= 1.f) && (nearp[c] < hs_) && (hs_ < bestm[c]);
+                        if (take) { best[c] = hs_; bestm[c] = fadd(hs_, -1.e-4f); loc[c] = ht_; idx[c] = gbase + j; }
+                        if (STATS) tests++;
+                        if (!more) break;
+                        j = jn; q = qn; snum = snn;
+                    }
+                }
+            } else {
+                while (mask) {
+                    const int j = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float4 q = scr[j];
+                    const float snum = scr[32 + j].x;
                     // raycast_kernel inner loop (kernels.cu:353-376), branch-free. A near-parallel line
                     // (|UxV| < 1e-3: s = t = inf in the reference) can never be accepted, so its s/t need no forcing.
                     const float UxV = cross2(rux[c], q.y, ruy[c], q.x);
@@ -528,8 +557,6 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
                     const bool take = !(fabsf(UxV) < PARALLEL_EPS) && (ht_ >= 0.f) && (ht_ <= 1.f) && (nearp[c] < hs_) && (hs_ < bestm[c]);
                     if (take) { best[c] = hs_; bestm[c] = fadd(hs_, -1.e-4f); loc[c] = ht_; idx[c] = gbase + j; }
                     if (STATS) tests++;
-                    if (!more) break;
-                    j = jn; q = qn; snum = snn;
                 }
             }
         }
@@ -910,6 +937,7 @@ static long long g_launches = 0;
 static long long g_opt_nch = 0;          // 0 = auto
 static long long g_opt_threads = 0;      // 0 = auto
 static long long g_opt_skip_dyn = 0;     // debug
+static long long g_opt_variant = 0;      // experiment switches (see KArgs::variant)
 static long long g_opt_fused_step = 0;   // 1: msb_step runs physics and render in ONE kernel (slower: see DESIGN.md)
 static unsigned long long* g_stats = nullptr;   // device counters, enabled by option "stats"
 
@@ -946,6 +974,7 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "threads")) { g_opt_threads = value; return 0; }
     if (!strcmp(name, "debug_skip_dyn")) { g_opt_skip_dyn = value; return 0; }
     if (!strcmp(name, "fused_step")) { g_opt_fused_step = value; return 0; }
+    if (!strcmp(name, "variant")) { g_opt_variant = value; return 0; }
     if (!strcmp(name, "stats")) {
         if (value && !g_stats) {
             if (check(cudaMalloc(&g_stats, 8 * sizeof(unsigned long long)), "cudaMalloc(stats)")) return 1;
@@ -1033,6 +1062,7 @@ static void fill(KArgs& k, const msb_params* p, const msb_scenery* s, const msb_
     k.ray_blocks = 1;
     k.stats = g_stats;
     k.debug_skip_dyn = (int32_t)g_opt_skip_dyn;
+    k.variant = (int32_t)g_opt_variant;
     k.bin_kappa = (float)p->res / (2.f * p->half_screen);
     k.bin_rmid = 0.5f * ((float)p->res - 1.f);
     k.bin_xclip = 0.5f * p->agent_radius / sqrtf(1.f + p->half_screen * p->half_screen);

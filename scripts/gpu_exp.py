@@ -51,6 +51,15 @@ if __name__ == '__main__':
         cuda.set_option('stats', 0)
         print(json.dumps(res))
         sys.exit(0)
+    if mode == 'variants':
+        out = {}
+        for v in (0, 1, 2, 3):
+            cuda.set_option('variant', v)
+            out[f'render_us/variant{v}'] = timeit(lambda: c.render())
+            cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0); c.render(); torch.cuda.synchronize()
+            out[f'tests/variant{v}'] = cuda.get_option('stat_tests'); cuda.set_option('stats', 0)
+        cuda.set_option('variant', 0)
+        print(json.dumps(out)); sys.exit(0)
     out = {}
     for skip in (0, 1):
         cuda.set_option('debug_skip_dyn', skip)

@@ -238,17 +238,20 @@ def test_every_kernel_variant_gives_identical_results(res):
     c = common.to_device(arrays, st, res, 70.)
     base = c.render()
     try:
-        for nch in (1, 2, 4):
-            for threads in (64, 128, 256):
-                cuda.set_option('nch', nch)
-                cuda.set_option('threads', threads)
-                r = c.render()
-                for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
-                    a, b = getattr(r, k), getattr(base, k)
-                    assert ((a == b) | (a != a) & (b != b)).all(), f'nch={nch} threads={threads}: {k} differs'
+        for variant in (0, 1, 2, 3):        # depth culling on/off x plain/pipelined candidate loop
+            for nch in (1, 2, 4):
+                for threads in (64, 128, 256):
+                    cuda.set_option('variant', variant)
+                    cuda.set_option('nch', nch)
+                    cuda.set_option('threads', threads)
+                    r = c.render()
+                    for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
+                        a, b = getattr(r, k), getattr(base, k)
+                        assert ((a == b) | (a != a) & (b != b)).all(), f'variant={variant} nch={nch} threads={threads}: {k} differs'
     finally:
         cuda.set_option('nch', 0)
         cuda.set_option('threads', 0)
+        cuda.set_option('variant', 0)
 
 
 def _same(a, b):
