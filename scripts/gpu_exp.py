@@ -29,6 +29,7 @@ if __name__ == '__main__':
     mode = sys.argv[1] if len(sys.argv) > 1 else 'exp'
     if len(sys.argv) > 2: cuda.OCCLUDER_RUN = int(sys.argv[2])
     c = setup()
+    if len(sys.argv) > 3: cuda.set_option('variant', int(sys.argv[3]))
     if mode == 'ncu':
         for _ in range(3): c.render()
         torch.cuda.synchronize()
