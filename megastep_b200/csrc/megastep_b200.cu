@@ -53,6 +53,7 @@ struct KArgs {
     float bin_kappa, bin_rmid, bin_xclip;               // screen-space binning constants (culling only)
     unsigned long long* stats;  // optional diagnostics counters (may be null)
     int32_t debug_skip_dyn;     // timing experiments only: leave agent-hit rays unlit
+    int32_t two_phase;          // render: bin every (agent, segment) once into shared memory, then one warp per ray chunk
     int32_t variant;            // bit 0: depth culling off; bit 1: software-pipelined candidate loop
     // queue of pixel groups whose dynamic lighting is resolved by dyn_kernel (load-balanced second pass)
     int* dyn_ctrl;              // [0] entries reserved, [1] CTAs of dyn_kernel done
@@ -75,9 +76,10 @@ struct Smem {
     int* ncand;         // [A] physics: segments that survived the bounding-box cull
     unsigned short* cand;   // [A][seg_cap] their indices
     uint64_t* bar;
+    float4* rec;        // two-phase render: [2][A][seg_cap] per-(agent, segment) records
 };
 
-__device__ __forceinline__ Smem carve(unsigned char* base, int seg_cap, int nwarps, int A) {
+__device__ __forceinline__ Smem carve(unsigned char* base, int seg_cap, int nwarps, int A, bool two_phase = false) {
     Smem m;
     m.seg = reinterpret_cast<float4*>(base);
     m.scratch = m.seg + seg_cap;
@@ -89,14 +91,15 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int seg_cap, int nwar
     uintptr_t p = reinterpret_cast<uintptr_t>(m.cand + (size_t)A * seg_cap);
     p = (p + 15) & ~uintptr_t(15);
     m.bar = reinterpret_cast<uint64_t*>(p);
+    m.rec = two_phase ? reinterpret_cast<float4*>(p + 16) : nullptr;
     return m;
 }
 
-static size_t smem_bytes(int seg_cap, int nwarps, int A) {
+static size_t smem_bytes(int seg_cap, int nwarps, int A, bool two_phase = false) {
     size_t b = (size_t)seg_cap * 16 + (size_t)nwarps * 64 * 16 + (size_t)A * ST_STRIDE * 4 * 2 + (size_t)A * 8 +
                (size_t)A * seg_cap * 2;
     b = (b + 15) & ~size_t(15);
-    return b + 16;
+    return b + 16 + (two_phase ? (size_t)2 * A * seg_cap * 16 : 0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -440,9 +443,49 @@ __device__ __forceinline__ void draw_stage(const KArgs& k, const Smem& m, int n,
     }
 }
 
+// Per-(agent, segment) work shared by every ray of the agent: the exact ray-independent terms of intersect()
+// (kernels.cu:83-85: V, PQ, cross(PQ, V)) and a CONSERVATIVE screen-space summary used only to skip work — the
+// interval [rlo, rhi] of rays the segment can touch and a lower bound smin of the hit parameter s over it.
+struct SegBin { float4 q0; float snum; float smin; int rlo, rhi; };
+
+__device__ __forceinline__ SegBin bin_segment(const KArgs& k, float4 s4, float px, float py, float cs, float sn,
+                                              float lo_ray, float hi_ray) {
+    SegBin b;
+    const float Vx = fsub(s4.z, s4.x), Vy = fsub(s4.w, s4.y);
+    const float PQx = fsub(s4.x, px), PQy = fsub(s4.y, py);
+    b.q0 = make_float4(Vx, Vy, PQx, PQy);
+    b.snum = cross2(Vy, PQx, Vx, PQy);
+    b.rlo = 1; b.rhi = 0; b.smin = CUDART_INF_F;
+    // approximate camera-space endpoints: x' forward, y' left; screen coordinate = y'/x'
+    const float kappa = k.bin_kappa;     // rays per unit of screen coordinate, R / (2 tan(fov/2))
+    const float rmid = k.bin_rmid;       // (R - 1) / 2
+    const float xclip = k.bin_xclip;     // well inside every ray's near plane
+    const float delta = 0.05f;
+    const float bxr = s4.z - px, byr = s4.w - py;
+    float xa = PQx * cs + PQy * sn, ya = PQy * cs - PQx * sn;
+    float xb = bxr * cs + byr * sn, yb = byr * cs - bxr * sn;
+    const bool behind = (xa < xclip) && (xb < xclip);
+    if (!behind) {
+        if (xa < xclip) { const float tt = __fdividef(xclip - xa, xb - xa); ya = ya + tt * (yb - ya); xa = xclip; }
+        if (xb < xclip) { const float tt = __fdividef(xclip - xb, xa - xb); yb = yb + tt * (ya - yb); xb = xclip; }
+        const float sa = __fdividef(ya, xa), sb = __fdividef(yb, xb);
+        const float rf_first = rmid - fmaxf(sa, sb) * kappa - delta;
+        const float rf_last = rmid - fminf(sa, sb) * kappa + delta;
+        // fmaxf/fminf return the non-NaN operand, so a NaN leaves the full range and the exact test still runs
+        b.rlo = (int)fminf(fmaxf(ceilf(rf_first), lo_ray), hi_ray + 1.f);
+        b.rhi = (int)fmaxf(fminf(floorf(rf_last), hi_ray), lo_ray - 1.f);
+        b.smin = fminf(xa, xb) - 1e-3f - 1e-4f * fmaxf(fabsf(xa), fabsf(xb));
+    }
+    return b;
+}
+
 template <int NCH, bool STATS>
 __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int n, int64_t g0, int L, int a, int rb,
                                              float4* __restrict__ scr, int lane) {
+    // two-phase mode: the per-(agent, segment) records were written to shared memory by the binning phase
+    const bool pre = m.rec != nullptr;
+    const float4* rec0 = pre ? m.rec + (size_t)a * k.seg_cap : nullptr;
+    const float4* rec1 = pre ? m.rec + (size_t)(k.s.n_agents + a) * k.seg_cap : nullptr;
     const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
     const float* st = m.st_out + a * ST_STRIDE;
     const float px = st[ST_PX], py = st[ST_PY];
@@ -469,11 +512,6 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
         idx[c] = -1;
     }
 
-    // ---- conservative screen-space binning constants (never affect results, only which exact tests are skipped)
-    const float kappa = k.bin_kappa;     // rays per unit of screen coordinate, R / (2 tan(fov/2))
-    const float rmid = k.bin_rmid;       // (R - 1) / 2
-    const float xclip = k.bin_xclip;     // well inside every ray's near plane
-    const float delta = 0.05f;
     const float lo_chunk = (float)r0, hi_chunk = (float)(r0 + 32 * NCH - 1);
     unsigned tests = 0, groups = 0;
 
@@ -481,31 +519,24 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
         const int l = gbase + lane;
         int rlo = 1, rhi = 0;
         float smin = CUDART_INF_F;          // conservative lower bound of s (= forward distance) over the segment
-        if (l < L) {
-            const float4 s4 = m.seg[l];
-            // exact per-(agent, line) terms of intersect() (kernels.cu:83-85), hoisted out of the per-ray loop
-            const float Vx = fsub(s4.z, s4.x), Vy = fsub(s4.w, s4.y);
-            const float PQx = fsub(s4.x, px), PQy = fsub(s4.y, py);
-            scr[lane] = make_float4(Vx, Vy, PQx, PQy);
-            scr[32 + lane].x = cross2(Vy, PQx, Vx, PQy);
-            // approximate camera-space endpoints: x' forward, y' left; screen coordinate = y'/x'
-            const float bxr = s4.z - px, byr = s4.w - py;
-            float xa = PQx * cs + PQy * sn, ya = PQy * cs - PQx * sn;
-            float xb = bxr * cs + byr * sn, yb = byr * cs - bxr * sn;
-            const bool behind = (xa < xclip) && (xb < xclip);
-            if (!behind) {
-                if (xa < xclip) { const float tt = __fdividef(xclip - xa, xb - xa); ya = ya + tt * (yb - ya); xa = xclip; }
-                if (xb < xclip) { const float tt = __fdividef(xclip - xb, xa - xb); yb = yb + tt * (ya - yb); xb = xclip; }
-                const float sa = __fdividef(ya, xa), sb = __fdividef(yb, xb);
-                const float rf_first = rmid - fmaxf(sa, sb) * kappa - delta;
-                const float rf_last = rmid - fminf(sa, sb) * kappa + delta;
-                // fmaxf/fminf return the non-NaN operand, so a NaN leaves the full range and the exact test still runs
-                rlo = (int)fminf(fmaxf(ceilf(rf_first), lo_chunk), hi_chunk + 1.f);
-                rhi = (int)fmaxf(fminf(floorf(rf_last), hi_chunk), lo_chunk - 1.f);
-                smin = fminf(xa, xb) - 1e-3f - 1e-4f * fmaxf(fabsf(xa), fabsf(xb));
+        const float4* q0p = scr;            // candidate j's terms: q0p[j] = {V, PQ}, q1p[j].x = cross(PQ, V)
+        const float4* q1p = scr + 32;
+        if (pre) {
+            q0p = rec0 + gbase;
+            q1p = rec1 + gbase;
+            if (l < L) {
+                const float4 r1 = q1p[lane];
+                smin = r1.y; rlo = __float_as_int(r1.z); rhi = __float_as_int(r1.w);
             }
+        } else {
+            if (l < L) {
+                const SegBin b = bin_segment(k, m.seg[l], px, py, cs, sn, lo_chunk, hi_chunk);
+                scr[lane] = b.q0;
+                scr[32 + lane].x = b.snum;
+                rlo = b.rlo; rhi = b.rhi; smin = b.smin;
+            }
+            __syncwarp();
         }
-        __syncwarp();
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
             const int c_lo = r0 + 32 * c, c_hi = c_lo + 31;
@@ -522,15 +553,15 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
                 if (mask) {
                     int j = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    float4 q = scr[j];
-                    float snum = scr[32 + j].x;
+                    float4 q = q0p[j];
+                    float snum = q1p[j].x;
                     while (true) {
                         // fetch the next candidate's terms before the arithmetic of this one (hides the LDS latency)
                         const bool more = mask != 0;
                         const int jn = more ? __ffs(mask) - 1 : j;
                         mask &= mask - 1;
-                        const float4 qn = scr[jn];
-                        const float snn = scr[32 + jn].x;
+                        const float4 qn = q0p[jn];
+                        const float snn = q1p[jn].x;
                         const float UxV = cross2(rux[c], q.y, ruy[c], q.x);
                         const float rc = rcp(UxV);
                         const float hs_ = fmul(snum, rc);
@@ -546,8 +577,8 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
                 while (mask) {
                     const int j = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    const float4 q = scr[j];
-                    const float snum = scr[32 + j].x;
+                    const float4 q = q0p[j];
+                    const float snum = q1p[j].x;
                     // raycast_kernel inner loop (kernels.cu:353-376), branch-free. A near-parallel line
                     // (|UxV| < 1e-3: s = t = inf in the reference) can never be accepted, so its s/t need no forcing.
                     const float UxV = cross2(rux[c], q.y, ruy[c], q.x);
@@ -561,7 +592,7 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
             }
         }
         if (STATS) groups++;
-        __syncwarp();
+        if (!pre) __syncwarp();
     }
 
     // ---- shade + store (shader_kernel, kernels.cu:407-450)
@@ -733,12 +764,12 @@ __device__ __forceinline__ void imu_stage(const KArgs& k, const Smem& m, int n) 
 // the per-env kernel: any of physics / render / both
 // ---------------------------------------------------------------------------------------------------------------
 template <int MODE, int NCH, bool STATS>
-__global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ KArgs k) {
+__global__ void __launch_bounds__(512) env_kernel(const __grid_constant__ KArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = blockIdx.x;
     const int A = k.s.n_agents, AF = A * k.s.n_model;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const Smem m = carve(smem_raw, k.seg_cap, nwarps, A);
+    const Smem m = carve(smem_raw, k.seg_cap, nwarps, A, (MODE & MODE_RENDER) && k.two_phase);
 
     const int L = __ldg(k.s.line_widths + n);
     const int64_t g0 = __ldg(k.s.line_starts + n);
@@ -787,6 +818,23 @@ __global__ void __launch_bounds__(256) env_kernel(const __grid_constant__ KArgs 
         draw_stage(k, m, n, g0);
         __syncthreads();
         const int RB = k.ray_blocks;
+        if (m.rec) {
+            // phase 1 of two-phase render: every (agent, segment) binned once, by whichever warp gets to it
+            const int ngroups = (L + 31) >> 5;
+            const float hi_ray = (float)(k.p.res - 1);
+            for (int item = warp; item < A * ngroups; item += nwarps) {
+                const int a = item / ngroups, l = 32 * (item - a * ngroups) + lane;
+                const float* st = m.st_out + a * ST_STRIDE;
+                float sn, cs;
+                sincos_deg(st[ST_ANG], sn, cs);
+                if (l < L) {
+                    const SegBin b = bin_segment(k, m.seg[l], st[ST_PX], st[ST_PY], cs, sn, 0.f, hi_ray);
+                    m.rec[(size_t)a * k.seg_cap + l] = b.q0;
+                    m.rec[(size_t)(A + a) * k.seg_cap + l] = make_float4(b.snum, b.smin, __int_as_float(b.rlo), __int_as_float(b.rhi));
+                }
+            }
+            __syncthreads();
+        }
         for (int w = warp; w < A * RB; w += nwarps) {
             render_agent<NCH, STATS>(k, m, n, g0, L, w / RB, w % RB, m.scratch + warp * 64, lane);
         }
@@ -937,6 +985,7 @@ static long long g_launches = 0;
 static long long g_opt_nch = 0;          // 0 = auto
 static long long g_opt_threads = 0;      // 0 = auto
 static long long g_opt_skip_dyn = 0;     // debug
+static long long g_opt_two_phase = 1;    // 0: every warp bins for itself (the one-phase render)
 static long long g_opt_variant = 0;      // experiment switches (see KArgs::variant)
 static long long g_opt_fused_step = 0;   // 1: msb_step runs physics and render in ONE kernel (slower: see DESIGN.md)
 static unsigned long long* g_stats = nullptr;   // device counters, enabled by option "stats"
@@ -975,6 +1024,7 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "debug_skip_dyn")) { g_opt_skip_dyn = value; return 0; }
     if (!strcmp(name, "fused_step")) { g_opt_fused_step = value; return 0; }
     if (!strcmp(name, "variant")) { g_opt_variant = value; return 0; }
+    if (!strcmp(name, "two_phase")) { g_opt_two_phase = value; return 0; }
     if (!strcmp(name, "stats")) {
         if (value && !g_stats) {
             if (check(cudaMalloc(&g_stats, 8 * sizeof(unsigned long long)), "cudaMalloc(stats)")) return 1;
@@ -1014,7 +1064,7 @@ static int validate(const msb_params* p, const msb_scenery* s) {
 
 template <int MODE>
 static int launch_env(const KArgs& k, int nch, int threads, cudaStream_t st) {
-    const size_t sm = smem_bytes(k.seg_cap, threads / 32, k.s.n_agents);
+    const size_t sm = smem_bytes(k.seg_cap, threads / 32, k.s.n_agents, (MODE & MODE_RENDER) && k.two_phase);
     if (sm > 227 * 1024) return fail("%s", "scene too large: an env's segments do not fit in shared memory (227 KB)");
 #define MSB_LAUNCH(N)                                                                                            \
     {                                                                                                            \
@@ -1034,8 +1084,23 @@ static int launch_env(const KArgs& k, int nch, int threads, cudaStream_t st) {
     return check(cudaGetLastError(), "kernel launch");
 }
 
-static void plan_render(const msb_params* p, const msb_scenery* s, int* nch, int* rb, int* threads) {
+static void plan_render(const msb_params* p, const msb_scenery* s, KArgs& k, int* nch, int* rb, int* threads) {
     const int chunks = (p->res + 31) / 32;
+    // two-phase render when the per-(agent, segment) records leave room for at least two CTAs per SM
+    const size_t rec = (size_t)2 * s->n_agents * k.seg_cap * 16;
+    k.two_phase = (g_opt_two_phase != 0) && rec + (size_t)k.seg_cap * 18 + 4096 <= 100 * 1024;
+    if (k.two_phase) {
+        int n1 = (g_opt_nch == 1 || g_opt_nch == 2 || g_opt_nch == 4) ? (int)g_opt_nch : 1;
+        while (n1 > chunks) n1 >>= 1;
+        *nch = n1;
+        *rb = (chunks + n1 - 1) / n1;
+        int t = 32 * s->n_agents * (*rb);
+        if (t < 64) t = 64;
+        if (t > 512) t = 512;
+        if (g_opt_threads >= 32 && g_opt_threads <= 1024) t = (int)(g_opt_threads / 32) * 32;
+        *threads = t;
+        return;
+    }
     int n = 4;
     if (g_opt_nch == 1 || g_opt_nch == 2 || g_opt_nch == 4) n = (int)g_opt_nch;
     else {
@@ -1153,7 +1218,7 @@ extern "C" int msb_render(const msb_params* p, const msb_scenery* s, const msb_a
     set_obs(k, obs);
     if (set_workspace(k, ws)) return 1;
     int nch, rb, threads;
-    plan_render(p, s, &nch, &rb, &threads);
+    plan_render(p, s, k, &nch, &rb, &threads);
     k.ray_blocks = rb;
     if (launch_env<MODE_RENDER>(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
     return launch_dyn(k, (cudaStream_t)cuda_stream);
@@ -1180,7 +1245,7 @@ extern "C" int msb_step(const msb_params* p, const msb_scenery* s, const msb_age
     }
     if (set_workspace(k, ws)) return 1;
     int nch, rb, threads;
-    plan_render(p, s, &nch, &rb, &threads);
+    plan_render(p, s, k, &nch, &rb, &threads);
     k.ray_blocks = rb;
     if (g_opt_fused_step) {
         if (launch_env<MODE_STEP>(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
