@@ -57,7 +57,7 @@ if __name__ == '__main__':
         for tp in (0, 1):
             cuda.set_option('two_phase', tp)
             for nch in ((0,) if tp == 0 else (1, 2, 4)):
-                for threads in ((0,) if tp == 0 else (0, 256, 512, 1024)):
+                for threads in ((0,) if tp == 0 else (0, 128, 256, 512)):
                     cuda.set_option('nch', nch); cuda.set_option('threads', threads)
                     out[f'render_us/tp{tp}/nch{nch}/t{threads}'] = round(timeit(lambda: c.render()), 1)
         cuda.set_option('two_phase', 1); cuda.set_option('nch', 0); cuda.set_option('threads', 0)
