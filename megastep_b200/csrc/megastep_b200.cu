@@ -64,6 +64,9 @@ struct KArgs {
 };
 
 enum { MODE_PHYSICS = 1, MODE_RENDER = 2, MODE_STEP = 3 };
+#ifndef MSB_MIN_BLOCKS
+#define MSB_MIN_BLOCKS 4      // 256 threads x 4 blocks -> at most 64 registers per thread
+#endif
 enum { ST_ANG = 0, ST_PX = 1, ST_PY = 2, ST_AV = 3, ST_VX = 4, ST_VY = 5, ST_STRIDE = 8 };
 enum { STAT_TESTS = 0, STAT_GROUPS = 1, STAT_DYN_RAYS = 2, STAT_DYN_ITERS = 3, STAT_COLL = 4 };
 
@@ -764,7 +767,7 @@ __device__ __forceinline__ void imu_stage(const KArgs& k, const Smem& m, int n) 
 // the per-env kernel: any of physics / render / both
 // ---------------------------------------------------------------------------------------------------------------
 template <int MODE, int NCH, bool STATS>
-__global__ void __launch_bounds__(512) env_kernel(const __grid_constant__ KArgs k) {
+__global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) env_kernel(const __grid_constant__ KArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = blockIdx.x;
     const int A = k.s.n_agents, AF = A * k.s.n_model;
@@ -985,7 +988,8 @@ static long long g_launches = 0;
 static long long g_opt_nch = 0;          // 0 = auto
 static long long g_opt_threads = 0;      // 0 = auto
 static long long g_opt_skip_dyn = 0;     // debug
-static long long g_opt_two_phase = 1;    // 0: every warp bins for itself (the one-phase render)
+static long long g_opt_two_phase = 0;    // 1: bin every (agent, segment) once into shared memory first (measured slower: the
+                                         // records cost 70 KB per CTA, which halves residency)
 static long long g_opt_variant = 0;      // experiment switches (see KArgs::variant)
 static long long g_opt_fused_step = 0;   // 1: msb_step runs physics and render in ONE kernel (slower: see DESIGN.md)
 static unsigned long long* g_stats = nullptr;   // device counters, enabled by option "stats"
@@ -1096,8 +1100,8 @@ static void plan_render(const msb_params* p, const msb_scenery* s, KArgs& k, int
         *rb = (chunks + n1 - 1) / n1;
         int t = 32 * s->n_agents * (*rb);
         if (t < 64) t = 64;
-        if (t > 512) t = 512;
-        if (g_opt_threads >= 32 && g_opt_threads <= 1024) t = (int)(g_opt_threads / 32) * 32;
+        if (t > 256) t = 256;
+        if (g_opt_threads >= 32 && g_opt_threads <= 256) t = (int)(g_opt_threads / 32) * 32;
         *threads = t;
         return;
     }

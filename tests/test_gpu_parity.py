@@ -238,10 +238,10 @@ def test_every_kernel_variant_gives_identical_results(res):
     c = common.to_device(arrays, st, res, 70.)
     base = c.render()
     try:
-        for variant in (0, 1, 2, 3, 4, 5):  # depth culling on/off x plain/pipelined candidate loop; 4, 5: one-phase render
+        for variant in (0, 1, 2, 3, 4, 5):  # depth culling on/off x plain/pipelined candidate loop; 4, 5: two-phase render
             for nch in (1, 2, 4):
                 for threads in (64, 128, 256):
-                    cuda.set_option('two_phase', 0 if variant >= 4 else 1)
+                    cuda.set_option('two_phase', 1 if variant >= 4 else 0)
                     cuda.set_option('variant', variant % 4)
                     cuda.set_option('nch', nch)
                     cuda.set_option('threads', threads)
@@ -253,7 +253,7 @@ def test_every_kernel_variant_gives_identical_results(res):
         cuda.set_option('nch', 0)
         cuda.set_option('threads', 0)
         cuda.set_option('variant', 0)
-        cuda.set_option('two_phase', 1)
+        cuda.set_option('two_phase', 0)
 
 
 def _same(a, b):
