@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBPATH = os.path.join(_HERE, 'libmegastep_b200.so')
+_LIBPATH = os.environ.get('MEGASTEP_B200_LIB') or os.path.join(_HERE, 'libmegastep_b200.so')   # override: A/B builds
 
 c_f32p = ctypes.c_void_p
 
