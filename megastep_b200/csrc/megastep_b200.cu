@@ -53,6 +53,7 @@ struct KArgs {
     float bin_kappa, bin_rmid, bin_xclip;               // screen-space binning constants (culling only)
     unsigned long long* stats;  // optional diagnostics counters (may be null)
     int32_t debug_skip_dyn;     // timing experiments only: leave agent-hit rays unlit
+    int32_t split_render;       // cast kernel writes the four scalar Render outputs, shade_kernel does the rest
     int32_t two_phase;          // render: bin every (agent, segment) once into shared memory, then one warp per ray chunk
     int32_t variant;            // bit 0: depth culling off; bit 1: software-pipelined candidate loop
     // queue of pixel groups whose dynamic lighting is resolved by dyn_kernel (load-balanced second pass)
@@ -446,6 +447,149 @@ __device__ __forceinline__ void draw_stage(const KArgs& k, const Smem& m, int n,
     }
 }
 
+// shader_kernel (kernels.cu:407-450) for one 32-ray chunk of one agent's view, lane = ray: filter + texel/baked
+// gathers, dynamic light for agent hits (queued for dyn_kernel, or inline), the five Render outputs, and the fused
+// Depth / RGB heads. `seg` = this env's segments (shared memory in the one-kernel render, HBM in shade_kernel).
+struct ShadeCtx { int nlights; const float* lt; LaneLight ll; unsigned dyn_rays, dyn_iters; };
+
+template <bool STATS>
+__device__ __forceinline__ void shade_chunk(const KArgs& k, const float4* __restrict__ seg, int n, int a, int64_t g0,
+                                            int L, int r, int lane, int l0, float locv, float dotv, float dist,
+                                            bool write_raw, ShadeCtx& sc_) {
+    const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
+    const int sub_ = k.has_obs ? k.obs.subsample : 1;
+    const int nlights = sc_.nlights;
+    const float* lt = sc_.lt;
+    LaneLight& ll = sc_.ll;
+    unsigned& dyn_rays = sc_.dyn_rays;
+    unsigned& dyn_iters = sc_.dyn_iters;
+    const bool live = r < R;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        float lw = 0.f, rw = 0.f, tl0 = 0.f, tl1 = 0.f, tl2 = 0.f, tr0 = 0.f, tr1 = 0.f, tr2 = 0.f, intensity = 0.f;
+        float Cx = 0.f, Cy = 0.f;
+        const bool hitany = live && (l0 >= 0);
+        if (hitany) {
+            const int64_t g = g0 + l0;
+            const int w = __ldg(k.s.tex_widths + g);
+            const int64_t ts = __ldg(k.s.tex_starts + g);
+            // filter() (kernels.cu:394-405)
+            const float yy = fminf(fmul(locv, (float)(w + 1)), (float)(w - 1));
+            const int fl = __float2int_rz(fmaxf(fadd(yy, -1.f), 0.f));
+            const int fr = __float2int_rz(yy);
+            const float ld = fadd(fabsf(fsub(yy, (float)(fl + 1))), 1.e-3f);
+            const float rd = fadd(fabsf(fsub(yy, (float)(fr + 1))), 1.e-3f);
+            const float rc = rcp(fadd(rd, ld));
+            lw = fmul(rd, rc);
+            rw = fmul(ld, rc);
+            const float* tl = k.s.textures + 3 * (ts + fl);
+            const float* tr = k.s.textures + 3 * (ts + fr);
+            tl0 = __ldg(tl); tl1 = __ldg(tl + 1); tl2 = __ldg(tl + 2);
+            tr0 = __ldg(tr); tr1 = __ldg(tr + 1); tr2 = __ldg(tr + 2);
+            if (l0 >= AF) {
+                intensity = ffma(lw, __ldg(k.s.baked + ts + fl), fmul(rw, __ldg(k.s.baked + ts + fr)));   // :438
+            } else {
+                const float om = fsub(1.f, locv);                                                       // :435
+                const float4 s4 = seg[l0];
+                Cx = ffma(s4.x, om, fmul(locv, s4.z));
+                Cy = ffma(s4.y, om, fmul(locv, s4.w));
+            }
+        }
+        // (1 - dot^2) and the filtered texel, common to static and dynamic lighting (:442-445)
+        const bool isdyn = hitany && (l0 < AF);
+        float kk0 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        if (hitany) {
+            kk0 = ffma(-dotv, dotv, 1.f);
+            b0 = ffma(lw, tl0, fmul(rw, tr0));
+            b1 = ffma(lw, tl1, fmul(rw, tr1));
+            b2 = ffma(lw, tl2, fmul(rw, tr2));
+        }
+        // dynamic lighting for rays that hit an agent's model (:434-436). Preferred: queue the pixel group for the
+        // load-balanced second pass (dyn_kernel). Fallback (no workspace / queue full): this warp resolves them
+        // one ray at a time.
+        unsigned dm = __ballot_sync(0xffffffffu, isdyn);
+        if (k.debug_skip_dyn) dm = 0;
+        const int gl = lane & ~(sub_ - 1);                                    // first lane of my pixel group
+        const unsigned subm = sub_ == 32 ? 0xffffffffu : ((1u << sub_) - 1u);
+        const unsigned gmask = (dm >> gl) & subm;                             // my group's agent-hit pixels
+        bool queued = false;
+        if (dm && k.dyn_entries) {
+            const unsigned leaders = __ballot_sync(0xffffffffu, gmask != 0 && lane == gl);
+            const int cnt = __popc(leaders);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(k.dyn_ctrl, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            queued = base + cnt <= k.dyn_cap;
+            // which agent the group's first agent-hit pixel landed on: keys the persistent occluder cache
+            const int tgt = __shfl_sync(0xffffffffu, l0, gl + (gmask ? __ffs(gmask) - 1 : 0)) / k.s.n_model;
+            if (gmask) {
+                const int slot = base + __popc(leaders & ((1u << gl) - 1u));
+                if (slot < k.dyn_cap) {
+                    unsigned char* e = k.dyn_entries + (size_t)slot * k.dyn_stride;
+                    if (lane == gl) {
+                        *reinterpret_cast<int4*>(e) = make_int4(n, a * R + (r - lane + gl), queued ? (int)gmask : 0, sub_ | (tgt << 8));
+                    }
+                    if (queued) {
+                        float4* rec = reinterpret_cast<float4*>(e + 16) + 2 * (lane - gl);
+                        rec[0] = make_float4(b0, b1, b2, kk0);
+                        rec[1] = make_float4(Cx, Cy, intensity, isdyn ? 1.f : 0.f);
+                    }
+                }
+            }
+        }
+        if (!queued) {
+            while (dm) {
+                const int j = __ffs(dm) - 1;
+                dm &= dm - 1;
+                const float cx = __shfl_sync(0xffffffffu, Cx, j), cy = __shfl_sync(0xffffffffu, Cy, j);
+                const float v = light_intensity_cached<STATS>(seg, L, AF, nlights, lt, cx, cy, lane, ll, dyn_iters);
+                if (lane == j) intensity = v;
+                if (STATS) dyn_rays++;
+            }
+        }
+        if (hitany) {
+            const float kk = fmul(kk0, intensity);
+            s0 = fmul(kk, b0);
+            s1 = fmul(kk, b1);
+            s2 = fmul(kk, b2);
+        }
+        const bool deferred = queued && gmask != 0;      // dyn_kernel writes this group's screen / rgb
+        if (live) {
+            const int64_t o = ((int64_t)n * A + a) * R + r;
+            if (write_raw) {
+                if (k.out.indices) k.out.indices[o] = l0;
+                if (k.out.locations) k.out.locations[o] = locv;
+                if (k.out.dots) k.out.dots[o] = dotv;
+                if (k.out.distances) k.out.distances[o] = dist;
+            }
+            if (k.out.screen && !(queued && isdyn)) { float* sc = k.out.screen + 3 * o; sc[0] = s0; sc[1] = s1; sc[2] = s2; }
+        }
+        // fused observation heads: Depth (modules.py:181-183) and RGB (:222-223), mean over `subsample` pixels
+        if (k.has_obs) {
+            float d = 0.f;
+            if (live) {
+                const float z = __fmul_rn(__fsub_rn(dist, k.p.agent_radius), k.inv_max_depth);
+                d = __fsub_rn(1.f, fminf(fmaxf(z, 0.f), 1.f));
+            }
+            float v0 = s0, v1 = s1, v2 = s2, v3 = d;
+            for (int o = 1; o < sub_; o <<= 1) {
+                v0 = __fadd_rn(v0, __shfl_xor_sync(0xffffffffu, v0, o));
+                v1 = __fadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+                v2 = __fadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
+                v3 = __fadd_rn(v3, __shfl_xor_sync(0xffffffffu, v3, o));
+            }
+            if (live && lane == gl) {
+                const int Ro = R / sub_, ro = r / sub_;
+                const float inv = k.inv_sub;
+                const int64_t ag = (int64_t)n * A + a;
+                if (k.obs.rgb && !deferred) {
+                    float* q = k.obs.rgb + ag * 3 * Ro + ro;
+                    q[0] = __fmul_rn(v0, inv); q[Ro] = __fmul_rn(v1, inv); q[2 * Ro] = __fmul_rn(v2, inv);
+                }
+                if (k.obs.depth) k.obs.depth[ag * Ro + ro] = __fmul_rn(v3, inv);
+            }
+        }
+}
+
 // Per-(agent, segment) work shared by every ray of the agent: the exact ray-independent terms of intersect()
 // (kernels.cu:83-85: V, PQ, cross(PQ, V)) and a CONSERVATIVE screen-space summary used only to skip work — the
 // interval [rlo, rhi] of rays the segment can touch and a lower bound smin of the hit parameter s over it.
@@ -482,7 +626,7 @@ __device__ __forceinline__ SegBin bin_segment(const KArgs& k, float4 s4, float p
     return b;
 }
 
-template <int NCH, bool STATS>
+template <int NCH, bool STATS, bool SPLIT>
 __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int n, int64_t g0, int L, int a, int rb,
                                              float4* __restrict__ scr, int lane) {
     // two-phase mode: the per-(agent, segment) records were written to shared memory by the binning phase
@@ -598,148 +742,39 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
         if (!pre) __syncwarp();
     }
 
-    // ---- shade + store (shader_kernel, kernels.cu:407-450)
-    unsigned dyn_rays = 0, dyn_iters = 0;
-    const int sub_ = k.has_obs ? k.obs.subsample : 1;
-    const int nlights = __ldg(k.s.light_widths + n);
-    const float* lt = k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n);
-    LaneLight ll;
-    ll.occ = -1;
-    if (lane < nlights) { ll.x = __ldg(lt + 3 * lane); ll.y = __ldg(lt + 3 * lane + 1); ll.i = __ldg(lt + 3 * lane + 2); }
-    else { ll.x = 0.f; ll.y = 0.f; ll.i = 0.f; }
+    // ---- per chunk: the winner's ray . line cosine (kernels.cu:362-364, winner only), then either hand the hit to
+    // shade_kernel through the four scalar Render outputs (split render) or shade right here
+    ShadeCtx sc_;
+    sc_.nlights = __ldg(k.s.light_widths + n);
+    sc_.lt = k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n);
+    sc_.ll.occ = -1;
+    sc_.dyn_rays = sc_.dyn_iters = 0;
+    if (!SPLIT && lane < sc_.nlights) { sc_.ll.x = __ldg(sc_.lt + 3 * lane); sc_.ll.y = __ldg(sc_.lt + 3 * lane + 1); sc_.ll.i = __ldg(sc_.lt + 3 * lane + 2); }
+    else { sc_.ll.x = 0.f; sc_.ll.y = 0.f; sc_.ll.i = 0.f; }
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
         const int r = r0 + 32 * c + lane;
-        const bool live = r < R;
         const int l0 = idx[c];
         float dotv = __int_as_float(0x7fffffff);
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        float lw = 0.f, rw = 0.f, tl0 = 0.f, tl1 = 0.f, tl2 = 0.f, tr0 = 0.f, tr1 = 0.f, tr2 = 0.f, intensity = 0.f;
-        float Cx = 0.f, Cy = 0.f;
-        const bool hitany = live && (l0 >= 0);
-        if (hitany) {
+        if (l0 >= 0) {
             const float4 s4 = m.seg[l0];
             const float Vx = fsub(s4.z, s4.x), Vy = fsub(s4.w, s4.y);
-            // ray . line cosine for the winner only (kernels.cu:362-364)
             dotv = fmul(dot2(rux[c], Vx, ruy[c], Vy), rcp(ffma(rlen[c], sqrt_(ffma(Vx, Vx, fmul(Vy, Vy))), 1.e-6f)));
-            const int64_t g = g0 + l0;
-            const int w = __ldg(k.s.tex_widths + g);
-            const int64_t ts = __ldg(k.s.tex_starts + g);
-            // filter() (kernels.cu:394-405)
-            const float yy = fminf(fmul(loc[c], (float)(w + 1)), (float)(w - 1));
-            const int fl = __float2int_rz(fmaxf(fadd(yy, -1.f), 0.f));
-            const int fr = __float2int_rz(yy);
-            const float ld = fadd(fabsf(fsub(yy, (float)(fl + 1))), 1.e-3f);
-            const float rd = fadd(fabsf(fsub(yy, (float)(fr + 1))), 1.e-3f);
-            const float rc = rcp(fadd(rd, ld));
-            lw = fmul(rd, rc);
-            rw = fmul(ld, rc);
-            const float* tl = k.s.textures + 3 * (ts + fl);
-            const float* tr = k.s.textures + 3 * (ts + fr);
-            tl0 = __ldg(tl); tl1 = __ldg(tl + 1); tl2 = __ldg(tl + 2);
-            tr0 = __ldg(tr); tr1 = __ldg(tr + 1); tr2 = __ldg(tr + 2);
-            if (l0 >= AF) {
-                intensity = ffma(lw, __ldg(k.s.baked + ts + fl), fmul(rw, __ldg(k.s.baked + ts + fr)));   // :438
-            } else {
-                const float om = fsub(1.f, loc[c]);                                                       // :435
-                Cx = ffma(s4.x, om, fmul(loc[c], s4.z));
-                Cy = ffma(s4.y, om, fmul(loc[c], s4.w));
-            }
         }
-        // (1 - dot^2) and the filtered texel, common to static and dynamic lighting (:442-445)
-        const bool isdyn = hitany && (l0 < AF);
-        float kk0 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
-        if (hitany) {
-            kk0 = ffma(-dotv, dotv, 1.f);
-            b0 = ffma(lw, tl0, fmul(rw, tr0));
-            b1 = ffma(lw, tl1, fmul(rw, tr1));
-            b2 = ffma(lw, tl2, fmul(rw, tr2));
-        }
-        // dynamic lighting for rays that hit an agent's model (:434-436). Preferred: queue the pixel group for the
-        // load-balanced second pass (dyn_kernel). Fallback (no workspace / queue full): this warp resolves them
-        // one ray at a time.
-        unsigned dm = __ballot_sync(0xffffffffu, isdyn);
-        if (k.debug_skip_dyn) dm = 0;
-        const int gl = lane & ~(sub_ - 1);                                    // first lane of my pixel group
-        const unsigned subm = sub_ == 32 ? 0xffffffffu : ((1u << sub_) - 1u);
-        const unsigned gmask = (dm >> gl) & subm;                             // my group's agent-hit pixels
-        bool queued = false;
-        if (dm && k.dyn_entries) {
-            const unsigned leaders = __ballot_sync(0xffffffffu, gmask != 0 && lane == gl);
-            const int cnt = __popc(leaders);
-            int base = 0;
-            if (lane == 0) base = atomicAdd(k.dyn_ctrl, cnt);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            queued = base + cnt <= k.dyn_cap;
-            // which agent the group's first agent-hit pixel landed on: keys the persistent occluder cache
-            const int tgt = __shfl_sync(0xffffffffu, l0, gl + (gmask ? __ffs(gmask) - 1 : 0)) / k.s.n_model;
-            if (gmask) {
-                const int slot = base + __popc(leaders & ((1u << gl) - 1u));
-                if (slot < k.dyn_cap) {
-                    unsigned char* e = k.dyn_entries + (size_t)slot * k.dyn_stride;
-                    if (lane == gl) {
-                        *reinterpret_cast<int4*>(e) = make_int4(n, a * R + (r0 + 32 * c + gl), queued ? (int)gmask : 0, sub_ | (tgt << 8));
-                    }
-                    if (queued) {
-                        float4* rec = reinterpret_cast<float4*>(e + 16) + 2 * (lane - gl);
-                        rec[0] = make_float4(b0, b1, b2, kk0);
-                        rec[1] = make_float4(Cx, Cy, intensity, isdyn ? 1.f : 0.f);
-                    }
-                }
-            }
-        }
-        if (!queued) {
-            while (dm) {
-                const int j = __ffs(dm) - 1;
-                dm &= dm - 1;
-                const float cx = __shfl_sync(0xffffffffu, Cx, j), cy = __shfl_sync(0xffffffffu, Cy, j);
-                const float v = light_intensity_cached<STATS>(m.seg, L, AF, nlights, lt, cx, cy, lane, ll, dyn_iters);
-                if (lane == j) intensity = v;
-                if (STATS) dyn_rays++;
-            }
-        }
-        if (hitany) {
-            const float kk = fmul(kk0, intensity);
-            s0 = fmul(kk, b0);
-            s1 = fmul(kk, b1);
-            s2 = fmul(kk, b2);
-        }
-        const bool deferred = queued && gmask != 0;      // dyn_kernel writes this group's screen / rgb
         const float dist = fmul(rlen[c], best[c]);
-        if (live) {
-            const int64_t o = ((int64_t)n * A + a) * R + r;
-            if (k.out.indices) k.out.indices[o] = l0;
-            if (k.out.locations) k.out.locations[o] = loc[c];
-            if (k.out.dots) k.out.dots[o] = dotv;
-            if (k.out.distances) k.out.distances[o] = dist;
-            if (k.out.screen && !(queued && isdyn)) { float* sc = k.out.screen + 3 * o; sc[0] = s0; sc[1] = s1; sc[2] = s2; }
-        }
-        // fused observation heads: Depth (modules.py:181-183) and RGB (:222-223), mean over `subsample` pixels
-        if (k.has_obs) {
-            float d = 0.f;
-            if (live) {
-                const float z = __fmul_rn(__fsub_rn(dist, k.p.agent_radius), k.inv_max_depth);
-                d = __fsub_rn(1.f, fminf(fmaxf(z, 0.f), 1.f));
+        if (SPLIT) {
+            if (r < R) {
+                const int64_t o = ((int64_t)n * A + a) * R + r;
+                k.out.indices[o] = l0;
+                k.out.locations[o] = loc[c];
+                k.out.dots[o] = dotv;
+                k.out.distances[o] = dist;
             }
-            float v0 = s0, v1 = s1, v2 = s2, v3 = d;
-            for (int o = 1; o < sub_; o <<= 1) {
-                v0 = __fadd_rn(v0, __shfl_xor_sync(0xffffffffu, v0, o));
-                v1 = __fadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, o));
-                v2 = __fadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
-                v3 = __fadd_rn(v3, __shfl_xor_sync(0xffffffffu, v3, o));
-            }
-            if (live && lane == gl) {
-                const int Ro = R / sub_, ro = r / sub_;
-                const float inv = k.inv_sub;
-                const int64_t ag = (int64_t)n * A + a;
-                if (k.obs.rgb && !deferred) {
-                    float* q = k.obs.rgb + ag * 3 * Ro + ro;
-                    q[0] = __fmul_rn(v0, inv); q[Ro] = __fmul_rn(v1, inv); q[2 * Ro] = __fmul_rn(v2, inv);
-                }
-                if (k.obs.depth) k.obs.depth[ag * Ro + ro] = __fmul_rn(v3, inv);
-            }
+        } else {
+            shade_chunk<STATS>(k, m.seg, n, a, g0, L, r, lane, l0, loc[c], dotv, dist, true, sc_);
         }
     }
+    const unsigned dyn_rays = sc_.dyn_rays, dyn_iters = sc_.dyn_iters;
     if (STATS && k.stats && lane == 0) {
         atomicAdd(k.stats + STAT_TESTS, (unsigned long long)tests);
         atomicAdd(k.stats + STAT_GROUPS, (unsigned long long)groups);
@@ -766,7 +801,7 @@ __device__ __forceinline__ void imu_stage(const KArgs& k, const Smem& m, int n) 
 // ---------------------------------------------------------------------------------------------------------------
 // the per-env kernel: any of physics / render / both
 // ---------------------------------------------------------------------------------------------------------------
-template <int MODE, int NCH, bool STATS>
+template <int MODE, int NCH, bool STATS, bool SPLIT>
 __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) env_kernel(const __grid_constant__ KArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = blockIdx.x;
@@ -839,9 +874,54 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) env_kernel(const __grid_c
             __syncthreads();
         }
         for (int w = warp; w < A * RB; w += nwarps) {
-            render_agent<NCH, STATS>(k, m, n, g0, L, w / RB, w % RB, m.scratch + warp * 64, lane);
+            render_agent<NCH, STATS, SPLIT>(k, m, n, g0, L, w / RB, w % RB, m.scratch + warp * 64, lane);
         }
         if (k.has_obs && k.obs.imu) imu_stage(k, m, n);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shade_kernel: second half of the split render. One warp per (agent, 32-ray chunk), lane = ray; reads the hit the
+// cast kernel left in the Render outputs and does everything that is memory-latency bound (texel / baked-light
+// gathers, the queue for agent hits, screen, Depth/RGB heads) at full occupancy, with no shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool STATS>
+__global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ KArgs k) {
+    const int lane = threadIdx.x & 31;
+    const int A = k.s.n_agents, R = k.p.res;
+    const int chunks = (R + 31) >> 5;
+    const int64_t wg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t total = (int64_t)k.s.n_envs * A * chunks;
+    if (wg >= total) return;
+    const int64_t ag = wg / chunks;
+    const int c = (int)(wg - ag * chunks);
+    const int n = (int)(ag / A), a = (int)(ag - (int64_t)n * A);
+    const int r = 32 * c + lane;
+    const int L = __ldg(k.s.line_widths + n);
+    const int64_t g0 = __ldg(k.s.line_starts + n);
+    const float4* seg = reinterpret_cast<const float4*>(k.s.lines) + g0;
+    int l0 = -1;
+    float locv = __int_as_float(0x7fffffff), dotv = __int_as_float(0x7fffffff), dist = CUDART_INF_F;
+    if (r < R) {
+        const int64_t o = ag * R + r;
+        l0 = k.out.indices[o];
+        locv = k.out.locations[o];
+        dotv = k.out.dots[o];
+        dist = k.out.distances[o];
+    }
+    ShadeCtx sc_;
+    sc_.nlights = __ldg(k.s.light_widths + n);
+    sc_.lt = k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n);
+    sc_.ll.occ = -1;
+    sc_.dyn_rays = sc_.dyn_iters = 0;
+    sc_.ll.x = sc_.ll.y = sc_.ll.i = 0.f;
+    if (!k.dyn_entries && lane < sc_.nlights) {      // only the inline fallback needs the lights here
+        sc_.ll.x = __ldg(sc_.lt + 3 * lane); sc_.ll.y = __ldg(sc_.lt + 3 * lane + 1); sc_.ll.i = __ldg(sc_.lt + 3 * lane + 2);
+    }
+    shade_chunk<STATS>(k, seg, n, a, g0, L, r, lane, l0, locv, dotv, dist, false, sc_);
+    if (STATS && k.stats && lane == 0) {
+        atomicAdd(k.stats + STAT_DYN_RAYS, (unsigned long long)sc_.dyn_rays);
+        atomicAdd(k.stats + STAT_DYN_ITERS, (unsigned long long)sc_.dyn_iters);
     }
 }
 
@@ -988,6 +1068,7 @@ static long long g_launches = 0;
 static long long g_opt_nch = 0;          // 0 = auto
 static long long g_opt_threads = 0;      // 0 = auto
 static long long g_opt_skip_dyn = 0;     // debug
+static long long g_opt_split = 1;        // 0: cast and shade in one kernel
 static long long g_opt_two_phase = 0;    // 1: bin every (agent, segment) once into shared memory first (measured slower: the
                                          // records cost 70 KB per CTA, which halves residency)
 static long long g_opt_variant = 0;      // experiment switches (see KArgs::variant)
@@ -1029,6 +1110,7 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "fused_step")) { g_opt_fused_step = value; return 0; }
     if (!strcmp(name, "variant")) { g_opt_variant = value; return 0; }
     if (!strcmp(name, "two_phase")) { g_opt_two_phase = value; return 0; }
+    if (!strcmp(name, "split_render")) { g_opt_split = value; return 0; }
     if (!strcmp(name, "stats")) {
         if (value && !g_stats) {
             if (check(cudaMalloc(&g_stats, 8 * sizeof(unsigned long long)), "cudaMalloc(stats)")) return 1;
@@ -1072,7 +1154,8 @@ static int launch_env(const KArgs& k, int nch, int threads, cudaStream_t st) {
     if (sm > 227 * 1024) return fail("%s", "scene too large: an env's segments do not fit in shared memory (227 KB)");
 #define MSB_LAUNCH(N)                                                                                            \
     {                                                                                                            \
-        auto fn = k.stats ? env_kernel<MODE, N, true> : env_kernel<MODE, N, false>;                              \
+        auto fn = k.split_render ? (k.stats ? env_kernel<MODE, N, true, true> : env_kernel<MODE, N, false, true>)    \
+                                 : (k.stats ? env_kernel<MODE, N, true, false> : env_kernel<MODE, N, false, false>); \
         if (sm > 48 * 1024 && check(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), \
                                     "cudaFuncSetAttribute"))                                                     \
             return 1;                                                                                            \
@@ -1090,6 +1173,8 @@ static int launch_env(const KArgs& k, int nch, int threads, cudaStream_t st) {
 
 static void plan_render(const msb_params* p, const msb_scenery* s, KArgs& k, int* nch, int* rb, int* threads) {
     const int chunks = (p->res + 31) / 32;
+    // split render needs the four scalar Render outputs as the hand-over buffers
+    k.split_render = g_opt_split && k.out.indices && k.out.locations && k.out.dots && k.out.distances;
     // two-phase render when the per-(agent, segment) records leave room for at least two CTAs per SM
     const size_t rec = (size_t)2 * s->n_agents * k.seg_cap * 16;
     k.two_phase = (g_opt_two_phase != 0) && rec + (size_t)k.seg_cap * 18 + 4096 <= 100 * 1024;
@@ -1172,6 +1257,16 @@ static int set_workspace(KArgs& k, const msb_workspace* ws) {
     return 0;
 }
 
+static int launch_shade(const KArgs& k, cudaStream_t st) {
+    if (!k.split_render) return 0;
+    const int64_t warps = (int64_t)k.s.n_envs * k.s.n_agents * ((k.p.res + 31) / 32);
+    const int64_t blocks = (warps + 7) / 8;
+    if (k.stats) shade_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(k);
+    else shade_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(k);
+    g_launches++;
+    return check(cudaGetLastError(), "shade_kernel launch");
+}
+
 static int launch_dyn(const KArgs& k, cudaStream_t st) {
     if (!k.dyn_entries) return 0;
     int dev = 0, sms = 148;
@@ -1225,6 +1320,7 @@ extern "C" int msb_render(const msb_params* p, const msb_scenery* s, const msb_a
     plan_render(p, s, k, &nch, &rb, &threads);
     k.ray_blocks = rb;
     if (launch_env<MODE_RENDER>(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
+    if (launch_shade(k, (cudaStream_t)cuda_stream)) return 1;
     return launch_dyn(k, (cudaStream_t)cuda_stream);
 }
 
@@ -1252,6 +1348,7 @@ extern "C" int msb_step(const msb_params* p, const msb_scenery* s, const msb_age
     plan_render(p, s, k, &nch, &rb, &threads);
     k.ray_blocks = rb;
     if (g_opt_fused_step) {
+        k.split_render = 0;
         if (launch_env<MODE_STEP>(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
     } else {
         // physics (with the movement prologue) and render (with the heads) as two launches: the physics stage needs
@@ -1262,6 +1359,7 @@ extern "C" int msb_step(const msb_params* p, const msb_scenery* s, const msb_age
         if (launch_env<MODE_PHYSICS>(k, 1, pthreads, (cudaStream_t)cuda_stream)) return 1;
         if (launch_env<MODE_RENDER>(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
     }
+    if (launch_shade(k, (cudaStream_t)cuda_stream)) return 1;
     return launch_dyn(k, (cudaStream_t)cuda_stream);
 }
 
