@@ -238,10 +238,11 @@ def test_every_kernel_variant_gives_identical_results(res):
     c = common.to_device(arrays, st, res, 70.)
     base = c.render()
     try:
-        for variant in (0, 1, 2, 3, 4, 5):  # depth culling on/off x plain/pipelined candidate loop; 4, 5: two-phase render
+        for variant in (0, 1, 2, 3, 4, 5, 6):  # depth culling on/off x plain/pipelined loop; 4, 5: two-phase; 6: split render
             for nch in (1, 2, 4):
                 for threads in (64, 128, 256):
-                    cuda.set_option('two_phase', 1 if variant >= 4 else 0)
+                    cuda.set_option('two_phase', 1 if variant in (4, 5) else 0)
+                    cuda.set_option('split_render', 1 if variant == 6 else 0)
                     cuda.set_option('variant', variant % 4)
                     cuda.set_option('nch', nch)
                     cuda.set_option('threads', threads)
@@ -254,6 +255,7 @@ def test_every_kernel_variant_gives_identical_results(res):
         cuda.set_option('threads', 0)
         cuda.set_option('variant', 0)
         cuda.set_option('two_phase', 0)
+        cuda.set_option('split_render', 0)
 
 
 def _same(a, b):
@@ -272,8 +274,9 @@ def test_second_pass_inline_and_overflow_paths_agree(sub):
     st['positions'] = (3.5 + rng.uniform(-.6, .6, st['positions'].shape)).astype(np.float32)
     res = 128
     outs = []
-    for mode in ('workspace', 'inline', 'overflow', 'unsorted'):
+    for mode in ('workspace', 'inline', 'overflow', 'unsorted', 'split', 'split-overflow'):
         cuda.USE_WORKSPACE = mode != 'inline'
+        cuda.set_option('split_render', 1 if mode.startswith('split') else 0)
         cuda.BUILD_OCCLUDERS = mode != 'unsorted'
         try:
             c = common.to_device(arrays, st, res, 100.)
@@ -281,7 +284,7 @@ def test_second_pass_inline_and_overflow_paths_agree(sub):
         finally:
             cuda.USE_WORKSPACE = True
             cuda.BUILD_OCCLUDERS = True
-        if mode == 'overflow':
+        if mode.endswith('overflow'):
             small = 16 + 6 * 4 * 32 * 4 + 3 * (16 + 32 * sub)      # ctrl + occluder cache + room for three pixel groups only
             plan._wsbuf = torch.zeros(small, dtype=torch.uint8, device='cuda')
             plan._ws = cuda._Workspace(plan._wsbuf.data_ptr(), small)
@@ -289,6 +292,7 @@ def test_second_pass_inline_and_overflow_paths_agree(sub):
             plan.render_only()
         torch.cuda.synchronize()
         outs.append((plan.render.screen.clone(), plan.rgb.clone(), plan.render.indices.clone()))
+    cuda.set_option('split_render', 0)
     n_dyn = int(((outs[0][2] >= 0) & (outs[0][2] < 32)).sum())
     assert n_dyn > 50, 'the scene should have plenty of agent-hit rays'
     for other in outs[1:]:
