@@ -55,7 +55,7 @@ struct KArgs {
     int32_t debug_skip_dyn;     // timing experiments only: leave agent-hit rays unlit
     int32_t split_render;       // cast kernel writes the four scalar Render outputs, shade_kernel does the rest
     int32_t two_phase;          // render: bin every (agent, segment) once into shared memory, then one warp per ray chunk
-    int32_t variant;            // bit 0: depth culling off; bit 1: software-pipelined candidate loop
+    int32_t variant;            // bit 0: depth culling off; bit 2: chunk-major candidate stage (bit 1: pipelined loop in it)
     // queue of pixel groups whose dynamic lighting is resolved by dyn_kernel (load-balanced second pass)
     int* dyn_ctrl;              // [0] entries reserved, [1] CTAs of dyn_kernel done
     unsigned char* dyn_entries; // null -> dynamic lights are resolved inline by the ray's own warp
@@ -684,31 +684,51 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
             }
             __syncwarp();
         }
-#pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            const int c_lo = r0 + 32 * c, c_hi = c_lo + 31;
-            // depth cull (exact): a hit on this segment has s >= smin; if that is beyond the current hit of EVERY ray
-            // of the chunk it cannot satisfy s < best - 1e-4 for any of them
-            float cmax = CUDART_INF_F;
-            if (!(k.variant & 1)) {
-                // best >= 0 (or +inf), so its bit pattern orders like an unsigned integer: one REDUX instead of a
-                // shuffle tree
-                cmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best[c])));
-            }
-            unsigned mask = __ballot_sync(0xffffffffu, (rlo <= c_hi) && (rhi >= c_lo) && (rlo <= rhi) && !(smin > cmax));
-            if (k.variant & 2) {
-                if (mask) {
-                    int j = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    float4 q = q0p[j];
-                    float snum = q1p[j].x;
-                    while (true) {
-                        // fetch the next candidate's terms before the arithmetic of this one (hides the LDS latency)
-                        const bool more = mask != 0;
-                        const int jn = more ? __ffs(mask) - 1 : j;
+        if (k.variant & 4) {
+    #pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const int c_lo = r0 + 32 * c, c_hi = c_lo + 31;
+                // depth cull (exact): a hit on this segment has s >= smin; if that is beyond the current hit of EVERY ray
+                // of the chunk it cannot satisfy s < best - 1e-4 for any of them
+                float cmax = CUDART_INF_F;
+                if (!(k.variant & 1)) {
+                    // best >= 0 (or +inf), so its bit pattern orders like an unsigned integer: one REDUX instead of a
+                    // shuffle tree
+                    cmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best[c])));
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, (rlo <= c_hi) && (rhi >= c_lo) && (rlo <= rhi) && !(smin > cmax));
+                if (k.variant & 2) {
+                    if (mask) {
+                        int j = __ffs(mask) - 1;
                         mask &= mask - 1;
-                        const float4 qn = q0p[jn];
-                        const float snn = q1p[jn].x;
+                        float4 q = q0p[j];
+                        float snum = q1p[j].x;
+                        while (true) {
+                            // fetch the next candidate's terms before the arithmetic of this one (hides the LDS latency)
+                            const bool more = mask != 0;
+                            const int jn = more ? __ffs(mask) - 1 : j;
+                            mask &= mask - 1;
+                            const float4 qn = q0p[jn];
+                            const float snn = q1p[jn].x;
+                            const float UxV = cross2(rux[c], q.y, ruy[c], q.x);
+                            const float rc = rcp(UxV);
+                            const float hs_ = fmul(snum, rc);
+                            const float ht_ = fmul(cross2(ruy[c], q.z, rux[c], q.w), rc);
+                            const bool take = !(fabsf(UxV) < PARALLEL_EPS) && (ht_ >= 0.f) && (ht_ <= 1.f) && (nearp[c] < hs_) && (hs_ < bestm[c]);
+                            if (take) { best[c] = hs_; bestm[c] = fadd(hs_, -1.e-4f); loc[c] = ht_; idx[c] = gbase + j; }
+                            if (STATS) tests++;
+                            if (!more) break;
+                            j = jn; q = qn; snum = snn;
+                        }
+                    }
+                } else {
+                    while (mask) {
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const float4 q = q0p[j];
+                        const float snum = q1p[j].x;
+                        // raycast_kernel inner loop (kernels.cu:353-376), branch-free. A near-parallel line
+                        // (|UxV| < 1e-3: s = t = inf in the reference) can never be accepted, so its s/t need no forcing.
                         const float UxV = cross2(rux[c], q.y, ruy[c], q.x);
                         const float rc = rcp(UxV);
                         const float hs_ = fmul(snum, rc);
@@ -716,25 +736,44 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
                         const bool take = !(fabsf(UxV) < PARALLEL_EPS) && (ht_ >= 0.f) && (ht_ <= 1.f) && (nearp[c] < hs_) && (hs_ < bestm[c]);
                         if (take) { best[c] = hs_; bestm[c] = fadd(hs_, -1.e-4f); loc[c] = ht_; idx[c] = gbase + j; }
                         if (STATS) tests++;
-                        if (!more) break;
-                        j = jn; q = qn; snum = snn;
                     }
                 }
-            } else {
-                while (mask) {
-                    const int j = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const float4 q = q0p[j];
-                    const float snum = q1p[j].x;
-                    // raycast_kernel inner loop (kernels.cu:353-376), branch-free. A near-parallel line
-                    // (|UxV| < 1e-3: s = t = inf in the reference) can never be accepted, so its s/t need no forcing.
-                    const float UxV = cross2(rux[c], q.y, ruy[c], q.x);
-                    const float rc = rcp(UxV);
-                    const float hs_ = fmul(snum, rc);
-                    const float ht_ = fmul(cross2(ruy[c], q.z, rux[c], q.w), rc);
-                    const bool take = !(fabsf(UxV) < PARALLEL_EPS) && (ht_ >= 0.f) && (ht_ <= 1.f) && (nearp[c] < hs_) && (hs_ < bestm[c]);
-                    if (take) { best[c] = hs_; bestm[c] = fadd(hs_, -1.e-4f); loc[c] = ht_; idx[c] = gbase + j; }
-                    if (STATS) tests++;
+            }
+        } else {
+            // Segment-major candidate stage. cm = the chunks of this warp's ray block that my segment can still matter
+            // to: its ray interval overlaps the chunk, and (depth cull, exact) its nearest point is not behind the
+            // current hit of EVERY ray of the chunk — a hit on it has s >= smin, so it could not satisfy
+            // s < best - 1e-4 for any of them. One ballot finds the segments to visit; each is loaded once and tested
+            // against all its chunks. Rays still meet their candidates in ascending line order.
+            unsigned cm = 0;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const int c_lo = r0 + 32 * c, c_hi = c_lo + 31;
+                // best >= 0 (or +inf): its bit pattern orders like an unsigned integer, one REDUX gives the chunk max
+                const float cmax = (k.variant & 1) ? CUDART_INF_F
+                                                   : __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(best[c])));
+                if ((rlo <= c_hi) && (rhi >= c_lo) && (rlo <= rhi) && !(smin > cmax)) cm |= 1u << c;
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, cm != 0);
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const unsigned cj = __shfl_sync(0xffffffffu, cm, j);
+                const float4 q = q0p[j];
+                const float snum = q1p[j].x;
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+                    if (cj & (1u << c)) {
+                        // raycast_kernel inner loop (kernels.cu:353-376), branch-free per lane. A near-parallel line
+                        // (|UxV| < 1e-3: s = t = inf in the reference) can never be accepted: its s/t need no forcing.
+                        const float UxV = cross2(rux[c], q.y, ruy[c], q.x);
+                        const float rc = rcp(UxV);
+                        const float hs_ = fmul(snum, rc);
+                        const float ht_ = fmul(cross2(ruy[c], q.z, rux[c], q.w), rc);
+                        const bool take = !(fabsf(UxV) < PARALLEL_EPS) && (ht_ >= 0.f) && (ht_ <= 1.f) && (nearp[c] < hs_) && (hs_ < bestm[c]);
+                        if (take) { best[c] = hs_; bestm[c] = fadd(hs_, -1.e-4f); loc[c] = ht_; idx[c] = gbase + j; }
+                        if (STATS) tests++;
+                    }
                 }
             }
         }

@@ -64,9 +64,10 @@ if __name__ == '__main__':
         print(json.dumps(out)); sys.exit(0)
     if mode == 'variants':
         out = {}
-        for v in (0, 1, 2, 3):
+        for v in (0, 1, 4, 5, 6):
             cuda.set_option('variant', v)
-            out[f'render_us/variant{v}'] = timeit(lambda: c.render())
+            cuda.set_option('debug_skip_dyn', 1); out[f'main_us/variant{v}'] = round(timeit(lambda: c.render()), 1); cuda.set_option('debug_skip_dyn', 0)
+            out[f'render_us/variant{v}'] = round(timeit(lambda: c.render()), 1)
             cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0); c.render(); torch.cuda.synchronize()
             out[f'tests/variant{v}'] = cuda.get_option('stat_tests'); cuda.set_option('stats', 0)
         cuda.set_option('variant', 0)

@@ -238,12 +238,12 @@ def test_every_kernel_variant_gives_identical_results(res):
     c = common.to_device(arrays, st, res, 70.)
     base = c.render()
     try:
-        for variant in (0, 1, 2, 3, 4, 5, 6):  # depth culling on/off x plain/pipelined loop; 4, 5: two-phase; 6: split render
+        for variant in (0, 1, 4, 5, 6, 7, 8, 9, 10):  # 0/1: segment-major, depth cull on/off; 4-7: chunk-major variants; 8, 9: two-phase; 10: split
             for nch in (1, 2, 4):
                 for threads in (64, 128, 256):
-                    cuda.set_option('two_phase', 1 if variant in (4, 5) else 0)
-                    cuda.set_option('split_render', 1 if variant == 6 else 0)
-                    cuda.set_option('variant', variant % 4)
+                    cuda.set_option('two_phase', 1 if variant in (8, 9) else 0)
+                    cuda.set_option('split_render', 1 if variant == 10 else 0)
+                    cuda.set_option('variant', variant % 8)
                     cuda.set_option('nch', nch)
                     cuda.set_option('threads', threads)
                     r = c.render()
