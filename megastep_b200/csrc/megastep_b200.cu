@@ -685,7 +685,7 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
             }
             __syncwarp();
         }
-        if (k.variant & 4) {
+        if (!(k.variant & 4)) {
     #pragma unroll
             for (int c = 0; c < NCH; c++) {
                 const int c_lo = r0 + 32 * c, c_hi = c_lo + 31;
