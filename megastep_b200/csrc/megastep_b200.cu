@@ -66,6 +66,9 @@ struct KArgs {
 };
 
 enum { MODE_PHYSICS = 1, MODE_RENDER = 2, MODE_STEP = 3 };
+#ifndef MSB_SHADE_ILP
+#define MSB_SHADE_ILP 2       // chunks whose texel gathers are in flight together
+#endif
 #ifndef MSB_MIN_BLOCKS
 #define MSB_MIN_BLOCKS 4      // 256 threads x 4 blocks -> at most 64 registers per thread
 #endif
@@ -81,6 +84,8 @@ struct Smem {
     int* ncand;         // [A] physics: segments that survived the bounding-box cull
     unsigned short* cand;   // [A][seg_cap] their indices
     uint64_t* bar;
+    long long* tstart;  // [seg_cap] render: this env's texel offsets (tex_starts) ...
+    int* twidth;        // [seg_cap] ... and texel counts (tex_widths), so shading's first lookup is a shared-memory read
     float4* rec;        // two-phase render: [2][A][seg_cap] per-(agent, segment) records
 };
 
@@ -96,7 +101,11 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int seg_cap, int nwar
     uintptr_t p = reinterpret_cast<uintptr_t>(m.cand + (size_t)A * seg_cap);
     p = (p + 15) & ~uintptr_t(15);
     m.bar = reinterpret_cast<uint64_t*>(p);
-    m.rec = two_phase ? reinterpret_cast<float4*>(p + 16) : nullptr;
+    m.tstart = reinterpret_cast<long long*>(p + 16);
+    m.twidth = reinterpret_cast<int*>(m.tstart + seg_cap);
+    uintptr_t q = reinterpret_cast<uintptr_t>(m.twidth + seg_cap);
+    q = (q + 15) & ~uintptr_t(15);
+    m.rec = two_phase ? reinterpret_cast<float4*>(q) : nullptr;
     return m;
 }
 
@@ -104,7 +113,9 @@ static size_t smem_bytes(int seg_cap, int nwarps, int A, bool two_phase = false)
     size_t b = (size_t)seg_cap * 16 + (size_t)nwarps * 64 * 16 + (size_t)A * ST_STRIDE * 4 * 2 + (size_t)A * 8 +
                (size_t)A * seg_cap * 2;
     b = (b + 15) & ~size_t(15);
-    return b + 16 + (two_phase ? (size_t)2 * A * seg_cap * 16 : 0);
+    b += 16 + (size_t)seg_cap * 12;
+    b = (b + 15) & ~size_t(15);
+    return b + (two_phase ? (size_t)2 * A * seg_cap * 16 : 0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -448,15 +459,46 @@ __device__ __forceinline__ void draw_stage(const KArgs& k, const Smem& m, int n,
     }
 }
 
-// shader_kernel (kernels.cu:407-450) for one 32-ray chunk of one agent's view, lane = ray: filter + texel/baked
-// gathers, dynamic light for agent hits (queued for dyn_kernel, or inline), the five Render outputs, and the fused
-// Depth / RGB heads. `seg` = this env's segments (shared memory in the one-kernel render, HBM in shade_kernel).
+// shader_kernel (kernels.cu:407-450) for one 32-ray chunk of one agent's view, lane = ray, in two steps: shade_fetch
+// (filter + texel/baked gathers) and shade_finish (dynamic light for agent hits — queued for dyn_kernel, or inline —
+// the five Render outputs, and the fused Depth / RGB heads). `seg` = this env's segments (shared memory in the
+// one-kernel render, HBM in shade_kernel).
 struct ShadeCtx { int nlights; const float* lt; LaneLight ll; unsigned dyn_rays, dyn_iters; };
 
+// What shading gathers for one ray: the two texels (and baked lights) around the hit, with the filter weights.
+struct Texels { float lw, rw, tl0, tl1, tl2, tr0, tr1, tr2, bl, br; };
+
+// filter() (kernels.cu:394-405) + the gathers of shader_kernel (:427-430, :438). `tw`/`ts` = texel count / offset per
+// line of this env (shared memory in the one-kernel render, HBM in shade_kernel). Only issues loads; nothing here
+// waits on them, so several chunks' gathers can be in flight before shade_finish() consumes the first.
+__device__ __forceinline__ Texels shade_fetch(const KArgs& k, const int* __restrict__ tw, const long long* __restrict__ ts_,
+                                              int AF, bool hitany, int l0, float locv) {
+    Texels t;
+    t.lw = t.rw = t.tl0 = t.tl1 = t.tl2 = t.tr0 = t.tr1 = t.tr2 = t.bl = t.br = 0.f;
+    if (hitany) {
+        const int w = tw[l0];
+        const int64_t ts = ts_[l0];
+        const float yy = fminf(fmul(locv, (float)(w + 1)), (float)(w - 1));
+        const int fl = __float2int_rz(fmaxf(fadd(yy, -1.f), 0.f));
+        const int fr = __float2int_rz(yy);
+        const float ld = fadd(fabsf(fsub(yy, (float)(fl + 1))), 1.e-3f);
+        const float rd = fadd(fabsf(fsub(yy, (float)(fr + 1))), 1.e-3f);
+        const float rc = rcp(fadd(rd, ld));
+        t.lw = fmul(rd, rc);
+        t.rw = fmul(ld, rc);
+        const float* tl = k.s.textures + 3 * (ts + fl);
+        const float* tr = k.s.textures + 3 * (ts + fr);
+        t.tl0 = __ldg(tl); t.tl1 = __ldg(tl + 1); t.tl2 = __ldg(tl + 2);
+        t.tr0 = __ldg(tr); t.tr1 = __ldg(tr + 1); t.tr2 = __ldg(tr + 2);
+        if (l0 >= AF) { t.bl = __ldg(k.s.baked + ts + fl); t.br = __ldg(k.s.baked + ts + fr); }
+    }
+    return t;
+}
+
 template <bool STATS>
-__device__ __forceinline__ void shade_chunk(const KArgs& k, const float4* __restrict__ seg, int n, int a, int64_t g0,
-                                            int L, int r, int lane, int l0, float locv, float dotv, float dist,
-                                            bool write_raw, ShadeCtx& sc_) {
+__device__ __forceinline__ void shade_finish(const KArgs& k, const float4* __restrict__ seg, int n, int a, int L, int r,
+                                             int lane, int l0, float locv, float dotv, float dist, const Texels& t,
+                                             bool write_raw, ShadeCtx& sc_) {
     const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
     const int sub_ = k.has_obs ? k.obs.subsample : 1;
     const int nlights = sc_.nlights;
@@ -466,28 +508,13 @@ __device__ __forceinline__ void shade_chunk(const KArgs& k, const float4* __rest
     unsigned& dyn_iters = sc_.dyn_iters;
     const bool live = r < R;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        float lw = 0.f, rw = 0.f, tl0 = 0.f, tl1 = 0.f, tl2 = 0.f, tr0 = 0.f, tr1 = 0.f, tr2 = 0.f, intensity = 0.f;
+        const float lw = t.lw, rw = t.rw, tl0 = t.tl0, tl1 = t.tl1, tl2 = t.tl2, tr0 = t.tr0, tr1 = t.tr1, tr2 = t.tr2;
+        float intensity = 0.f;
         float Cx = 0.f, Cy = 0.f;
         const bool hitany = live && (l0 >= 0);
         if (hitany) {
-            const int64_t g = g0 + l0;
-            const int w = __ldg(k.s.tex_widths + g);
-            const int64_t ts = __ldg(k.s.tex_starts + g);
-            // filter() (kernels.cu:394-405)
-            const float yy = fminf(fmul(locv, (float)(w + 1)), (float)(w - 1));
-            const int fl = __float2int_rz(fmaxf(fadd(yy, -1.f), 0.f));
-            const int fr = __float2int_rz(yy);
-            const float ld = fadd(fabsf(fsub(yy, (float)(fl + 1))), 1.e-3f);
-            const float rd = fadd(fabsf(fsub(yy, (float)(fr + 1))), 1.e-3f);
-            const float rc = rcp(fadd(rd, ld));
-            lw = fmul(rd, rc);
-            rw = fmul(ld, rc);
-            const float* tl = k.s.textures + 3 * (ts + fl);
-            const float* tr = k.s.textures + 3 * (ts + fr);
-            tl0 = __ldg(tl); tl1 = __ldg(tl + 1); tl2 = __ldg(tl + 2);
-            tr0 = __ldg(tr); tr1 = __ldg(tr + 1); tr2 = __ldg(tr + 2);
             if (l0 >= AF) {
-                intensity = ffma(lw, __ldg(k.s.baked + ts + fl), fmul(rw, __ldg(k.s.baked + ts + fr)));   // :438
+                intensity = ffma(lw, t.bl, fmul(rw, t.br));                                             // :438
             } else {
                 const float om = fsub(1.f, locv);                                                       // :435
                 const float4 s4 = seg[l0];
@@ -784,6 +811,7 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
 
     // ---- per chunk: the winner's ray . line cosine (kernels.cu:362-364, winner only), then either hand the hit to
     // shade_kernel through the four scalar Render outputs (split render) or shade right here
+    float dots_[NCH];
     ShadeCtx sc_;
     sc_.nlights = __ldg(k.s.light_widths + n);
     sc_.lt = k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n);
@@ -811,7 +839,26 @@ __device__ __forceinline__ void render_agent(const KArgs& k, const Smem& m, int 
                 k.out.distances[o] = dist;
             }
         } else {
-            shade_chunk<STATS>(k, m.seg, n, a, g0, L, r, lane, l0, loc[c], dotv, dist, true, sc_);
+            dots_[c] = dotv;
+        }
+    }
+    if (!SPLIT) {
+        // gathers of two chunks in flight at a time, then their arithmetic, stores and queueing
+#pragma unroll
+        for (int c0 = 0; c0 < NCH; c0 += MSB_SHADE_ILP) {
+            Texels tx[MSB_SHADE_ILP];
+#pragma unroll
+            for (int u = 0; u < MSB_SHADE_ILP; u++) {
+                const int c = c0 + u;
+                if (c < NCH) tx[u] = shade_fetch(k, m.twidth, m.tstart, AF, (r0 + 32 * c + lane < R) && idx[c] >= 0, idx[c], loc[c]);
+            }
+#pragma unroll
+            for (int u = 0; u < MSB_SHADE_ILP; u++) {
+                const int c = c0 + u;
+                if (c < NCH)
+                    shade_finish<STATS>(k, m.seg, n, a, L, r0 + 32 * c + lane, lane, idx[c], loc[c], dots_[c],
+                                        fmul(rlen[c], best[c]), tx[u], true, sc_);
+            }
         }
     }
     const unsigned dyn_rays = sc_.dyn_rays, dyn_iters = sc_.dyn_iters;
@@ -884,6 +931,12 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) env_kernel(const __grid_c
         st[ST_ANG] = ang; st[ST_PX] = pos.x; st[ST_PY] = pos.y; st[ST_AV] = av; st[ST_VX] = vel.x; st[ST_VY] = vel.y;
         m.xmin[a] = __float_as_int(1.f);
         m.ncand[a] = 0;
+    }
+    if (MODE & MODE_RENDER) {
+        for (int l = tid; l < L; l += blockDim.x) {
+            m.twidth[l] = __ldg(k.s.tex_widths + g0 + l);
+            m.tstart[l] = __ldg(reinterpret_cast<const long long*>(k.s.tex_starts) + g0 + l);
+        }
     }
     __syncthreads();
     if (W > 0) mbar_wait(m.bar, 0);
@@ -958,7 +1011,10 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ KArg
     if (lane < sc_.nlights) {                        // for the inline fallback (no workspace, or the queue is full)
         sc_.ll.x = __ldg(sc_.lt + 3 * lane); sc_.ll.y = __ldg(sc_.lt + 3 * lane + 1); sc_.ll.i = __ldg(sc_.lt + 3 * lane + 2);
     }
-    shade_chunk<STATS>(k, seg, n, a, g0, L, r, lane, l0, locv, dotv, dist, false, sc_);
+    const int AFk = A * k.s.n_model;
+    const Texels tx = shade_fetch(k, k.s.tex_widths + g0, reinterpret_cast<const long long*>(k.s.tex_starts) + g0, AFk,
+                                  (r < R) && l0 >= 0, l0, locv);
+    shade_finish<STATS>(k, seg, n, a, L, r, lane, l0, locv, dotv, dist, tx, false, sc_);
     if (STATS && k.stats && lane == 0) {
         atomicAdd(k.stats + STAT_DYN_RAYS, (unsigned long long)sc_.dyn_rays);
         atomicAdd(k.stats + STAT_DYN_ITERS, (unsigned long long)sc_.dyn_iters);
