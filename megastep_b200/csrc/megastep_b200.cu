@@ -67,7 +67,7 @@ struct KArgs {
 
 enum { MODE_PHYSICS = 1, MODE_RENDER = 2, MODE_STEP = 3 };
 #ifndef MSB_SHADE_ILP
-#define MSB_SHADE_ILP 2       // chunks whose texel gathers are in flight together
+#define MSB_SHADE_ILP 1       // chunks whose texel gathers are in flight together (2 spills at 64 registers, no gain)
 #endif
 #ifndef MSB_MIN_BLOCKS
 #define MSB_MIN_BLOCKS 4      // 256 threads x 4 blocks -> at most 64 registers per thread
