@@ -54,6 +54,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-raw', action='store_true', help='skip materialising the five Render tensors (obs heads only)')
     ap.add_argument('--gather', action='store_true', help='all-gather the observations to every rank each step (NCCL)')
+    ap.add_argument('--no-graph', action='store_true', help='e2e leg: plain launches instead of a CUDA-graph replay')
     ap.add_argument('--dry-run', action='store_true', help='build the scene and the CPU baseline only (no GPU)')
     return ap.parse_args()
 
@@ -186,7 +187,13 @@ class Ours:
         self.core.agents.angles.copy_(torch.as_tensor(ang))
         self.stepper = modules.FusedStep(self.core, subsample=cfg['subsample'], raw=raw)
         self.actions = self.stepper.actions
+        self.graphed = False
         self.fused = False                   # physics and render are separate launches: each stages the segments
+
+    def use_graph(self):
+        """The public API's CUDA-graph mode (modules.FusedStep(graph=True)): one graph replay per step on the host."""
+        self.stepper._capture()
+        self.graphed = True
 
     def step(self):
         self.stepper()                       # movement+physics | render+heads | agent-hit lighting: 3 launches, no host sync
@@ -316,6 +323,8 @@ def run_gpu(args, cfg, arm_cls, rank, world, local_rank):
     step_ms = float(per_step_ms.sum())
 
     # ---- e2e: host actions in pinned memory -> H2D -> step through the public API -> D2H of the step's result -----
+    if hasattr(arm, 'use_graph') and not args.no_graph:
+        arm.use_graph()
     result_host = torch.empty((N, A), dtype=torch.float32).pin_memory()
     for i in range(W):
         arm.actions.copy_(acts_host[i], non_blocking=True)
@@ -340,7 +349,7 @@ def run_gpu(args, cfg, arm_cls, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     step_ms, e2e_ms = t.tolist()
     total_bytes, mean_w = algorithmic_bytes(cfg, arrays, arm.fused, raw)
-    return dict(N=N, A=A, step_ms=step_ms, e2e_ms=e2e_ms, wall_s=wall, launches=launches, clocks=clocks,
+    return dict(arm=arm, N=N, A=A, step_ms=step_ms, e2e_ms=e2e_ms, wall_s=wall, launches=launches, clocks=clocks,
                 bytes_per_step=total_bytes, mean_walls=mean_w, arrays=arrays, pos=pos, ang=ang,
                 per_step_ms=per_step_ms)
 
@@ -353,6 +362,7 @@ def peaks():
 
 
 def main():
+    os.environ['NCCL_DEBUG'] = 'WARN'      # NCCL's version banner would otherwise land on stdout next to the JSON line
     args = parse()
     cfg = dict(WORKLOADS[args.workload])
     if args.res:
@@ -420,7 +430,7 @@ def main():
         'data': 'synthetic', 'config': base_cfg, 'impl': args.impl,
         'e2e': {'value': e2e, 'unit': 'agent-frames/s', 'h2d_bytes_per_step': out['N'] * out['A'] * 4,
                 'd2h_bytes_per_step': out['N'] * out['A'] * 4, 'ms_per_step': out['e2e_ms'] / K,
-                'what': 'pinned-host actions -> H2D -> step via the public API -> D2H of progress (the physics result) + stream sync, every step; observations stay on the device as in the reference'},
+                'what': 'pinned-host actions -> H2D -> step via the public API (modules.FusedStep' + (', CUDA-graph replay' if getattr(out.get('arm'), 'graphed', False) else '') + ') -> D2H of progress (the physics result) + stream sync, every step; observations stay on the device as in the reference'},
         'gpu_launches': out['launches'],
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                      'kernel': 'whole step = env_kernel<PHYSICS> (movement+physics) + env_kernel<RENDER> (draw+raycast+shade+heads) + dyn_kernel; env_kernel<RENDER> dominates (~65%)' if args.impl == 'ours' else 'whole step (physics + render + ~40 ATen launches)',

@@ -187,6 +187,7 @@ __device__ __forceinline__ float collide_line(float px, float py, float vx, floa
 
 // One env's physics tick. st_in holds the start-of-step state of all A agents; results go to global memory and to
 // st_out (for a following render stage).
+template <bool BOXES>
 __device__ __forceinline__ void physics_stage(const KArgs& k, const Smem& m, int n, int L) {
     const int A = k.s.n_agents, AF = A * k.s.n_model;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -207,25 +208,10 @@ __device__ __forceinline__ void physics_stage(const KArgs& k, const Smem& m, int
         const float px = me[ST_PX], py = me[ST_PY], mx = me[ST_VX], my = me[ST_VY];
         const float vx = fmul(mx, rF), vy = fmul(my, rF);
         const float vlen = sqrt_(ffma(vx, vx, fmul(vy, vy)));
-        const bool can_cull = vlen >= 1e-3f;          // for slower agents project()'s +1e-6 distorts distances: test all
+        // slow but moving agents: project()'s +1e-6 distorts distances -> test everything; exactly stationary ones can
+        // only trigger the end-point branch (:163-168: every other branch needs s > 0), which the same radius covers
+        const bool can_cull = vlen >= 1e-3f || (vx == 0.f && vy == 0.f);
         const float rho = 1.05f * vlen + 2.2f * r1 + 0.02f;
-        unsigned short* mine = m.cand + a * cap;
-        int nc = 0;
-        for (int base = AF; base < L; base += 32) {
-            const int l = base + lane;
-            bool keep = false;
-            if (l < L) {
-                const float4 s4 = m.seg[l];
-                const bool outside = (fminf(s4.x, s4.z) > px + rho) || (fmaxf(s4.x, s4.z) < px - rho) ||
-                                     (fminf(s4.y, s4.w) > py + rho) || (fmaxf(s4.y, s4.w) < py - rho);
-                keep = !(can_cull && outside);
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, keep);
-            if (keep) mine[nc + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)l;
-            nc += __popc(bal);
-        }
-        __syncwarp();
-        // pass 2: exact tests
         float x = 1.f;
         // other agents (:193-200): start-of-step state, no sequential resolution
         for (int d1 = lane; d1 < A; d1 += 32) {
@@ -234,10 +220,58 @@ __device__ __forceinline__ void physics_stage(const KArgs& k, const Smem& m, int
                 x = fminf(x, collide_agents(px, py, mx, my, o[ST_PX], o[ST_PY], o[ST_VX], o[ST_VY], rF, r2));
             }
         }
-        // static lines (:203-205); the agents' own model lines [0, AF) are skipped
         const float u = fadd(vlen, 1e-6f), uu = fmul(u, u);
-        for (int i = lane; i < nc; i += 32) {
-            x = fminf(x, collide_line(px, py, vx, vy, vlen, u, uu, m.seg[mine[i]], r1, r1sq));
+        if (BOXES) {
+            // static lines (:203-205) from the occluder table (sorted copy of the env's static segments + a bounding
+            // box per run): min over segments does not care about order. Lane b tests box b against the square the
+            // agent can reach; only overlapping runs are read (straight from HBM/L2: no staging in this kernel).
+            const int W = L - AF, run = k.s.occ_run, per = 32 / run;
+            const int nb = (W + run - 1) / run;
+            const float4* occ = reinterpret_cast<const float4*>(k.s.occ_lines) + __ldg(k.s.occ_starts + n);
+            const float4* boxes = reinterpret_cast<const float4*>(k.s.occ_boxes) + __ldg(k.s.box_starts + n);
+            const int slot = lane / run, within = lane - slot * run;
+            for (int b0 = 0; b0 < nb; b0 += 32) {
+                bool visit = false;
+                if (b0 + lane < nb) {
+                    const float4 bx = __ldg(boxes + b0 + lane);
+                    visit = !(can_cull && (bx.x > px + rho || bx.z < px - rho || bx.y > py + rho || bx.w < py - rho));
+                }
+                unsigned runs = __ballot_sync(0xffffffffu, visit);
+                while (runs) {
+                    const unsigned rest = runs & (runs - 1);
+                    const int n0 = __ffs(runs) - 1, n1 = rest ? __ffs(rest) - 1 : -1;
+                    const int nth = (per == 1 || slot == 0) ? n0 : ((slot == 1) ? n1 : -1);
+                    const int l = nth >= 0 ? run * (b0 + nth) + within : W;
+                    if (l < W) {
+                        const float4 s4 = __ldg(occ + l);
+                        const bool outside = (fminf(s4.x, s4.z) > px + rho) || (fmaxf(s4.x, s4.z) < px - rho) ||
+                                             (fminf(s4.y, s4.w) > py + rho) || (fmaxf(s4.y, s4.w) < py - rho);
+                        if (!(can_cull && outside)) x = fminf(x, collide_line(px, py, vx, vy, vlen, u, uu, s4, r1, r1sq));
+                    }
+                    for (int d = 0; d < per && runs; d++) runs &= runs - 1;
+                }
+            }
+        } else {
+            unsigned short* mine = m.cand + a * cap;
+            int nc = 0;
+            for (int base = AF; base < L; base += 32) {
+                const int l = base + lane;
+                bool keep = false;
+                if (l < L) {
+                    const float4 s4 = m.seg[l];
+                    const bool outside = (fminf(s4.x, s4.z) > px + rho) || (fmaxf(s4.x, s4.z) < px - rho) ||
+                                         (fminf(s4.y, s4.w) > py + rho) || (fmaxf(s4.y, s4.w) < py - rho);
+                    keep = !(can_cull && outside);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) mine[nc + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)l;
+                nc += __popc(bal);
+            }
+            __syncwarp();
+            // pass 2: exact tests on dense lanes; the agents' own model lines [0, AF) are never candidates
+            for (int i = lane; i < nc; i += 32) {
+                x = fminf(x, collide_line(px, py, vx, vy, vlen, u, uu, m.seg[mine[i]], r1, r1sq));
+            }
         }
         x = warp_min(x);
         if (lane == 0) m.xmin[a] = __float_as_int(x);
@@ -900,8 +934,10 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) env_kernel(const __grid_c
     const int64_t g0 = __ldg(k.s.line_starts + n);
     const int W = L - AF;
 
+    // physics on its own reads the few segments it needs from the occluder table and skips the staging altogether
+    const bool boxes = (MODE == MODE_PHYSICS) && k.s.occ_lines != nullptr;
     // stage this env's static segments: one bulk (TMA) copy, ragged-packed HBM -> shared memory
-    if (tid == 0) {
+    if (tid == 0 && !boxes) {
         mbar_init(m.bar, 1);
         if (W > 0) {
             mbar_expect_tx(m.bar, (uint32_t)W * 16u);
@@ -939,10 +975,11 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) env_kernel(const __grid_c
         }
     }
     __syncthreads();
-    if (W > 0) mbar_wait(m.bar, 0);
+    if (W > 0 && !boxes) mbar_wait(m.bar, 0);
 
     if (MODE & MODE_PHYSICS) {
-        physics_stage(k, m, n, L);
+        if (boxes) physics_stage<true>(k, m, n, L);
+        else physics_stage<false>(k, m, n, L);
         if (MODE & MODE_RENDER) __syncthreads();
     }
     if (MODE & MODE_RENDER) {

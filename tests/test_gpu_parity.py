@@ -262,6 +262,31 @@ def _same(a, b):
     return bool(((a == b) | (a != a) & (b != b)).all())
 
 
+def test_physics_with_and_without_the_occluder_table_agree():
+    """physics() reads its candidate segments through the box-culled occluder table when the scenery has one, else it
+    culls the staged segments itself; slow (|v| < 1e-3 per tick), stationary and fast agents must all agree bitwise."""
+    from megastep_b200 import cuda
+    gs, arrays, st = make('synthetic', 12, 4, seed=71)
+    st['velocity'][:3] = 0.                                   # exactly stationary
+    st['velocity'][3:6] *= 1e-4                                # slow but moving: the no-cull path
+    outs = []
+    for table in (True, False):
+        cuda.BUILD_OCCLUDERS = table
+        try:
+            c = common.to_device(arrays, st, 64, 90.)
+            ps = []
+            for _ in range(3):
+                ps.append(c.physics().progress.clone())
+                c.agents.velocity.add_(torch.as_tensor(np.random.RandomState(1).normal(size=st['velocity'].shape).astype(np.float32)).cuda())
+            outs.append((ps, common.read_state(c)))
+        finally:
+            cuda.BUILD_OCCLUDERS = True
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert torch.equal(a, b)
+    for k in outs[0][1]:
+        assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
+
+
 @pytest.mark.parametrize('sub', [1, 4])
 def test_second_pass_inline_and_overflow_paths_agree(sub):
     """Agent-hit rays are lit by dyn_kernel over the sorted occluder table (workspace), inline by the first pass (no
