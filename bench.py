@@ -88,6 +88,31 @@ def algorithmic_bytes(cfg, arrays, fused, raw=True):
     return b_env * N, W
 
 
+def render_kernel_bytes(cfg, arrays, raw=True):
+    """Algorithmic bytes of ONE launch of env_kernel<RENDER> (draw + raycast + shade + heads), the dominant kernel:
+    the render terms of SURVEY.md §8(d) — 16AF (draw) + [12A + 16L + 8] + 16AR (raycast) + (40 + 12)AR (shade) — plus
+    the fused heads, 16AR/sub + 12A. Texel gathers are counted per ray with no reuse, as §8(d) specifies."""
+    A, R, F = cfg['n_agents'], cfg['res'], 8
+    N = len(arrays['line_widths'])
+    L = float(arrays['line_widths'].mean())
+    b_env = 16 * A * F + (12 * A + 16 * L + 8) + 16 * A * R + 52 * A * R + 16 * A * R / cfg['subsample'] + 12 * A
+    if not raw:
+        b_env -= 28 * A * R
+    return b_env * N
+
+
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of env_kernel<RENDER>, from the committed ncu --set full
+    capture of this same command (profiles/r01_step_full_summary.json)."""
+    path = os.path.join(ROOT, 'profiles', 'r01_step_full_summary.json')
+    try:
+        recs = [r for r in json.load(open(path)) if 'env_kernel<2' in r['Kernel Name']]
+        mb = [float(r['dram__bytes_read.sum']) + float(r['dram__bytes_write.sum']) for r in recs]
+        return sum(mb) / len(mb) * 1e6, os.path.relpath(path, ROOT)
+    except (OSError, KeyError, ValueError, ZeroDivisionError):
+        return None, None
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------------------------
@@ -302,6 +327,8 @@ def run_gpu(args, cfg, arm_cls, rank, world, local_rank):
     barrier()
     if sampler:
         sampler.mark()
+    if hasattr(arm, 'cuda'):
+        arm.cuda.set_option('timing', 1)       # per-kernel CUDA events inside the library, on the launching stream
     barrier()
     launches0 = arm.launches()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
@@ -319,6 +346,11 @@ def run_gpu(args, cfg, arm_cls, rank, world, local_rank):
     barrier()
     wall = time.perf_counter() - t0
     launches = arm.launches() - launches0
+    kernel_ms = None
+    if hasattr(arm, 'cuda'):
+        kernel_ms = {kind: arm.cuda.get_option(f'time_ns_{kind}') / 1e6 / max(arm.cuda.get_option(f'time_count_{kind}'), 1)
+                     for kind in ('physics', 'render', 'dyn') if arm.cuda.get_option(f'time_count_{kind}') > 0}
+        arm.cuda.set_option('timing', 0)
     per_step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
     step_ms = float(per_step_ms.sum())
 
@@ -349,7 +381,7 @@ def run_gpu(args, cfg, arm_cls, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     step_ms, e2e_ms = t.tolist()
     total_bytes, mean_w = algorithmic_bytes(cfg, arrays, arm.fused, raw)
-    return dict(arm=arm, N=N, A=A, step_ms=step_ms, e2e_ms=e2e_ms, wall_s=wall, launches=launches, clocks=clocks,
+    return dict(arm=arm, kernel_ms=kernel_ms, N=N, A=A, step_ms=step_ms, e2e_ms=e2e_ms, wall_s=wall, launches=launches, clocks=clocks,
                 bytes_per_step=total_bytes, mean_walls=mean_w, arrays=arrays, pos=pos, ang=ang,
                 per_step_ms=per_step_ms)
 
@@ -423,7 +455,23 @@ def main():
     frames = out['N'] * out['A'] * eff_world
     value = frames * K / (out['step_ms'] * 1e-3)
     e2e = frames * K / (out['e2e_ms'] * 1e-3)
-    achieved = out['bytes_per_step'] / (out['step_ms'] / K * 1e-3) / 1e9
+    step_achieved = out['bytes_per_step'] / (out['step_ms'] / K * 1e-3) / 1e9
+    km = out.get('kernel_ms')
+    if km and 'render' in km:
+        # the dominant kernel, timed live with CUDA events on its stream (inside the library)
+        rb = render_kernel_bytes(cfg, out['arrays'], not args.no_raw)
+        achieved = rb / (km['render'] * 1e-3) / 1e9
+        traffic, traffic_src = profiled_traffic() if (args.workload == 'deathmatch' and not args.envs and not args.res and not args.no_raw) else (None, None)
+        roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                    'kernel': 'env_kernel<MODE_RENDER> (draw + raycast + shade + Depth/RGB/IMU heads)', 'kernel_ms': km['render'],
+                    'kernel_share_of_step': km['render'] / sum(km.values()), 'algorithmic_bytes_per_launch': rb,
+                    'traffic_source': traffic_src, 'all_kernels_ms': km, 'peak_source': peak_src,
+                    'whole_step': {'achieved': step_achieved, 'frac': step_achieved / peak, 'algorithmic_bytes_per_step': out['bytes_per_step']},
+                    'note': 'not HBM-bound yet: issue/latency-bound (ncu: issue-active 60%, DRAM throughput ~10% of peak); see DESIGN.md'}
+    else:
+        roofline = {'bound': 'hbm', 'achieved': step_achieved, 'peak': peak, 'unit': 'GB/s', 'frac': step_achieved / peak, 'traffic': None,
+                    'kernel': 'whole step (physics + render + ~40 ATen launches)', 'algorithmic_bytes_per_step': out['bytes_per_step'],
+                    'mean_walls_per_env': out['mean_walls'], 'peak_source': peak_src}
     line = {
         'metric': 'agent-frames/sec', 'value': value, 'unit': 'agent-frames/s', 'n_gpus': eff_world, 'steps': K, 'warmup': args.warmup,
         'ms_per_step': out['step_ms'] / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -432,9 +480,7 @@ def main():
                 'd2h_bytes_per_step': out['N'] * out['A'] * 4, 'ms_per_step': out['e2e_ms'] / K,
                 'what': 'pinned-host actions -> H2D -> step via the public API (modules.FusedStep' + (', CUDA-graph replay' if getattr(out.get('arm'), 'graphed', False) else '') + ') -> D2H of progress (the physics result) + stream sync, every step; observations stay on the device as in the reference'},
         'gpu_launches': out['launches'],
-        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
-                     'kernel': 'whole step = env_kernel<PHYSICS> (movement+physics) + env_kernel<RENDER> (draw+raycast+shade+heads) + dyn_kernel; env_kernel<RENDER> dominates (~65%)' if args.impl == 'ours' else 'whole step (physics + render + ~40 ATen launches)',
-                     'algorithmic_bytes_per_step': out['bytes_per_step'], 'mean_walls_per_env': out['mean_walls'], 'peak_source': peak_src},
+        'roofline': roofline,
         'clocks': out['clocks'],
         'step_ms_percentiles': {p: float(np.percentile(out['per_step_ms'], p)) for p in (5, 50, 95)},
     }

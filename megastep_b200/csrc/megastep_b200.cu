@@ -1208,6 +1208,45 @@ static long long g_opt_variant = 0;      // experiment switches (see KArgs::vari
 static long long g_opt_fused_step = 0;   // 1: msb_step runs physics and render in ONE kernel (slower: see DESIGN.md)
 static unsigned long long* g_stats = nullptr;   // device counters, enabled by option "stats"
 
+// Optional per-kernel timing with CUDA events on the launching stream (option "timing" = 1): bench.py uses it to
+// report each kernel's live share of the step. Kinds: 0 physics, 1 render, 2 shade, 3 dyn, 4 fused step, 5 bake.
+enum { TK_PHYSICS = 0, TK_RENDER = 1, TK_SHADE = 2, TK_DYN = 3, TK_STEP = 4, TK_BAKE = 5, TK_KINDS = 6 };
+static long long g_opt_timing = 0;
+static const int TIMING_RING = 4096;
+static cudaEvent_t g_ev[2 * TIMING_RING];
+static int g_ev_kind[TIMING_RING];
+static int g_ev_n = 0;
+static bool g_ev_ready = false;
+static double g_time_ms[TK_KINDS] = {0, 0, 0, 0, 0, 0};
+static long long g_time_n[TK_KINDS] = {0, 0, 0, 0, 0, 0};
+
+static void timing_flush() {
+    for (int i = 0; i < g_ev_n; i++) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(g_ev[2 * i + 1]) == cudaSuccess && cudaEventElapsedTime(&ms, g_ev[2 * i], g_ev[2 * i + 1]) == cudaSuccess) {
+            g_time_ms[g_ev_kind[i]] += ms;
+            g_time_n[g_ev_kind[i]]++;
+        }
+    }
+    g_ev_n = 0;
+}
+struct TimedLaunch {
+    int slot;
+    cudaStream_t st;
+    TimedLaunch(int kind, cudaStream_t st_) : slot(-1), st(st_) {
+        if (!g_opt_timing) return;
+        if (!g_ev_ready) {
+            for (int i = 0; i < 2 * TIMING_RING; i++) cudaEventCreate(&g_ev[i]);
+            g_ev_ready = true;
+        }
+        if (g_ev_n == TIMING_RING) timing_flush();
+        slot = g_ev_n++;
+        g_ev_kind[slot] = kind;
+        cudaEventRecord(g_ev[2 * slot], st);
+    }
+    ~TimedLaunch() { if (slot >= 0) cudaEventRecord(g_ev[2 * slot + 1], st); }
+};
+
 static int fail(const char* fmt, const char* detail) {
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return 1;
@@ -1242,6 +1281,12 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "debug_skip_dyn")) { g_opt_skip_dyn = value; return 0; }
     if (!strcmp(name, "fused_step")) { g_opt_fused_step = value; return 0; }
     if (!strcmp(name, "variant")) { g_opt_variant = value; return 0; }
+    if (!strcmp(name, "timing")) {
+        timing_flush();
+        g_opt_timing = value;
+        for (int i = 0; i < TK_KINDS; i++) { g_time_ms[i] = 0; g_time_n[i] = 0; }
+        return 0;
+    }
     if (!strcmp(name, "two_phase")) { g_opt_two_phase = value; return 0; }
     if (!strcmp(name, "split_render")) { g_opt_split = value; return 0; }
     if (!strcmp(name, "stats")) {
@@ -1260,6 +1305,19 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
 }
 
 extern "C" int64_t msb_get_option(const char* name) {
+    // "time_ns_<kind>" / "time_count_<kind>": accumulated device time of that kernel since "timing" was set
+    static const char* kinds[TK_KINDS] = {"physics", "render", "shade", "dyn", "step", "bake"};
+    if (!strncmp(name, "time_", 5)) {
+        timing_flush();
+        for (int i = 0; i < TK_KINDS; i++) {
+            char a[64], b[64];
+            snprintf(a, sizeof(a), "time_ns_%s", kinds[i]);
+            snprintf(b, sizeof(b), "time_count_%s", kinds[i]);
+            if (!strcmp(name, a)) return (int64_t)(g_time_ms[i] * 1e6);
+            if (!strcmp(name, b)) return (int64_t)g_time_n[i];
+        }
+        return -1;
+    }
     if (!strcmp(name, "nch")) return g_opt_nch;
     if (!strcmp(name, "threads")) return g_opt_threads;
     if (!strncmp(name, "stat", 4) && g_stats) {
@@ -1294,10 +1352,13 @@ static int launch_env(const KArgs& k, int nch, int threads, cudaStream_t st) {
             return 1;                                                                                            \
         fn<<<k.s.n_envs, threads, sm, st>>>(k);                                                                  \
     }
-    switch (nch) {
-        case 1: MSB_LAUNCH(1); break;
-        case 2: MSB_LAUNCH(2); break;
-        default: MSB_LAUNCH(4); break;
+    {
+        TimedLaunch timed(MODE == MODE_PHYSICS ? TK_PHYSICS : (MODE == MODE_RENDER ? TK_RENDER : TK_STEP), st);
+        switch (nch) {
+            case 1: MSB_LAUNCH(1); break;
+            case 2: MSB_LAUNCH(2); break;
+            default: MSB_LAUNCH(4); break;
+        }
     }
 #undef MSB_LAUNCH
     g_launches++;
@@ -1394,8 +1455,11 @@ static int launch_shade(const KArgs& k, cudaStream_t st) {
     if (!k.split_render) return 0;
     const int64_t warps = (int64_t)k.s.n_envs * k.s.n_agents * ((k.p.res + 31) / 32);
     const int64_t blocks = (warps + 7) / 8;
-    if (k.stats) shade_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(k);
-    else shade_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(k);
+    {
+        TimedLaunch timed(TK_SHADE, st);
+        if (k.stats) shade_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(k);
+        else shade_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(k);
+    }
     g_launches++;
     return check(cudaGetLastError(), "shade_kernel launch");
 }
@@ -1406,8 +1470,11 @@ static int launch_dyn(const KArgs& k, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = sms * 12;                      // 48 warps per SM, each striding over the queue
-    if (k.stats) dyn_kernel<true><<<grid, 128, 0, st>>>(k);
-    else dyn_kernel<false><<<grid, 128, 0, st>>>(k);
+    {
+        TimedLaunch timed(TK_DYN, st);
+        if (k.stats) dyn_kernel<true><<<grid, 128, 0, st>>>(k);
+        else dyn_kernel<false><<<grid, 128, 0, st>>>(k);
+    }
     g_launches++;
     return check(cudaGetLastError(), "dyn_kernel launch");
 }
