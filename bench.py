@@ -327,8 +327,6 @@ def run_gpu(args, cfg, arm_cls, rank, world, local_rank):
     barrier()
     if sampler:
         sampler.mark()
-    if hasattr(arm, 'cuda'):
-        arm.cuda.set_option('timing', 1)       # per-kernel CUDA events inside the library, on the launching stream
     barrier()
     launches0 = arm.launches()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
@@ -346,8 +344,16 @@ def run_gpu(args, cfg, arm_cls, rank, world, local_rank):
     barrier()
     wall = time.perf_counter() - t0
     launches = arm.launches() - launches0
+    # ---- per-kernel durations: a short extra loop with CUDA events around every kernel of the library (same L2
+    # flush between steps); kept out of the loop above so that the events' own launch gaps do not touch `value`
     kernel_ms = None
     if hasattr(arm, 'cuda'):
+        arm.cuda.set_option('timing', 1)
+        for i in range(min(K, 100)):
+            arm.actions.copy_(acts_dev[W + i])
+            flush.fill_(0.)
+            arm.step()
+        torch.cuda.synchronize()
         kernel_ms = {kind: arm.cuda.get_option(f'time_ns_{kind}') / 1e6 / max(arm.cuda.get_option(f'time_count_{kind}'), 1)
                      for kind in ('physics', 'render', 'dyn') if arm.cuda.get_option(f'time_count_{kind}') > 0}
         arm.cuda.set_option('timing', 0)
