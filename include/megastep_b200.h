@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MSB_ABI_VERSION 1
+#define MSB_ABI_VERSION 2
 
 /* Replaces initialize(agent_radius, res, fov, fps) — megastep/src/wrappers.cpp:53, kernels.cu:18-27. */
 typedef struct msb_params {
@@ -49,7 +49,7 @@ typedef struct msb_scenery {
     int32_t n_model;            /* F: lines in the agent model */
     int32_t max_lines;          /* max over envs of line_widths (shared-memory sizing) */
     int32_t max_lights;         /* max over envs of light_widths */
-    int32_t occ_run;            /* segments per occluder box: 16 or 32 (only read when occ_lines is set) */
+    int32_t occ_run;            /* segments per run of the spatial table: 16 (only read when occ_lines is set) */
     float* lines;               /* (sum L, 4) — render()/step() write the agents' lines in place */
     const int32_t* line_widths; /* (N) */
     const int32_t* line_starts; /* (N) exclusive prefix sum of line_widths */
@@ -63,13 +63,16 @@ typedef struct msb_scenery {
     const float* model;         /* (F, 4) */
     int64_t n_lines;            /* sum L */
     int64_t n_texels;           /* sum T */
-    /* Optional occluder table (all NULL to disable): a spatially sorted copy of every env's STATIC segments, used
-     * only for shadow tests (whose any-of-the-lines answer does not depend on order). Built once per scenery. */
-    const float* occ_lines;     /* (sum W, 4) static segments, sorted by Morton code of their midpoint within each env */
-    const int32_t* occ_starts;  /* (N) start of env n's rows in occ_lines; it has line_widths[n] - A*F rows */
-    const float* occ_boxes;     /* (sum ceil(W/occ_run), 4) {xmin, ymin, xmax, ymax} of each run of occ_run sorted segments */
+    /* Optional spatial table (all NULL to disable): a copy of every env's STATIC segments sorted along a Morton
+     * curve, in runs of occ_run = 16 with one bounding box per run; each env's rows are padded to a whole number of
+     * runs (so every env's block is 16-byte aligned for bulk copies). Built once per scenery. Used to skip work only:
+     * shadow tests and collisions are order-free, and render() restores the reference's line-order rule exactly. */
+    const float* occ_lines;     /* (16 * sum nb, 4) sorted static segments; nb = ceil((line_widths[n] - A*F) / 16) per env */
+    const int32_t* occ_starts;  /* (N) start of env n's rows in occ_lines (= 16 * box_starts[n]) */
+    const float* occ_boxes;     /* (sum nb, 4) {xmin, ymin, xmax, ymax} of each run */
     const int32_t* box_starts;  /* (N) start of env n's rows in occ_boxes */
     const float* occ_meta;      /* (N, 2) per env: longest static segment extent (max |dx|,|dy|), extent of the env */
+    const uint16_t* occ_ids;    /* (16 * sum nb) each sorted row's line index within its env (A*F <= id < L); 0xffff = padding */
 } msb_scenery;
 
 /* The Agents struct of megastep/src/common.h:162-177. Updated in place by msb_physics. */

@@ -47,6 +47,7 @@ struct KArgs {
     int32_t has_mv;
     int32_t ray_blocks;     // RB: warps per agent in the render stage
     int32_t seg_cap;        // float4 slots reserved for segments in shared memory (>= max_lines)
+    int32_t wcap;           // view_kernel: slots for the env's padded run table (multiple of 16)
     float inv_fps;          // IEEE 1/fps (ATen's tensor/scalar == tensor*(1/scalar), kernels.cu:224,226)
     float mv_keep, mv_dv, mv_dw;   // 1-decay, accel/fps, ang_accel/fps evaluated in double like the Python does
     float inv_max_depth, inv_speed, inv_ang, inv_sub;   // reciprocals ATen would multiply by
@@ -1059,6 +1060,489 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ KArg
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// view_kernel: render over the env's spatial table (Morton-sorted static segments in runs of 16 with bounding boxes).
+//
+// One CTA per env, one warp per (agent, block of 32*NCH rays). Thread 0 stages the env's table — sorted segments,
+// their line ids and the run boxes — with three 1-D bulk (TMA) copies on one mbarrier. Each warp then
+//   1. puts one run box per lane, finds which of its 32-ray chunks each box can touch (half-plane tests against the
+//      chunk boundaries in camera space) and a lower bound of its depth;
+//   2. repeatedly takes the two NEAREST boxes that can still matter (REDUX min over a depth|lane key), bins their 32
+//      segments (lane = segment: exact per-(agent, segment) terms of intersect(), chunk mask, depth bound), and runs
+//      the reference's ray test, lane = ray, on the candidates a ballot yields per chunk. Front to back, boxes whose
+//      depth bound lies behind the current hit of every ray they could touch are never visited: walls of the
+//      agent's own room hide the rest of the floorplan (measured on the benchmark scenes: 4.5 of 18 runs visited);
+//   3. the agents' model lines, last (mostly hidden by then).
+// Exactness. The reference keeps, per ray, the hit with s < best - 1e-4 scanning lines in index order
+// (kernels.cu:369-376): order-dependent. Here lines arrive in any order and a ray keeps its true minimum, flagging
+// itself when two valid hits lie within AMB_EPS of each other. For an unflagged ray every other hit is more than
+// 3e-4 behind the minimum, so the reference accepts the minimum when it reaches it and nothing after: same winner.
+// A flagged ray (a ray through a wall corner: ~0.03% of rays) is replayed in line order by the whole warp, with the
+// reference's rule. Culls only drop segments whose every hit is more than CULL_EPS (> AMB_EPS) behind the current
+// minimum of every ray they could touch, so they change neither the minimum nor the flags' meaning.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr float AMB_EPS = 3.e-4f;
+constexpr float CULL_EPS = 4.e-4f;
+enum { VRUN = 16 };
+
+struct VSmem {
+    float4* seg;            // [AF + wcap]: [0, AF) the agents' model lines at their current poses; then the sorted static rows
+    float4* boxes;          // [wcap / 16]
+    unsigned short* ids;    // [wcap]
+    float4* scr;            // [nwarps][128] per warp: 64 candidate records while casting, then the chunk results
+    float* st_in;           // [A][8]
+    float* st_out;          // [A][8]
+    int* xmin;              // [A]
+    uint64_t* bar;
+};
+
+__device__ __forceinline__ VSmem vcarve(unsigned char* base, int wcap, int nwarps, int A, int AF) {
+    VSmem m;
+    m.seg = reinterpret_cast<float4*>(base);
+    m.boxes = m.seg + AF + wcap;
+    m.scr = m.boxes + wcap / VRUN;
+    m.ids = reinterpret_cast<unsigned short*>(m.scr + nwarps * 128);       // wcap * 2 bytes: a multiple of 32
+    m.st_in = reinterpret_cast<float*>(m.ids + wcap);
+    m.st_out = m.st_in + A * ST_STRIDE;
+    m.xmin = reinterpret_cast<int*>(m.st_out + A * ST_STRIDE);
+    uintptr_t p = reinterpret_cast<uintptr_t>(m.xmin + A);
+    p = (p + 15) & ~uintptr_t(15);
+    m.bar = reinterpret_cast<uint64_t*>(p);
+    return m;
+}
+
+static size_t vsmem_bytes(int wcap, int nwarps, int A, int AF) {
+    size_t b = (size_t)(AF + wcap) * 16 + (size_t)(wcap / VRUN) * 16 + (size_t)nwarps * 128 * 16 + (size_t)wcap * 2 +
+               (size_t)A * ST_STRIDE * 4 * 2 + (size_t)A * 4;
+    b = (b + 15) & ~size_t(15);
+    return b + 16;
+}
+
+template <int NCH>
+struct Rays {
+    float rux[NCH], ruy[NCH], nearp[NCH], best[NCH], loc[NCH], cmax[NCH];
+    int tag[NCH];           // winner: (row in VSmem::seg) << 16 | line id; -1 = no hit
+    unsigned amb;           // bit c: this lane's ray of chunk c saw two hits within AMB_EPS
+};
+
+struct View { float px, py, cs, sn, xclip, B0, dB; };   // chunk c spans slopes (B0 - (c+1) dB, B0 - c dB) in camera space
+
+// One batch of up to 32 segments against this warp's rays. Lane = segment while binning, lane = ray while testing.
+template <int NCH, bool STATS>
+__device__ __forceinline__ void cast_batch(const View& v, Rays<NCH>& ry, bool valid, float4 s4, unsigned tag,
+                                           float4* __restrict__ scr, int lane, unsigned& tests) {
+    // exact, ray-independent terms of intersect() (kernels.cu:83-85)
+    const float Vx = fsub(s4.z, s4.x), Vy = fsub(s4.w, s4.y);
+    const float PQx = fsub(s4.x, v.px), PQy = fsub(s4.y, v.py);
+    scr[lane] = make_float4(Vx, Vy, PQx, PQy);
+    *reinterpret_cast<float2*>(scr + 32 + lane) = make_float2(cross2(Vy, PQx, Vx, PQy), __uint_as_float(tag));
+    // conservative summary in camera space (x' forward = the hit parameter s, y' left): culling only
+    const float bxr = s4.z - v.px, byr = s4.w - v.py;
+    const float xa = PQx * v.cs + PQy * v.sn, ya = PQy * v.cs - PQx * v.sn;
+    const float xb = bxr * v.cs + byr * v.sn, yb = byr * v.cs - bxr * v.sn;
+    unsigned cm = 0;
+    if (valid && !((xa < v.xclip) && (xb < v.xclip))) {
+        float ea = ya - xa * v.B0, eb = yb - xb * v.B0;             // > 0: left of the chunk's left boundary
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const float Bn = v.B0 - (float)(c + 1) * v.dB;
+            const float ea1 = ya - xa * Bn, eb1 = yb - xb * Bn;     // < 0: right of the chunk's right boundary
+            const bool outside = ((ea > 0.f) && (eb > 0.f)) || ((ea1 < 0.f) && (eb1 < 0.f));
+            if (!outside) cm |= 1u << c;                            // (NaNs compare false: the exact test decides)
+            ea = ea1; eb = eb1;
+        }
+    }
+    const float smin = fminf(xa, xb) - 1e-3f - 1e-4f * fmaxf(fabsf(xa), fabsf(xb));
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        unsigned mask = __ballot_sync(0xffffffffu, ((cm >> c) & 1u) && !(smin > ry.cmax[c] + CULL_EPS));
+        if (mask) {
+            do {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const float4 q = scr[j];
+                const float2 w = *reinterpret_cast<const float2*>(scr + 32 + j);
+                // raycast_kernel's test (kernels.cu:353-376), the reference's arithmetic op for op
+                const float UxV = cross2(ry.rux[c], q.y, ry.ruy[c], q.x);
+                const float rc = rcp(UxV);
+                const float hs_ = fmul(w.x, rc);
+                const float ht_ = fmul(cross2(ry.ruy[c], q.z, ry.rux[c], q.w), rc);
+                const bool hit = !(fabsf(UxV) < PARALLEL_EPS) && (ht_ >= 0.f) && (ht_ <= 1.f) && (ry.nearp[c] < hs_);
+                if (hit) {
+                    if (fabsf(hs_ - ry.best[c]) <= AMB_EPS) ry.amb |= 1u << c;
+                    if (hs_ < ry.best[c]) { ry.best[c] = hs_; ry.loc[c] = ht_; ry.tag[c] = (int)__float_as_uint(w.y); }
+                }
+                if (STATS) tests++;
+            } while (mask);
+            // the chunk's farthest current hit; best >= 0 (or +inf), so its bit pattern orders like an unsigned integer
+            ry.cmax[c] = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ry.best[c])));
+        }
+    }
+    __syncwarp();
+}
+
+// A flagged ray, replayed by the whole warp exactly as the reference scans it: lines in index order, lane = line,
+// valid hits taken in ascending order with the s < best - 1e-4 rule (kernels.cu:353-376). Returns {s, t, line, dot}
+// of the winner in every lane.
+__device__ __noinline__ float4 replay_ray(const KArgs& k, const float4* __restrict__ dynseg, int64_t g0, int L, int AF,
+                                             float px, float py, float ux, float uy, float nearp, float rlen, int lane) {
+    const float4* __restrict__ lines = reinterpret_cast<const float4*>(k.s.lines) + g0;
+    float best = CUDART_INF_F, bestm = CUDART_INF_F, loc = __int_as_float(0x7fffffff), dotv = __int_as_float(0x7fffffff);
+    int idx = -1;
+    for (int base = 0; base < L; base += 32) {
+        const int l = base + lane;
+        float hs_ = 0.f, ht_ = 0.f, Vx = 0.f, Vy = 0.f;
+        bool hit = false;
+        if (l < L) {
+            const float4 s4 = l < AF ? dynseg[l] : __ldg(lines + l);
+            Vx = fsub(s4.z, s4.x); Vy = fsub(s4.w, s4.y);
+            const float PQx = fsub(s4.x, px), PQy = fsub(s4.y, py);
+            const float UxV = cross2(ux, Vy, uy, Vx);
+            const float rc = rcp(UxV);
+            hs_ = fmul(cross2(Vy, PQx, Vx, PQy), rc);
+            ht_ = fmul(cross2(uy, PQx, ux, PQy), rc);
+            hit = !(fabsf(UxV) < PARALLEL_EPS) && (ht_ >= 0.f) && (ht_ <= 1.f) && (nearp < hs_);
+        }
+        unsigned hm = __ballot_sync(0xffffffffu, hit);
+        while (hm) {
+            const int i = __ffs(hm) - 1;
+            hm &= hm - 1;
+            const float si = __shfl_sync(0xffffffffu, hs_, i), ti = __shfl_sync(0xffffffffu, ht_, i);
+            const float vxi = __shfl_sync(0xffffffffu, Vx, i), vyi = __shfl_sync(0xffffffffu, Vy, i);
+            if (si < bestm) {
+                best = si; bestm = fadd(si, -1.e-4f); loc = ti; idx = base + i;
+                dotv = fmul(dot2(ux, vxi, uy, vyi), rcp(ffma(rlen, sqrt_(ffma(vxi, vxi, fmul(vyi, vyi))), 1.e-6f)));
+            }
+        }
+    }
+    return make_float4(best, loc, __int_as_float(idx), dotv);
+}
+
+// Dynamic light for the agent-hit rays of one chunk when they cannot be queued for dyn_kernel (no workspace, or the
+// queue is full): the warp resolves them one ray at a time. Cold path, kept out of line.
+__device__ __noinline__ float dyn_inline(const float4* seg, int L, int AF, int nlights, const float* lt, unsigned dm,
+                                         float Cx, float Cy, float intensity) {
+    const int lane = threadIdx.x & 31;
+    LaneLight ll;
+    ll.x = ll.y = ll.i = 0.f;
+    ll.occ = -1;
+    if (lane < nlights) { ll.x = __ldg(lt + 3 * lane); ll.y = __ldg(lt + 3 * lane + 1); ll.i = __ldg(lt + 3 * lane + 2); }
+    unsigned iters = 0;
+    while (dm) {
+        const int j = __ffs(dm) - 1;
+        dm &= dm - 1;
+        const float cx = __shfl_sync(0xffffffffu, Cx, j), cy = __shfl_sync(0xffffffffu, Cy, j);
+        const float v = light_intensity_cached<false>(seg, L, AF, nlights, lt, cx, cy, lane, ll, iters);
+        if (lane == j) intensity = v;
+    }
+    return intensity;
+}
+
+// shader_kernel (kernels.cu:407-450) + the Depth / RGB heads for one 32-ray chunk, lane = ray.
+// hit = {line index (int bits), location, dot, distance}. seg = VSmem::seg (rows [0, AF) are the agents' lines).
+__device__ __forceinline__ void shade_chunk(const KArgs& k, const float4* __restrict__ seg, int n, int64_t g0, int a, int AF,
+                                            int Lrows, int r, int lane, float4 hitrec) {
+    const int A = k.s.n_agents, R = k.p.res;
+    const int sub_ = k.has_obs ? k.obs.subsample : 1;
+    const bool live = r < R;
+    const int l0 = __float_as_int(hitrec.x);
+    const float locv = hitrec.y, dotv = hitrec.z, dist = hitrec.w;
+    const bool hitany = live && (l0 >= 0);
+    const Texels t = shade_fetch(k, k.s.tex_widths + g0, reinterpret_cast<const long long*>(k.s.tex_starts) + g0, AF, hitany, l0, locv);
+    float intensity = 0.f, Cx = 0.f, Cy = 0.f;
+    float kk0 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    const bool isdyn = hitany && (l0 < AF);
+    if (hitany) {
+        if (!isdyn) {
+            intensity = ffma(t.lw, t.bl, fmul(t.rw, t.br));                                           // :438
+        } else {
+            const float om = fsub(1.f, locv);                                                         // :435
+            const float4 s4 = seg[l0];
+            Cx = ffma(s4.x, om, fmul(locv, s4.z));
+            Cy = ffma(s4.y, om, fmul(locv, s4.w));
+        }
+        kk0 = ffma(-dotv, dotv, 1.f);                                                                 // :442-445
+        b0 = ffma(t.lw, t.tl0, fmul(t.rw, t.tr0));
+        b1 = ffma(t.lw, t.tl1, fmul(t.rw, t.tr1));
+        b2 = ffma(t.lw, t.tl2, fmul(t.rw, t.tr2));
+    }
+    // rays that hit an agent's model need the light at the hit point (:434-436): queue the pixel group for dyn_kernel
+    unsigned dm = __ballot_sync(0xffffffffu, isdyn);
+    if (k.debug_skip_dyn) dm = 0;
+    const int gl = lane & ~(sub_ - 1);                                    // first lane of my pixel group
+    bool queued = false, deferred = false;
+    if (dm) {
+        const unsigned subm = sub_ == 32 ? 0xffffffffu : ((1u << sub_) - 1u);
+        const unsigned gmask = (dm >> gl) & subm;                         // my group's agent-hit pixels
+        if (k.dyn_entries) {
+            const unsigned leaders = __ballot_sync(0xffffffffu, gmask != 0 && lane == gl);
+            const int cnt = __popc(leaders);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(k.dyn_ctrl, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            queued = base + cnt <= k.dyn_cap;
+            // which agent the group's first agent-hit pixel landed on: keys the persistent occluder cache
+            const int tgt = __shfl_sync(0xffffffffu, l0, gl + (gmask ? __ffs(gmask) - 1 : 0)) / k.s.n_model;
+            if (gmask) {
+                const int slot = base + __popc(leaders & ((1u << gl) - 1u));
+                if (slot < k.dyn_cap) {
+                    unsigned char* e = k.dyn_entries + (size_t)slot * k.dyn_stride;
+                    if (lane == gl) *reinterpret_cast<int4*>(e) = make_int4(n, a * R + (r - lane + gl), queued ? (int)gmask : 0, sub_ | (tgt << 8));
+                    if (queued) {
+                        float4* rec = reinterpret_cast<float4*>(e + 16) + 2 * (lane - gl);
+                        rec[0] = make_float4(b0, b1, b2, kk0);
+                        rec[1] = make_float4(Cx, Cy, intensity, isdyn ? 1.f : 0.f);
+                    }
+                }
+            }
+        }
+        if (!queued) intensity = dyn_inline(seg, Lrows, AF, __ldg(k.s.light_widths + n), k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n), dm, Cx, Cy, intensity);
+        deferred = queued && gmask != 0;                                  // dyn_kernel writes this group's screen / rgb
+    }
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if (hitany) {
+        const float kk = fmul(kk0, intensity);
+        s0 = fmul(kk, b0);
+        s1 = fmul(kk, b1);
+        s2 = fmul(kk, b2);
+    }
+    const int64_t ag = (int64_t)n * A + a;
+    if (live) {
+        const int64_t o = ag * R + r;
+        if (k.out.indices) k.out.indices[o] = l0;
+        if (k.out.locations) k.out.locations[o] = locv;
+        if (k.out.dots) k.out.dots[o] = dotv;
+        if (k.out.distances) k.out.distances[o] = dist;
+        if (k.out.screen && !(queued && isdyn)) { float* sc = k.out.screen + 3 * o; sc[0] = s0; sc[1] = s1; sc[2] = s2; }
+    }
+    // fused observation heads: Depth (modules.py:181-183) and RGB (:222-223), mean over `subsample` pixels
+    if (k.has_obs) {
+        float d = 0.f;
+        if (live) {
+            const float z = __fmul_rn(__fsub_rn(dist, k.p.agent_radius), k.inv_max_depth);
+            d = __fsub_rn(1.f, fminf(fmaxf(z, 0.f), 1.f));
+        }
+        float v0 = s0, v1 = s1, v2 = s2, v3 = d;
+        for (int o = 1; o < sub_; o <<= 1) {
+            v0 = __fadd_rn(v0, __shfl_xor_sync(0xffffffffu, v0, o));
+            v1 = __fadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+            v2 = __fadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
+            v3 = __fadd_rn(v3, __shfl_xor_sync(0xffffffffu, v3, o));
+        }
+        if (live && lane == gl) {
+            const int Ro = R / sub_, ro = r / sub_;
+            const float inv = k.inv_sub;
+            if (k.obs.rgb && !deferred) {
+                float* q = k.obs.rgb + ag * 3 * Ro + ro;
+                q[0] = __fmul_rn(v0, inv); q[Ro] = __fmul_rn(v1, inv); q[2 * Ro] = __fmul_rn(v2, inv);
+            }
+            if (k.obs.depth) k.obs.depth[ag * Ro + ro] = __fmul_rn(v3, inv);
+        }
+    }
+}
+
+template <int NCH, bool STATS>
+__device__ __forceinline__ void view_agent(const KArgs& k, const VSmem& m, int n, int64_t g0, int L, int W, int nb, int a,
+                                           int rb, float4* __restrict__ scr, int lane) {
+    const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
+    const float* st = m.st_out + a * ST_STRIDE;
+    View v;
+    v.px = st[ST_PX]; v.py = st[ST_PY];
+    sincos_deg(st[ST_ANG], v.sn, v.cs);
+    v.xclip = k.bin_xclip;
+    const float Rf = (float)R;
+    const float rcpR = rcp(Rf);
+    const int r0 = rb * (32 * NCH);
+    v.B0 = (Rf - (float)(2 * r0)) * k.p.half_screen * rcpR;          // half a ray spacing left of ray r0
+    v.dB = 64.f * k.p.half_screen * rcpR;
+
+    // ---- rays (kernels.cu:341-344, ray_y :234-236). Lane = ray within each of this warp's NCH 32-ray chunks.
+    Rays<NCH> ry;
+    ry.amb = 0;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        const int r = r0 + 32 * c + lane;
+        const float y = fmul(fmul(fadd(fsub(Rf, (float)(unsigned)(2 * r)), -1.f), k.p.half_screen), rcpR);
+        ry.rux[c] = ffma(v.sn, -y, v.cs);
+        ry.ruy[c] = ffma(v.cs, y, v.sn);
+        const float rlen = sqrt_(ffma(ry.rux[c], ry.rux[c], fmul(ry.ruy[c], ry.ruy[c])));
+        ry.nearp[c] = fmul(rcp(rlen), k.p.agent_radius);
+        ry.best[c] = r < R ? CUDART_INF_F : 0.f;                    // rays beyond R never take a hit
+        ry.cmax[c] = (r0 + 32 * c) < R ? CUDART_INF_F : 0.f;
+        ry.loc[c] = __int_as_float(0x7fffffff);
+        ry.tag[c] = -1;
+    }
+    unsigned tests = 0, groups = 0;
+
+    // ---- static lines: run boxes, nearest first; then the agents' model lines (kernels.cu:297-318 drew them), after
+    // the walls that hide most of them. One loop, so that the batch code exists once.
+    int bb = 0, dyn_next = 0;                       // first box of the current round of 32; next model line
+    bool fresh = true;                              // the round's boxes have not been summarised yet
+    unsigned key = 0xffffffffu, bcm = 0;
+    float bsmin = 0.f;
+    while (true) {
+        bool valid;
+        int row;                                    // row of VSmem::seg this lane bins
+        if (bb < nb) {
+            if (fresh) {
+                fresh = false;
+                key = 0xffffffffu; bcm = 0; bsmin = 0.f;
+                if (bb + lane < nb) {
+                    const float4 bx = m.boxes[bb + lane];
+                    const float dx0 = bx.x - v.px, dx1 = bx.z - v.px, dy0 = bx.y - v.py, dy1 = bx.w - v.py;
+                    const float cx0 = dx0 * v.cs, cx1 = dx1 * v.cs, sx0 = dx0 * v.sn, sx1 = dx1 * v.sn;
+                    const float cy0 = dy0 * v.cs, cy1 = dy1 * v.cs, sy0 = dy0 * v.sn, sy1 = dy1 * v.sn;
+                    // corners (x0,y0) (x1,y0) (x1,y1) (x0,y1) in camera space
+                    const float X0 = cx0 + sy0, X1 = cx1 + sy0, X2 = cx1 + sy1, X3 = cx0 + sy1;
+                    const float Y0 = cy0 - sx0, Y1 = cy0 - sx1, Y2 = cy1 - sx1, Y3 = cy1 - sx0;
+                    const float xmax = fmaxf(fmaxf(X0, X1), fmaxf(X2, X3)), xmin = fminf(fminf(X0, X1), fminf(X2, X3));
+                    if (!(xmax < v.xclip)) {
+                        float B = v.B0;
+                        bool left = (Y0 - X0 * B > 0.f) && (Y1 - X1 * B > 0.f) && (Y2 - X2 * B > 0.f) && (Y3 - X3 * B > 0.f);
+#pragma unroll
+                        for (int c = 0; c < NCH; c++) {
+                            B = v.B0 - (float)(c + 1) * v.dB;
+                            const float e0 = Y0 - X0 * B, e1 = Y1 - X1 * B, e2 = Y2 - X2 * B, e3 = Y3 - X3 * B;
+                            const bool right = (e0 < 0.f) && (e1 < 0.f) && (e2 < 0.f) && (e3 < 0.f);
+                            if (!left && !right) bcm |= 1u << c;
+                            left = (e0 > 0.f) && (e1 > 0.f) && (e2 > 0.f) && (e3 > 0.f);
+                        }
+                        bsmin = fmaxf(xmin - 1e-3f - 1e-4f * fmaxf(fabsf(xmin), fabsf(xmax)), 0.f);
+                        if (bcm) key = (__float_as_uint(bsmin) & ~31u) | (unsigned)lane;
+                    }
+                }
+            }
+            // a box is still worth visiting while some chunk it touches has a ray whose hit is not nearer than the box
+            bool alive = false;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) alive = alive || (((bcm >> c) & 1u) && !(bsmin > ry.cmax[c] + CULL_EPS));
+            alive = alive && key != 0xffffffffu;
+            const unsigned k0 = __reduce_min_sync(0xffffffffu, alive ? key : 0xffffffffu);
+            if (k0 == 0xffffffffu) { bb += 32; fresh = true; continue; }
+            const int j0 = (int)(k0 & 31u);
+            const unsigned k1 = __reduce_min_sync(0xffffffffu, (alive && lane != j0) ? key : 0xffffffffu);
+            const int j1 = k1 == 0xffffffffu ? -1 : (int)(k1 & 31u);
+            if (lane == j0 || lane == j1) key = 0xffffffffu;
+            const int run = lane < VRUN ? j0 : j1;
+            const int srow = (bb + run) * VRUN + (lane & (VRUN - 1));
+            valid = run >= 0 && srow < W;
+            row = AF + (valid ? srow : 0);
+        } else {
+            if (dyn_next >= AF) break;
+            valid = dyn_next + lane < AF;
+            row = valid ? dyn_next + lane : 0;
+            dyn_next += 32;
+        }
+        const unsigned id = row < AF ? (unsigned)row : (unsigned)m.ids[row - AF];
+        cast_batch<NCH, STATS>(v, ry, valid, m.seg[row], ((unsigned)row << 16) | id, scr, lane, tests);
+        if (STATS) groups++;
+    }
+
+    // ---- per chunk: the winner's ray . line cosine (kernels.cu:362-364, winner only), flagged rays replayed in line
+    // order, results parked in shared memory for the (rolled) shading loop
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        const int r = r0 + 32 * c + lane;
+        const float rlen = sqrt_(ffma(ry.rux[c], ry.rux[c], fmul(ry.ruy[c], ry.ruy[c])));
+        float dotv = __int_as_float(0x7fffffff);
+        int l0 = -1;
+        if (ry.tag[c] >= 0) {
+            const float4 s4 = m.seg[ry.tag[c] >> 16];
+            const float Vx = fsub(s4.z, s4.x), Vy = fsub(s4.w, s4.y);
+            dotv = fmul(dot2(ry.rux[c], Vx, ry.ruy[c], Vy), rcp(ffma(rlen, sqrt_(ffma(Vx, Vx, fmul(Vy, Vy))), 1.e-6f)));
+            l0 = ry.tag[c] & 0xffff;
+        }
+        float best = ry.best[c], loc = ry.loc[c];
+        unsigned am = __ballot_sync(0xffffffffu, ((ry.amb >> c) & 1u) && r < R);
+        while (am) {
+            const int j = __ffs(am) - 1;
+            am &= am - 1;
+            const float ux = __shfl_sync(0xffffffffu, ry.rux[c], j), uy = __shfl_sync(0xffffffffu, ry.ruy[c], j);
+            const float np_ = __shfl_sync(0xffffffffu, ry.nearp[c], j), rl = __shfl_sync(0xffffffffu, rlen, j);
+            const float4 w = replay_ray(k, m.seg, g0, L, AF, v.px, v.py, ux, uy, np_, rl, lane);
+            if (lane == j) { best = w.x; loc = w.y; l0 = __float_as_int(w.z); dotv = w.w; }
+            if (STATS) groups++;
+        }
+        scr[32 * c + lane] = make_float4(__int_as_float(l0), loc, dotv, fmul(rlen, best));
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int c = 0; c < NCH; c++) {
+        shade_chunk(k, m.seg, n, g0, a, AF, AF + W, r0 + 32 * c + lane, lane, scr[32 * c + lane]);
+    }
+    __syncwarp();
+    if (STATS && k.stats && lane == 0) {
+        atomicAdd(k.stats + STAT_TESTS, (unsigned long long)tests);
+        atomicAdd(k.stats + STAT_GROUPS, (unsigned long long)groups);
+    }
+}
+
+template <int NCH, bool STATS>
+__global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_constant__ KArgs k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = blockIdx.x;
+    const int A = k.s.n_agents, AF = A * k.s.n_model;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const VSmem m = vcarve(smem_raw, k.wcap, nwarps, A, AF);
+    const int L = __ldg(k.s.line_widths + n);
+    const int64_t g0 = __ldg(k.s.line_starts + n);
+    const int W = L - AF;
+    const int nb = (W + VRUN - 1) / VRUN;
+    // stage this env's table: three bulk (TMA) copies, ragged-packed HBM -> shared memory, one mbarrier
+    if (tid == 0) {
+        mbar_init(m.bar, 1);
+        if (nb > 0) {
+            const int64_t b0 = __ldg(k.s.box_starts + n);
+            mbar_expect_tx(m.bar, (uint32_t)nb * (VRUN * 18u + 16u));
+            bulk_g2s(m.seg + AF, k.s.occ_lines + 4 * VRUN * b0, (uint32_t)nb * VRUN * 16u, m.bar);
+            bulk_g2s(m.ids, k.s.occ_ids + VRUN * b0, (uint32_t)nb * VRUN * 2u, m.bar);
+            bulk_g2s(m.boxes, k.s.occ_boxes + 4 * b0, (uint32_t)nb * 16u, m.bar);
+        }
+    }
+    for (int a = tid; a < A; a += blockDim.x) {
+        const int64_t i = (int64_t)n * A + a;
+        const float2 pos = reinterpret_cast<const float2*>(k.a.positions)[i];
+        const float2 vel = reinterpret_cast<const float2*>(k.a.velocity)[i];
+        float* st = m.st_out + a * ST_STRIDE;
+        st[ST_ANG] = k.a.angles[i]; st[ST_PX] = pos.x; st[ST_PY] = pos.y;
+        st[ST_AV] = k.a.angvelocity[i]; st[ST_VX] = vel.x; st[ST_VY] = vel.y;
+    }
+    __syncthreads();
+    // draw_kernel (kernels.cu:297-318): the agents' model lines, at their current poses, into shared and global memory
+    {
+        const int F = k.s.n_model;
+        for (int t = tid; t < AF * 2; t += blockDim.x) {
+            const int e = t & 1, mm = (t >> 1) % F, a = (t >> 1) / F;
+            const float* st = m.st_out + a * ST_STRIDE;
+            float s, c;
+            sincos_deg(st[ST_ANG], s, c);
+            const float mx = __ldg(k.s.model + 4 * mm + 2 * e), my = __ldg(k.s.model + 4 * mm + 2 * e + 1);
+            const float2 pt = make_float2(fadd(st[ST_PX], cross2(c, mx, s, my)), fadd(st[ST_PY], dot2(s, mx, c, my)));
+            reinterpret_cast<float2*>(m.seg)[2 * (a * F + mm) + e] = pt;
+            reinterpret_cast<float2*>(k.s.lines)[2 * (g0 + a * F + mm) + e] = pt;
+        }
+    }
+    __syncthreads();
+    if (nb > 0) mbar_wait(m.bar, 0);
+    const int RB = k.ray_blocks;
+    for (int w = warp; w < A * RB; w += nwarps) {
+        view_agent<NCH, STATS>(k, m, n, g0, L, W, nb, w / RB, w % RB, m.scr + warp * 128, lane);
+    }
+    if (k.has_obs && k.obs.imu) {
+        for (int a = tid; a < A; a += blockDim.x) {
+            const float* st = m.st_out + a * ST_STRIDE;
+            const float ang = __fmul_rn(0.017453292519943295f, st[ST_ANG]);
+            const float c = cosf(ang), s = sinf(ang);
+            const float vx = st[ST_VX], vy = st[ST_VY];
+            float* q = k.obs.imu + 3 * ((int64_t)n * A + a);
+            q[0] = __fmul_rn(st[ST_AV], k.inv_ang);
+            q[1] = __fmul_rn(__fadd_rn(__fmul_rn(c, vx), __fmul_rn(s, vy)), k.inv_speed);
+            q[2] = __fmul_rn(__fadd_rn(__fmul_rn(-s, vx), __fmul_rn(c, vy)), k.inv_speed);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // dyn_kernel: the load-balanced second pass over pixel groups that contain agent-hit rays.
 // Entry = 16-byte header {env, agent*R + first ray, mask of agent-hit pixels, subsample | hit agent << 8} + per pixel two float4:
 //   {texel rgb, 1-dot^2} and {hit point x, hit point y, static intensity, is-agent-hit}.
@@ -1205,6 +1689,7 @@ static long long g_opt_split = 0;        // 1: cast kernel + shade kernel (measu
 static long long g_opt_two_phase = 0;    // 1: bin every (agent, segment) once into shared memory first (measured slower: the
                                          // records cost 70 KB per CTA, which halves residency)
 static long long g_opt_variant = 0;      // experiment switches (see KArgs::variant)
+static long long g_opt_legacy = 0;       // 1: render with the line-order env_kernel instead of view_kernel
 static long long g_opt_fused_step = 0;   // 1: msb_step runs physics and render in ONE kernel (slower: see DESIGN.md)
 static unsigned long long* g_stats = nullptr;   // device counters, enabled by option "stats"
 
@@ -1280,6 +1765,7 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "threads")) { g_opt_threads = value; return 0; }
     if (!strcmp(name, "debug_skip_dyn")) { g_opt_skip_dyn = value; return 0; }
     if (!strcmp(name, "fused_step")) { g_opt_fused_step = value; return 0; }
+    if (!strcmp(name, "legacy_render")) { g_opt_legacy = value; return 0; }
     if (!strcmp(name, "variant")) { g_opt_variant = value; return 0; }
     if (!strcmp(name, "timing")) {
         timing_flush();
@@ -1365,6 +1851,34 @@ static int launch_env(const KArgs& k, int nch, int threads, cudaStream_t st) {
     return check(cudaGetLastError(), "kernel launch");
 }
 
+static bool use_view(const KArgs& k) {
+    return !g_opt_legacy && k.s.occ_lines && k.s.occ_ids && !k.split_render && !k.two_phase;
+}
+
+static int launch_view(const KArgs& k, int nch, int threads, cudaStream_t st) {
+    const size_t sm = vsmem_bytes(k.wcap, threads / 32, k.s.n_agents, k.s.n_agents * k.s.n_model);
+    if (sm > 227 * 1024) return fail("%s", "scene too large: an env's segments do not fit in shared memory (227 KB)");
+#define MSB_LAUNCH(N)                                                                                            \
+    {                                                                                                            \
+        auto fn = k.stats ? view_kernel<N, true> : view_kernel<N, false>;                                        \
+        if (sm > 48 * 1024 && check(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), \
+                                    "cudaFuncSetAttribute"))                                                     \
+            return 1;                                                                                            \
+        fn<<<k.s.n_envs, threads, sm, st>>>(k);                                                                  \
+    }
+    {
+        TimedLaunch timed(TK_RENDER, st);
+        switch (nch) {
+            case 1: MSB_LAUNCH(1); break;
+            case 2: MSB_LAUNCH(2); break;
+            default: MSB_LAUNCH(4); break;
+        }
+    }
+#undef MSB_LAUNCH
+    g_launches++;
+    return check(cudaGetLastError(), "kernel launch");
+}
+
 static void plan_render(const msb_params* p, const msb_scenery* s, KArgs& k, int* nch, int* rb, int* threads) {
     const int chunks = (p->res + 31) / 32;
     // split render needs the four scalar Render outputs as the hand-over buffers
@@ -1405,7 +1919,12 @@ static void fill(KArgs& k, const msb_params* p, const msb_scenery* s, const msb_
     k.s = *s;
     if (a) k.a = *a;
     k.seg_cap = s->max_lines > 0 ? s->max_lines : 1;
-    if (k.s.occ_run != 16 && k.s.occ_run != 32) { k.s.occ_run = 32; if (k.s.occ_lines) k.s.occ_lines = nullptr; }
+    if (k.s.occ_run != VRUN) { k.s.occ_run = VRUN; k.s.occ_lines = nullptr; }      // the table's runs must be 16 long
+    if (!k.s.occ_lines || !k.s.occ_boxes || !k.s.box_starts || !k.s.occ_starts) { k.s.occ_lines = nullptr; k.s.occ_ids = nullptr; }
+    {
+        const int w = s->max_lines - s->n_agents * s->n_model;
+        k.wcap = w > 0 ? ((w + VRUN - 1) / VRUN) * VRUN : VRUN;
+    }
     k.inv_fps = 1.0f / p->fps;
     k.ray_blocks = 1;
     k.stats = g_stats;
@@ -1519,7 +2038,9 @@ extern "C" int msb_render(const msb_params* p, const msb_scenery* s, const msb_a
     int nch, rb, threads;
     plan_render(p, s, k, &nch, &rb, &threads);
     k.ray_blocks = rb;
-    if (launch_env<MODE_RENDER>(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
+    if (use_view(k)) {
+        if (launch_view(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
+    } else if (launch_env<MODE_RENDER>(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
     if (launch_shade(k, (cudaStream_t)cuda_stream)) return 1;
     return launch_dyn(k, (cudaStream_t)cuda_stream);
 }
@@ -1557,7 +2078,9 @@ extern "C" int msb_step(const msb_params* p, const msb_scenery* s, const msb_age
         int pthreads = 128;
         if (g_opt_threads >= 32 && g_opt_threads <= 256) pthreads = (int)(g_opt_threads / 32) * 32;
         if (launch_env<MODE_PHYSICS>(k, 1, pthreads, (cudaStream_t)cuda_stream)) return 1;
-        if (launch_env<MODE_RENDER>(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
+        if (use_view(k)) {
+            if (launch_view(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
+        } else if (launch_env<MODE_RENDER>(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
     }
     if (launch_shade(k, (cudaStream_t)cuda_stream)) return 1;
     return launch_dyn(k, (cudaStream_t)cuda_stream);

@@ -43,7 +43,7 @@ class _Scenery(ctypes.Structure):
                 ('baked', ctypes.c_void_p), ('model', ctypes.c_void_p),
                 ('n_lines', ctypes.c_int64), ('n_texels', ctypes.c_int64),
                 ('occ_lines', ctypes.c_void_p), ('occ_starts', ctypes.c_void_p), ('occ_boxes', ctypes.c_void_p),
-                ('box_starts', ctypes.c_void_p), ('occ_meta', ctypes.c_void_p)]
+                ('box_starts', ctypes.c_void_p), ('occ_meta', ctypes.c_void_p), ('occ_ids', ctypes.c_void_p)]
 
 
 class _Agents(ctypes.Structure):
@@ -92,8 +92,8 @@ def _load():
     lib.msb_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
     lib.msb_get_option.argtypes = [ctypes.c_char_p]
     lib.msb_get_option.restype = ctypes.c_int64
-    if lib.msb_abi_version() != 1:
-        raise ImportError(f'{_LIBPATH} has ABI version {lib.msb_abi_version()}, expected 1; rebuild it')
+    if lib.msb_abi_version() != 2:
+        raise ImportError(f'{_LIBPATH} has ABI version {lib.msb_abi_version()}, expected 2; rebuild it')
     return lib
 
 
@@ -276,7 +276,7 @@ class Scenery:
             if BUILD_OCCLUDERS and self._lines.vals.size(0) > 0:
                 self._occ = _occluder_table(self._lines, self._n_agents * self._model.size(0), OCCLUDER_RUN)
                 (self._c.occ_lines, self._c.occ_starts, self._c.occ_boxes, self._c.box_starts,
-                 self._c.occ_meta) = (t.data_ptr() for t in self._occ)
+                 self._c.occ_meta, self._c.occ_ids) = (t.data_ptr() for t in self._occ)
         return self._c
 
 
@@ -309,47 +309,54 @@ def _morton16(x, y):
 
 
 @torch.no_grad()
-def _occluder_table(lines, n_dynamic, run=32):
-    """(occ_lines, occ_starts, occ_boxes, box_starts) of include/megastep_b200.h: every env's static segments sorted
-    along a Morton curve, plus the bounding box of each run of 32. Shadow tests ask "does ANY static segment cross
-    this light ray", which no ordering can change; the sort only lets the kernel skip runs that are nowhere near."""
+def _occluder_table(lines, n_dynamic, run=16):
+    """(occ_lines, occ_starts, occ_boxes, box_starts, occ_meta, occ_ids) of include/megastep_b200.h: every env's
+    static segments sorted along a Morton curve in runs of `run`, each env padded to a whole number of runs, plus the
+    bounding box of each run and each row's original line index. Shadow tests and collisions ask order-free questions
+    (any occluder / nearest obstacle); render() uses the ids to restore the reference's line-order rule."""
     vals, widths = lines.vals.reshape(-1, 4), lines.widths.long()
     dev = vals.device
     env = lines.inverse.long()
     local = torch.arange(vals.size(0), device=dev) - lines.starts.long()[env]
     static = local >= n_dynamic
-    sv, senv = vals[static], env[static]
+    sv, senv, sid = vals[static], env[static], local[static]
     mid = (sv[:, :2] + sv[:, 2:]) * .5
     lo = mid.min(0).values if len(mid) else torch.zeros(2, device=dev)
     cell = ((mid - lo) / .25).clamp(0, 65535).long()
     key = (senv << 32) | _morton16(cell[:, 0], cell[:, 1])
     order = torch.argsort(key)
-    occ = sv[order].contiguous()
     W = (widths - n_dynamic).clamp(min=0)
-    occ_starts = (W.cumsum(0) - W)
+    wstarts = W.cumsum(0) - W
     nb = (W + run - 1) // run
     box_starts = nb.cumsum(0) - nb
-    oenv = senv[order]
-    rank = torch.arange(occ.size(0), device=dev) - occ_starts[oenv]
-    box = box_starts[oenv] + rank // run
+    occ_starts = box_starts * run
     nbox = int(nb.sum().item())
+    oenv = senv[order]
+    rank = torch.arange(order.size(0), device=dev) - wstarts[oenv]
+    row = occ_starts[oenv] + rank                       # where each sorted segment lands in the padded table
     big = torch.finfo(torch.float32).max
-    xmin = torch.full((nbox,), big, device=dev).scatter_reduce(0, box, torch.minimum(occ[:, 0], occ[:, 2]), 'amin')
-    ymin = torch.full((nbox,), big, device=dev).scatter_reduce(0, box, torch.minimum(occ[:, 1], occ[:, 3]), 'amin')
-    xmax = torch.full((nbox,), -big, device=dev).scatter_reduce(0, box, torch.maximum(occ[:, 0], occ[:, 2]), 'amax')
-    ymax = torch.full((nbox,), -big, device=dev).scatter_reduce(0, box, torch.maximum(occ[:, 1], occ[:, 3]), 'amax')
+    occ = torch.full((nbox * run, 4), 1e30, dtype=torch.float32, device=dev)    # padding: a far, zero-length segment
+    occ[row] = sv[order]
+    ids = torch.full((nbox * run,), -1, dtype=torch.int16, device=dev)           # 0xffff
+    ids[row] = sid[order].to(torch.int16)
+    box = box_starts[oenv] + rank // run
+    so = sv[order]
+    xmin = torch.full((nbox,), big, device=dev).scatter_reduce(0, box, torch.minimum(so[:, 0], so[:, 2]), 'amin')
+    ymin = torch.full((nbox,), big, device=dev).scatter_reduce(0, box, torch.minimum(so[:, 1], so[:, 3]), 'amin')
+    xmax = torch.full((nbox,), -big, device=dev).scatter_reduce(0, box, torch.maximum(so[:, 0], so[:, 2]), 'amax')
+    ymax = torch.full((nbox,), -big, device=dev).scatter_reduce(0, box, torch.maximum(so[:, 1], so[:, 3]), 'amax')
     boxes = torch.stack([xmin, ymin, xmax, ymax], -1).contiguous()
     # per env: the longest segment extent and the extent of the env (they size the shadow cull's safety margin)
     n = widths.size(0)
-    ext = torch.maximum((occ[:, 2] - occ[:, 0]).abs(), (occ[:, 3] - occ[:, 1]).abs())
+    ext = torch.maximum((so[:, 2] - so[:, 0]).abs(), (so[:, 3] - so[:, 1]).abs())
     vmax = torch.zeros(n, device=dev).scatter_reduce(0, oenv, ext, 'amax')
-    lo_x = torch.full((n,), big, device=dev).scatter_reduce(0, oenv, torch.minimum(occ[:, 0], occ[:, 2]), 'amin')
-    lo_y = torch.full((n,), big, device=dev).scatter_reduce(0, oenv, torch.minimum(occ[:, 1], occ[:, 3]), 'amin')
-    hi_x = torch.full((n,), -big, device=dev).scatter_reduce(0, oenv, torch.maximum(occ[:, 0], occ[:, 2]), 'amax')
-    hi_y = torch.full((n,), -big, device=dev).scatter_reduce(0, oenv, torch.maximum(occ[:, 1], occ[:, 3]), 'amax')
+    lo_x = torch.full((n,), big, device=dev).scatter_reduce(0, oenv, torch.minimum(so[:, 0], so[:, 2]), 'amin')
+    lo_y = torch.full((n,), big, device=dev).scatter_reduce(0, oenv, torch.minimum(so[:, 1], so[:, 3]), 'amin')
+    hi_x = torch.full((n,), -big, device=dev).scatter_reduce(0, oenv, torch.maximum(so[:, 0], so[:, 2]), 'amax')
+    hi_y = torch.full((n,), -big, device=dev).scatter_reduce(0, oenv, torch.maximum(so[:, 1], so[:, 3]), 'amax')
     diam = torch.where(W > 0, torch.maximum(hi_x - lo_x, hi_y - lo_y), torch.zeros_like(vmax))
     meta = torch.stack([vmax, diam], -1).contiguous()
-    return occ, occ_starts.int().contiguous(), boxes, box_starts.int().contiguous(), meta
+    return occ, occ_starts.int().contiguous(), boxes, box_starts.int().contiguous(), meta, ids
 
 
 class Render:
@@ -371,7 +378,7 @@ class Physics:
 # functions
 # --------------------------------------------------------------------------------------------------------------
 _PARAMS = None
-OCCLUDER_RUN = 16        # segments per bounding box in the occluder table (16 or 32)
+OCCLUDER_RUN = 16        # segments per run / bounding box of the spatial table
 BUILD_OCCLUDERS = True  # False: the second pass scans the segments in their original order (same results, slower)
 USE_WORKSPACE = True   # False: agent-hit rays are lit inline by the first pass (same results; used by tests)
 

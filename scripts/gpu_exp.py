@@ -52,6 +52,32 @@ if __name__ == '__main__':
         cuda.set_option('stats', 0)
         print(json.dumps(res))
         sys.exit(0)
+    if mode == 'view':
+        out = {}
+        cuda.set_option('legacy_render', 1)
+        base = c.render()
+        out['legacy/render_us'] = round(timeit(lambda: c.render()), 1)
+        cuda.set_option('debug_skip_dyn', 1); out['legacy/main_us'] = round(timeit(lambda: c.render()), 1); cuda.set_option('debug_skip_dyn', 0)
+        cuda.set_option('legacy_render', 0)
+        r = c.render()
+        for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
+            a, b = getattr(r, k), getattr(base, k)
+            out[f'identical/{k}'] = bool(((a == b) | (a != a) & (b != b)).all())
+            out[f'mismatches/{k}'] = int((~((a == b) | (a != a) & (b != b))).sum())
+        for nch, threads in ((0, 0), (4, 128), (2, 256), (2, 128), (1, 256), (4, 256)):
+            cuda.set_option('nch', nch); cuda.set_option('threads', threads)
+            out[f'view/render_us/nch{nch}/t{threads}'] = round(timeit(lambda: c.render()), 1)
+            cuda.set_option('debug_skip_dyn', 1); out[f'view/main_us/nch{nch}/t{threads}'] = round(timeit(lambda: c.render()), 1); cuda.set_option('debug_skip_dyn', 0)
+        cuda.set_option('nch', 0); cuda.set_option('threads', 0)
+        cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0)
+        c.render(); torch.cuda.synchronize()
+        for k in ('stat_tests', 'stat_groups', 'stat_dyn_rays', 'stat_dyn_iters'): out['view/' + k] = cuda.get_option(k)
+        cuda.set_option('stats', 0)
+        step = modules.FusedStep(c, subsample=1, raw=True)
+        acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')
+        out['view/step_us'] = round(timeit(lambda: step(acts)), 1)
+        out['physics_us'] = round(timeit(lambda: c.physics()), 1)
+        print(json.dumps(out)); sys.exit(0)
     if mode == 'twophase':
         out = {}
         for tp in (0, 1):

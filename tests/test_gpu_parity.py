@@ -230,32 +230,37 @@ def test_rgbd_head_equals_rgb_and_depth_modules():
     torch.testing.assert_close(obs.imu, want_imu, rtol=0, atol=1e-6)
 
 
-@pytest.mark.parametrize('res', [64, 128, 512])
+@pytest.mark.parametrize('res', [48, 64, 128, 512])
 def test_every_kernel_variant_gives_identical_results(res):
-    """The chunking / thread-count options change which exact tests are skipped and who runs them, never results."""
+    """render() through view_kernel (the spatial table, nearest boxes first, any line order) and through the line-order
+    env_kernel, under every chunking / thread-count option: what is skipped and who runs it changes, results never."""
     from megastep_b200 import cuda
     gs, arrays, st = make('synthetic', 10, 4, seed=51)
     c = common.to_device(arrays, st, res, 70.)
     base = c.render()
+
+    def check(what):
+        r = c.render()
+        for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
+            a, b = getattr(r, k), getattr(base, k)
+            assert ((a == b) | (a != a) & (b != b)).all(), f'{what}: {k} differs'
+
     try:
-        for variant in (0, 1, 4, 5, 6, 7, 8, 9, 10):  # 0/1: segment-major, depth cull on/off; 4-7: chunk-major variants; 8, 9: two-phase; 10: split
-            for nch in (1, 2, 4):
-                for threads in (64, 128, 256):
+        for nch in (1, 2, 4):
+            for threads in (64, 128, 256):
+                cuda.set_option('nch', nch)
+                cuda.set_option('threads', threads)
+                cuda.set_option('legacy_render', 0)
+                check(f'view nch={nch} threads={threads}')
+                cuda.set_option('legacy_render', 1)
+                for variant in (0, 1, 4, 5, 6, 7, 8, 9, 10):  # 0/1: depth cull on/off; 4-7: segment-major variants; 8, 9: two-phase; 10: split
                     cuda.set_option('two_phase', 1 if variant in (8, 9) else 0)
                     cuda.set_option('split_render', 1 if variant == 10 else 0)
                     cuda.set_option('variant', variant % 8)
-                    cuda.set_option('nch', nch)
-                    cuda.set_option('threads', threads)
-                    r = c.render()
-                    for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
-                        a, b = getattr(r, k), getattr(base, k)
-                        assert ((a == b) | (a != a) & (b != b)).all(), f'variant={variant} nch={nch} threads={threads}: {k} differs'
+                    check(f'legacy variant={variant} nch={nch} threads={threads}')
     finally:
-        cuda.set_option('nch', 0)
-        cuda.set_option('threads', 0)
-        cuda.set_option('variant', 0)
-        cuda.set_option('two_phase', 0)
-        cuda.set_option('split_render', 0)
+        for name in ('nch', 'threads', 'variant', 'two_phase', 'split_render', 'legacy_render'):
+            cuda.set_option(name, 0)
 
 
 def _same(a, b):
