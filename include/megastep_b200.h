@@ -72,7 +72,8 @@ typedef struct msb_scenery {
     const float* occ_boxes;     /* (sum nb, 4) {xmin, ymin, xmax, ymax} of each run */
     const int32_t* box_starts;  /* (N) start of env n's rows in occ_boxes */
     const float* occ_meta;      /* (N, 2) per env: longest static segment extent (max |dx|,|dy|), extent of the env */
-    const uint16_t* occ_ids;    /* (16 * sum nb) each sorted row's line index within its env (A*F <= id < L); 0xffff = padding */
+    const int32_t* occ_rec;     /* (16 * sum nb, 4) per sorted row: {tex_starts lo, hi, tex_widths, line index within its env};
+                                 * padding rows have line index -1 */
 } msb_scenery;
 
 /* The Agents struct of megastep/src/common.h:162-177. Updated in place by msb_physics. */

@@ -74,7 +74,7 @@ enum { MODE_PHYSICS = 1, MODE_RENDER = 2, MODE_STEP = 3 };
 #define MSB_MIN_BLOCKS 4      // 256 threads x 4 blocks -> at most 64 registers per thread
 #endif
 enum { ST_ANG = 0, ST_PX = 1, ST_PY = 2, ST_AV = 3, ST_VX = 4, ST_VY = 5, ST_STRIDE = 8 };
-enum { STAT_TESTS = 0, STAT_GROUPS = 1, STAT_DYN_RAYS = 2, STAT_DYN_ITERS = 3, STAT_COLL = 4 };
+enum { STAT_TESTS = 0, STAT_GROUPS = 1, STAT_DYN_RAYS = 2, STAT_DYN_ITERS = 3, STAT_COLL = 4, STAT_REPLAYS = 5 };
 
 struct Smem {
     float4* seg;        // [seg_cap] this env's segments {ax, ay, bx, by}
@@ -1087,7 +1087,7 @@ enum { VRUN = 16 };
 struct VSmem {
     float4* seg;            // [AF + wcap]: [0, AF) the agents' model lines at their current poses; then the sorted static rows
     float4* boxes;          // [wcap / 16]
-    unsigned short* ids;    // [wcap]
+    int4* rec;              // [wcap] per sorted row: {texel offset lo, hi, texel count, line id}
     float4* scr;            // [nwarps][128] per warp: 64 candidate records while casting, then the chunk results
     float* st_in;           // [A][8]
     float* st_out;          // [A][8]
@@ -1099,9 +1099,9 @@ __device__ __forceinline__ VSmem vcarve(unsigned char* base, int wcap, int nwarp
     VSmem m;
     m.seg = reinterpret_cast<float4*>(base);
     m.boxes = m.seg + AF + wcap;
-    m.scr = m.boxes + wcap / VRUN;
-    m.ids = reinterpret_cast<unsigned short*>(m.scr + nwarps * 128);       // wcap * 2 bytes: a multiple of 32
-    m.st_in = reinterpret_cast<float*>(m.ids + wcap);
+    m.rec = reinterpret_cast<int4*>(m.boxes + wcap / VRUN);
+    m.scr = reinterpret_cast<float4*>(m.rec + wcap);
+    m.st_in = reinterpret_cast<float*>(m.scr + nwarps * 128);
     m.st_out = m.st_in + A * ST_STRIDE;
     m.xmin = reinterpret_cast<int*>(m.st_out + A * ST_STRIDE);
     uintptr_t p = reinterpret_cast<uintptr_t>(m.xmin + A);
@@ -1111,7 +1111,7 @@ __device__ __forceinline__ VSmem vcarve(unsigned char* base, int wcap, int nwarp
 }
 
 static size_t vsmem_bytes(int wcap, int nwarps, int A, int AF) {
-    size_t b = (size_t)(AF + wcap) * 16 + (size_t)(wcap / VRUN) * 16 + (size_t)nwarps * 128 * 16 + (size_t)wcap * 2 +
+    size_t b = (size_t)(AF + wcap) * 16 + (size_t)(wcap / VRUN) * 16 + (size_t)nwarps * 128 * 16 + (size_t)wcap * 16 +
                (size_t)A * ST_STRIDE * 4 * 2 + (size_t)A * 4;
     b = (b + 15) & ~size_t(15);
     return b + 16;
@@ -1120,21 +1120,21 @@ static size_t vsmem_bytes(int wcap, int nwarps, int A, int AF) {
 template <int NCH>
 struct Rays {
     float rux[NCH], ruy[NCH], nearp[NCH], best[NCH], loc[NCH], cmax[NCH];
-    int tag[NCH];           // winner: (row in VSmem::seg) << 16 | line id; -1 = no hit
-    unsigned amb;           // bit c: this lane's ray of chunk c saw two hits within AMB_EPS
+    float tie[NCH];         // the running minimum right after the latest near-tie (two hits within AMB_EPS), else +inf
+    int row[NCH];           // winner's row in VSmem::seg; -1 = no hit
 };
 
 struct View { float px, py, cs, sn, xclip, B0, dB; };   // chunk c spans slopes (B0 - (c+1) dB, B0 - c dB) in camera space
 
 // One batch of up to 32 segments against this warp's rays. Lane = segment while binning, lane = ray while testing.
 template <int NCH, bool STATS>
-__device__ __forceinline__ void cast_batch(const View& v, Rays<NCH>& ry, bool valid, float4 s4, unsigned tag,
+__device__ __forceinline__ void cast_batch(const View& v, Rays<NCH>& ry, bool valid, float4 s4, int row,
                                            float4* __restrict__ scr, int lane, unsigned& tests) {
     // exact, ray-independent terms of intersect() (kernels.cu:83-85)
     const float Vx = fsub(s4.z, s4.x), Vy = fsub(s4.w, s4.y);
     const float PQx = fsub(s4.x, v.px), PQy = fsub(s4.y, v.py);
     scr[lane] = make_float4(Vx, Vy, PQx, PQy);
-    *reinterpret_cast<float2*>(scr + 32 + lane) = make_float2(cross2(Vy, PQx, Vx, PQy), __uint_as_float(tag));
+    *reinterpret_cast<float2*>(scr + 32 + lane) = make_float2(cross2(Vy, PQx, Vx, PQy), __int_as_float(row));
     // conservative summary in camera space (x' forward = the hit parameter s, y' left): culling only
     const float bxr = s4.z - v.px, byr = s4.w - v.py;
     const float xa = PQx * v.cs + PQy * v.sn, ya = PQy * v.cs - PQx * v.sn;
@@ -1168,10 +1168,14 @@ __device__ __forceinline__ void cast_batch(const View& v, Rays<NCH>& ry, bool va
                 const float hs_ = fmul(w.x, rc);
                 const float ht_ = fmul(cross2(ry.ruy[c], q.z, ry.rux[c], q.w), rc);
                 const bool hit = !(fabsf(UxV) < PARALLEL_EPS) && (ht_ >= 0.f) && (ht_ <= 1.f) && (ry.nearp[c] < hs_);
-                if (hit) {
-                    if (fabsf(hs_ - ry.best[c]) <= AMB_EPS) ry.amb |= 1u << c;
-                    if (hs_ < ry.best[c]) { ry.best[c] = hs_; ry.loc[c] = ht_; ry.tag[c] = (int)__float_as_uint(w.y); }
-                }
+                // near-tie bookkeeping: remember the minimum whenever a hit lands within AMB_EPS of the running minimum;
+                // at the end the ray is ambiguous iff that memory is still within AMB_EPS of the final minimum
+                const float d = hs_ - ry.best[c];
+                const bool tie = hit && (fabsf(d) <= AMB_EPS), take = hit && (d < 0.f);
+                ry.tie[c] = tie ? fminf(hs_, ry.best[c]) : ry.tie[c];
+                ry.best[c] = take ? hs_ : ry.best[c];
+                ry.loc[c] = take ? ht_ : ry.loc[c];
+                ry.row[c] = take ? __float_as_int(w.y) : ry.row[c];
                 if (STATS) tests++;
             } while (mask);
             // the chunk's farthest current hit; best >= 0 (or +inf), so its bit pattern orders like an unsigned integer
@@ -1238,17 +1242,63 @@ __device__ __noinline__ float dyn_inline(const float4* seg, int L, int AF, int n
     return intensity;
 }
 
-// shader_kernel (kernels.cu:407-450) + the Depth / RGB heads for one 32-ray chunk, lane = ray.
-// hit = {line index (int bits), location, dot, distance}. seg = VSmem::seg (rows [0, AF) are the agents' lines).
-__device__ __forceinline__ void shade_chunk(const KArgs& k, const float4* __restrict__ seg, int n, int64_t g0, int a, int AF,
-                                            int Lrows, int r, int lane, float4 hitrec) {
+// shader_kernel (kernels.cu:407-450) + the Depth / RGB heads for one 32-ray chunk, lane = ray, in three steps so that
+// several chunks' gathers can be in flight: shade_prepare (decode the parked hit, texel offset / count of its line from
+// the staged table), shade_fetch (filter + texel / baked-light gathers; only issues loads), shade_chunk (the rest).
+enum { ROW_UNKNOWN = 0x7fff };
+struct ShadeIn { int l0; float locv, dotv, dist; int w; int64_t ts; bool hitany; };
+
+__device__ __forceinline__ ShadeIn shade_prepare(const KArgs& k, const VSmem& m, int64_t g0, int AF, int r, float4 hitrec) {
+    ShadeIn in;
+    const int packed = __float_as_int(hitrec.x);
+    in.l0 = packed < 0 ? -1 : (packed & 0xffff);
+    in.locv = hitrec.y; in.dotv = hitrec.z; in.dist = hitrec.w;
+    in.hitany = (r < k.p.res) && (packed >= 0);
+    in.w = 0; in.ts = 0;
+    if (in.hitany) {
+        const int row = packed >> 16;
+        if (row >= AF && row != ROW_UNKNOWN) {
+            const int4 rc = m.rec[row - AF];
+            in.w = rc.z;
+            in.ts = (int64_t)(((uint64_t)(uint32_t)rc.y << 32) | (uint32_t)rc.x);
+        } else {                                            // an agent's model line, or a replayed ray: rare
+            in.w = __ldg(k.s.tex_widths + g0 + in.l0);
+            in.ts = __ldg(k.s.tex_starts + g0 + in.l0);
+        }
+    }
+    return in;
+}
+
+// filter() (kernels.cu:394-405) + the gathers of shader_kernel (:427-430, :438)
+__device__ __forceinline__ Texels shade_fetch(const KArgs& k, bool hitany, bool is_static, float locv, int w, int64_t ts) {
+    Texels t;
+    t.lw = t.rw = t.tl0 = t.tl1 = t.tl2 = t.tr0 = t.tr1 = t.tr2 = t.bl = t.br = 0.f;
+    if (hitany) {
+        const float yy = fminf(fmul(locv, (float)(w + 1)), (float)(w - 1));
+        const int fl = __float2int_rz(fmaxf(fadd(yy, -1.f), 0.f));
+        const int fr = __float2int_rz(yy);
+        const float ld = fadd(fabsf(fsub(yy, (float)(fl + 1))), 1.e-3f);
+        const float rd = fadd(fabsf(fsub(yy, (float)(fr + 1))), 1.e-3f);
+        const float rc = rcp(fadd(rd, ld));
+        t.lw = fmul(rd, rc);
+        t.rw = fmul(ld, rc);
+        const float* tl = k.s.textures + 3 * (ts + fl);
+        const float* tr = k.s.textures + 3 * (ts + fr);
+        t.tl0 = __ldg(tl); t.tl1 = __ldg(tl + 1); t.tl2 = __ldg(tl + 2);
+        t.tr0 = __ldg(tr); t.tr1 = __ldg(tr + 1); t.tr2 = __ldg(tr + 2);
+        if (is_static) { t.bl = __ldg(k.s.baked + ts + fl); t.br = __ldg(k.s.baked + ts + fr); }
+    }
+    return t;
+}
+
+__device__ __forceinline__ void shade_chunk(const KArgs& k, const float4* __restrict__ seg, int n, int a, int AF, int Lrows,
+                                            int r, int lane, const ShadeIn& in, const Texels& t) {
     const int A = k.s.n_agents, R = k.p.res;
     const int sub_ = k.has_obs ? k.obs.subsample : 1;
     const bool live = r < R;
-    const int l0 = __float_as_int(hitrec.x);
-    const float locv = hitrec.y, dotv = hitrec.z, dist = hitrec.w;
-    const bool hitany = live && (l0 >= 0);
-    const Texels t = shade_fetch(k, k.s.tex_widths + g0, reinterpret_cast<const long long*>(k.s.tex_starts) + g0, AF, hitany, l0, locv);
+    const int l0 = in.l0;
+    const float locv = in.locv, dotv = in.dotv, dist = in.dist;
+    const bool hitany = in.hitany;
     float intensity = 0.f, Cx = 0.f, Cy = 0.f;
     float kk0 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
     const bool isdyn = hitany && (l0 < AF);
@@ -1358,7 +1408,6 @@ __device__ __forceinline__ void view_agent(const KArgs& k, const VSmem& m, int n
 
     // ---- rays (kernels.cu:341-344, ray_y :234-236). Lane = ray within each of this warp's NCH 32-ray chunks.
     Rays<NCH> ry;
-    ry.amb = 0;
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
         const int r = r0 + 32 * c + lane;
@@ -1370,9 +1419,10 @@ __device__ __forceinline__ void view_agent(const KArgs& k, const VSmem& m, int n
         ry.best[c] = r < R ? CUDART_INF_F : 0.f;                    // rays beyond R never take a hit
         ry.cmax[c] = (r0 + 32 * c) < R ? CUDART_INF_F : 0.f;
         ry.loc[c] = __int_as_float(0x7fffffff);
-        ry.tag[c] = -1;
+        ry.tie[c] = CUDART_INF_F;
+        ry.row[c] = -1;
     }
-    unsigned tests = 0, groups = 0;
+    unsigned tests = 0, groups = 0, replays = 0;
 
     // ---- static lines: run boxes, nearest first; then the agents' model lines (kernels.cu:297-318 drew them), after
     // the walls that hide most of them. One loop, so that the batch code exists once.
@@ -1433,47 +1483,65 @@ __device__ __forceinline__ void view_agent(const KArgs& k, const VSmem& m, int n
             row = valid ? dyn_next + lane : 0;
             dyn_next += 32;
         }
-        const unsigned id = row < AF ? (unsigned)row : (unsigned)m.ids[row - AF];
-        cast_batch<NCH, STATS>(v, ry, valid, m.seg[row], ((unsigned)row << 16) | id, scr, lane, tests);
+        cast_batch<NCH, STATS>(v, ry, valid, m.seg[row], row, scr, lane, tests);
         if (STATS) groups++;
     }
 
-    // ---- per chunk: the winner's ray . line cosine (kernels.cu:362-364, winner only), flagged rays replayed in line
-    // order, results parked in shared memory for the (rolled) shading loop
+    // ---- per chunk: the winner's ray . line cosine (kernels.cu:362-364, winner only), near-tied rays replayed in line
+    // order, results parked in shared memory for the shading loop as {row << 16 | line, location, dot, distance}
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
         const int r = r0 + 32 * c + lane;
         const float rlen = sqrt_(ffma(ry.rux[c], ry.rux[c], fmul(ry.ruy[c], ry.ruy[c])));
         float dotv = __int_as_float(0x7fffffff);
-        int l0 = -1;
-        if (ry.tag[c] >= 0) {
-            const float4 s4 = m.seg[ry.tag[c] >> 16];
+        int packed = -1;
+        if (ry.row[c] >= 0) {
+            const int row = ry.row[c];
+            const float4 s4 = m.seg[row];
             const float Vx = fsub(s4.z, s4.x), Vy = fsub(s4.w, s4.y);
             dotv = fmul(dot2(ry.rux[c], Vx, ry.ruy[c], Vy), rcp(ffma(rlen, sqrt_(ffma(Vx, Vx, fmul(Vy, Vy))), 1.e-6f)));
-            l0 = ry.tag[c] & 0xffff;
+            packed = (row << 16) | (row < AF ? row : m.rec[row - AF].w);
         }
         float best = ry.best[c], loc = ry.loc[c];
-        unsigned am = __ballot_sync(0xffffffffu, ((ry.amb >> c) & 1u) && r < R);
+        unsigned am = __ballot_sync(0xffffffffu, (ry.tie[c] - ry.best[c] <= AMB_EPS) && r < R);
         while (am) {
             const int j = __ffs(am) - 1;
             am &= am - 1;
             const float ux = __shfl_sync(0xffffffffu, ry.rux[c], j), uy = __shfl_sync(0xffffffffu, ry.ruy[c], j);
             const float np_ = __shfl_sync(0xffffffffu, ry.nearp[c], j), rl = __shfl_sync(0xffffffffu, rlen, j);
             const float4 w = replay_ray(k, m.seg, g0, L, AF, v.px, v.py, ux, uy, np_, rl, lane);
-            if (lane == j) { best = w.x; loc = w.y; l0 = __float_as_int(w.z); dotv = w.w; }
-            if (STATS) groups++;
+            if (lane == j) {
+                best = w.x; loc = w.y; dotv = w.w;
+                const int l = __float_as_int(w.z);                  // its row is unknown: shading looks its texels up by line
+                packed = l < 0 ? -1 : ((l < AF ? l : ROW_UNKNOWN) << 16) | l;
+            }
+            if (STATS) replays++;
         }
-        scr[32 * c + lane] = make_float4(__int_as_float(l0), loc, dotv, fmul(rlen, best));
+        scr[32 * c + lane] = make_float4(__int_as_float(packed), loc, dotv, fmul(rlen, best));
     }
     __syncwarp();
+    // ---- shading: the texel gathers of two chunks in flight at a time
 #pragma unroll 1
-    for (int c = 0; c < NCH; c++) {
-        shade_chunk(k, m.seg, n, g0, a, AF, AF + W, r0 + 32 * c + lane, lane, scr[32 * c + lane]);
+    for (int c0 = 0; c0 < NCH; c0 += 2) {
+        ShadeIn in[2];
+        Texels tx[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (c0 + u < NCH) {
+                in[u] = shade_prepare(k, m, g0, AF, r0 + 32 * (c0 + u) + lane, scr[32 * (c0 + u) + lane]);
+                tx[u] = shade_fetch(k, in[u].hitany, in[u].l0 >= AF, in[u].locv, in[u].w, in[u].ts);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (c0 + u < NCH) shade_chunk(k, m.seg, n, a, AF, AF + W, r0 + 32 * (c0 + u) + lane, lane, in[u], tx[u]);
+        }
     }
     __syncwarp();
     if (STATS && k.stats && lane == 0) {
         atomicAdd(k.stats + STAT_TESTS, (unsigned long long)tests);
         atomicAdd(k.stats + STAT_GROUPS, (unsigned long long)groups);
+        atomicAdd(k.stats + STAT_REPLAYS, (unsigned long long)replays);
     }
 }
 
@@ -1493,9 +1561,9 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_
         mbar_init(m.bar, 1);
         if (nb > 0) {
             const int64_t b0 = __ldg(k.s.box_starts + n);
-            mbar_expect_tx(m.bar, (uint32_t)nb * (VRUN * 18u + 16u));
+            mbar_expect_tx(m.bar, (uint32_t)nb * (VRUN * 32u + 16u));
             bulk_g2s(m.seg + AF, k.s.occ_lines + 4 * VRUN * b0, (uint32_t)nb * VRUN * 16u, m.bar);
-            bulk_g2s(m.ids, k.s.occ_ids + VRUN * b0, (uint32_t)nb * VRUN * 2u, m.bar);
+            bulk_g2s(m.rec, k.s.occ_rec + 4 * VRUN * b0, (uint32_t)nb * VRUN * 16u, m.bar);
             bulk_g2s(m.boxes, k.s.occ_boxes + 4 * b0, (uint32_t)nb * 16u, m.bar);
         }
     }
@@ -1511,15 +1579,16 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_
     // draw_kernel (kernels.cu:297-318): the agents' model lines, at their current poses, into shared and global memory
     {
         const int F = k.s.n_model;
-        for (int t = tid; t < AF * 2; t += blockDim.x) {
-            const int e = t & 1, mm = (t >> 1) % F, a = (t >> 1) / F;
+        for (int a = warp; a < A; a += nwarps) {
             const float* st = m.st_out + a * ST_STRIDE;
-            float s, c;
-            sincos_deg(st[ST_ANG], s, c);
-            const float mx = __ldg(k.s.model + 4 * mm + 2 * e), my = __ldg(k.s.model + 4 * mm + 2 * e + 1);
-            const float2 pt = make_float2(fadd(st[ST_PX], cross2(c, mx, s, my)), fadd(st[ST_PY], dot2(s, mx, c, my)));
-            reinterpret_cast<float2*>(m.seg)[2 * (a * F + mm) + e] = pt;
-            reinterpret_cast<float2*>(k.s.lines)[2 * (g0 + a * F + mm) + e] = pt;
+            float sn, cs;
+            sincos_deg(st[ST_ANG], sn, cs);
+            for (int t = lane; t < 2 * F; t += 32) {            // t = 2 * model line + endpoint
+                const float2 mp = __ldg(reinterpret_cast<const float2*>(k.s.model) + t);
+                const float2 pt = make_float2(fadd(st[ST_PX], cross2(cs, mp.x, sn, mp.y)), fadd(st[ST_PY], dot2(sn, mp.x, cs, mp.y)));
+                reinterpret_cast<float2*>(m.seg)[2 * a * F + t] = pt;
+                reinterpret_cast<float2*>(k.s.lines)[2 * (g0 + a * F) + t] = pt;
+            }
         }
     }
     __syncthreads();
@@ -1813,6 +1882,7 @@ extern "C" int64_t msb_get_option(const char* name) {
         if (!strcmp(name, "stat_groups")) return (int64_t)h[STAT_GROUPS];
         if (!strcmp(name, "stat_dyn_rays")) return (int64_t)h[STAT_DYN_RAYS];
         if (!strcmp(name, "stat_dyn_iters")) return (int64_t)h[STAT_DYN_ITERS];
+        if (!strcmp(name, "stat_replays")) return (int64_t)h[STAT_REPLAYS];
     }
     return -1;
 }
@@ -1852,7 +1922,7 @@ static int launch_env(const KArgs& k, int nch, int threads, cudaStream_t st) {
 }
 
 static bool use_view(const KArgs& k) {
-    return !g_opt_legacy && k.s.occ_lines && k.s.occ_ids && !k.split_render && !k.two_phase;
+    return !g_opt_legacy && k.s.occ_lines && k.s.occ_rec && !k.split_render && !k.two_phase;
 }
 
 static int launch_view(const KArgs& k, int nch, int threads, cudaStream_t st) {
@@ -1920,7 +1990,7 @@ static void fill(KArgs& k, const msb_params* p, const msb_scenery* s, const msb_
     if (a) k.a = *a;
     k.seg_cap = s->max_lines > 0 ? s->max_lines : 1;
     if (k.s.occ_run != VRUN) { k.s.occ_run = VRUN; k.s.occ_lines = nullptr; }      // the table's runs must be 16 long
-    if (!k.s.occ_lines || !k.s.occ_boxes || !k.s.box_starts || !k.s.occ_starts) { k.s.occ_lines = nullptr; k.s.occ_ids = nullptr; }
+    if (!k.s.occ_lines || !k.s.occ_boxes || !k.s.box_starts || !k.s.occ_starts) { k.s.occ_lines = nullptr; k.s.occ_rec = nullptr; }
     {
         const int w = s->max_lines - s->n_agents * s->n_model;
         k.wcap = w > 0 ? ((w + VRUN - 1) / VRUN) * VRUN : VRUN;

@@ -43,7 +43,7 @@ class _Scenery(ctypes.Structure):
                 ('baked', ctypes.c_void_p), ('model', ctypes.c_void_p),
                 ('n_lines', ctypes.c_int64), ('n_texels', ctypes.c_int64),
                 ('occ_lines', ctypes.c_void_p), ('occ_starts', ctypes.c_void_p), ('occ_boxes', ctypes.c_void_p),
-                ('box_starts', ctypes.c_void_p), ('occ_meta', ctypes.c_void_p), ('occ_ids', ctypes.c_void_p)]
+                ('box_starts', ctypes.c_void_p), ('occ_meta', ctypes.c_void_p), ('occ_rec', ctypes.c_void_p)]
 
 
 class _Agents(ctypes.Structure):
@@ -274,9 +274,10 @@ class Scenery:
                 tex_starts=self._tex_starts.data_ptr(), baked=self._baked.vals.data_ptr(), model=self._model.data_ptr(),
                 n_lines=self._lines.vals.size(0), n_texels=self._textures.vals.size(0))
             if BUILD_OCCLUDERS and self._lines.vals.size(0) > 0:
-                self._occ = _occluder_table(self._lines, self._n_agents * self._model.size(0), OCCLUDER_RUN)
+                self._occ = _occluder_table(self._lines, self._n_agents * self._model.size(0), OCCLUDER_RUN,
+                                            self._textures.widths, self._tex_starts)
                 (self._c.occ_lines, self._c.occ_starts, self._c.occ_boxes, self._c.box_starts,
-                 self._c.occ_meta, self._c.occ_ids) = (t.data_ptr() for t in self._occ)
+                 self._c.occ_meta, self._c.occ_rec) = (t.data_ptr() for t in self._occ)
         return self._c
 
 
@@ -309,11 +310,12 @@ def _morton16(x, y):
 
 
 @torch.no_grad()
-def _occluder_table(lines, n_dynamic, run=16):
-    """(occ_lines, occ_starts, occ_boxes, box_starts, occ_meta, occ_ids) of include/megastep_b200.h: every env's
+def _occluder_table(lines, n_dynamic, run=16, tex_widths=None, tex_starts=None):
+    """(occ_lines, occ_starts, occ_boxes, box_starts, occ_meta, occ_rec) of include/megastep_b200.h: every env's
     static segments sorted along a Morton curve in runs of `run`, each env padded to a whole number of runs, plus the
-    bounding box of each run and each row's original line index. Shadow tests and collisions ask order-free questions
-    (any occluder / nearest obstacle); render() uses the ids to restore the reference's line-order rule."""
+    bounding box of each run and, per row, its line's texel offset / count and original line index. Shadow tests and
+    collisions ask order-free questions (any occluder / nearest obstacle); render() uses the line indices to restore
+    the reference's line-order rule."""
     vals, widths = lines.vals.reshape(-1, 4), lines.widths.long()
     dev = vals.device
     env = lines.inverse.long()
@@ -337,8 +339,13 @@ def _occluder_table(lines, n_dynamic, run=16):
     big = torch.finfo(torch.float32).max
     occ = torch.full((nbox * run, 4), 1e30, dtype=torch.float32, device=dev)    # padding: a far, zero-length segment
     occ[row] = sv[order]
-    ids = torch.full((nbox * run,), -1, dtype=torch.int16, device=dev)           # 0xffff
-    ids[row] = sid[order].to(torch.int16)
+    rec = torch.zeros((nbox * run, 4), dtype=torch.int32, device=dev)
+    rec[:, 3] = -1
+    rec[row, 3] = sid[order].int()
+    if tex_widths is not None:
+        gl = lines.starts.long()[oenv] + sid[order]            # global line of each sorted row
+        rec[row, :2] = tex_starts[gl].contiguous().view(torch.int32).reshape(-1, 2)     # little-endian {lo, hi}
+        rec[row, 2] = tex_widths[gl]
     box = box_starts[oenv] + rank // run
     so = sv[order]
     xmin = torch.full((nbox,), big, device=dev).scatter_reduce(0, box, torch.minimum(so[:, 0], so[:, 2]), 'amin')
@@ -356,7 +363,7 @@ def _occluder_table(lines, n_dynamic, run=16):
     hi_y = torch.full((n,), -big, device=dev).scatter_reduce(0, oenv, torch.maximum(so[:, 1], so[:, 3]), 'amax')
     diam = torch.where(W > 0, torch.maximum(hi_x - lo_x, hi_y - lo_y), torch.zeros_like(vmax))
     meta = torch.stack([vmax, diam], -1).contiguous()
-    return occ, occ_starts.int().contiguous(), boxes, box_starts.int().contiguous(), meta, ids
+    return occ, occ_starts.int().contiguous(), boxes, box_starts.int().contiguous(), meta, rec
 
 
 class Render:

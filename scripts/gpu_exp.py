@@ -71,7 +71,7 @@ if __name__ == '__main__':
         cuda.set_option('nch', 0); cuda.set_option('threads', 0)
         cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0)
         c.render(); torch.cuda.synchronize()
-        for k in ('stat_tests', 'stat_groups', 'stat_dyn_rays', 'stat_dyn_iters'): out['view/' + k] = cuda.get_option(k)
+        for k in ('stat_tests', 'stat_groups', 'stat_dyn_rays', 'stat_dyn_iters', 'stat_replays'): out['view/' + k] = cuda.get_option(k)
         cuda.set_option('stats', 0)
         step = modules.FusedStep(c, subsample=1, raw=True)
         acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')

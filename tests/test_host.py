@@ -255,3 +255,34 @@ def test_downsample_and_observation_heads_on_a_fake_render():
     rgb = modules.RGB(FakeCore(), subsample=4)(r)
     assert rgb.shape == (1, 1, 3, 1, 2)
     torch.testing.assert_close(rgb[0, 0, 0, 0], torch.tensor([1.5, 5.5]))
+
+
+def test_spatial_table_is_a_padded_permutation_with_tight_boxes():
+    """cuda._occluder_table on CPU tensors: every env's static lines appear exactly once (in runs of 16, padded per
+    env), each run's box bounds its segments, and every row carries its line's texel offset / count and index."""
+    from megastep_b200 import scene, synthetic
+    A = 2
+    gs = synthetic.sample(5, seed=3)
+    arrays = scene.scene_arrays(gs, A, np.random.RandomState(3))
+    lines = cuda.Ragged3D(torch.as_tensor(arrays['lines']), torch.as_tensor(arrays['line_widths']))
+    tw = torch.as_tensor(arrays['tex_widths'])
+    ts = tw.long().cumsum(0) - tw.long()
+    AF = A * len(arrays['model'])
+    occ, occ_starts, boxes, box_starts, meta, rec = cuda._occluder_table(lines, AF, 16, tw, ts)
+    assert occ.shape[0] == rec.shape[0] == 16 * boxes.shape[0]
+    for n in range(5):
+        L = int(lines.widths[n]); W = L - AF; nb = (W + 15) // 16
+        assert int(occ_starts[n]) == 16 * int(box_starts[n])
+        rows = slice(int(occ_starts[n]), int(occ_starts[n]) + 16 * nb)
+        ids = rec[rows, 3].numpy()
+        assert sorted(ids[:W]) == list(range(AF, L)) and (ids[W:] == -1).all()
+        mine = lines[n].reshape(-1, 4)
+        assert torch.equal(occ[rows][:W], mine[ids[:W]])
+        g = int(lines.starts[n]) + ids[:W]
+        got_ts = (rec[rows, 1][:W].long() << 32) | (rec[rows, 0][:W].long() & 0xffffffff)
+        assert torch.equal(got_ts, ts[g]) and torch.equal(rec[rows, 2][:W], tw[g])
+        for b in range(nb):
+            seg = occ[rows][16 * b:min(16 * b + 16, W)]
+            bx = boxes[int(box_starts[n]) + b]
+            assert bx[0] == seg[:, [0, 2]].min() and bx[2] == seg[:, [0, 2]].max()
+            assert bx[1] == seg[:, [1, 3]].min() and bx[3] == seg[:, [1, 3]].max()
