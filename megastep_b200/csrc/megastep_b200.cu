@@ -1520,7 +1520,7 @@ __device__ __forceinline__ void view_agent(const KArgs& k, const VSmem& m, int n
         scr[32 * c + lane] = make_float4(__int_as_float(packed), loc, dotv, fmul(rlen, best));
     }
     __syncwarp();
-    // ---- shading: the texel gathers of two chunks in flight at a time
+    // ---- shading: the texel gathers of two chunks in flight at a time (all four cost more in spills than they hide)
 #pragma unroll 1
     for (int c0 = 0; c0 < NCH; c0 += 2) {
         ShadeIn in[2];
@@ -1545,7 +1545,92 @@ __device__ __forceinline__ void view_agent(const KArgs& k, const VSmem& m, int n
     }
 }
 
-template <int NCH, bool STATS>
+// collision_kernel (kernels.cu:179-210) for one agent, by one warp, over the env's run table: lane b tests run b's box
+// against the square the agent can reach this tick; only the overlapping runs are read, two per iteration (a run per
+// half warp), and a segment runs the reference's circle-vs-segment test only if its own bounding box overlaps too.
+// The minimum over obstacles is order-free. See DESIGN.md ("physics cull") for why the skipped ones cannot matter.
+// SHARED: the table is staged in shared memory (view_kernel); otherwise it is read through the read-only path.
+template <bool SHARED>
+__device__ __forceinline__ float physics_agent(const float* st_in, int A, int a, int lane, const float4* occ,
+                                               const float4* boxes, int W, int nb, float rF, float r1, float r2) {
+    const float* me = st_in + a * ST_STRIDE;
+    const float px = me[ST_PX], py = me[ST_PY], mx = me[ST_VX], my = me[ST_VY];
+    const float vx = fmul(mx, rF), vy = fmul(my, rF);
+    const float vlen = sqrt_(ffma(vx, vx, fmul(vy, vy)));
+    const float r1sq = fmul(r1, r1);
+    // slow but moving agents: project()'s +1e-6 distorts distances -> test everything; exactly stationary ones can
+    // only trigger the end-point branch (:163-168: every other branch needs s > 0), which the same radius covers
+    const bool can_cull = vlen >= 1e-3f || (vx == 0.f && vy == 0.f);
+    const float rho = 1.05f * vlen + 2.2f * r1 + 0.02f;
+    float x = 1.f;
+    // other agents (:193-200): start-of-step state, no sequential resolution
+    for (int d1 = lane; d1 < A; d1 += 32) {
+        if (d1 != a) {
+            const float* o = st_in + d1 * ST_STRIDE;
+            x = fminf(x, collide_agents(px, py, mx, my, o[ST_PX], o[ST_PY], o[ST_VX], o[ST_VY], rF, r2));
+        }
+    }
+    const float u = fadd(vlen, 1e-6f), uu = fmul(u, u);
+    const int slot = lane / VRUN, within = lane - slot * VRUN;
+    for (int b0 = 0; b0 < nb; b0 += 32) {
+        bool visit = false;
+        if (b0 + lane < nb) {
+            const float4 bx = SHARED ? boxes[b0 + lane] : __ldg(boxes + b0 + lane);
+            visit = !(can_cull && (bx.x > px + rho || bx.z < px - rho || bx.y > py + rho || bx.w < py - rho));
+        }
+        unsigned runs = __ballot_sync(0xffffffffu, visit);
+        while (runs) {
+            const unsigned rest = runs & (runs - 1);
+            const int n0 = __ffs(runs) - 1, n1 = rest ? __ffs(rest) - 1 : -1;
+            const int nth = slot == 0 ? n0 : n1;
+            const int l = nth >= 0 ? VRUN * (b0 + nth) + within : W;
+            if (l < W) {
+                const float4 s4 = SHARED ? occ[l] : __ldg(occ + l);
+                const bool outside = (fminf(s4.x, s4.z) > px + rho) || (fmaxf(s4.x, s4.z) < px - rho) ||
+                                     (fminf(s4.y, s4.w) > py + rho) || (fmaxf(s4.y, s4.w) < py - rho);
+                if (!(can_cull && outside)) x = fminf(x, collide_line(px, py, vx, vy, vlen, u, uu, s4, r1, r1sq));
+            }
+            runs = rest & (rest - 1);
+        }
+    }
+    return warp_min(x);
+}
+
+// The ATen epilogue of physics() (kernels.cu:223-227) for one agent: integrate, wrap the angle, kill the momentum of
+// agents that hit something. Plain in-place stores (no storage swap). Leaves the new state in st_out.
+__device__ __forceinline__ void physics_integrate(const KArgs& k, const float* st_in, float* st_out, int n, int a, float x) {
+    const float* me = st_in + a * ST_STRIDE;
+    float* o = st_out + a * ST_STRIDE;
+    const int64_t i = (int64_t)n * k.s.n_agents + a;
+    const float npx = __fadd_rn(me[ST_PX], __fmul_rn(__fmul_rn(x, me[ST_VX]), k.inv_fps));
+    const float npy = __fadd_rn(me[ST_PY], __fmul_rn(__fmul_rn(x, me[ST_VY]), k.inv_fps));
+    float ang = __fadd_rn(me[ST_ANG], __fmul_rn(__fmul_rn(x, me[ST_AV]), k.inv_fps));
+    ang = __fsub_rn(remainder_(__fadd_rn(remainder_(ang, 360.f), 180.f), 360.f), 180.f);
+    const bool hit = x < 1.f;
+    const float nvx = hit ? 0.f : me[ST_VX], nvy = hit ? 0.f : me[ST_VY], nav = hit ? 0.f : me[ST_AV];
+    k.a.angles[i] = ang;
+    reinterpret_cast<float2*>(k.a.positions)[i] = make_float2(npx, npy);
+    k.a.angvelocity[i] = nav;
+    reinterpret_cast<float2*>(k.a.velocity)[i] = make_float2(nvx, nvy);
+    if (k.progress) k.progress[i] = x;
+    o[ST_ANG] = ang; o[ST_PX] = npx; o[ST_PY] = npy; o[ST_AV] = nav; o[ST_VX] = nvx; o[ST_VY] = nvy;
+}
+
+// MomentumMovement (modules.py:106-118) for one agent: velocities decay and take the chosen action's impulse.
+__device__ __forceinline__ void momentum_movement(const KArgs& k, int act, float ang, float& av, float2& vel) {
+    const float keep = k.mv_keep, dv = k.mv_dv, dw = k.mv_dw;
+    // action table of modules.py:95-96: 0 noop, 1 +y, 2 -y, 3 +x, 4 -x (agent-local), 5 +turn, 6 -turn
+    const float lx = (act == 3) ? dv : ((act == 4) ? -dv : 0.f);
+    const float ly = (act == 1) ? dv : ((act == 2) ? -dv : 0.f);
+    const float lw = (act == 5) ? dw : ((act == 6) ? -dw : 0.f);
+    const float rad = __fmul_rn(0.017453292519943295f, ang);
+    const float c = cosf(rad), s = sinf(rad);
+    av = __fadd_rn(__fmul_rn(keep, av), lw);
+    vel.x = __fadd_rn(__fmul_rn(keep, vel.x), __fsub_rn(__fmul_rn(c, lx), __fmul_rn(s, ly)));
+    vel.y = __fadd_rn(__fmul_rn(keep, vel.y), __fadd_rn(__fmul_rn(s, lx), __fmul_rn(c, ly)));
+}
+
+template <int NCH, bool PHYS, bool STATS>
 __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_constant__ KArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = blockIdx.x;
@@ -1567,15 +1652,30 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_
             bulk_g2s(m.boxes, k.s.occ_boxes + 4 * b0, (uint32_t)nb * 16u, m.bar);
         }
     }
+    // agent state -> shared memory (through MomentumMovement when the step carries actions)
     for (int a = tid; a < A; a += blockDim.x) {
         const int64_t i = (int64_t)n * A + a;
         const float2 pos = reinterpret_cast<const float2*>(k.a.positions)[i];
-        const float2 vel = reinterpret_cast<const float2*>(k.a.velocity)[i];
-        float* st = m.st_out + a * ST_STRIDE;
-        st[ST_ANG] = k.a.angles[i]; st[ST_PX] = pos.x; st[ST_PY] = pos.y;
-        st[ST_AV] = k.a.angvelocity[i]; st[ST_VX] = vel.x; st[ST_VY] = vel.y;
+        float2 vel = reinterpret_cast<const float2*>(k.a.velocity)[i];
+        const float ang = k.a.angles[i];
+        float av = k.a.angvelocity[i];
+        if (PHYS && k.has_mv) momentum_movement(k, k.mv.actions[i], ang, av, vel);
+        float* st = (PHYS ? m.st_in : m.st_out) + a * ST_STRIDE;
+        st[ST_ANG] = ang; st[ST_PX] = pos.x; st[ST_PY] = pos.y; st[ST_AV] = av; st[ST_VX] = vel.x; st[ST_VY] = vel.y;
     }
     __syncthreads();
+    if (nb > 0) mbar_wait(m.bar, 0);
+    if (PHYS) {
+        // physics (kernels.cu:179-230) over the staged table: one warp per agent, then the fused integration
+        const float rF = rcp(k.p.fps);
+        const float r2 = fmul(k.p.agent_radius, 2.0020000934600830078f);
+        const float r1 = fmul(k.p.agent_radius, 1.0010000467300415039f);
+        for (int a = warp; a < A; a += nwarps) {
+            const float x = physics_agent<true>(m.st_in, A, a, lane, m.seg + AF, m.boxes, W, nb, rF, r1, r2);
+            if (lane == 0) physics_integrate(k, m.st_in, m.st_out, n, a, x);
+        }
+        __syncthreads();
+    }
     // draw_kernel (kernels.cu:297-318): the agents' model lines, at their current poses, into shared and global memory
     {
         const int F = k.s.n_model;
@@ -1592,7 +1692,6 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_
         }
     }
     __syncthreads();
-    if (nb > 0) mbar_wait(m.bar, 0);
     const int RB = k.ray_blocks;
     for (int w = warp; w < A * RB; w += nwarps) {
         view_agent<NCH, STATS>(k, m, n, g0, L, W, nb, w / RB, w % RB, m.scr + warp * 128, lane);
@@ -1758,6 +1857,7 @@ static long long g_opt_split = 0;        // 1: cast kernel + shade kernel (measu
 static long long g_opt_two_phase = 0;    // 1: bin every (agent, segment) once into shared memory first (measured slower: the
                                          // records cost 70 KB per CTA, which halves residency)
 static long long g_opt_variant = 0;      // experiment switches (see KArgs::variant)
+static long long g_opt_split_step = 0;   // 1: msb_step launches physics and render separately
 static long long g_opt_legacy = 0;       // 1: render with the line-order env_kernel instead of view_kernel
 static long long g_opt_fused_step = 0;   // 1: msb_step runs physics and render in ONE kernel (slower: see DESIGN.md)
 static unsigned long long* g_stats = nullptr;   // device counters, enabled by option "stats"
@@ -1835,6 +1935,7 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "debug_skip_dyn")) { g_opt_skip_dyn = value; return 0; }
     if (!strcmp(name, "fused_step")) { g_opt_fused_step = value; return 0; }
     if (!strcmp(name, "legacy_render")) { g_opt_legacy = value; return 0; }
+    if (!strcmp(name, "split_step")) { g_opt_split_step = value; return 0; }
     if (!strcmp(name, "variant")) { g_opt_variant = value; return 0; }
     if (!strcmp(name, "timing")) {
         timing_flush();
@@ -1925,19 +2026,20 @@ static bool use_view(const KArgs& k) {
     return !g_opt_legacy && k.s.occ_lines && k.s.occ_rec && !k.split_render && !k.two_phase;
 }
 
-static int launch_view(const KArgs& k, int nch, int threads, cudaStream_t st) {
+static int launch_view(const KArgs& k, bool phys, int nch, int threads, cudaStream_t st) {
     const size_t sm = vsmem_bytes(k.wcap, threads / 32, k.s.n_agents, k.s.n_agents * k.s.n_model);
     if (sm > 227 * 1024) return fail("%s", "scene too large: an env's segments do not fit in shared memory (227 KB)");
 #define MSB_LAUNCH(N)                                                                                            \
     {                                                                                                            \
-        auto fn = k.stats ? view_kernel<N, true> : view_kernel<N, false>;                                        \
+        auto fn = phys ? (k.stats ? view_kernel<N, true, true> : view_kernel<N, true, false>)                    \
+                       : (k.stats ? view_kernel<N, false, true> : view_kernel<N, false, false>);                 \
         if (sm > 48 * 1024 && check(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), \
                                     "cudaFuncSetAttribute"))                                                     \
             return 1;                                                                                            \
         fn<<<k.s.n_envs, threads, sm, st>>>(k);                                                                  \
     }
     {
-        TimedLaunch timed(TK_RENDER, st);
+        TimedLaunch timed(phys ? TK_STEP : TK_RENDER, st);
         switch (nch) {
             case 1: MSB_LAUNCH(1); break;
             case 2: MSB_LAUNCH(2); break;
@@ -2109,7 +2211,7 @@ extern "C" int msb_render(const msb_params* p, const msb_scenery* s, const msb_a
     plan_render(p, s, k, &nch, &rb, &threads);
     k.ray_blocks = rb;
     if (use_view(k)) {
-        if (launch_view(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
+        if (launch_view(k, false, nch, threads, (cudaStream_t)cuda_stream)) return 1;
     } else if (launch_env<MODE_RENDER>(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
     if (launch_shade(k, (cudaStream_t)cuda_stream)) return 1;
     return launch_dyn(k, (cudaStream_t)cuda_stream);
@@ -2138,18 +2240,18 @@ extern "C" int msb_step(const msb_params* p, const msb_scenery* s, const msb_age
     int nch, rb, threads;
     plan_render(p, s, k, &nch, &rb, &threads);
     k.ray_blocks = rb;
-    if (g_opt_fused_step) {
+    if (use_view(k) && !g_opt_split_step) {
+        // the whole tick in ONE kernel: movement + physics over the staged table, draw, render, heads
+        if (launch_view(k, true, nch, threads, (cudaStream_t)cuda_stream)) return 1;
+    } else if (g_opt_fused_step) {
         k.split_render = 0;
         if (launch_env<MODE_STEP>(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
     } else {
-        // physics (with the movement prologue) and render (with the heads) as two launches: the physics stage needs
-        // ~40 registers and runs at twice the occupancy on its own; inside the one-kernel variant it inherits the
-        // render stage's ~77 (measured: 221 us fused vs 194 us split at Deathmatch 4096x4x128)
         int pthreads = 128;
         if (g_opt_threads >= 32 && g_opt_threads <= 256) pthreads = (int)(g_opt_threads / 32) * 32;
         if (launch_env<MODE_PHYSICS>(k, 1, pthreads, (cudaStream_t)cuda_stream)) return 1;
         if (use_view(k)) {
-            if (launch_view(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
+            if (launch_view(k, false, nch, threads, (cudaStream_t)cuda_stream)) return 1;
         } else if (launch_env<MODE_RENDER>(k, nch, threads, (cudaStream_t)cuda_stream)) return 1;
     }
     if (launch_shade(k, (cudaStream_t)cuda_stream)) return 1;

@@ -76,6 +76,8 @@ if __name__ == '__main__':
         step = modules.FusedStep(c, subsample=1, raw=True)
         acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')
         out['view/step_us'] = round(timeit(lambda: step(acts)), 1)
+        cuda.set_option('split_step', 1); out['view/step_split_us'] = round(timeit(lambda: step(acts)), 1); cuda.set_option('split_step', 0)
+        cuda.set_option('debug_skip_dyn', 1); out['view/step_nodyn_us'] = round(timeit(lambda: step(acts)), 1); cuda.set_option('debug_skip_dyn', 0)
         out['physics_us'] = round(timeit(lambda: c.physics()), 1)
         print(json.dumps(out)); sys.exit(0)
     if mode == 'twophase':
