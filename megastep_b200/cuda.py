@@ -273,7 +273,7 @@ class Scenery:
                 textures=self._textures.vals.data_ptr(), tex_widths=self._textures.widths.data_ptr(),
                 tex_starts=self._tex_starts.data_ptr(), baked=self._baked.vals.data_ptr(), model=self._model.data_ptr(),
                 n_lines=self._lines.vals.size(0), n_texels=self._textures.vals.size(0))
-            if BUILD_OCCLUDERS and self._lines.vals.size(0) > 0:
+            if self._lines.vals.size(0) > 0:
                 self._occ = _occluder_table(self._lines, self._n_agents * self._model.size(0), OCCLUDER_RUN,
                                             self._textures.widths, self._tex_starts)
                 (self._c.occ_lines, self._c.occ_starts, self._c.occ_boxes, self._c.box_starts,
@@ -386,7 +386,6 @@ class Physics:
 # --------------------------------------------------------------------------------------------------------------
 _PARAMS = None
 OCCLUDER_RUN = 16        # segments per run / bounding box of the spatial table
-BUILD_OCCLUDERS = True  # False: the second pass scans the segments in their original order (same results, slower)
 USE_WORKSPACE = True   # False: agent-hit rays are lit inline by the first pass (same results; used by tests)
 
 

@@ -29,7 +29,6 @@ if __name__ == '__main__':
     mode = sys.argv[1] if len(sys.argv) > 1 else 'exp'
     if len(sys.argv) > 2: cuda.OCCLUDER_RUN = int(sys.argv[2])
     c = setup()
-    if len(sys.argv) > 3: cuda.set_option('variant', int(sys.argv[3]))
     if mode == 'ncu':
         for _ in range(3): c.render()
         torch.cuda.synchronize()
@@ -54,51 +53,24 @@ if __name__ == '__main__':
         sys.exit(0)
     if mode == 'view':
         out = {}
-        cuda.set_option('legacy_render', 1)
-        base = c.render()
-        out['legacy/render_us'] = round(timeit(lambda: c.render()), 1)
-        cuda.set_option('debug_skip_dyn', 1); out['legacy/main_us'] = round(timeit(lambda: c.render()), 1); cuda.set_option('debug_skip_dyn', 0)
-        cuda.set_option('legacy_render', 0)
-        r = c.render()
-        for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
-            a, b = getattr(r, k), getattr(base, k)
-            out[f'identical/{k}'] = bool(((a == b) | (a != a) & (b != b)).all())
-            out[f'mismatches/{k}'] = int((~((a == b) | (a != a) & (b != b))).sum())
-        for nch, threads in ((0, 0), (4, 128), (2, 256), (2, 128), (1, 256), (4, 256)):
+        for nch, threads in ((0, 0), (4, 128), (2, 256), (2, 128), (2, 64), (1, 128), (1, 256)):
             cuda.set_option('nch', nch); cuda.set_option('threads', threads)
-            out[f'view/render_us/nch{nch}/t{threads}'] = round(timeit(lambda: c.render()), 1)
-            cuda.set_option('debug_skip_dyn', 1); out[f'view/main_us/nch{nch}/t{threads}'] = round(timeit(lambda: c.render()), 1); cuda.set_option('debug_skip_dyn', 0)
+            out[f'render_us/nch{nch}/t{threads}'] = round(timeit(lambda: c.render()), 1)
+            cuda.set_option('debug_skip_dyn', 1); out[f'main_us/nch{nch}/t{threads}'] = round(timeit(lambda: c.render()), 1); cuda.set_option('debug_skip_dyn', 0)
         cuda.set_option('nch', 0); cuda.set_option('threads', 0)
         cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0)
         c.render(); torch.cuda.synchronize()
-        for k in ('stat_tests', 'stat_groups', 'stat_dyn_rays', 'stat_dyn_iters', 'stat_replays'): out['view/' + k] = cuda.get_option(k)
+        for k in ('stat_tests', 'stat_groups', 'stat_dyn_rays', 'stat_dyn_iters', 'stat_dyn_entries', 'stat_replays'): out[k] = cuda.get_option(k)
         cuda.set_option('stats', 0)
-        step = modules.FusedStep(c, subsample=1, raw=True)
-        acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')
-        out['view/step_us'] = round(timeit(lambda: step(acts)), 1)
-        cuda.set_option('split_step', 1); out['view/step_split_us'] = round(timeit(lambda: step(acts)), 1); cuda.set_option('split_step', 0)
-        cuda.set_option('debug_skip_dyn', 1); out['view/step_nodyn_us'] = round(timeit(lambda: step(acts)), 1); cuda.set_option('debug_skip_dyn', 0)
         out['physics_us'] = round(timeit(lambda: c.physics()), 1)
-        print(json.dumps(out)); sys.exit(0)
-    if mode == 'twophase':
-        out = {}
-        for tp in (0, 1):
-            cuda.set_option('two_phase', tp)
-            for nch in ((0,) if tp == 0 else (1, 2, 4)):
-                for threads in ((0,) if tp == 0 else (0, 128, 256, 512)):
-                    cuda.set_option('nch', nch); cuda.set_option('threads', threads)
-                    out[f'render_us/tp{tp}/nch{nch}/t{threads}'] = round(timeit(lambda: c.render()), 1)
-        cuda.set_option('two_phase', 1); cuda.set_option('nch', 0); cuda.set_option('threads', 0)
-        print(json.dumps(out)); sys.exit(0)
-    if mode == 'variants':
-        out = {}
-        for v in (0, 1, 4, 5, 6):
-            cuda.set_option('variant', v)
-            cuda.set_option('debug_skip_dyn', 1); out[f'main_us/variant{v}'] = round(timeit(lambda: c.render()), 1); cuda.set_option('debug_skip_dyn', 0)
-            out[f'render_us/variant{v}'] = round(timeit(lambda: c.render()), 1)
-            cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0); c.render(); torch.cuda.synchronize()
-            out[f'tests/variant{v}'] = cuda.get_option('stat_tests'); cuda.set_option('stats', 0)
-        cuda.set_option('variant', 0)
+        torch.manual_seed(0)
+        acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')
+        for fused in (0, 1):
+            cuda.set_option('fused_step', fused)
+            c2 = setup()
+            step = modules.FusedStep(c2, subsample=1, raw=True)
+            out[f'step_us/fused{fused}'] = round(timeit(lambda: step(acts)), 1)
+        cuda.set_option('fused_step', 0)
         print(json.dumps(out)); sys.exit(0)
     out = {}
     for skip in (0, 1):

@@ -232,97 +232,83 @@ def test_rgbd_head_equals_rgb_and_depth_modules():
 
 @pytest.mark.parametrize('res', [48, 64, 128, 512])
 def test_every_kernel_variant_gives_identical_results(res):
-    """render() through view_kernel (the spatial table, nearest boxes first, any line order) and through the line-order
-    env_kernel, under every chunking / thread-count option: what is skipped and who runs it changes, results never."""
+    """The chunking / thread-count options change which boxes a warp opens, which segments it skips and who runs
+    what, never results."""
     from megastep_b200 import cuda
     gs, arrays, st = make('synthetic', 10, 4, seed=51)
     c = common.to_device(arrays, st, res, 70.)
     base = c.render()
-
-    def check(what):
-        r = c.render()
-        for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
-            a, b = getattr(r, k), getattr(base, k)
-            assert ((a == b) | (a != a) & (b != b)).all(), f'{what}: {k} differs'
-
     try:
         for nch in (1, 2, 4):
-            for threads in (64, 128, 256):
+            for threads in (32, 64, 128, 256):
                 cuda.set_option('nch', nch)
                 cuda.set_option('threads', threads)
-                cuda.set_option('legacy_render', 0)
-                check(f'view nch={nch} threads={threads}')
-                cuda.set_option('legacy_render', 1)
-                for variant in (0, 1, 4, 5, 6, 7, 8, 9, 10):  # 0/1: depth cull on/off; 4-7: segment-major variants; 8, 9: two-phase; 10: split
-                    cuda.set_option('two_phase', 1 if variant in (8, 9) else 0)
-                    cuda.set_option('split_render', 1 if variant == 10 else 0)
-                    cuda.set_option('variant', variant % 8)
-                    check(f'legacy variant={variant} nch={nch} threads={threads}')
+                r = c.render()
+                for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
+                    a, b = getattr(r, k), getattr(base, k)
+                    assert ((a == b) | (a != a) & (b != b)).all(), f'nch={nch} threads={threads}: {k} differs'
     finally:
-        for name in ('nch', 'threads', 'variant', 'two_phase', 'split_render', 'legacy_render'):
-            cuda.set_option(name, 0)
+        cuda.set_option('nch', 0)
+        cuda.set_option('threads', 0)
 
 
 def _same(a, b):
     return bool(((a == b) | (a != a) & (b != b)).all())
 
 
-def test_physics_with_and_without_the_occluder_table_agree():
-    """physics() reads its candidate segments through the box-culled occluder table when the scenery has one, else it
-    culls the staged segments itself; slow (|v| < 1e-3 per tick), stationary and fast agents must all agree bitwise."""
-    from megastep_b200 import cuda
+def test_step_with_physics_inside_the_render_kernel_agrees():
+    """msb_step with physics as its own launch (default) and fused into view_kernel (option fused_step): same
+    progress, same agent state, same observations, over several ticks with slow, stationary and fast agents."""
+    from megastep_b200 import cuda, modules
     gs, arrays, st = make('synthetic', 12, 4, seed=71)
     st['velocity'][:3] = 0.                                   # exactly stationary
     st['velocity'][3:6] *= 1e-4                                # slow but moving: the no-cull path
     outs = []
-    for table in (True, False):
-        cuda.BUILD_OCCLUDERS = table
+    for fused in (0, 1):
+        cuda.set_option('fused_step', fused)
         try:
             c = common.to_device(arrays, st, 64, 90.)
-            ps = []
-            for _ in range(3):
-                ps.append(c.physics().progress.clone())
-                c.agents.velocity.add_(torch.as_tensor(np.random.RandomState(1).normal(size=st['velocity'].shape).astype(np.float32)).cuda())
-            outs.append((ps, common.read_state(c)))
+            step = modules.FusedStep(c, subsample=2, raw=True)
+            acts = torch.as_tensor(np.random.RandomState(5).randint(0, 7, (3, 12, 4)).astype(np.int32)).cuda()
+            rec = []
+            for t in range(3):
+                out = step(acts[t])
+                rec.append((out.progress.clone(), out.obs.rgb.clone(), out.obs.d.clone(), out.obs.imu.clone(), out.render.indices.clone()))
+            outs.append((rec, common.read_state(c)))
         finally:
-            cuda.BUILD_OCCLUDERS = True
+            cuda.set_option('fused_step', 0)
     for a, b in zip(outs[0][0], outs[1][0]):
-        assert torch.equal(a, b)
+        assert all(_same(x, y) for x, y in zip(a, b))
     for k in outs[0][1]:
         assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
 
 
 @pytest.mark.parametrize('sub', [1, 4])
 def test_second_pass_inline_and_overflow_paths_agree(sub):
-    """Agent-hit rays are lit by dyn_kernel over the sorted occluder table (workspace), inline by the first pass (no
-    workspace), by a mix (workspace too small), or by dyn_kernel over the unsorted segments: all must give identical
-    screens and observations. Agents are packed close so many rays hit agents."""
-    import ctypes
-    from megastep_b200 import cuda, modules
+    """Agent-hit rays are lit by dyn_kernel (workspace), inline by the first pass (no workspace), or by a mix
+    (workspace too small): all must give identical screens and observations. Agents are packed close so many rays
+    hit agents."""
+    from megastep_b200 import cuda
     gs, arrays, st = make('box', 6, 4, seed=61)
     rng = np.random.RandomState(0)
     st['positions'] = (3.5 + rng.uniform(-.6, .6, st['positions'].shape)).astype(np.float32)
     res = 128
     outs = []
-    for mode in ('workspace', 'inline', 'overflow', 'unsorted', 'split', 'split-overflow'):
+    for mode in ('workspace', 'inline', 'overflow'):
         cuda.USE_WORKSPACE = mode != 'inline'
-        cuda.set_option('split_render', 1 if mode.startswith('split') else 0)
-        cuda.BUILD_OCCLUDERS = mode != 'unsorted'
         try:
             c = common.to_device(arrays, st, res, 100.)
             plan = cuda.StepPlan(c.scenery, c.agents, c.params, actions=None, raw=True, subsample=sub)
         finally:
             cuda.USE_WORKSPACE = True
-            cuda.BUILD_OCCLUDERS = True
-        if mode.endswith('overflow'):
-            small = 16 + 6 * 4 * 32 * 4 + 3 * (16 + 32 * sub)      # ctrl + occluder cache + room for three pixel groups only
+        if mode == 'overflow':
+            small = 16 + 6 * 4 * 32 * 4 + 3 * (16 + 32 * 32)        # ctrl + occluder cache + room for three ray chunks only
             plan._wsbuf = torch.zeros(small, dtype=torch.uint8, device='cuda')
             plan._ws = cuda._Workspace(plan._wsbuf.data_ptr(), small)
         for _ in range(2):                                          # twice: the queue must re-arm itself
             plan.render_only()
         torch.cuda.synchronize()
         outs.append((plan.render.screen.clone(), plan.rgb.clone(), plan.render.indices.clone()))
-    cuda.set_option('split_render', 0)
     n_dyn = int(((outs[0][2] >= 0) & (outs[0][2] < 32)).sum())
     assert n_dyn > 50, 'the scene should have plenty of agent-hit rays'
     for other in outs[1:]:
