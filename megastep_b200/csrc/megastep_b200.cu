@@ -54,9 +54,10 @@ struct KArgs {
     unsigned long long* stats;  // optional diagnostics counters (may be null)
     int32_t debug_skip_dyn;     // timing experiments only: leave agent-hit rays unlit
     // queue of ray chunks whose agent-hit pixels are lit by dyn_kernel (load-balanced second pass)
-    int* dyn_ctrl;              // [0] entries reserved, [1] CTAs of dyn_kernel done, [2] entries handed out
+    int* dyn_ctrl;              // [0] entries reserved, [1] CTAs of dyn_kernel done
     unsigned char* dyn_entries; // null -> dynamic lights are resolved inline by the ray's own warp
     int32_t dyn_cap;            // entries that fit
+    int32_t dyn_window;         // PS: pixels per entry = max(DYN_MIN_WINDOW, subsample); entry = 16 + 32 * PS bytes
     int* dyn_cache;             // [N][A][32] last occluder of each light as seen from (around) each agent; a hint
 };
 
@@ -66,7 +67,7 @@ struct KArgs {
 enum { ST_ANG = 0, ST_PX = 1, ST_PY = 2, ST_AV = 3, ST_VX = 4, ST_VY = 5, ST_STRIDE = 8 };
 enum { STAT_TESTS = 0, STAT_GROUPS = 1, STAT_DYN_RAYS = 2, STAT_DYN_ITERS = 3, STAT_DYN_ENTRIES = 4, STAT_REPLAYS = 5 };
 enum { VRUN = 16 };                       // segments per run of the spatial table
-enum { DYN_STRIDE = 16 + 32 * 32 };       // bytes per queue entry: header + two float4 per pixel of a 32-ray chunk
+enum { DYN_MIN_WINDOW = 4 };               // pixels per queue entry: max(4, subsample) adjacent pixels (a 'window')
 
 // ---------------------------------------------------------------------------------------------------------------
 // physics
@@ -626,19 +627,28 @@ __device__ __forceinline__ void shade_chunk(const KArgs& k, const float4* __rest
         const unsigned subm = sub_ == 32 ? 0xffffffffu : ((1u << sub_) - 1u);
         const unsigned gmask = (dm >> gl) & subm;                         // my group's agent-hit pixels
         if (k.dyn_entries) {
-            int slot = 0;
-            if (lane == 0) slot = atomicAdd(k.dyn_ctrl, 1);
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            queued = slot < k.dyn_cap;
-            if (queued) {
-                unsigned char* e = k.dyn_entries + (size_t)slot * DYN_STRIDE;
-                // which agent the chunk's first agent-hit pixel landed on: keys the persistent occluder cache
-                const int tgt = __shfl_sync(0xffffffffu, l0, __ffs(dm) - 1) / k.s.n_model;
-                if (lane == 0) *reinterpret_cast<int4*>(e) = make_int4(n, a * R + (r - lane), (int)dm, sub_ | (tgt << 8));
-                if (gmask && live) {
-                    float4* rec = reinterpret_cast<float4*>(e + 16) + 2 * lane;
-                    rec[0] = make_float4(b0, b1, b2, kk0);
-                    rec[1] = make_float4(Cx, Cy, intensity, 0.f);
+            // one entry per window of PS adjacent pixels that contains an agent-hit pixel (PS a multiple of sub_)
+            const int PS = k.dyn_window, wl = lane & ~(PS - 1);
+            const unsigned wmask = (dm >> wl) & (PS == 32 ? 0xffffffffu : ((1u << PS) - 1u));
+            const unsigned leaders = __ballot_sync(0xffffffffu, wmask != 0 && lane == wl);
+            const int cnt = __popc(leaders);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(k.dyn_ctrl, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            queued = base + cnt <= k.dyn_cap;
+            // which agent the window's first agent-hit pixel landed on: keys the persistent occluder cache
+            const int tgt = __shfl_sync(0xffffffffu, l0, wl + (wmask ? __ffs(wmask) - 1 : 0)) / k.s.n_model;
+            if (wmask) {
+                const int slot = base + __popc(leaders & ((1u << wl) - 1u));
+                if (slot < k.dyn_cap) {
+                    unsigned char* e = k.dyn_entries + (size_t)slot * (16 + 32 * PS);
+                    // a chunk that does not fit as a whole falls back inline: its reserved slots carry an empty mask
+                    if (lane == wl) *reinterpret_cast<int4*>(e) = make_int4(n, a * R + (r - lane + wl), queued ? (int)wmask : 0, sub_ | (tgt << 8));
+                    if (queued && gmask && live) {
+                        float4* rec = reinterpret_cast<float4*>(e + 16) + 2 * (lane - wl);
+                        rec[0] = make_float4(b0, b1, b2, kk0);
+                        rec[1] = make_float4(Cx, Cy, intensity, 0.f);
+                    }
                 }
             }
         }
@@ -923,11 +933,13 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_
 
 // ---------------------------------------------------------------------------------------------------------------
 // dyn_kernel: the load-balanced second pass over ray chunks that contain agent-hit pixels.
-// Entry = 16-byte header {env, agent*R + first ray of the chunk, mask of agent-hit pixels, subsample | hit agent << 8}
-// + per pixel (lane) two float4: {texel rgb, 1-dot^2} and {hit point x, hit point y, static intensity, -}; only the
-// pixels of pooling groups that contain an agent-hit pixel are filled in.
-// One warp per entry, handed out by an atomic counter (every entry is an independent unit of work, so the whole machine
-// is busy whatever the scene). light_intensity() (kernels.cu:238-268) for all the entry's pixels at once:
+// Entry = a window of PS = max(4, subsample) adjacent pixels with at least one agent-hit pixel: 16-byte header {env,
+// agent*R + first ray of the window, mask of agent-hit pixels, subsample | hit agent << 8} + per pixel two float4:
+// {texel rgb, 1-dot^2} and {hit point x, hit point y, static intensity, -}; only the pixels of pooling groups that
+// contain an agent-hit pixel are filled in. Small windows bound the serial work per entry; sharing the scans between
+// the few pixels of a window (they land centimetres apart on one agent's outline) divides the work per pixel.
+// One warp per entry, entries strided over one resident wave of warps (every entry is an independent unit of work, so the
+// whole machine is busy whatever the scene). light_intensity() (kernels.cu:238-268) for all the entry's pixels at once:
 //   1. lane = light: each light's remembered occluder (persistent per (env, hit agent) in the workspace; a hint,
 //      re-verified by the exact test) settles most occluded lights, one test per (pixel, light);
 //   2. light by light, for the lights some pixel still needs: lane b tests run b's box against the box around the
@@ -946,24 +958,23 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
     const int reserved = *reinterpret_cast<volatile int*>(k.dyn_ctrl);
     const int count = reserved < k.dyn_cap ? reserved : k.dyn_cap;
     unsigned dyn_rays = 0, dyn_iters = 0, dyn_entries = 0;
-    while (true) {
-        int ei = 0;
-        if (lane == 0) ei = atomicAdd(k.dyn_ctrl + 2, 1);
-        ei = __shfl_sync(0xffffffffu, ei, 0);
-        if (ei >= count) break;
-        const unsigned char* e = k.dyn_entries + (size_t)ei * DYN_STRIDE;
+    // entries are strided over the grid's warps (a shared counter would serialise thousands of warps on one address)
+    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
+    for (int ei = wg; ei < count; ei += tw) {
+        const int PS = k.dyn_window;
+        const unsigned char* e = k.dyn_entries + (size_t)ei * (16 + 32 * PS);
         const int4 hdr = *reinterpret_cast<const int4*>(e);
         const unsigned mask = (unsigned)hdr.z;
         if (!mask) continue;                                   // slot reserved by a chunk that fell back inline
         const int sub = hdr.w & 0xff, tgt = hdr.w >> 8;
-        const int n = hdr.x, ar = hdr.y;                       // env; agent * R + first ray of the chunk
+        const int n = hdr.x, ar = hdr.y;                       // env; agent * R + first ray of the window
         const int av = ar / R, r0 = ar - av * R;
         const int64_t ag = (int64_t)n * A + av;
         const int gl = lane & ~(sub - 1);
         const unsigned subm = sub == 32 ? 0xffffffffu : ((1u << sub) - 1u);
-        const unsigned gmask = (mask >> gl) & subm;            // my pooling group's agent-hit pixels
-        const bool have = gmask != 0 && (r0 + lane < R);       // my pixel's records were filled in
-        const bool isdyn = (mask >> lane) & 1u;
+        const unsigned gmask = lane < PS ? (mask >> gl) & subm : 0u;   // my pooling group's agent-hit pixels
+        const bool have = lane < PS && gmask != 0 && (r0 + lane < R);       // my pixel's records were filled in
+        const bool isdyn = lane < PS && ((mask >> lane) & 1u);
         float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (have) {
             const float4* rec = reinterpret_cast<const float4*>(e + 16) + 2 * lane;
@@ -1033,17 +1044,26 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
                 todo_any &= todo_any - 1;
                 const float Ix = __shfl_sync(0xffffffffu, lx, i), Iy = __shfl_sync(0xffffffffu, ly, i);
                 unsigned need = __ballot_sync(0xffffffffu, isdyn && ((mytodo >> i) & 1u));
-                // conservative query box (see DESIGN.md "shadow cull"): rounding can move the computed crossing by at
-                // most delta (a fraction of each segment's length) along either segment
+                // conservative query (see DESIGN.md "shadow cull"): rounding can move the computed crossing by at most
+                // delta (a fraction of each segment's length) along either segment. A run can only hold an occluder if
+                // its box comes within mg (+ the spread of the hit points) of the segment from the light to the middle
+                // of the hit points: slab test of that segment against the grown box.
                 const float ulen = fmaxf(fmaxf(fabsf(cx0 - Ix), fabsf(cx1 - Ix)), fmaxf(fabsf(cy0 - Iy), fabsf(cy1 - Iy)));
                 const float delta = 4e-4f * vmax * (diam + ulen);
-                const float mg = delta * (ulen + vmax) + 0.01f;
-                const float qx0 = fminf(Ix, cx0) - mg, qx1 = fmaxf(Ix, cx1) + mg, qy0 = fminf(Iy, cy0) - mg, qy1 = fmaxf(Iy, cy1) + mg;
+                const float mg = delta * (ulen + vmax) + 0.01f + fmaxf(cx1 - cx0, cy1 - cy0);
+                const float mx_ = 0.5f * (cx0 + cx1) - Ix, my_ = 0.5f * (cy0 + cy1) - Iy;      // light -> middle of the hit points
+                const float irx = 1.f / mx_, iry = 1.f / my_;                                  // +-inf when axis-parallel
                 int found = -1;
                 for (int bb = 0; bb < nb && need; bb += 32) {
                     float4 bx = bx0;
                     if (bb) bx = (bb + lane < nb) ? __ldg(boxes + bb + lane) : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-                    const bool visit = !(bx.x > qx1 || bx.z < qx0 || bx.y > qy1 || bx.w < qy0);
+                    // parameters at which the segment is inside each slab of the grown box; NaN (0 * inf: the segment runs
+                    // along a slab boundary) compares false below, i.e. errs on the side of visiting
+                    const float tx0 = (bx.x - mg - Ix) * irx, tx1 = (bx.z + mg - Ix) * irx;
+                    const float ty0 = (bx.y - mg - Iy) * iry, ty1 = (bx.w + mg - Iy) * iry;
+                    const float tlo = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), 0.f);
+                    const float thi = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), 1.f);
+                    const bool visit = (bb + lane < nb) && !(tlo > thi);
                     unsigned runs = __ballot_sync(0xffffffffu, visit);
                     while (runs && need) {
                         // lanes [0, 16) take the first run still to visit, lanes [16, 32) the second
@@ -1076,7 +1096,8 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
             if (hint != hint_before) cache[lane] = hint;           // racy on purpose: any stored value is only a hint
             // 3. lane = pixel: sum the unoccluded lights in light order (:261-264)
             float acc = 0.1f;                                      // AMBIENT (kernels.cu:9)
-            for (int i = 0; i < nlights; i++) {
+            for (unsigned lit = __reduce_or_sync(0xffffffffu, mylit); lit; lit &= lit - 1) {
+                const int i = __ffs(lit) - 1;
                 const float Ix = __shfl_sync(0xffffffffu, lx, i), Iy = __shfl_sync(0xffffffffu, ly, i);
                 const float Ii = __shfl_sync(0xffffffffu, li, i);
                 if ((mylit >> i) & 1u) {
@@ -1115,7 +1136,7 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(k.dyn_ctrl + 1, 1) == (int)gridDim.x - 1) { k.dyn_ctrl[0] = 0; k.dyn_ctrl[1] = 0; k.dyn_ctrl[2] = 0; }
+        if (atomicAdd(k.dyn_ctrl + 1, 1) == (int)gridDim.x - 1) { k.dyn_ctrl[0] = 0; k.dyn_ctrl[1] = 0; }
     }
 }
 
@@ -1164,6 +1185,7 @@ static long long g_launches = 0;
 static long long g_opt_nch = 0;          // 0 = auto
 static long long g_opt_threads = 0;      // 0 = auto
 static long long g_opt_skip_dyn = 0;     // debug
+static long long g_opt_dyn_window = 0;   // 0 = default (DYN_MIN_WINDOW); 1, 2, 4, 8: pixels per queue entry when subsample is smaller
 static long long g_opt_fused_step = 0;   // 1: msb_step runs physics inside view_kernel (measured slower: the physics latency
                                          // chain adds to every CTA's life instead of running at its own high occupancy)
 static unsigned long long* g_stats = nullptr;   // device counters, enabled by option "stats"
@@ -1240,6 +1262,7 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "threads")) { g_opt_threads = value; return 0; }
     if (!strcmp(name, "debug_skip_dyn")) { g_opt_skip_dyn = value; return 0; }
     if (!strcmp(name, "fused_step")) { g_opt_fused_step = value; return 0; }
+    if (!strcmp(name, "dyn_window")) { g_opt_dyn_window = value; return 0; }
     if (!strcmp(name, "timing")) {
         timing_flush();
         g_opt_timing = value;
@@ -1379,7 +1402,13 @@ static int launch_view(const KArgs& k, bool phys, int nch, int threads, cudaStre
     return check(cudaGetLastError(), "view_kernel launch");
 }
 
-// workspace layout: int ctrl[4] (16 bytes) | occluder cache int[N][A][32] | queue entries of DYN_STRIDE bytes
+static int dyn_window(int sub) {
+    int w = DYN_MIN_WINDOW;
+    if (g_opt_dyn_window == 1 || g_opt_dyn_window == 2 || g_opt_dyn_window == 4 || g_opt_dyn_window == 8) w = (int)g_opt_dyn_window;
+    return sub > w ? sub : w;
+}
+
+// workspace layout: int ctrl[4] (16 bytes) | occluder cache int[N][A][32] | queue entries of 16 + 32 * PS bytes
 static int64_t cache_bytes(const msb_scenery* s) { return (int64_t)s->n_envs * s->n_agents * 32 * 4; }
 
 static int set_workspace(KArgs& k, const msb_workspace* ws) {
@@ -1389,8 +1418,10 @@ static int set_workspace(KArgs& k, const msb_workspace* ws) {
     k.dyn_cap = 0;
     if (!ws || !ws->ptr) return 0;
     if (((uintptr_t)ws->ptr & 15) != 0) return fail("%s", "workspace must be 16-byte aligned");
+    const int sub = k.has_obs ? k.obs.subsample : 1;
+    k.dyn_window = dyn_window(sub);
     const int64_t head = 16 + cache_bytes(&k.s);
-    const int64_t cap = (ws->bytes - head) / DYN_STRIDE;
+    const int64_t cap = (ws->bytes - head) / (16 + 32 * k.dyn_window);
     if (cap < 1) return 0;
     k.dyn_ctrl = reinterpret_cast<int*>(ws->ptr);
     k.dyn_cache = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws->ptr) + 16);
@@ -1401,7 +1432,7 @@ static int set_workspace(KArgs& k, const msb_workspace* ws) {
 
 static int launch_dyn(const KArgs& k, cudaStream_t st) {
     if (!k.dyn_entries) return 0;
-    static int per_sm[2] = {0, 0};          // resident CTAs per SM of dyn_kernel<false/true>: one wave, entries by atomic counter
+    static int per_sm[2] = {0, 0};          // resident CTAs per SM of dyn_kernel<false/true>: exactly one wave
     static int sms = 0;
     if (!sms) {
         int dev = 0;
@@ -1423,11 +1454,12 @@ static int launch_dyn(const KArgs& k, cudaStream_t st) {
 
 extern "C" int64_t msb_workspace_bytes(const msb_params* p, const msb_scenery* s, int32_t subsample) {
     if (!p || !s || subsample < 1) return 0;
-    const int64_t chunks = (int64_t)s->n_envs * s->n_agents * ((p->res + 31) / 32);
-    // room for a quarter of all ray chunks to contain an agent-hit ray (overflow falls back to inline, still exact)
-    int64_t cap = chunks / 4;
-    if (cap < 4096) cap = chunks < 4096 ? chunks : 4096;
-    return 16 + cache_bytes(s) + cap * DYN_STRIDE;
+    const int PS = subsample > 8 ? subsample : 8;          // sized for the largest window the options allow
+    const int64_t windows = (int64_t)s->n_envs * s->n_agents * ((p->res + PS - 1) / PS);
+    // room for a quarter of all pixel windows to contain an agent-hit ray (overflow falls back to inline, still exact)
+    int64_t cap = windows / 4;
+    if (cap < 16384) cap = windows < 16384 ? windows : 16384;
+    return 16 + cache_bytes(s) + cap * (16 + 32 * PS);
 }
 
 static void set_obs(KArgs& k, const msb_obs_out* obs) {

@@ -58,6 +58,19 @@ if __name__ == '__main__':
             out[f'render_us/nch{nch}/t{threads}'] = round(timeit(lambda: c.render()), 1)
             cuda.set_option('debug_skip_dyn', 1); out[f'main_us/nch{nch}/t{threads}'] = round(timeit(lambda: c.render()), 1); cuda.set_option('debug_skip_dyn', 0)
         cuda.set_option('nch', 0); cuda.set_option('threads', 0)
+        for w in (1, 2, 4, 8):
+            cuda.set_option('dyn_window', w)
+            out[f'render_us/window{w}'] = round(timeit(lambda: c.render()), 1)
+            cuda.set_option('timing', 1)
+            for _ in range(30): c.render()
+            torch.cuda.synchronize()
+            out[f'dyn_kernel_us/window{w}'] = round(cuda.get_option('time_ns_dyn') / max(1, cuda.get_option('time_count_dyn')) / 1e3, 1)
+            cuda.set_option('timing', 0)
+            cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0)
+            c.render(); torch.cuda.synchronize()
+            out[f'dyn_entries/window{w}'] = cuda.get_option('stat_dyn_entries'); out[f'dyn_iters/window{w}'] = cuda.get_option('stat_dyn_iters')
+            cuda.set_option('stats', 0)
+        cuda.set_option('dyn_window', 0)
         cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0)
         c.render(); torch.cuda.synchronize()
         for k in ('stat_tests', 'stat_groups', 'stat_dyn_rays', 'stat_dyn_iters', 'stat_dyn_entries', 'stat_replays'): out[k] = cuda.get_option(k)
@@ -70,6 +83,17 @@ if __name__ == '__main__':
             c2 = setup()
             step = modules.FusedStep(c2, subsample=1, raw=True)
             out[f'step_us/fused{fused}'] = round(timeit(lambda: step(acts)), 1)
+            cuda.set_option('timing', 1)
+            for _ in range(50): step(acts)
+            torch.cuda.synchronize()
+            for kind in ('physics', 'render', 'dyn', 'step'):
+                cnt = cuda.get_option(f'time_count_{kind}')
+                if cnt: out[f'kernel_us/fused{fused}/{kind}'] = round(cuda.get_option(f'time_ns_{kind}') / cnt / 1e3, 1)
+            cuda.set_option('timing', 0)
+            cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0)
+            step(acts); torch.cuda.synchronize()
+            for k in ('stat_tests', 'stat_groups', 'stat_dyn_rays', 'stat_dyn_iters', 'stat_dyn_entries'): out[f'after_steps/fused{fused}/{k}'] = cuda.get_option(k)
+            cuda.set_option('stats', 0)
         cuda.set_option('fused_step', 0)
         print(json.dumps(out)); sys.exit(0)
     out = {}

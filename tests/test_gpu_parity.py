@@ -302,7 +302,7 @@ def test_second_pass_inline_and_overflow_paths_agree(sub):
         finally:
             cuda.USE_WORKSPACE = True
         if mode == 'overflow':
-            small = 16 + 6 * 4 * 32 * 4 + 3 * (16 + 32 * 32)        # ctrl + occluder cache + room for three ray chunks only
+            small = 16 + 6 * 4 * 32 * 4 + 3 * (16 + 32 * max(4, sub))   # ctrl + occluder cache + room for three pixel windows only
             plan._wsbuf = torch.zeros(small, dtype=torch.uint8, device='cuda')
             plan._ws = cuda._Workspace(plan._wsbuf.data_ptr(), small)
         for _ in range(2):                                          # twice: the queue must re-arm itself
