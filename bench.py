@@ -89,7 +89,7 @@ def algorithmic_bytes(cfg, arrays, fused, raw=True):
 
 
 def render_kernel_bytes(cfg, arrays, raw=True):
-    """Algorithmic bytes of ONE launch of env_kernel<RENDER> (draw + raycast + shade + heads), the dominant kernel:
+    """Algorithmic bytes of ONE launch of view_kernel (draw + raycast + shade + heads), the dominant kernel:
     the render terms of SURVEY.md §8(d) — 16AF (draw) + [12A + 16L + 8] + 16AR (raycast) + (40 + 12)AR (shade) — plus
     the fused heads, 16AR/sub + 12A. Texel gathers are counted per ray with no reuse, as §8(d) specifies."""
     A, R, F = cfg['n_agents'], cfg['res'], 8
@@ -102,11 +102,11 @@ def render_kernel_bytes(cfg, arrays, raw=True):
 
 
 def profiled_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of env_kernel<RENDER>, from the committed ncu --set full
-    capture of this same command (profiles/r01_step_full_summary.json)."""
-    path = os.path.join(ROOT, 'profiles', 'r01_step_full_summary.json')
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of view_kernel, from the committed ncu --set full
+    capture of the same workload (profiles/r01_view_kernel_full_summary.json)."""
+    path = os.path.join(ROOT, 'profiles', 'r01_view_kernel_full_summary.json')
     try:
-        recs = [r for r in json.load(open(path)) if 'env_kernel<2' in r['Kernel Name']]
+        recs = [r for r in json.load(open(path)) if 'view_kernel' in r['Kernel Name']]
         mb = [float(r['dram__bytes_read.sum']) + float(r['dram__bytes_write.sum']) for r in recs]
         return sum(mb) / len(mb) * 1e6, os.path.relpath(path, ROOT)
     except (OSError, KeyError, ValueError, ZeroDivisionError):
@@ -469,7 +469,7 @@ def main():
         achieved = rb / (km['render'] * 1e-3) / 1e9
         traffic, traffic_src = profiled_traffic() if (args.workload == 'deathmatch' and not args.envs and not args.res and not args.no_raw) else (None, None)
         roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
-                    'kernel': 'env_kernel<MODE_RENDER> (draw + raycast + shade + Depth/RGB/IMU heads)', 'kernel_ms': km['render'],
+                    'kernel': 'view_kernel (draw + raycast + shade + Depth/RGB/IMU heads)', 'kernel_ms': km['render'],
                     'kernel_share_of_step': km['render'] / sum(km.values()), 'algorithmic_bytes_per_launch': rb,
                     'traffic_source': traffic_src, 'all_kernels_ms': km, 'peak_source': peak_src,
                     'whole_step': {'achieved': step_achieved, 'frac': step_achieved / peak, 'algorithmic_bytes_per_step': out['bytes_per_step']},
