@@ -45,6 +45,7 @@ struct KArgs {
     int32_t has_obs;
     int32_t has_mv;
     int32_t ray_blocks;     // RB: warps per agent in view_kernel
+    int32_t rb_shift;       // log2(RB) when RB is a power of two, else -1
     int32_t seg_cap;        // bake_kernel: float4 slots for an env's lines in shared memory (>= max_lines)
     int32_t wcap;           // view_kernel: slots for the env's padded run table (multiple of 16)
     float inv_fps;          // IEEE 1/fps (ATen's tensor/scalar == tensor*(1/scalar), kernels.cu:224,226)
@@ -54,20 +55,22 @@ struct KArgs {
     unsigned long long* stats;  // optional diagnostics counters (may be null)
     int32_t debug_skip_dyn;     // timing experiments only: leave agent-hit rays unlit
     // queue of ray chunks whose agent-hit pixels are lit by dyn_kernel (load-balanced second pass)
-    int* dyn_ctrl;              // [0] entries reserved, [1] CTAs of dyn_kernel done
+    int* dyn_ctrl;              // [0] entries reserved, [1] CTAs of dyn_kernel done, [2] entries handed out beyond each CTA's first
     unsigned char* dyn_entries; // null -> dynamic lights are resolved inline by the ray's own warp
     int32_t dyn_cap;            // entries that fit
-    int32_t dyn_window;         // PS: pixels per entry = max(DYN_MIN_WINDOW, subsample); entry = 16 + 32 * PS bytes
+    int32_t dyn_window;         // PS: pixels per entry = max(DYN_MIN_WINDOW, subsample); entry = DYN_HDR + 32 * PS bytes
     int* dyn_cache;             // [N][A][32] last occluder of each light as seen from (around) each agent; a hint
 };
 
 #ifndef MSB_MIN_BLOCKS
 #define MSB_MIN_BLOCKS 4      // 256 threads x 4 blocks -> at most 64 registers per thread
 #endif
-enum { ST_ANG = 0, ST_PX = 1, ST_PY = 2, ST_AV = 3, ST_VX = 4, ST_VY = 5, ST_STRIDE = 8 };
-enum { STAT_TESTS = 0, STAT_GROUPS = 1, STAT_DYN_RAYS = 2, STAT_DYN_ITERS = 3, STAT_DYN_ENTRIES = 4, STAT_REPLAYS = 5 };
+enum { ST_ANG = 0, ST_PX = 1, ST_PY = 2, ST_AV = 3, ST_VX = 4, ST_VY = 5, ST_SN = 6, ST_CS = 7, ST_STRIDE = 8 };   // SN, CS: view_kernel only
+enum { STAT_TESTS = 0, STAT_GROUPS = 1, STAT_DYN_RAYS = 2, STAT_DYN_ITERS = 3, STAT_DYN_ENTRIES = 4, STAT_REPLAYS = 5,
+       STAT_DYN_CYCLES = 6, STAT_DYN_MAXCYC = 7, STAT_DYN_WARPMAX = 8, STAT_DYN_SLOW = 9, STAT_DYN_KERNEL = 10, STAT_SLOTS = 16 };
 enum { VRUN = 16 };                       // segments per run of the spatial table
 enum { DYN_MIN_WINDOW = 4 };               // pixels per queue entry: max(4, subsample) adjacent pixels (a 'window')
+enum { DYN_HDR = 48 };                     // bytes of a queue entry's header; 32 bytes per pixel follow
 
 // ---------------------------------------------------------------------------------------------------------------
 // physics
@@ -189,7 +192,8 @@ __device__ __forceinline__ float physics_agent(const float* st_in, int A, int a,
 
 // The ATen epilogue of physics() (kernels.cu:223-227) for one agent: integrate, wrap the angle, kill the momentum of
 // agents that hit something. Plain in-place stores (no storage swap). Leaves the new state in st_out.
-__device__ __forceinline__ void physics_integrate(const KArgs& k, const float* st_in, float* st_out, int n, int a, float x) {
+__device__ __forceinline__ void physics_integrate(const KArgs& k, const float* st_in, float* st_out, int n, int a, float x,
+                                                  bool want_sincos = false) {
     const float* me = st_in + a * ST_STRIDE;
     float* o = st_out + a * ST_STRIDE;
     const int64_t i = (int64_t)n * k.s.n_agents + a;
@@ -205,6 +209,7 @@ __device__ __forceinline__ void physics_integrate(const KArgs& k, const float* s
     reinterpret_cast<float2*>(k.a.velocity)[i] = make_float2(nvx, nvy);
     if (k.progress) k.progress[i] = x;
     o[ST_ANG] = ang; o[ST_PX] = npx; o[ST_PY] = npy; o[ST_AV] = nav; o[ST_VX] = nvx; o[ST_VY] = nvy;
+    if (want_sincos) sincos_deg(ang, o[ST_SN], o[ST_CS]);
 }
 
 // MomentumMovement (modules.py:106-118) for one agent: velocities decay and take the chosen action's impulse.
@@ -225,6 +230,7 @@ __device__ __forceinline__ void momentum_movement(const KArgs& k, int act, float
 // touches the one or two runs around it, so staging the whole table would cost more than it saves).
 __global__ void __launch_bounds__(128) physics_kernel(const __grid_constant__ KArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    griddep_launch();        // view_kernel's CTAs may start staging their tables (static data) while this grid drains
     const int n = blockIdx.x;
     const int A = k.s.n_agents, AF = A * k.s.n_model;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -390,8 +396,9 @@ struct VSmem {
     float4* scr;            // [nwarps][128] per warp: 64 candidate records while casting, then the chunk results
     float* st_in;           // [A][8]
     float* st_out;          // [A][8]
-    int* xmin;              // [A]
+    int* mrad;              // [A] ([0]: bits of the model's radius, max |endpoint|)
     uint64_t* bar;
+    int* meta;              // [8] {W, lights, first light, first box, bits of occ_meta[0], [1]} of this env, for queue entries
 };
 
 __device__ __forceinline__ VSmem vcarve(unsigned char* base, int wcap, int nwarps, int A, int AF) {
@@ -402,10 +409,11 @@ __device__ __forceinline__ VSmem vcarve(unsigned char* base, int wcap, int nwarp
     m.scr = reinterpret_cast<float4*>(m.rec + wcap);
     m.st_in = reinterpret_cast<float*>(m.scr + nwarps * 128);
     m.st_out = m.st_in + A * ST_STRIDE;
-    m.xmin = reinterpret_cast<int*>(m.st_out + A * ST_STRIDE);
-    uintptr_t p = reinterpret_cast<uintptr_t>(m.xmin + A);
+    m.mrad = reinterpret_cast<int*>(m.st_out + A * ST_STRIDE);
+    uintptr_t p = reinterpret_cast<uintptr_t>(m.mrad + A);
     p = (p + 15) & ~uintptr_t(15);
     m.bar = reinterpret_cast<uint64_t*>(p);
+    m.meta = reinterpret_cast<int*>(p + 16);
     return m;
 }
 
@@ -413,7 +421,7 @@ static size_t vsmem_bytes(int wcap, int nwarps, int A, int AF) {
     size_t b = (size_t)(AF + wcap) * 16 + (size_t)(wcap / VRUN) * 16 + (size_t)nwarps * 128 * 16 + (size_t)wcap * 16 +
                (size_t)A * ST_STRIDE * 4 * 2 + (size_t)A * 4;
     b = (b + 15) & ~size_t(15);
-    return b + 16;
+    return b + 16 + 32;
 }
 
 template <int NCH>
@@ -593,8 +601,9 @@ __device__ __forceinline__ Texels shade_fetch(const KArgs& k, bool hitany, bool 
     return t;
 }
 
-__device__ __forceinline__ void shade_chunk(const KArgs& k, const float4* __restrict__ seg, int n, int a, int AF, int Lrows,
+__device__ __forceinline__ void shade_chunk(const KArgs& k, const VSmem& m, int n, int a, int AF, int Lrows,
                                             int r, int lane, const ShadeIn& in, const Texels& t) {
+    const float4* __restrict__ seg = m.seg;
     const int A = k.s.n_agents, R = k.p.res;
     const int sub_ = k.has_obs ? k.obs.subsample : 1;
     const bool live = r < R;
@@ -641,18 +650,29 @@ __device__ __forceinline__ void shade_chunk(const KArgs& k, const float4* __rest
             if (wmask) {
                 const int slot = base + __popc(leaders & ((1u << wl) - 1u));
                 if (slot < k.dyn_cap) {
-                    unsigned char* e = k.dyn_entries + (size_t)slot * (16 + 32 * PS);
+                    unsigned char* e = k.dyn_entries + (size_t)slot * (DYN_HDR + 32 * PS);
                     // a chunk that does not fit as a whole falls back inline: its reserved slots carry an empty mask
-                    if (lane == wl) *reinterpret_cast<int4*>(e) = make_int4(n, a * R + (r - lane + wl), queued ? (int)wmask : 0, sub_ | (tgt << 8));
+                    if (lane == wl) {
+                        int4* h = reinterpret_cast<int4*>(e);
+                        h[0] = make_int4(n, a * R + (r - lane + wl), queued ? (int)wmask : 0, sub_ | (tgt << 8));
+                        h[1] = *reinterpret_cast<const int4*>(m.meta);          // what dyn_kernel would otherwise look up by env
+                        h[2] = *reinterpret_cast<const int4*>(m.meta + 4);
+                        // dyn_kernel's first loads: this (env, hit agent)'s occluder hints; the other lanes of the window
+                        // below: the env's lights. Warm L2 now, a kernel ahead of their use.
+                        if (queued) prefetch_l2(k.dyn_cache + ((size_t)n * A + (tgt < A ? tgt : 0)) * 32);
+                    } else if (queued && lane - wl <= 3) {
+                        const int line = lane - wl - 1;                           // 128-byte line of the env's lights (32 x 12 bytes: 3 lines)
+                        if (32 * line < 3 * m.meta[1]) prefetch_l2(k.s.lights + 3 * (int64_t)m.meta[2] + 32 * line);
+                    }
                     if (queued && gmask && live) {
-                        float4* rec = reinterpret_cast<float4*>(e + 16) + 2 * (lane - wl);
+                        float4* rec = reinterpret_cast<float4*>(e + DYN_HDR) + 2 * (lane - wl);
                         rec[0] = make_float4(b0, b1, b2, kk0);
                         rec[1] = make_float4(Cx, Cy, intensity, 0.f);
                     }
                 }
             }
         }
-        if (!queued) intensity = dyn_inline(seg, Lrows, AF, __ldg(k.s.light_widths + n), k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n), dm, Cx, Cy, intensity);
+        if (!queued) intensity = dyn_inline(seg, Lrows, AF, m.meta[1], k.s.lights + 3 * (int64_t)m.meta[2], dm, Cx, Cy, intensity);
         deferred = queued && gmask != 0;                                  // dyn_kernel writes this group's screen / rgb
     }
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
@@ -704,7 +724,7 @@ __device__ __forceinline__ void view_agent(const KArgs& k, const VSmem& m, int n
     const float* st = m.st_out + a * ST_STRIDE;
     View v;
     v.px = st[ST_PX]; v.py = st[ST_PY];
-    sincos_deg(st[ST_ANG], v.sn, v.cs);
+    v.sn = st[ST_SN]; v.cs = st[ST_CS];
     v.xclip = k.xclip;
     const float Rf = (float)R;
     const float rcpR = rcp(Rf);
@@ -785,6 +805,32 @@ __device__ __forceinline__ void view_agent(const KArgs& k, const VSmem& m, int n
             row = AF + (valid ? srow : 0);
         } else {
             if (dyn_next >= AF) break;
+            if (dyn_next == 0) {
+                // Can any agent's model be seen at all? Its lines lie within mrad of its position: if that disc is inside
+                // the near plane's cull depth, wholly left / right of this warp's rays, or behind what every ray already
+                // hit, cast_batch would drop each of its lines (same tests, per line) — and the own model always fails
+                // the near-plane test (kernels.cu:369: its hits are nearer than agent_radius) when mrad < agent_radius.
+                const float mrad = __int_as_float(m.mrad[0]);
+                const float rho = mrad * 1.001f + 1e-3f;
+                float cmaxall = ry.cmax[0];
+#pragma unroll
+                for (int c = 1; c < NCH; c++) cmaxall = fmaxf(cmaxall, ry.cmax[c]);
+                const float Bn = v.B0 - (float)NCH * v.dB;
+                const float sec0 = sqrtf(1.f + v.B0 * v.B0), secn = sqrtf(1.f + Bn * Bn);
+                bool vis = false;
+                for (int a2 = lane; a2 < A; a2 += 32) {
+                    if (a2 == a) { vis = vis || !(mrad * 1.001f + 1e-4f < k.p.agent_radius); continue; }
+                    const float* o = m.st_out + a2 * ST_STRIDE;
+                    const float dx = o[ST_PX] - v.px, dy = o[ST_PY] - v.py;
+                    const float X = dx * v.cs + dy * v.sn, Y = dy * v.cs - dx * v.sn;
+                    const bool behind = X + rho < v.xclip;
+                    const bool left = (Y - X * v.B0) - rho * sec0 > 0.f;
+                    const bool right = (Y - X * Bn) + rho * secn < 0.f;
+                    const bool hidden = X - rho - 1e-3f - 1e-4f * (fabsf(X) + rho) > cmaxall + CULL_EPS;
+                    vis = vis || !(behind || left || right || hidden);      // (NaNs compare false: visible)
+                }
+                if (!__any_sync(0xffffffffu, vis)) break;
+            }
             valid = dyn_next + lane < AF;
             row = valid ? dyn_next + lane : 0;
             dyn_next += 32;
@@ -840,7 +886,7 @@ __device__ __forceinline__ void view_agent(const KArgs& k, const VSmem& m, int n
         }
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            if (c0 + u < NCH) shade_chunk(k, m.seg, n, a, AF, AF + W, r0 + 32 * (c0 + u) + lane, lane, in[u], tx[u]);
+            if (c0 + u < NCH) shade_chunk(k, m, n, a, AF, AF + W, r0 + 32 * (c0 + u) + lane, lane, in[u], tx[u]);
         }
     }
     __syncwarp();
@@ -863,7 +909,14 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_
     const int W = L - AF;
     const int nb = (W + VRUN - 1) / VRUN;
     // stage this env's table: three bulk (TMA) copies, ragged-packed HBM -> shared memory, one mbarrier
+    if (tid == 32 % blockDim.x) {
+        m.meta[0] = W; m.meta[1] = __ldg(k.s.light_widths + n); m.meta[2] = __ldg(k.s.light_starts + n);
+        m.meta[3] = __ldg(k.s.box_starts + n);
+        m.meta[4] = __float_as_int(__ldg(k.s.occ_meta + 2 * n)); m.meta[5] = __float_as_int(__ldg(k.s.occ_meta + 2 * n + 1));
+        m.meta[6] = 0; m.meta[7] = 0;
+    }
     if (tid == 0) {
+        m.mrad[0] = 0;
         mbar_init(m.bar, 1);
         if (nb > 0) {
             const int64_t b0 = __ldg(k.s.box_starts + n);
@@ -873,6 +926,10 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_
             bulk_g2s(m.boxes, k.s.occ_boxes + 4 * b0, (uint32_t)nb * 16u, m.bar);
         }
     }
+    // Everything above reads static scenery only. The agents' state (and everything written below) belongs to the
+    // kernels ahead in the stream: wait for them here. dyn_kernel may queue up behind this grid from now on.
+    griddep_wait();
+    griddep_launch();
     // agent state -> shared memory (through MomentumMovement when the step carries actions)
     for (int a = tid; a < A; a += blockDim.x) {
         const int64_t i = (int64_t)n * A + a;
@@ -883,6 +940,7 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_
         if (PHYS && k.has_mv) momentum_movement(k, k.mv.actions[i], ang, av, vel);
         float* st = (PHYS ? m.st_in : m.st_out) + a * ST_STRIDE;
         st[ST_ANG] = ang; st[ST_PX] = pos.x; st[ST_PY] = pos.y; st[ST_AV] = av; st[ST_VX] = vel.x; st[ST_VY] = vel.y;
+        if (!PHYS) sincos_deg(ang, st[ST_SN], st[ST_CS]);       // once per agent (kernels.cu:304-306, 335-337 redo it per thread)
     }
     __syncthreads();
     if (nb > 0) mbar_wait(m.bar, 0);
@@ -893,17 +951,20 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_
         const float r1 = fmul(k.p.agent_radius, 1.0010000467300415039f);
         for (int a = warp; a < A; a += nwarps) {
             const float x = physics_agent<true>(m.st_in, A, a, lane, m.seg + AF, m.boxes, W, nb, rF, r1, r2);
-            if (lane == 0) physics_integrate(k, m.st_in, m.st_out, n, a, x);
+            if (lane == 0) physics_integrate(k, m.st_in, m.st_out, n, a, x, true);
         }
         __syncthreads();
     }
     // draw_kernel (kernels.cu:297-318): the agents' model lines, at their current poses, into shared and global memory
     {
         const int F = k.s.n_model;
+        for (int t = tid; t < 2 * F; t += blockDim.x) {         // the model's radius: lets a warp skip agents it cannot see
+            const float2 mp = __ldg(reinterpret_cast<const float2*>(k.s.model) + t);
+            atomicMax(m.mrad, __float_as_int(sqrtf(mp.x * mp.x + mp.y * mp.y)));
+        }
         for (int a = warp; a < A; a += nwarps) {
             const float* st = m.st_out + a * ST_STRIDE;
-            float sn, cs;
-            sincos_deg(st[ST_ANG], sn, cs);
+            const float sn = st[ST_SN], cs = st[ST_CS];
             for (int t = lane; t < 2 * F; t += 32) {            // t = 2 * model line + endpoint
                 const float2 mp = __ldg(reinterpret_cast<const float2*>(k.s.model) + t);
                 const float2 pt = make_float2(fadd(st[ST_PX], cross2(cs, mp.x, sn, mp.y)), fadd(st[ST_PY], dot2(sn, mp.x, cs, mp.y)));
@@ -913,9 +974,10 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_
         }
     }
     __syncthreads();
-    const int RB = k.ray_blocks;
+    const int RB = k.ray_blocks, rbs = k.rb_shift;          // rb_shift >= 0: RB is that power of two
     for (int w = warp; w < A * RB; w += nwarps) {
-        view_agent<NCH, STATS>(k, m, n, g0, L, W, nb, w / RB, w % RB, m.scr + warp * 128, lane);
+        const int a = rbs >= 0 ? w >> rbs : w / RB;
+        view_agent<NCH, STATS>(k, m, n, g0, L, W, nb, a, w - a * RB, m.scr + warp * 128, lane);
     }
     if (k.has_obs && k.obs.imu) {
         for (int a = tid; a < A; a += blockDim.x) {
@@ -953,19 +1015,32 @@ __device__ __forceinline__ bool occludes(const Hit h) { return (h.t > 0.f) && (h
 
 template <bool STATS>
 __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs k) {
-    const int lane = threadIdx.x & 31;
+    __shared__ unsigned s_lit[4][32];                          // per warp: the lights it found unoccluded, per pixel lane
+    __shared__ int s_next;                                     // the CTA's next entry
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
     const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
+    griddep_wait();          // the queue is view_kernel's output
     const int reserved = *reinterpret_cast<volatile int*>(k.dyn_ctrl);
     const int count = reserved < k.dyn_cap ? reserved : k.dyn_cap;
     unsigned dyn_rays = 0, dyn_iters = 0, dyn_entries = 0;
-    // entries are strided over the grid's warps (a shared counter would serialise thousands of warps on one address)
-    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, tw = (gridDim.x * blockDim.x) >> 5;
-    for (int ei = wg; ei < count; ei += tw) {
+    // One entry per CTA at a time, entries strided over the grid (every entry is an independent unit of work; a shared
+    // counter would serialise thousands of CTAs on one address). The CTA's warps split the entry's LIGHTS between them:
+    // the kernel lasts as long as its slowest entry (an agent in a large open room: ~20 lights to scan one after the
+    // other), so the per-entry chain is what has to be short.
+    const long long t_start = STATS ? clock64() : 0;
+    long long t_entries = 0;
+    // the first entry is the CTA's own index; the following ones come off a shared counter (ctrl[2]) — CTAs that drew
+    // heavy entries take fewer. The counter is bumped at the start of an entry, so its round trip is off the chain.
+    for (int ei = blockIdx.x; ei < count;) {
+        const long long t_e0 = STATS ? clock64() : 0;
         const int PS = k.dyn_window;
-        const unsigned char* e = k.dyn_entries + (size_t)ei * (16 + 32 * PS);
+        int nxt = 0;
+        if (threadIdx.x == 0) nxt = atomicAdd(k.dyn_ctrl + 2, 1) + (int)gridDim.x;
+        const unsigned char* e = k.dyn_entries + (size_t)ei * (DYN_HDR + 32 * PS);
         const int4 hdr = *reinterpret_cast<const int4*>(e);
-        const unsigned mask = (unsigned)hdr.z;
-        if (!mask) continue;                                   // slot reserved by a chunk that fell back inline
+        const int4 hdr1 = *reinterpret_cast<const int4*>(e + 16);      // {W, lights, first light, first box} of the env
+        const float2 hdr2 = *reinterpret_cast<const float2*>(e + 32);   // occ_meta of the env
+        const unsigned mask = (unsigned)hdr.z;                          // 0: slot reserved by a chunk that fell back inline
         const int sub = hdr.w & 0xff, tgt = hdr.w >> 8;
         const int n = hdr.x, ar = hdr.y;                       // env; agent * R + first ray of the window
         const int av = ar / R, r0 = ar - av * R;
@@ -977,48 +1052,50 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
         const bool isdyn = lane < PS && ((mask >> lane) & 1u);
         float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (have) {
-            const float4* rec = reinterpret_cast<const float4*>(e + 16) + 2 * lane;
+            const float4* rec = reinterpret_cast<const float4*>(e + DYN_HDR) + 2 * lane;
             ra = rec[0];
             rb = rec[1];
         }
         const float Cx = rb.x, Cy = rb.y;
-        const int L = __ldg(k.s.line_widths + n);
-        const int W = L - AF, nb = (W + VRUN - 1) / VRUN;
-        const int nlights = __ldg(k.s.light_widths + n);
-        const float* lt = k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n);
+        const int W = hdr1.x, L = W + AF, nb = (W + VRUN - 1) / VRUN;
+        const int nlights = mask ? hdr1.y : 0;
+        const float* lt = k.s.lights + 3 * (int64_t)hdr1.z;
         float intensity = rb.z;
-        if (STATS) { dyn_rays += __popc(mask); dyn_entries++; }
+        if (STATS && warp == 0 && mask) { dyn_rays += __popc(mask); dyn_entries++; }
+        unsigned mylit = 0;
+        float lx = 0.f, ly = 0.f, li = 0.f;
         if (nlights > 32) {
-            // rare: more lights than lanes. One pixel at a time over the env's lines in their original order.
-            const float4* seg = reinterpret_cast<const float4*>(k.s.lines) + __ldg(k.s.line_starts + n);
-            LaneLight ll;
-            ll.occ = -1;
-            ll.x = __ldg(lt + 3 * lane); ll.y = __ldg(lt + 3 * lane + 1); ll.i = __ldg(lt + 3 * lane + 2);
-            for (unsigned m = mask; m; m &= m - 1) {
-                const int p = __ffs(m) - 1;
-                const float cx = __shfl_sync(0xffffffffu, Cx, p), cy = __shfl_sync(0xffffffffu, Cy, p);
-                const float v = light_intensity_cached<STATS>(seg, L, AF, nlights, lt, cx, cy, lane, ll, dyn_iters);
-                if (lane == p) intensity = v;
+            // rare: more lights than lanes. Warp 0 alone, one pixel at a time over the env's lines in their original order.
+            if (warp == 0) {
+                const float4* seg = reinterpret_cast<const float4*>(k.s.lines) + __ldg(k.s.line_starts + n);
+                LaneLight ll;
+                ll.occ = -1;
+                ll.x = __ldg(lt + 3 * lane); ll.y = __ldg(lt + 3 * lane + 1); ll.i = __ldg(lt + 3 * lane + 2);
+                for (unsigned m = mask; m; m &= m - 1) {
+                    const int p = __ffs(m) - 1;
+                    const float cx = __shfl_sync(0xffffffffu, Cx, p), cy = __shfl_sync(0xffffffffu, Cy, p);
+                    const float v = light_intensity_cached<STATS>(seg, L, AF, nlights, lt, cx, cy, lane, ll, dyn_iters);
+                    if (lane == p) intensity = v;
+                }
             }
         } else {
-            const int64_t b0 = __ldg(k.s.box_starts + n);
+            const int64_t b0 = hdr1.w;
             const float4* occ = reinterpret_cast<const float4*>(k.s.occ_lines) + VRUN * b0;
             const float4* boxes = reinterpret_cast<const float4*>(k.s.occ_boxes) + b0;
-            const float vmax = __ldg(k.s.occ_meta + 2 * n), diam = __ldg(k.s.occ_meta + 2 * n + 1);
+            const float vmax = hdr2.x, diam = hdr2.y;
             // lights one per lane, each with the occluder remembered for this (env, agent that was hit)
             int* cache = k.dyn_cache + ((size_t)n * A + (tgt < A ? tgt : 0)) * 32;
-            float lx = 0.f, ly = 0.f, li = 0.f;
-            int hint = cache[lane];
+            int hint = mask ? cache[lane] : -1;
             if (lane < nlights) { lx = __ldg(lt + 3 * lane); ly = __ldg(lt + 3 * lane + 1); li = __ldg(lt + 3 * lane + 2); }
             const int hint_before = hint;
             const unsigned resident = nlights == 32 ? 0xffffffffu : ((1u << nlights) - 1u);
             float4 bx0 = make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
             if (lane < nb) bx0 = __ldg(boxes + lane);
-            // 1. the remembered occluders
+            // 1. the remembered occluders (every warp, redundantly: one test per pixel)
             const bool has_hint = lane < nlights && hint >= 0 && hint < W;
             float4 hseg = make_float4(0.f, 0.f, 0.f, 0.f);
             if (has_hint) hseg = __ldg(occ + hint);
-            unsigned mytodo = 0, mylit = 0;
+            unsigned mytodo = 0;
             for (unsigned m = mask; m; m &= m - 1) {
                 const int p = __ffs(m) - 1;
                 const float cx = __shfl_sync(0xffffffffu, Cx, p), cy = __shfl_sync(0xffffffffu, Cy, p);
@@ -1036,8 +1113,11 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
                 cx0 = fminf(cx0, __shfl_xor_sync(0xffffffffu, cx0, o)); cx1 = fmaxf(cx1, __shfl_xor_sync(0xffffffffu, cx1, o));
                 cy0 = fminf(cy0, __shfl_xor_sync(0xffffffffu, cy0, o)); cy1 = fmaxf(cy1, __shfl_xor_sync(0xffffffffu, cy1, o));
             }
-            // 2. scans, light by light
-            unsigned todo_any = __reduce_or_sync(0xffffffffu, isdyn ? mytodo : 0u);
+            // 2. scans, light by light; warp w owns the lights i = w (mod NW). (Ownership must not depend on which lights
+            // still need a scan: the hints are shared with other CTAs and may change between two warps' reads.)
+            unsigned owned = 0x11111111u;                                   // NW = 4
+            if (NW == 1) owned = 0xffffffffu; else if (NW == 2) owned = 0x55555555u; else if (NW == 3) owned = 0x49249249u;
+            unsigned todo_any = __reduce_or_sync(0xffffffffu, isdyn ? mytodo : 0u) & (owned << warp);
             const int slot = lane / VRUN, within = lane - slot * VRUN;
             while (todo_any) {
                 const int i = __ffs(todo_any) - 1;
@@ -1065,16 +1145,30 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
                     const float thi = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), 1.f);
                     const bool visit = (bb + lane < nb) && !(tlo > thi);
                     unsigned runs = __ballot_sync(0xffffffffu, visit);
-                    while (runs && need) {
-                        // lanes [0, 16) take the first run still to visit, lanes [16, 32) the second
+                    // lanes [0, 16) take the first run still to visit, lanes [16, 32) the second; the next pair's
+                    // segments are requested before this pair's are tested (one L2 round trip per light, not per pair)
+                    int l = W;
+                    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (runs) {
                         const unsigned rest = runs & (runs - 1);
-                        const int n0 = __ffs(runs) - 1, n1 = rest ? __ffs(rest) - 1 : -1;
-                        const int nth = slot == 0 ? n0 : n1;
-                        const int l = nth >= 0 ? VRUN * (bb + nth) + within : W;
+                        const int nth = slot == 0 ? __ffs(runs) - 1 : (rest ? __ffs(rest) - 1 : -1);
+                        l = nth >= 0 ? VRUN * (bb + nth) + within : W;
+                        if (l < W) s4 = __ldg(occ + l);
+                    }
+                    while (runs && need) {
+                        const unsigned rest = runs & (runs - 1);
+                        const unsigned after = rest & (rest - 1);
+                        int l_next = W;
+                        float4 s4_next = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (after) {
+                            const unsigned rest2 = after & (after - 1);
+                            const int nth = slot == 0 ? __ffs(after) - 1 : (rest2 ? __ffs(rest2) - 1 : -1);
+                            l_next = nth >= 0 ? VRUN * (bb + nth) + within : W;
+                            if (l_next < W) s4_next = __ldg(occ + l_next);
+                        }
                         const bool real = l < W;
                         float Vx = 0.f, Vy = 0.f, PQx = 0.f, PQy = 0.f, snum = 0.f;
                         if (real) {
-                            const float4 s4 = __ldg(occ + l);
                             Vx = fsub(s4.z, s4.x); Vy = fsub(s4.w, s4.y);
                             PQx = fsub(s4.x, Ix); PQy = fsub(s4.y, Iy);
                             snum = cross2(Vy, PQx, Vx, PQy);
@@ -1087,56 +1181,78 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
                             if (bal) { need &= ~(1u << p); found = __shfl_sync(0xffffffffu, l, __ffs(bal) - 1); }
                         }
                         if (STATS) dyn_iters++;
-                        runs = rest & (rest - 1);
+                        runs = after; l = l_next; s4 = s4_next;
                     }
                 }
                 if (found >= 0 && lane == i) hint = found;
                 if ((need >> lane) & 1u) mylit |= 1u << i;         // nothing in the way of light i for my pixel
             }
-            if (hint != hint_before) cache[lane] = hint;           // racy on purpose: any stored value is only a hint
-            // 3. lane = pixel: sum the unoccluded lights in light order (:261-264)
-            float acc = 0.1f;                                      // AMBIENT (kernels.cu:9)
-            for (unsigned lit = __reduce_or_sync(0xffffffffu, mylit); lit; lit &= lit - 1) {
-                const int i = __ffs(lit) - 1;
-                const float Ix = __shfl_sync(0xffffffffu, lx, i), Iy = __shfl_sync(0xffffffffu, ly, i);
-                const float Ii = __shfl_sync(0xffffffffu, li, i);
-                if ((mylit >> i) & 1u) {
-                    const float dx = fsub(Ix, Cx), dy = fsub(Iy, Cy);
-                    acc = ffma(fadd(Ii, Ii), rcp(fmaxf(ffma(dx, dx, fmul(dy, dy)), 1.f)), acc);   // LUMINANCE = 2 (:240)
+            if (mask && hint != hint_before) cache[lane] = hint;   // racy on purpose: any stored value is only a hint
+        }
+        s_lit[warp][lane] = mylit;
+        if (threadIdx.x == 0) s_next = nxt;
+        __syncthreads();
+        const int ei_next = s_next;
+        if (warp == 0) {
+            if (nlights <= 32) {
+                // 3. lane = pixel: sum the unoccluded lights in light order (:261-264)
+                for (int w = 1; w < NW; w++) mylit |= s_lit[w][lane];
+                float acc = 0.1f;                                  // AMBIENT (kernels.cu:9)
+                for (unsigned lit = __reduce_or_sync(0xffffffffu, mylit); lit; lit &= lit - 1) {
+                    const int i = __ffs(lit) - 1;
+                    const float Ix = __shfl_sync(0xffffffffu, lx, i), Iy = __shfl_sync(0xffffffffu, ly, i);
+                    const float Ii = __shfl_sync(0xffffffffu, li, i);
+                    if ((mylit >> i) & 1u) {
+                        const float dx = fsub(Ix, Cx), dy = fsub(Iy, Cy);
+                        acc = ffma(fadd(Ii, Ii), rcp(fmaxf(ffma(dx, dx, fmul(dy, dy)), 1.f)), acc);   // LUMINANCE = 2 (:240)
+                    }
+                }
+                if (isdyn) intensity = fminf(acc, 1.f);
+            }
+            const float kk = fmul(ra.w, intensity);
+            const float s0 = fmul(kk, ra.x), s1 = fmul(kk, ra.y), s2 = fmul(kk, ra.z);
+            if (k.out.screen && isdyn) {
+                float* sc = k.out.screen + 3 * (ag * R + r0 + lane);
+                sc[0] = s0; sc[1] = s1; sc[2] = s2;
+            }
+            if (k.has_obs && k.obs.rgb) {
+                float v0 = have ? s0 : 0.f, v1 = have ? s1 : 0.f, v2 = have ? s2 : 0.f;
+                for (int o = 1; o < sub; o <<= 1) {
+                    v0 = __fadd_rn(v0, __shfl_xor_sync(0xffffffffu, v0, o));
+                    v1 = __fadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+                    v2 = __fadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
+                }
+                if (have && lane == gl) {
+                    const int Ro = R / sub, ro = (r0 + lane) / sub;
+                    float* q = k.obs.rgb + ag * 3 * Ro + ro;
+                    q[0] = __fmul_rn(v0, k.inv_sub); q[Ro] = __fmul_rn(v1, k.inv_sub); q[2 * Ro] = __fmul_rn(v2, k.inv_sub);
                 }
             }
-            if (isdyn) intensity = fminf(acc, 1.f);
         }
-        const float kk = fmul(ra.w, intensity);
-        const float s0 = fmul(kk, ra.x), s1 = fmul(kk, ra.y), s2 = fmul(kk, ra.z);
-        if (k.out.screen && isdyn) {
-            float* sc = k.out.screen + 3 * (ag * R + r0 + lane);
-            sc[0] = s0; sc[1] = s1; sc[2] = s2;
+        __syncthreads();                                       // s_lit and s_next are reused by the next entry
+        if (STATS && k.stats && threadIdx.x == 0) {
+            const long long dt = clock64() - t_e0;
+            t_entries += dt;
+            atomicMax(k.stats + STAT_DYN_MAXCYC, (unsigned long long)dt);
+            if (dt > 20000) atomicAdd(k.stats + STAT_DYN_SLOW, 1ull);
         }
-        if (k.has_obs && k.obs.rgb) {
-            float v0 = have ? s0 : 0.f, v1 = have ? s1 : 0.f, v2 = have ? s2 : 0.f;
-            for (int o = 1; o < sub; o <<= 1) {
-                v0 = __fadd_rn(v0, __shfl_xor_sync(0xffffffffu, v0, o));
-                v1 = __fadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, o));
-                v2 = __fadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
-            }
-            if (have && lane == gl) {
-                const int Ro = R / sub, ro = (r0 + lane) / sub;
-                float* q = k.obs.rgb + ag * 3 * Ro + ro;
-                q[0] = __fmul_rn(v0, k.inv_sub); q[Ro] = __fmul_rn(v1, k.inv_sub); q[2 * Ro] = __fmul_rn(v2, k.inv_sub);
-            }
-        }
+        ei = ei_next;
     }
     if (STATS && k.stats && lane == 0) {
         atomicAdd(k.stats + STAT_DYN_RAYS, (unsigned long long)dyn_rays);
         atomicAdd(k.stats + STAT_DYN_ITERS, (unsigned long long)dyn_iters);
         atomicAdd(k.stats + STAT_DYN_ENTRIES, (unsigned long long)dyn_entries);
+        if (warp == 0) {
+            atomicAdd(k.stats + STAT_DYN_CYCLES, (unsigned long long)t_entries);
+            atomicMax(k.stats + STAT_DYN_WARPMAX, (unsigned long long)t_entries);
+            atomicMax(k.stats + STAT_DYN_KERNEL, (unsigned long long)(clock64() - t_start));
+        }
     }
     // the last CTA out re-arms the queue for the next step
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(k.dyn_ctrl + 1, 1) == (int)gridDim.x - 1) { k.dyn_ctrl[0] = 0; k.dyn_ctrl[1] = 0; }
+        if (atomicAdd(k.dyn_ctrl + 1, 1) == (int)gridDim.x - 1) { k.dyn_ctrl[0] = 0; k.dyn_ctrl[1] = 0; k.dyn_ctrl[2] = 0; }
     }
 }
 
@@ -1186,6 +1302,7 @@ static long long g_opt_nch = 0;          // 0 = auto
 static long long g_opt_threads = 0;      // 0 = auto
 static long long g_opt_skip_dyn = 0;     // debug
 static long long g_opt_dyn_window = 0;   // 0 = default (DYN_MIN_WINDOW); 1, 2, 4, 8: pixels per queue entry when subsample is smaller
+static long long g_opt_dyn_warps = 0;    // warps sharing one queue entry in dyn_kernel (default 2)
 static long long g_opt_fused_step = 0;   // 1: msb_step runs physics inside view_kernel (measured slower: the physics latency
                                          // chain adds to every CTA's life instead of running at its own high occupancy)
 static unsigned long long* g_stats = nullptr;   // device counters, enabled by option "stats"
@@ -1229,6 +1346,23 @@ struct TimedLaunch {
     ~TimedLaunch() { if (slot >= 0) cudaEventRecord(g_ev[2 * slot + 1], st); }
 };
 
+// Kernel launch, optionally as a programmatic dependent of the kernel ahead in the stream (see msb_math.cuh).
+static long long g_opt_pdl = 1;
+static cudaError_t launch(void (*fn)(KArgs), int grid, int block, size_t smem, cudaStream_t st, bool dependent, const KArgs& k) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (dependent && g_opt_pdl && !g_opt_timing) ? 1 : 0;   // per-kernel timing wants the kernels apart
+    return cudaLaunchKernelEx(&cfg, fn, k);
+}
+
 static int fail(const char* fmt, const char* detail) {
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return 1;
@@ -1263,6 +1397,8 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "debug_skip_dyn")) { g_opt_skip_dyn = value; return 0; }
     if (!strcmp(name, "fused_step")) { g_opt_fused_step = value; return 0; }
     if (!strcmp(name, "dyn_window")) { g_opt_dyn_window = value; return 0; }
+    if (!strcmp(name, "dyn_warps")) { g_opt_dyn_warps = value; return 0; }
+    if (!strcmp(name, "pdl")) { g_opt_pdl = value; return 0; }
     if (!strcmp(name, "timing")) {
         timing_flush();
         g_opt_timing = value;
@@ -1271,14 +1407,14 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     }
     if (!strcmp(name, "stats")) {
         if (value && !g_stats) {
-            if (check(cudaMalloc(&g_stats, 8 * sizeof(unsigned long long)), "cudaMalloc(stats)")) return 1;
-            return check(cudaMemset(g_stats, 0, 8 * sizeof(unsigned long long)), "cudaMemset(stats)");
+            if (check(cudaMalloc(&g_stats, STAT_SLOTS * sizeof(unsigned long long)), "cudaMalloc(stats)")) return 1;
+            return check(cudaMemset(g_stats, 0, STAT_SLOTS * sizeof(unsigned long long)), "cudaMemset(stats)");
         }
         if (!value && g_stats) { cudaFree(g_stats); g_stats = nullptr; }
         return 0;
     }
     if (!strcmp(name, "stats_reset")) {
-        if (g_stats) return check(cudaMemset(g_stats, 0, 8 * sizeof(unsigned long long)), "cudaMemset(stats)");
+        if (g_stats) return check(cudaMemset(g_stats, 0, STAT_SLOTS * sizeof(unsigned long long)), "cudaMemset(stats)");
         return 0;
     }
     return fail("msb_set_option: unknown option '%s'", name);
@@ -1301,7 +1437,7 @@ extern "C" int64_t msb_get_option(const char* name) {
     if (!strcmp(name, "nch")) return g_opt_nch;
     if (!strcmp(name, "threads")) return g_opt_threads;
     if (!strncmp(name, "stat", 4) && g_stats) {
-        unsigned long long h[8];
+        unsigned long long h[STAT_SLOTS];
         if (cudaMemcpy(h, g_stats, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
         if (!strcmp(name, "stat_tests")) return (int64_t)h[STAT_TESTS];
         if (!strcmp(name, "stat_groups")) return (int64_t)h[STAT_GROUPS];
@@ -1309,6 +1445,11 @@ extern "C" int64_t msb_get_option(const char* name) {
         if (!strcmp(name, "stat_dyn_iters")) return (int64_t)h[STAT_DYN_ITERS];
         if (!strcmp(name, "stat_dyn_entries")) return (int64_t)h[STAT_DYN_ENTRIES];
         if (!strcmp(name, "stat_replays")) return (int64_t)h[STAT_REPLAYS];
+        if (!strcmp(name, "stat_dyn_cycles")) return (int64_t)h[STAT_DYN_CYCLES];
+        if (!strcmp(name, "stat_dyn_maxcyc")) return (int64_t)h[STAT_DYN_MAXCYC];
+        if (!strcmp(name, "stat_dyn_warpmax")) return (int64_t)h[STAT_DYN_WARPMAX];
+        if (!strcmp(name, "stat_dyn_slow")) return (int64_t)h[STAT_DYN_SLOW];
+        if (!strcmp(name, "stat_dyn_kernel")) return (int64_t)h[STAT_DYN_KERNEL];
     }
     return -1;
 }
@@ -1356,7 +1497,7 @@ static int launch_physics(const KArgs& k, cudaStream_t st) {
     if (sm > 48 * 1024) return fail("%s", "too many agents per environment");
     {
         TimedLaunch timed(TK_PHYSICS, st);
-        physics_kernel<<<k.s.n_envs, 32 * warps, sm, st>>>(k);
+        launch(physics_kernel, k.s.n_envs, 32 * warps, sm, st, false, k);
     }
     g_launches++;
     return check(cudaGetLastError(), "physics_kernel launch");
@@ -1387,7 +1528,7 @@ static int launch_view(const KArgs& k, bool phys, int nch, int threads, cudaStre
         if (sm > 48 * 1024 && check(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), \
                                     "cudaFuncSetAttribute"))                                                     \
             return 1;                                                                                            \
-        fn<<<k.s.n_envs, threads, sm, st>>>(k);                                                                  \
+        launch(fn, k.s.n_envs, threads, sm, st, true, k);                                                        \
     }
     {
         TimedLaunch timed(phys ? TK_STEP : TK_RENDER, st);
@@ -1408,7 +1549,7 @@ static int dyn_window(int sub) {
     return sub > w ? sub : w;
 }
 
-// workspace layout: int ctrl[4] (16 bytes) | occluder cache int[N][A][32] | queue entries of 16 + 32 * PS bytes
+// workspace layout: int ctrl[4] (16 bytes) | occluder cache int[N][A][32] | queue entries of DYN_HDR + 32 * PS bytes
 static int64_t cache_bytes(const msb_scenery* s) { return (int64_t)s->n_envs * s->n_agents * 32 * 4; }
 
 static int set_workspace(KArgs& k, const msb_workspace* ws) {
@@ -1418,10 +1559,11 @@ static int set_workspace(KArgs& k, const msb_workspace* ws) {
     k.dyn_cap = 0;
     if (!ws || !ws->ptr) return 0;
     if (((uintptr_t)ws->ptr & 15) != 0) return fail("%s", "workspace must be 16-byte aligned");
+    if (k.s.n_agents == 1) return 0;    // a lone agent can only ever hit its own model (if at all): no second pass to launch
     const int sub = k.has_obs ? k.obs.subsample : 1;
     k.dyn_window = dyn_window(sub);
     const int64_t head = 16 + cache_bytes(&k.s);
-    const int64_t cap = (ws->bytes - head) / (16 + 32 * k.dyn_window);
+    const int64_t cap = (ws->bytes - head) / (DYN_HDR + 32 * k.dyn_window);
     if (cap < 1) return 0;
     k.dyn_ctrl = reinterpret_cast<int*>(ws->ptr);
     k.dyn_cache = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws->ptr) + 16);
@@ -1445,8 +1587,10 @@ static int launch_dyn(const KArgs& k, cudaStream_t st) {
     }
     {
         TimedLaunch timed(TK_DYN, st);
-        if (k.stats) dyn_kernel<true><<<sms * per_sm[1], 128, 0, st>>>(k);
-        else dyn_kernel<false><<<sms * per_sm[0], 128, 0, st>>>(k);
+        const int threads = (g_opt_dyn_warps >= 1 && g_opt_dyn_warps <= 4) ? 32 * (int)g_opt_dyn_warps : 64;   // measured: 2 warps per entry
+        const int scale = 128 / threads;            // same number of resident threads whatever the CTA size
+        if (k.stats) launch(dyn_kernel<true>, sms * per_sm[1] * scale, threads, 0, st, true, k);
+        else launch(dyn_kernel<false>, sms * per_sm[0] * scale, threads, 0, st, true, k);
     }
     g_launches++;
     return check(cudaGetLastError(), "dyn_kernel launch");
@@ -1459,7 +1603,7 @@ extern "C" int64_t msb_workspace_bytes(const msb_params* p, const msb_scenery* s
     // room for a quarter of all pixel windows to contain an agent-hit ray (overflow falls back to inline, still exact)
     int64_t cap = windows / 4;
     if (cap < 16384) cap = windows < 16384 ? windows : 16384;
-    return 16 + cache_bytes(s) + cap * (16 + 32 * PS);
+    return 16 + cache_bytes(s) + cap * (DYN_HDR + 32 * PS);
 }
 
 static void set_obs(KArgs& k, const msb_obs_out* obs) {
@@ -1503,6 +1647,7 @@ extern "C" int msb_render(const msb_params* p, const msb_scenery* s, const msb_a
     int nch, rb, threads;
     plan_view(p, s, &nch, &rb, &threads);
     k.ray_blocks = rb;
+    k.rb_shift = (rb & (rb - 1)) ? -1 : __builtin_ctz((unsigned)rb);
     if (launch_view(k, false, nch, threads, (cudaStream_t)cuda_stream)) return 1;
     return launch_dyn(k, (cudaStream_t)cuda_stream);
 }
@@ -1524,6 +1669,7 @@ extern "C" int msb_step(const msb_params* p, const msb_scenery* s, const msb_age
     int nch, rb, threads;
     plan_view(p, s, &nch, &rb, &threads);
     k.ray_blocks = rb;
+    k.rb_shift = (rb & (rb - 1)) ? -1 : __builtin_ctz((unsigned)rb);
     if (g_opt_fused_step) {
         if (launch_view(k, true, nch, threads, (cudaStream_t)cuda_stream)) return 1;
     } else {

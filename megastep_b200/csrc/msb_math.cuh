@@ -114,4 +114,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// hint: bring the 128-byte line at p into L2 (no register result, nothing to wait for)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start while the
+// kernel ahead of it in the stream is still running; it must not touch anything that kernel writes before
+// griddep_wait() returns (= the whole primary grid has completed and its writes are visible). griddep_launch() is the
+// primary's side: "my dependents may be scheduled as soon as every CTA of mine got here". Both are no-ops otherwise.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace msb

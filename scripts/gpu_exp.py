@@ -51,6 +51,54 @@ if __name__ == '__main__':
         cuda.set_option('stats', 0)
         print(json.dumps(res))
         sys.exit(0)
+    if mode == 'dynstat':
+        out = {}
+        torch.manual_seed(0)
+        acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')
+        step = modules.FusedStep(c, subsample=1, raw=True)
+        for _ in range(20): step(acts)
+        for dw in (1, 2, 4):
+            cuda.set_option('dyn_warps', dw)
+            cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0)
+            step(acts); torch.cuda.synchronize()
+            for k in ('stat_dyn_rays', 'stat_dyn_iters', 'stat_dyn_entries', 'stat_dyn_cycles', 'stat_dyn_maxcyc', 'stat_dyn_warpmax', 'stat_dyn_slow', 'stat_dyn_kernel'):
+                out[f'{k}/dw{dw}'] = cuda.get_option(k)
+            cuda.set_option('stats', 0)
+            cuda.set_option('timing', 1)
+            for _ in range(50): step(acts)
+            torch.cuda.synchronize()
+            out[f'dyn_us/dw{dw}'] = round(cuda.get_option('time_ns_dyn') / cuda.get_option('time_count_dyn') / 1e3, 1)
+            cuda.set_option('timing', 0)
+        cuda.set_option('dyn_warps', 0)
+        for skip in (0, 1):
+            cuda.set_option('debug_skip_dyn', skip)
+            cuda.set_option('timing', 1)
+            for _ in range(50): step(acts)
+            torch.cuda.synchronize()
+            for kind in ('physics', 'render', 'dyn'):
+                cnt = cuda.get_option(f'time_count_{kind}')
+                if cnt: out[f'kernel_us/skip{skip}/{kind}'] = round(cuda.get_option(f'time_ns_{kind}') / cnt / 1e3, 1)
+            cuda.set_option('timing', 0)
+        cuda.set_option('debug_skip_dyn', 0)
+        for threads in (32, 64, 128):
+            cuda.set_option('threads', threads)
+            out[f'physics_us/t{threads}'] = round(timeit(lambda: c.physics()), 1)
+        cuda.set_option('threads', 0)
+        print(json.dumps(out)); sys.exit(0)
+    if mode == 'pdl':
+        out = {}
+        torch.manual_seed(0)
+        acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')
+        step = modules.FusedStep(c, subsample=1, raw=True)
+        for _ in range(20): step(acts)
+        for rep in range(2):
+            for pdl in (0, 1):
+                for dw in (2, 4):
+                    cuda.set_option('pdl', pdl); cuda.set_option('dyn_warps', dw)
+                    out[f'step_us/pdl{pdl}/dw{dw}/rep{rep}'] = round(timeit(lambda: step(acts), iters=200), 1)
+                    out[f'render_us/pdl{pdl}/dw{dw}/rep{rep}'] = round(timeit(lambda: c.render(), iters=200), 1)
+        cuda.set_option('pdl', 1); cuda.set_option('dyn_warps', 0)
+        print(json.dumps(out)); sys.exit(0)
     if mode == 'view':
         out = {}
         for nch, threads in ((0, 0), (4, 128), (2, 256), (2, 128), (2, 64), (1, 128), (1, 256)):

@@ -285,8 +285,8 @@ def test_step_with_physics_inside_the_render_kernel_agrees():
 
 @pytest.mark.parametrize('sub', [1, 4])
 def test_second_pass_inline_and_overflow_paths_agree(sub):
-    """Agent-hit rays are lit by dyn_kernel (workspace), inline by the first pass (no workspace), or by a mix
-    (workspace too small): all must give identical screens and observations. Agents are packed close so many rays
+    """Agent-hit rays are lit by dyn_kernel (workspace; its warps share each entry's lights 2, 1 or 4 ways), inline by
+    the first pass (no workspace), or by a mix (workspace too small): all must give identical screens and observations. Agents are packed close so many rays
     hit agents."""
     from megastep_b200 import cuda
     gs, arrays, st = make('box', 6, 4, seed=61)
@@ -294,20 +294,24 @@ def test_second_pass_inline_and_overflow_paths_agree(sub):
     st['positions'] = (3.5 + rng.uniform(-.6, .6, st['positions'].shape)).astype(np.float32)
     res = 128
     outs = []
-    for mode in ('workspace', 'inline', 'overflow'):
+    for mode in ('workspace', 'inline', 'overflow', 'workspace-1warp', 'workspace-4warps'):
         cuda.USE_WORKSPACE = mode != 'inline'
+        cuda.set_option('dyn_warps', {'workspace-1warp': 1, 'workspace-4warps': 4}.get(mode, 0))
         try:
             c = common.to_device(arrays, st, res, 100.)
             plan = cuda.StepPlan(c.scenery, c.agents, c.params, actions=None, raw=True, subsample=sub)
         finally:
             cuda.USE_WORKSPACE = True
         if mode == 'overflow':
-            small = 16 + 6 * 4 * 32 * 4 + 3 * (16 + 32 * max(4, sub))   # ctrl + occluder cache + room for three pixel windows only
+            small = 16 + 6 * 4 * 32 * 4 + 3 * (48 + 32 * max(4, sub))   # ctrl + occluder cache + room for three pixel windows only
             plan._wsbuf = torch.zeros(small, dtype=torch.uint8, device='cuda')
             plan._ws = cuda._Workspace(plan._wsbuf.data_ptr(), small)
-        for _ in range(2):                                          # twice: the queue must re-arm itself
-            plan.render_only()
-        torch.cuda.synchronize()
+        try:
+            for _ in range(2):                                          # twice: the queue must re-arm itself
+                plan.render_only()
+            torch.cuda.synchronize()
+        finally:
+            cuda.set_option('dyn_warps', 0)
         outs.append((plan.render.screen.clone(), plan.rgb.clone(), plan.render.indices.clone()))
     n_dyn = int(((outs[0][2] >= 0) & (outs[0][2] < 32)).sum())
     assert n_dyn > 50, 'the scene should have plenty of agent-hit rays'
