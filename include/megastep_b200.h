@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MSB_ABI_VERSION 2
+#define MSB_ABI_VERSION 3
 
 /* Replaces initialize(agent_radius, res, fov, fps) — megastep/src/wrappers.cpp:53, kernels.cu:18-27. */
 typedef struct msb_params {
@@ -74,6 +74,14 @@ typedef struct msb_scenery {
     const float* occ_meta;      /* (N, 2) per env: longest static segment extent (max |dx|,|dy|), extent of the env */
     const int32_t* occ_rec;     /* (16 * sum nb, 4) per sorted row: {tex_starts lo, hi, tex_widths, line index within its env};
                                  * padding rows have line index -1 */
+    /* Optional light-visibility grid (vis NULL to disable; needs the spatial table): 0.25 m cells over each env's static
+     * geometry. Bit i of a cell's word is set when light i (< 32) of the env is CERTAINLY unoccluded from every point
+     * of the cell — no static segment comes near any segment light -> point, by a margin that covers the rounding of
+     * the reference's intersect() — so the dynamic light of a ray that hit an agent needs no shadow test for it.
+     * Unset bits promise nothing. Allocated by the caller, filled once per scenery by msb_build_visibility. */
+    uint32_t* vis;              /* (sum gx*gy) */
+    const int64_t* vis_starts;  /* (N) first cell of env n */
+    const float* vis_meta;      /* (N, 4) {x0, y0, gx, gy}: the grid's origin in metres and its dimensions (whole numbers) */
 } msb_scenery;
 
 /* The Agents struct of megastep/src/common.h:162-177. Updated in place by msb_physics. */
@@ -130,6 +138,9 @@ int msb_params_init(msb_params* p, float agent_radius, int32_t res, float fov, f
 
 /* bake(scenery) — megastep/src/wrappers.cpp:61, kernels.cu:270-293. Writes scenery->baked for every texel. */
 int msb_bake(const msb_params* p, const msb_scenery* s, void* cuda_stream);
+
+/* Fills s->vis (see msb_scenery) from the static segments (spatial table) and lights. One-off, like msb_bake. */
+int msb_build_visibility(const msb_scenery* s, void* cuda_stream);
 
 /* physics(scenery, agents) -> Physics{progress} — wrappers.cpp:69, kernels.cu:179-230.
  * progress: (N, A) out. Agents are advanced in place (positions, angles) and stopped where progress < 1. */

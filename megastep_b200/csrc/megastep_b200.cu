@@ -54,6 +54,7 @@ struct KArgs {
     float xclip;            // camera-space depth well inside every ray's near plane (culling only)
     unsigned long long* stats;  // optional diagnostics counters (may be null)
     int32_t debug_skip_dyn;     // timing experiments only: leave agent-hit rays unlit
+    int32_t debug_no_vis;       // tests: ignore the visibility grid (same results, more shadow scans)
     // queue of ray chunks whose agent-hit pixels are lit by dyn_kernel (load-balanced second pass)
     int* dyn_ctrl;              // [0] entries reserved, [1] CTAs of dyn_kernel done, [2] entries handed out beyond each CTA's first
     unsigned char* dyn_entries; // null -> dynamic lights are resolved inline by the ray's own warp
@@ -67,9 +68,10 @@ struct KArgs {
 #endif
 enum { ST_ANG = 0, ST_PX = 1, ST_PY = 2, ST_AV = 3, ST_VX = 4, ST_VY = 5, ST_SN = 6, ST_CS = 7, ST_STRIDE = 8 };   // SN, CS: view_kernel only
 enum { STAT_TESTS = 0, STAT_GROUPS = 1, STAT_DYN_RAYS = 2, STAT_DYN_ITERS = 3, STAT_DYN_ENTRIES = 4, STAT_REPLAYS = 5,
-       STAT_DYN_CYCLES = 6, STAT_DYN_MAXCYC = 7, STAT_DYN_WARPMAX = 8, STAT_DYN_SLOW = 9, STAT_DYN_KERNEL = 10, STAT_SLOTS = 16 };
+       STAT_DYN_CYCLES = 6, STAT_DYN_MAXCYC = 7, STAT_DYN_WARPMAX = 8, STAT_DYN_SLOW = 9, STAT_DYN_KERNEL = 10, STAT_DYN_SCANS = 11, STAT_DYN_SCANS_LIT = 12, STAT_DYN_ITERS_LIT = 13, STAT_SLOTS = 16 };
 enum { VRUN = 16 };                       // segments per run of the spatial table
 enum { DYN_MIN_WINDOW = 4 };               // pixels per queue entry: max(4, subsample) adjacent pixels (a 'window')
+constexpr float VIS_CELL = 0.25f, VIS_INV_CELL = 4.f;   // the light-visibility grid's cell, metres
 enum { DYN_HDR = 48 };                     // bytes of a queue entry's header; 32 bytes per pixel follow
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -398,7 +400,8 @@ struct VSmem {
     float* st_out;          // [A][8]
     int* mrad;              // [A] ([0]: bits of the model's radius, max |endpoint|)
     uint64_t* bar;
-    int* meta;              // [8] {W, lights, first light, first box, bits of occ_meta[0], [1]} of this env, for queue entries
+    int* meta;              // [16] this env's {W, lights, first light, first box, bits of occ_meta[0], [1], -, -} for queue entries;
+                            //      {bits of vis_meta x0, y0, gx, gy, vis_starts lo, hi, -, -}
 };
 
 __device__ __forceinline__ VSmem vcarve(unsigned char* base, int wcap, int nwarps, int A, int AF) {
@@ -421,7 +424,7 @@ static size_t vsmem_bytes(int wcap, int nwarps, int A, int AF) {
     size_t b = (size_t)(AF + wcap) * 16 + (size_t)(wcap / VRUN) * 16 + (size_t)nwarps * 128 * 16 + (size_t)wcap * 16 +
                (size_t)A * ST_STRIDE * 4 * 2 + (size_t)A * 4;
     b = (b + 15) & ~size_t(15);
-    return b + 16 + 32;
+    return b + 16 + 64;
 }
 
 template <int NCH>
@@ -665,9 +668,20 @@ __device__ __forceinline__ void shade_chunk(const KArgs& k, const VSmem& m, int 
                         if (32 * line < 3 * m.meta[1]) prefetch_l2(k.s.lights + 3 * (int64_t)m.meta[2] + 32 * line);
                     }
                     if (queued && gmask && live) {
+                        // the lights that are certainly unoccluded from the hit point's cell of the visibility grid
+                        unsigned sure = 0;
+                        if (isdyn) {
+                            const int ix = __float2int_rd((Cx - __int_as_float(m.meta[8])) * VIS_INV_CELL);
+                            const int iy = __float2int_rd((Cy - __int_as_float(m.meta[9])) * VIS_INV_CELL);
+                            const int gx = m.meta[10], gy = m.meta[11];
+                            if (ix >= 0 && ix < gx && iy >= 0 && iy < gy) {
+                                const int64_t vs = (int64_t)(((uint64_t)(uint32_t)m.meta[13] << 32) | (uint32_t)m.meta[12]);
+                                sure = __ldg(k.s.vis + vs + (int64_t)iy * gx + ix);
+                            }
+                        }
                         float4* rec = reinterpret_cast<float4*>(e + DYN_HDR) + 2 * (lane - wl);
                         rec[0] = make_float4(b0, b1, b2, kk0);
-                        rec[1] = make_float4(Cx, Cy, intensity, 0.f);
+                        rec[1] = make_float4(Cx, Cy, intensity, __uint_as_float(sure));
                     }
                 }
             }
@@ -914,6 +928,13 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_
         m.meta[3] = __ldg(k.s.box_starts + n);
         m.meta[4] = __float_as_int(__ldg(k.s.occ_meta + 2 * n)); m.meta[5] = __float_as_int(__ldg(k.s.occ_meta + 2 * n + 1));
         m.meta[6] = 0; m.meta[7] = 0;
+        m.meta[10] = 0; m.meta[11] = 0;                                  // no grid: every lookup falls outside
+        if (k.s.vis) {
+            const float4 vm = __ldg(reinterpret_cast<const float4*>(k.s.vis_meta) + n);
+            const int64_t vs = __ldg(k.s.vis_starts + n);
+            m.meta[8] = __float_as_int(vm.x); m.meta[9] = __float_as_int(vm.y); m.meta[10] = (int)vm.z; m.meta[11] = (int)vm.w;
+            m.meta[12] = (int)(uint32_t)vs; m.meta[13] = (int)(uint32_t)((uint64_t)vs >> 32);
+        }
     }
     if (tid == 0) {
         m.mrad[0] = 0;
@@ -1057,6 +1078,7 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
             rb = rec[1];
         }
         const float Cx = rb.x, Cy = rb.y;
+        const unsigned sure = (isdyn && !k.debug_no_vis) ? __float_as_uint(rb.w) : 0u;   // lights the visibility grid vouches for
         const int W = hdr1.x, L = W + AF, nb = (W + VRUN - 1) / VRUN;
         const int nlights = mask ? hdr1.y : 0;
         const float* lt = k.s.lights + 3 * (int64_t)hdr1.z;
@@ -1102,7 +1124,7 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
                 bool ob = false;
                 if (has_hint) ob = occludes(intersect(lx, ly, fsub(cx, lx), fsub(cy, ly), hseg));
                 const unsigned todo = resident & ~__ballot_sync(0xffffffffu, ob);
-                if (lane == p) mytodo = todo;
+                if (lane == p) mytodo = todo & ~sure;
             }
             if (STATS) dyn_iters++;
             // the box around the entry's hit points
@@ -1124,6 +1146,7 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
                 todo_any &= todo_any - 1;
                 const float Ix = __shfl_sync(0xffffffffu, lx, i), Iy = __shfl_sync(0xffffffffu, ly, i);
                 unsigned need = __ballot_sync(0xffffffffu, isdyn && ((mytodo >> i) & 1u));
+                const unsigned iters0 = dyn_iters;
                 // conservative query (see DESIGN.md "shadow cull"): rounding can move the computed crossing by at most
                 // delta (a fraction of each segment's length) along either segment. A run can only hold an occluder if
                 // its box comes within mg (+ the spread of the hit points) of the segment from the light to the middle
@@ -1186,6 +1209,10 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
                 }
                 if (found >= 0 && lane == i) hint = found;
                 if ((need >> lane) & 1u) mylit |= 1u << i;         // nothing in the way of light i for my pixel
+                if (STATS && k.stats && lane == 0) {
+                    atomicAdd(k.stats + STAT_DYN_SCANS, 1ull);
+                    if (need) { atomicAdd(k.stats + STAT_DYN_SCANS_LIT, 1ull); atomicAdd(k.stats + STAT_DYN_ITERS_LIT, (unsigned long long)(dyn_iters - iters0)); }
+                }
             }
             if (mask && hint != hint_before) cache[lane] = hint;   // racy on purpose: any stored value is only a hint
         }
@@ -1197,6 +1224,7 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
             if (nlights <= 32) {
                 // 3. lane = pixel: sum the unoccluded lights in light order (:261-264)
                 for (int w = 1; w < NW; w++) mylit |= s_lit[w][lane];
+                mylit |= sure & (nlights == 32 ? 0xffffffffu : ((1u << nlights) - 1u));
                 float acc = 0.1f;                                  // AMBIENT (kernels.cu:9)
                 for (unsigned lit = __reduce_or_sync(0xffffffffu, mylit); lit; lit &= lit - 1) {
                     const int i = __ffs(lit) - 1;
@@ -1257,6 +1285,79 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// vis_kernel: the light-visibility grid (msb_scenery::vis). One CTA per env, one warp per cell, lane = light.
+// A light is vouched for when NO static segment comes within `thr` of the segment light -> cell centre, where
+//   thr = mg + half the cell's diagonal + slack,   mg = delta * (|U| + vmax) + 0.01,   delta = 4e-4 * vmax * (diam + |U|)
+// is dyn_kernel's own shadow-cull margin (DESIGN.md "shadow cull": the reference's intersect() can only report a
+// crossing if the two segments truly come within delta * (|U| + |V|) of each other) evaluated for the farthest point of
+// the cell. Every segment light -> point-of-the-cell lies within half a diagonal of light -> centre, so for no point of
+// the cell can the reference's shadow test fire. The slack covers float rounding here and in the cell lookup.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pt_seg_d2(float x, float y, float px, float py, float dx, float dy) {
+    const float wx = x - px, wy = y - py;
+    const float t = fminf(fmaxf((wx * dx + wy * dy) / fmaxf(dx * dx + dy * dy, 1e-30f), 0.f), 1.f);
+    const float ex = wx - t * dx, ey = wy - t * dy;
+    return ex * ex + ey * ey;
+}
+
+__global__ void __launch_bounds__(256) vis_kernel(const __grid_constant__ KArgs k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = blockIdx.x;
+    const int AF = k.s.n_agents * k.s.n_model;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    float4* seg = reinterpret_cast<float4*>(smem_raw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(seg + k.wcap);
+    const int W = __ldg(k.s.line_widths + n) - AF;
+    const int nb = (W + VRUN - 1) / VRUN;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        if (nb > 0) {
+            mbar_expect_tx(bar, (uint32_t)nb * VRUN * 16u);
+            bulk_g2s(seg, k.s.occ_lines + 4 * VRUN * (int64_t)__ldg(k.s.box_starts + n), (uint32_t)nb * VRUN * 16u, bar);
+        }
+    }
+    __syncthreads();
+    if (nb > 0) mbar_wait(bar, 0);
+    const float4 vm = __ldg(reinterpret_cast<const float4*>(k.s.vis_meta) + n);
+    const int gx = (int)vm.z, gy = (int)vm.w;
+    uint32_t* out = k.s.vis + __ldg(k.s.vis_starts + n);
+    const int I = __ldg(k.s.light_widths + n);
+    const float* lt = k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n);
+    const float vmax = __ldg(k.s.occ_meta + 2 * n), diam = __ldg(k.s.occ_meta + 2 * n + 1);
+    const bool real = lane < I;
+    const float Ix = real ? __ldg(lt + 3 * lane) : 0.f, Iy = real ? __ldg(lt + 3 * lane + 1) : 0.f;
+    for (int cell = warp; cell < gx * gy; cell += nwarps) {
+        const int iy = cell / gx, ix = cell - iy * gx;
+        const float Cx = vm.x + ((float)ix + 0.5f) * VIS_CELL, Cy = vm.y + ((float)iy + 0.5f) * VIS_CELL;
+        const float Ux = Cx - Ix, Uy = Cy - Iy;
+        const float ulen = fmaxf(fabsf(Ux), fabsf(Uy)) + 0.5f * VIS_CELL;          // as dyn_kernel measures |U|, at the cell's far corner
+        const float delta = 4e-4f * vmax * (diam + ulen);
+        const float thr = delta * (ulen + vmax) + 0.01f + 0.70711f * VIS_CELL + 0.01f;
+        const float thr2 = thr * thr;
+        const float bx0 = fminf(Ix, Cx) - thr, bx1 = fmaxf(Ix, Cx) + thr, by0 = fminf(Iy, Cy) - thr, by1 = fmaxf(Iy, Cy) + thr;
+        bool sure = real;
+        for (int l = 0; l < W; l++) {
+            const float4 s4 = seg[l];                                               // (uniform address: a broadcast)
+            // nowhere near the box around light -> centre: the common case
+            const bool far = fmaxf(s4.x, s4.z) < bx0 || fminf(s4.x, s4.z) > bx1 || fmaxf(s4.y, s4.w) < by0 || fminf(s4.y, s4.w) > by1;
+            if (sure && !far) {
+                const float Vx = s4.z - s4.x, Vy = s4.w - s4.y;
+                // do they cross? (orientation signs; a near-miss shows up in the end-point distances below)
+                const float o1 = Ux * (s4.y - Iy) - Uy * (s4.x - Ix), o2 = Ux * (s4.w - Iy) - Uy * (s4.z - Ix);
+                const float o3 = Vx * (Iy - s4.y) - Vy * (Ix - s4.x), o4 = Vx * (Cy - s4.y) - Vy * (Cx - s4.x);
+                const bool cross = (o1 * o2 <= 0.f) && (o3 * o4 <= 0.f);
+                const float d2 = fminf(fminf(pt_seg_d2(s4.x, s4.y, Ix, Iy, Ux, Uy), pt_seg_d2(s4.z, s4.w, Ix, Iy, Ux, Uy)),
+                                       fminf(pt_seg_d2(Ix, Iy, s4.x, s4.y, Vx, Vy), pt_seg_d2(Cx, Cy, s4.x, s4.y, Vx, Vy)));
+                if (cross || !(d2 > thr2)) sure = false;                            // (NaN: not sure)
+            }
+            if ((l & 7) == 7 && !__any_sync(0xffffffffu, sure)) break;             // (l is warp-uniform)
+        }
+        const unsigned word = __ballot_sync(0xffffffffu, sure);
+        if (lane == 0) out[cell] = word;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // bake (kernels.cu:270-293): one CTA per env, one warp per line, one lane per texel
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bake_kernel(const __grid_constant__ KArgs k) {
@@ -1301,6 +1402,7 @@ static long long g_launches = 0;
 static long long g_opt_nch = 0;          // 0 = auto
 static long long g_opt_threads = 0;      // 0 = auto
 static long long g_opt_skip_dyn = 0;     // debug
+static long long g_opt_no_vis = 0;       // tests: ignore the visibility grid
 static long long g_opt_dyn_window = 0;   // 0 = default (DYN_MIN_WINDOW); 1, 2, 4, 8: pixels per queue entry when subsample is smaller
 static long long g_opt_dyn_warps = 0;    // warps sharing one queue entry in dyn_kernel (default 2)
 static long long g_opt_fused_step = 0;   // 1: msb_step runs physics inside view_kernel (measured slower: the physics latency
@@ -1399,6 +1501,7 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "dyn_window")) { g_opt_dyn_window = value; return 0; }
     if (!strcmp(name, "dyn_warps")) { g_opt_dyn_warps = value; return 0; }
     if (!strcmp(name, "pdl")) { g_opt_pdl = value; return 0; }
+    if (!strcmp(name, "no_vis")) { g_opt_no_vis = value; return 0; }
     if (!strcmp(name, "timing")) {
         timing_flush();
         g_opt_timing = value;
@@ -1450,6 +1553,9 @@ extern "C" int64_t msb_get_option(const char* name) {
         if (!strcmp(name, "stat_dyn_warpmax")) return (int64_t)h[STAT_DYN_WARPMAX];
         if (!strcmp(name, "stat_dyn_slow")) return (int64_t)h[STAT_DYN_SLOW];
         if (!strcmp(name, "stat_dyn_kernel")) return (int64_t)h[STAT_DYN_KERNEL];
+        if (!strcmp(name, "stat_dyn_scans")) return (int64_t)h[STAT_DYN_SCANS];
+        if (!strcmp(name, "stat_dyn_scans_lit")) return (int64_t)h[STAT_DYN_SCANS_LIT];
+        if (!strcmp(name, "stat_dyn_iters_lit")) return (int64_t)h[STAT_DYN_ITERS_LIT];
     }
     return -1;
 }
@@ -1478,6 +1584,7 @@ static void fill(KArgs& k, const msb_params* p, const msb_scenery* s, const msb_
     k.ray_blocks = 1;
     k.stats = g_stats;
     k.debug_skip_dyn = (int32_t)g_opt_skip_dyn;
+    k.debug_no_vis = (int32_t)g_opt_no_vis;
     k.xclip = 0.5f * p->agent_radius / sqrtf(1.f + p->half_screen * p->half_screen);
 }
 
@@ -1678,6 +1785,28 @@ extern "C" int msb_step(const msb_params* p, const msb_scenery* s, const msb_age
         if (launch_view(k, false, nch, threads, (cudaStream_t)cuda_stream)) return 1;
     }
     return launch_dyn(k, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int msb_build_visibility(const msb_scenery* s, void* cuda_stream) {
+    msb_params p;
+    memset(&p, 0, sizeof(p));
+    p.res = 1; p.fps = 1.f;
+    if (validate(&p, s, true)) return 1;
+    if (!s->vis || !s->vis_starts || !s->vis_meta) return fail("%s", "msb_build_visibility: scenery has no visibility grid to fill");
+    if (s->n_envs == 0) return 0;
+    KArgs k;
+    fill(k, &p, s, nullptr);
+    const size_t sm = (size_t)k.wcap * 16 + 16;
+    if (sm > 227 * 1024) return fail("%s", "scene too large: an env's segments do not fit in shared memory (227 KB)");
+    if (sm > 48 * 1024 &&
+        check(cudaFuncSetAttribute(vis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "cudaFuncSetAttribute"))
+        return 1;
+    {
+        TimedLaunch timed(TK_BAKE, (cudaStream_t)cuda_stream);
+        vis_kernel<<<s->n_envs, 256, sm, (cudaStream_t)cuda_stream>>>(k);
+    }
+    g_launches++;
+    return check(cudaGetLastError(), "vis_kernel launch");
 }
 
 extern "C" int msb_bake(const msb_params* p, const msb_scenery* s, void* cuda_stream) {

@@ -43,7 +43,8 @@ class _Scenery(ctypes.Structure):
                 ('baked', ctypes.c_void_p), ('model', ctypes.c_void_p),
                 ('n_lines', ctypes.c_int64), ('n_texels', ctypes.c_int64),
                 ('occ_lines', ctypes.c_void_p), ('occ_starts', ctypes.c_void_p), ('occ_boxes', ctypes.c_void_p),
-                ('box_starts', ctypes.c_void_p), ('occ_meta', ctypes.c_void_p), ('occ_rec', ctypes.c_void_p)]
+                ('box_starts', ctypes.c_void_p), ('occ_meta', ctypes.c_void_p), ('occ_rec', ctypes.c_void_p),
+                ('vis', ctypes.c_void_p), ('vis_starts', ctypes.c_void_p), ('vis_meta', ctypes.c_void_p)]
 
 
 class _Agents(ctypes.Structure):
@@ -83,6 +84,7 @@ def _load():
     lib.msb_launch_count.restype = ctypes.c_int64
     lib.msb_params_init.argtypes = [P(Params), ctypes.c_float, ctypes.c_int32, ctypes.c_float, ctypes.c_float]
     lib.msb_bake.argtypes = [P(Params), P(_Scenery), ctypes.c_void_p]
+    lib.msb_build_visibility.argtypes = [P(_Scenery), ctypes.c_void_p]
     lib.msb_physics.argtypes = [P(Params), P(_Scenery), P(_Agents), ctypes.c_void_p, ctypes.c_void_p]
     lib.msb_render.argtypes = [P(Params), P(_Scenery), P(_Agents), P(_RenderOut), P(_ObsOut), P(_Workspace), ctypes.c_void_p]
     lib.msb_step.argtypes = [P(Params), P(_Scenery), P(_Agents), P(_Movement), ctypes.c_void_p, P(_RenderOut),
@@ -92,8 +94,8 @@ def _load():
     lib.msb_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
     lib.msb_get_option.argtypes = [ctypes.c_char_p]
     lib.msb_get_option.restype = ctypes.c_int64
-    if lib.msb_abi_version() != 2:
-        raise ImportError(f'{_LIBPATH} has ABI version {lib.msb_abi_version()}, expected 2; rebuild it')
+    if lib.msb_abi_version() != 3:
+        raise ImportError(f'{_LIBPATH} has ABI version {lib.msb_abi_version()}, expected 3; rebuild it')
     return lib
 
 
@@ -278,6 +280,11 @@ class Scenery:
                                             self._textures.widths, self._tex_starts)
                 (self._c.occ_lines, self._c.occ_starts, self._c.occ_boxes, self._c.box_starts,
                  self._c.occ_meta, self._c.occ_rec) = (t.data_ptr() for t in self._occ)
+                if USE_VISIBILITY_GRID and self._n_agents > 1:      # only rays that hit ANOTHER agent ask for dynamic light
+                    self._vis = _visibility_grid(self._occ[2], self._occ[3], self._lines.widths, self._n_agents * self._model.size(0))
+                    self._c.vis, self._c.vis_starts, self._c.vis_meta = (t.data_ptr() for t in self._vis)
+                    with _on_device(self._model) as stream:
+                        _check(_lib.msb_build_visibility(ctypes.byref(self._c), stream))
         return self._c
 
 
@@ -366,6 +373,33 @@ def _occluder_table(lines, n_dynamic, run=16, tex_widths=None, tex_starts=None):
     return occ, occ_starts.int().contiguous(), boxes, box_starts.int().contiguous(), meta, rec
 
 
+VIS_CELL = .25     # metres; must match VIS_CELL in csrc/megastep_b200.cu
+
+
+@torch.no_grad()
+def _visibility_grid(boxes, box_starts, line_widths, n_dynamic):
+    """(vis, vis_starts, vis_meta) of include/megastep_b200.h: an (unfilled) grid of VIS_CELL cells over each env's
+    static geometry — the union of its run boxes — for msb_build_visibility to fill."""
+    dev = boxes.device
+    n = line_widths.size(0)
+    nb = ((line_widths.long() - n_dynamic).clamp(min=0) + OCCLUDER_RUN - 1) // OCCLUDER_RUN
+    env = torch.repeat_interleave(torch.arange(n, device=dev), nb)
+    big = torch.finfo(torch.float32).max
+    lo_x = torch.full((n,), big, device=dev).scatter_reduce(0, env, boxes[:, 0], 'amin')
+    lo_y = torch.full((n,), big, device=dev).scatter_reduce(0, env, boxes[:, 1], 'amin')
+    hi_x = torch.full((n,), -big, device=dev).scatter_reduce(0, env, boxes[:, 2], 'amax')
+    hi_y = torch.full((n,), -big, device=dev).scatter_reduce(0, env, boxes[:, 3], 'amax')
+    empty = nb == 0
+    gx = torch.where(empty, torch.zeros_like(nb), ((hi_x - lo_x).clamp(min=0) / VIS_CELL).ceil().long().clamp(min=1, max=4096))
+    gy = torch.where(empty, torch.zeros_like(nb), ((hi_y - lo_y).clamp(min=0) / VIS_CELL).ceil().long().clamp(min=1, max=4096))
+    cells = gx * gy
+    starts = (cells.cumsum(0) - cells).contiguous()
+    meta = torch.stack([torch.where(empty, torch.zeros_like(lo_x), lo_x), torch.where(empty, torch.zeros_like(lo_y), lo_y),
+                        gx.float(), gy.float()], -1).contiguous()
+    vis = torch.zeros(max(int(cells.sum().item()), 1), dtype=torch.int32, device=dev)
+    return vis, starts, meta
+
+
 class Render:
     """The result of a render() call. Exactly five public attributes (modules.unpack walks dir())."""
     __slots__ = ('screen', 'indices', 'locations', 'dots', 'distances')
@@ -387,6 +421,7 @@ class Physics:
 _PARAMS = None
 OCCLUDER_RUN = 16        # segments per run / bounding box of the spatial table
 USE_WORKSPACE = True   # False: agent-hit rays are lit inline by the first pass (same results; used by tests)
+USE_VISIBILITY_GRID = True   # False: sceneries are built without the light-visibility grid (same results, more shadow scans)
 
 
 def make_params(agent_radius, res, fov, fps):

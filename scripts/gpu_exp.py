@@ -33,6 +33,13 @@ if __name__ == '__main__':
         for _ in range(3): c.render()
         torch.cuda.synchronize()
         sys.exit(0)
+    if mode == 'ncu_step':
+        step = modules.FusedStep(c, subsample=1, raw=True)
+        torch.manual_seed(0)
+        acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')
+        for _ in range(24): step(acts)
+        torch.cuda.synchronize()
+        sys.exit(0)
     if mode == 'launches':
         step = modules.FusedStep(c, subsample=1, raw=True)
         acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')
@@ -57,11 +64,11 @@ if __name__ == '__main__':
         acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')
         step = modules.FusedStep(c, subsample=1, raw=True)
         for _ in range(20): step(acts)
-        for dw in (1, 2, 4):
+        for dw in (1, 2):
             cuda.set_option('dyn_warps', dw)
             cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0)
             step(acts); torch.cuda.synchronize()
-            for k in ('stat_dyn_rays', 'stat_dyn_iters', 'stat_dyn_entries', 'stat_dyn_cycles', 'stat_dyn_maxcyc', 'stat_dyn_warpmax', 'stat_dyn_slow', 'stat_dyn_kernel'):
+            for k in ('stat_dyn_rays', 'stat_dyn_iters', 'stat_dyn_entries', 'stat_dyn_cycles', 'stat_dyn_maxcyc', 'stat_dyn_warpmax', 'stat_dyn_slow', 'stat_dyn_kernel', 'stat_dyn_scans', 'stat_dyn_scans_lit', 'stat_dyn_iters_lit'):
                 out[f'{k}/dw{dw}'] = cuda.get_option(k)
             cuda.set_option('stats', 0)
             cuda.set_option('timing', 1)
@@ -98,6 +105,33 @@ if __name__ == '__main__':
                     out[f'step_us/pdl{pdl}/dw{dw}/rep{rep}'] = round(timeit(lambda: step(acts), iters=200), 1)
                     out[f'render_us/pdl{pdl}/dw{dw}/rep{rep}'] = round(timeit(lambda: c.render(), iters=200), 1)
         cuda.set_option('pdl', 1); cuda.set_option('dyn_warps', 0)
+        print(json.dumps(out)); sys.exit(0)
+    if mode == 'vis':
+        out = {}
+        torch.manual_seed(0)
+        acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')
+        step = modules.FusedStep(c, subsample=1, raw=True)
+        for _ in range(20): step(acts)
+        vis = c.scenery._vis[0]
+        out['vis_cells'] = vis.numel(); out['vis_bits_per_cell'] = round(float(sum(((vis >> i) & 1).sum().item() for i in range(32))) / vis.numel(), 2)
+        for no_vis in (1, 0):
+            cuda.set_option('no_vis', no_vis)
+            out[f'step_us/novis{no_vis}'] = round(timeit(lambda: step(acts), iters=200), 1)
+            cuda.set_option('timing', 1)
+            for _ in range(50): step(acts)
+            torch.cuda.synchronize()
+            for kind in ('physics', 'render', 'dyn'):
+                out[f'kernel_us/novis{no_vis}/{kind}'] = round(cuda.get_option(f'time_ns_{kind}') / cuda.get_option(f'time_count_{kind}') / 1e3, 1)
+            cuda.set_option('timing', 0)
+            cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0)
+            step(acts); torch.cuda.synchronize()
+            for k in ('stat_dyn_rays', 'stat_dyn_iters', 'stat_dyn_entries', 'stat_dyn_scans', 'stat_dyn_scans_lit'): out[f'{k}/novis{no_vis}'] = cuda.get_option(k)
+            cuda.set_option('stats', 0)
+        import time
+        from megastep_b200 import cuda as cu
+        torch.cuda.synchronize(); t0 = time.time()
+        cu._check(cu._lib.msb_build_visibility(__import__('ctypes').byref(c.scenery._c), torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize(); out['build_vis_ms'] = round((time.time() - t0) * 1e3, 1)
         print(json.dumps(out)); sys.exit(0)
     if mode == 'view':
         out = {}

@@ -319,6 +319,69 @@ def test_second_pass_inline_and_overflow_paths_agree(sub):
         assert _same(outs[0][0], other[0]) and _same(outs[0][1], other[1])
 
 
+def test_visibility_grid_is_conservative_and_changes_nothing():
+    """The light-visibility grid (msb_scenery::vis) may only vouch for lights that no static segment comes near, and
+    using it may not change a single output bit. Checked on a box scene with packed agents (lit by the room's light)
+    and on synthetic floorplans; the vouched-for (cell, light) pairs are re-derived in float64 at sampled points."""
+    from megastep_b200 import cuda
+    for kind, N, seed in (('box', 4, 61), ('synthetic', 12, 62)):
+        gs, arrays, st = make(kind, N, 4, seed=seed)
+        if kind == 'box':
+            st['positions'] = (3.5 + np.random.RandomState(0).uniform(-.6, .6, st['positions'].shape)).astype(np.float32)
+        outs = []
+        for no_vis in (0, 1):
+            cuda.set_option('no_vis', no_vis)
+            try:
+                c = common.to_device(arrays, st, 128, 100.)
+                plan = cuda.StepPlan(c.scenery, c.agents, c.params, actions=None, raw=True, subsample=1)
+                plan.render_only()
+                torch.cuda.synchronize()
+            finally:
+                cuda.set_option('no_vis', 0)
+            outs.append((plan.render.screen.clone(), plan.rgb.clone(), plan.render.indices.clone()))
+        n_dyn = int(((outs[0][2] >= 0) & (outs[0][2] < 32)).sum())
+        assert n_dyn > (50 if kind == 'box' else 0)
+        assert _same(outs[0][0], outs[1][0]) and _same(outs[0][1], outs[1][1])
+        # the table itself
+        sc = c.scenery
+        vis, starts, meta = (_np(t) for t in sc._vis)
+        lines = _np(sc.lines.vals).reshape(-1, 4).astype(np.float64)
+        lstarts, lwidths = _np(sc.lines.starts), _np(sc.lines.widths)
+        lights, istarts, iwidths = _np(sc.lights.vals).astype(np.float64), _np(sc.lights.starts), _np(sc.lights.widths)
+        rng = np.random.RandomState(3)
+        vouched = total = 0
+        for n in range(N):
+            x0, y0, gx, gy = meta[n]
+            gx, gy = int(gx), int(gy)
+            words = vis[starts[n]:starts[n] + gx * gy].view(np.uint32)
+            seg = lines[lstarts[n] + 32:lstarts[n] + lwidths[n]]
+            I = lights[istarts[n]:istarts[n] + iwidths[n]]
+            total += gx * gy * min(len(I), 32)
+            cells = rng.choice(gx * gy, size=min(gx * gy, 300), replace=False)
+            for cell in cells:
+                iy, ix = divmod(int(cell), gx)
+                for i in range(min(len(I), 32)):
+                    if not (words[cell] >> i) & 1:
+                        continue
+                    vouched += 1
+                    pts = np.array([x0, y0]) + (np.array([ix, iy]) + rng.uniform(0, 1, (4, 2))) * cuda.VIS_CELL
+                    for P in pts:
+                        U = P - I[i, :2]
+                        V = seg[:, 2:] - seg[:, :2]
+                        PQ = seg[:, :2] - I[i, :2]
+                        den = U[0] * V[:, 1] - U[1] * V[:, 0]
+                        with np.errstate(divide='ignore', invalid='ignore'):
+                            sp = (PQ[:, 0] * V[:, 1] - PQ[:, 1] * V[:, 0]) / den
+                            tp = (PQ[:, 0] * U[1] - PQ[:, 1] * U[0]) / den
+                        blocked = (np.abs(den) > 1e-9) & (sp > -1e-3) & (sp < 1 + 1e-3) & (tp > -1e-3) & (tp < 1 + 1e-3)
+                        assert not blocked.any(), (kind, n, cell, i)
+        assert vouched > 0 and total > 0
+        # it has to be worth its memory: a good share of the (cell, light) pairs of a box room is vouched for
+        if kind == 'box':
+            bits = sum(bin(int(w)).count('1') for w in vis.view(np.uint32))
+            assert bits > .3 * total, (bits, total)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # 3. properties at the benchmark's full size (Deathmatch 4096 x 4 x 128)
 # ------------------------------------------------------------------------------------------------------------------
