@@ -205,6 +205,9 @@ class Ours:
         import torch
         from megastep_b200 import core as core_, cuda, modules, scene
         self.cuda = cuda
+        for kv in filter(None, os.environ.get('MSB_OPTIONS', '').split(',')):   # A/B switches, e.g. MSB_OPTIONS=pdl=0,no_vis=1
+            name, value = kv.split('=')
+            cuda.set_option(name, int(value))
         s = scene.upload(arrays, device)
         cuda.bake(s, params=cuda.make_params(AGENT_RADIUS, cfg['res'], cfg['fov'], FPS))
         self.core = core_.Core(s, res=cfg['res'], fov=cfg['fov'], fps=FPS)

@@ -56,7 +56,8 @@ struct KArgs {
     int32_t debug_skip_dyn;     // timing experiments only: leave agent-hit rays unlit
     int32_t debug_no_vis;       // tests: ignore the visibility grid (same results, more shadow scans)
     // queue of ray chunks whose agent-hit pixels are lit by dyn_kernel (load-balanced second pass)
-    int* dyn_ctrl;              // [0] entries reserved, [1] CTAs of dyn_kernel done, [2] entries handed out beyond each CTA's first
+    int* dyn_ctrl;              // [0] entries reserved, [1] CTAs of dyn_kernel done, [2] entries handed out beyond each CTA's first,
+                                // [3] CTAs of view_kernel done
     unsigned char* dyn_entries; // null -> dynamic lights are resolved inline by the ray's own warp
     int32_t dyn_cap;            // entries that fit
     int32_t dyn_window;         // PS: pixels per entry = max(DYN_MIN_WINDOW, subsample); entry = DYN_HDR + 32 * PS bytes
@@ -72,7 +73,7 @@ enum { STAT_TESTS = 0, STAT_GROUPS = 1, STAT_DYN_RAYS = 2, STAT_DYN_ITERS = 3, S
 enum { VRUN = 16 };                       // segments per run of the spatial table
 enum { DYN_MIN_WINDOW = 4 };               // pixels per queue entry: max(4, subsample) adjacent pixels (a 'window')
 constexpr float VIS_CELL = 0.25f, VIS_INV_CELL = 4.f;   // the light-visibility grid's cell, metres
-enum { DYN_HDR = 48 };                     // bytes of a queue entry's header; 32 bytes per pixel follow
+enum { DYN_HDR = 48, DYN_FLAG = 44 };      // bytes of a queue entry's header (32 bytes per pixel follow); offset of its 'published' word
 
 // ---------------------------------------------------------------------------------------------------------------
 // physics
@@ -650,16 +651,17 @@ __device__ __forceinline__ void shade_chunk(const KArgs& k, const VSmem& m, int 
             queued = base + cnt <= k.dyn_cap;
             // which agent the window's first agent-hit pixel landed on: keys the persistent occluder cache
             const int tgt = __shfl_sync(0xffffffffu, l0, wl + (wmask ? __ffs(wmask) - 1 : 0)) / k.s.n_model;
-            if (wmask) {
-                const int slot = base + __popc(leaders & ((1u << wl) - 1u));
-                if (slot < k.dyn_cap) {
-                    unsigned char* e = k.dyn_entries + (size_t)slot * (DYN_HDR + 32 * PS);
+            const int slot = base + __popc(leaders & ((1u << wl) - 1u));
+            const bool mine = wmask != 0 && slot < k.dyn_cap;            // my window has a slot of the queue
+            unsigned char* e = k.dyn_entries + (size_t)(mine ? slot : 0) * (DYN_HDR + 32 * PS);
+            if (mine) {
+                {
                     // a chunk that does not fit as a whole falls back inline: its reserved slots carry an empty mask
                     if (lane == wl) {
                         int4* h = reinterpret_cast<int4*>(e);
                         h[0] = make_int4(n, a * R + (r - lane + wl), queued ? (int)wmask : 0, sub_ | (tgt << 8));
                         h[1] = *reinterpret_cast<const int4*>(m.meta);          // what dyn_kernel would otherwise look up by env
-                        h[2] = *reinterpret_cast<const int4*>(m.meta + 4);
+                        *reinterpret_cast<int2*>(e + 32) = *reinterpret_cast<const int2*>(m.meta + 4);
                         // dyn_kernel's first loads: this (env, hit agent)'s occluder hints; the other lanes of the window
                         // below: the env's lights. Warm L2 now, a kernel ahead of their use.
                         if (queued) prefetch_l2(k.dyn_cache + ((size_t)n * A + (tgt < A ? tgt : 0)) * 32);
@@ -684,6 +686,14 @@ __device__ __forceinline__ void shade_chunk(const KArgs& k, const VSmem& m, int 
                         rec[1] = make_float4(Cx, Cy, intensity, __uint_as_float(sure));
                     }
                 }
+            }
+            // publish: dyn_kernel may already be running (it is launched as a programmatic dependent and consumes the
+            // queue while this grid drains). The window's lanes have written; one of them raises the entry's flag.
+            __threadfence();
+            __syncwarp();
+            if (mine && lane == wl) {
+                __threadfence();
+                *reinterpret_cast<volatile int*>(e + DYN_FLAG) = 1;
             }
         }
         if (!queued) intensity = dyn_inline(seg, Lrows, AF, m.meta[1], k.s.lights + 3 * (int64_t)m.meta[2], dm, Cx, Cy, intensity);
@@ -1012,6 +1022,14 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_
             q[2] = __fmul_rn(__fadd_rn(__fmul_rn(-s, vx), __fmul_rn(c, vy)), k.inv_speed);
         }
     }
+    // tell dyn_kernel that this CTA will publish nothing more (its last act: dyn_kernel outlives the grid)
+    if (k.dyn_entries) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(k.dyn_ctrl + 3, 1);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1037,12 +1055,9 @@ __device__ __forceinline__ bool occludes(const Hit h) { return (h.t > 0.f) && (h
 template <bool STATS>
 __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs k) {
     __shared__ unsigned s_lit[4][32];                          // per warp: the lights it found unoccluded, per pixel lane
-    __shared__ int s_next;                                     // the CTA's next entry
+    __shared__ int s_next, s_ready;                            // the CTA's next entry; whether the current one was published
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
     const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
-    griddep_wait();          // the queue is view_kernel's output
-    const int reserved = *reinterpret_cast<volatile int*>(k.dyn_ctrl);
-    const int count = reserved < k.dyn_cap ? reserved : k.dyn_cap;
     unsigned dyn_rays = 0, dyn_iters = 0, dyn_entries = 0;
     // One entry per CTA at a time, entries strided over the grid (every entry is an independent unit of work; a shared
     // counter would serialise thousands of CTAs on one address). The CTA's warps split the entry's LIGHTS between them:
@@ -1052,15 +1067,38 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
     long long t_entries = 0;
     // the first entry is the CTA's own index; the following ones come off a shared counter (ctrl[2]) — CTAs that drew
     // heavy entries take fewer. The counter is bumped at the start of an entry, so its round trip is off the chain.
-    for (int ei = blockIdx.x; ei < count;) {
+    // The queue is consumed WHILE view_kernel fills it: this grid is launched as a programmatic dependent, its CTAs
+    // move in as view_kernel's leave (every one of those has started by then, so nothing here can starve them). An
+    // entry is ready when its flag is up; it never will be once every CTA of view_kernel has signed off with the flag
+    // still down — slots are reserved in order, so neither will any later one.
+    for (int ei = blockIdx.x; ei < k.dyn_cap;) {
         const long long t_e0 = STATS ? clock64() : 0;
         const int PS = k.dyn_window;
+        unsigned char* e = k.dyn_entries + (size_t)ei * (DYN_HDR + 32 * PS);
         int nxt = 0;
-        if (threadIdx.x == 0) nxt = atomicAdd(k.dyn_ctrl + 2, 1) + (int)gridDim.x;
-        const unsigned char* e = k.dyn_entries + (size_t)ei * (DYN_HDR + 32 * PS);
-        const int4 hdr = *reinterpret_cast<const int4*>(e);
-        const int4 hdr1 = *reinterpret_cast<const int4*>(e + 16);      // {W, lights, first light, first box} of the env
-        const float2 hdr2 = *reinterpret_cast<const float2*>(e + 32);   // occ_meta of the env
+        if (threadIdx.x == 0) {
+            volatile int* flag = reinterpret_cast<volatile int*>(e + DYN_FLAG);
+            volatile int* done = k.dyn_ctrl + 3;
+            int ready = *flag;
+            for (unsigned spins = 0; !ready && spins < (1u << 22); spins++) {       // (bounded: a lost signal must not hang the GPU)
+                if (*done >= k.s.n_envs) { __threadfence(); ready = *flag; break; }
+                __nanosleep(100);
+                ready = *flag;
+            }
+            if (ready) {
+                __threadfence();
+                *flag = 0;                                                          // re-armed for the next step
+                nxt = atomicAdd(k.dyn_ctrl + 2, 1) + (int)gridDim.x;
+            }
+            s_ready = ready;
+        }
+        __syncthreads();
+        if (!s_ready) break;
+        // (entries are read past L1: a neighbour's line fetched earlier by this SM may hold this entry's bytes from
+        // before they were written)
+        const int4 hdr = __ldcg(reinterpret_cast<const int4*>(e));
+        const int4 hdr1 = __ldcg(reinterpret_cast<const int4*>(e + 16));      // {W, lights, first light, first box} of the env
+        const float2 hdr2 = __ldcg(reinterpret_cast<const float2*>(e + 32));   // occ_meta of the env
         const unsigned mask = (unsigned)hdr.z;                          // 0: slot reserved by a chunk that fell back inline
         const int sub = hdr.w & 0xff, tgt = hdr.w >> 8;
         const int n = hdr.x, ar = hdr.y;                       // env; agent * R + first ray of the window
@@ -1074,8 +1112,8 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
         float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (have) {
             const float4* rec = reinterpret_cast<const float4*>(e + DYN_HDR) + 2 * lane;
-            ra = rec[0];
-            rb = rec[1];
+            ra = __ldcg(rec);
+            rb = __ldcg(rec + 1);
         }
         const float Cx = rb.x, Cy = rb.y;
         const unsigned sure = (isdyn && !k.debug_no_vis) ? __float_as_uint(rb.w) : 0u;   // lights the visibility grid vouches for
@@ -1276,11 +1314,13 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
             atomicMax(k.stats + STAT_DYN_KERNEL, (unsigned long long)(clock64() - t_start));
         }
     }
-    // the last CTA out re-arms the queue for the next step
+    // the last CTA out re-arms the queue for the next step (every CTA of view_kernel has signed off by then; the wait
+    // makes this grid's completion formally imply that grid's)
+    griddep_wait();
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(k.dyn_ctrl + 1, 1) == (int)gridDim.x - 1) { k.dyn_ctrl[0] = 0; k.dyn_ctrl[1] = 0; k.dyn_ctrl[2] = 0; }
+        if (atomicAdd(k.dyn_ctrl + 1, 1) == (int)gridDim.x - 1) { k.dyn_ctrl[0] = 0; k.dyn_ctrl[1] = 0; k.dyn_ctrl[2] = 0; k.dyn_ctrl[3] = 0; }
     }
 }
 
