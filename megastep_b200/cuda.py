@@ -330,13 +330,26 @@ def _occluder_table(lines, n_dynamic, run=16, tex_widths=None, tex_starts=None):
     static = local >= n_dynamic
     sv, senv, sid = vals[static], env[static], local[static]
     mid = (sv[:, :2] + sv[:, 2:]) * .5
-    lo = mid.min(0).values if len(mid) else torch.zeros(2, device=dev)
-    cell = ((mid - lo) / .25).clamp(0, 65535).long()
-    key = (senv << 32) | _morton16(cell[:, 0], cell[:, 1])
-    order = torch.argsort(key)
     W = (widths - n_dynamic).clamp(min=0)
     wstarts = W.cumsum(0) - W
     nb = (W + run - 1) // run
+    if TABLE_ORDER == 'morton':
+        lo = mid.min(0).values if len(mid) else torch.zeros(2, device=dev)
+        cell = ((mid - lo) / .25).clamp(0, 65535).long()
+        key = (senv << 32) | _morton16(cell[:, 0], cell[:, 1])
+        order = torch.argsort(key)
+    else:
+        # sort-tile-recursive packing (the R-tree bulk load): ~sqrt(nb) vertical strips of equal population, each
+        # sorted by y and cut into runs — tighter, less overlapping run boxes than a space-filling curve gives
+        by_x = torch.argsort(mid[:, 0], stable=True)
+        by_x = by_x[torch.argsort(senv[by_x], stable=True)]                 # by (env, x)
+        rank_x = torch.empty_like(by_x)
+        rank_x[by_x] = torch.arange(by_x.size(0), device=dev) - wstarts[senv[by_x]]
+        strips = nb.double().sqrt().ceil().long().clamp(min=1)
+        per_strip = ((nb + strips - 1) // strips) * run                      # segments per strip: whole runs
+        strip = rank_x // per_strip[senv].clamp(min=1)
+        by_y = torch.argsort(mid[:, 1], stable=True)
+        order = by_y[torch.argsort((senv[by_y] << 20) | strip[by_y], stable=True)]   # by (env, strip, y)
     box_starts = nb.cumsum(0) - nb
     occ_starts = box_starts * run
     nbox = int(nb.sum().item())
@@ -420,6 +433,7 @@ class Physics:
 # --------------------------------------------------------------------------------------------------------------
 _PARAMS = None
 OCCLUDER_RUN = 16        # segments per run / bounding box of the spatial table
+TABLE_ORDER = 'str'      # how the table's runs are formed: 'str' (sort-tile-recursive) or 'morton'
 USE_WORKSPACE = True   # False: agent-hit rays are lit inline by the first pass (same results; used by tests)
 USE_VISIBILITY_GRID = True   # False: sceneries are built without the light-visibility grid (same results, more shadow scans)
 

@@ -28,6 +28,26 @@ def setup(N=4096, A=4, res=128, fov=70.):
 if __name__ == '__main__':
     mode = sys.argv[1] if len(sys.argv) > 1 else 'exp'
     if len(sys.argv) > 2: cuda.OCCLUDER_RUN = int(sys.argv[2])
+    if mode == 'order':
+        out = {}
+        torch.manual_seed(0)
+        acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')
+        for order in ('morton', 'str', 'morton', 'str'):
+            cuda.TABLE_ORDER = order
+            c = setup()
+            step = modules.FusedStep(c, subsample=1, raw=True)
+            for _ in range(20): step(acts)
+            tag = order + ('2' if f'step_us/{order}' in out else '')
+            out[f'step_us/{tag}'] = round(timeit(lambda: step(acts), iters=200), 1)
+            out[f'render_us/{tag}'] = round(timeit(lambda: c.render(), iters=200), 1)
+            out[f'physics_us/{tag}'] = round(timeit(lambda: c.physics(), iters=200), 1)
+            cuda.set_option('debug_skip_dyn', 1); out[f'main_us/{tag}'] = round(timeit(lambda: c.render(), iters=200), 1); cuda.set_option('debug_skip_dyn', 0)
+            cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0)
+            c.render(); torch.cuda.synchronize()
+            for k in ('stat_tests', 'stat_groups', 'stat_dyn_iters', 'stat_dyn_scans', 'stat_replays'): out[f'{k}/{tag}'] = cuda.get_option(k)
+            cuda.set_option('stats', 0)
+            del step, c
+        print(json.dumps(out)); sys.exit(0)
     c = setup()
     if mode == 'ncu':
         for _ in range(3): c.render()
