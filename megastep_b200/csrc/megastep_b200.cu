@@ -43,6 +43,7 @@ struct KArgs {
     msb_obs_out obs;
     msb_movement mv;
     int32_t has_obs;
+    int32_t sub_shift;      // log2(obs.subsample)
     int32_t has_mv;
     int32_t ray_blocks;     // RB: warps per agent in view_kernel
     int32_t rb_shift;       // log2(RB) when RB is a power of two, else -1
@@ -401,6 +402,7 @@ struct VSmem {
     float* st_out;          // [A][8]
     int* mrad;              // [A] ([0]: bits of the model's radius, max |endpoint|)
     uint64_t* bar;
+    int* next_item;         // items handed out beyond each warp's first
     int* meta;              // [16] this env's {W, lights, first light, first box, bits of occ_meta[0], [1], -, -} for queue entries;
                             //      {bits of vis_meta x0, y0, gx, gy, vis_starts lo, hi, -, -}
 };
@@ -417,6 +419,7 @@ __device__ __forceinline__ VSmem vcarve(unsigned char* base, int wcap, int nwarp
     uintptr_t p = reinterpret_cast<uintptr_t>(m.mrad + A);
     p = (p + 15) & ~uintptr_t(15);
     m.bar = reinterpret_cast<uint64_t*>(p);
+    m.next_item = reinterpret_cast<int*>(p + 8);
     m.meta = reinterpret_cast<int*>(p + 16);
     return m;
 }
@@ -706,14 +709,14 @@ __device__ __forceinline__ void shade_chunk(const KArgs& k, const VSmem& m, int 
         s1 = fmul(kk, b1);
         s2 = fmul(kk, b2);
     }
-    const int64_t ag = (int64_t)n * A + a;
+    const int64_t ag = (int64_t)n * A + a;                 // warp-uniform: the 64-bit part of every address below
+    const int64_t o0 = ag * R;
     if (live) {
-        const int64_t o = ag * R + r;
-        if (k.out.indices) k.out.indices[o] = l0;
-        if (k.out.locations) k.out.locations[o] = locv;
-        if (k.out.dots) k.out.dots[o] = dotv;
-        if (k.out.distances) k.out.distances[o] = dist;
-        if (k.out.screen && !(queued && isdyn)) { float* sc = k.out.screen + 3 * o; sc[0] = s0; sc[1] = s1; sc[2] = s2; }
+        if (k.out.indices) (k.out.indices + o0)[r] = l0;
+        if (k.out.locations) (k.out.locations + o0)[r] = locv;
+        if (k.out.dots) (k.out.dots + o0)[r] = dotv;
+        if (k.out.distances) (k.out.distances + o0)[r] = dist;
+        if (k.out.screen && !(queued && isdyn)) { float* sc = k.out.screen + 3 * o0 + 3 * r; sc[0] = s0; sc[1] = s1; sc[2] = s2; }
     }
     // fused observation heads: Depth (modules.py:181-183) and RGB (:222-223), mean over `subsample` pixels
     if (k.has_obs) {
@@ -730,13 +733,13 @@ __device__ __forceinline__ void shade_chunk(const KArgs& k, const VSmem& m, int 
             v3 = __fadd_rn(v3, __shfl_xor_sync(0xffffffffu, v3, o));
         }
         if (live && lane == gl) {
-            const int Ro = R / sub_, ro = r / sub_;
+            const int Ro = R >> k.sub_shift, ro = r >> k.sub_shift;         // subsample is a power of two
             const float inv = k.inv_sub;
             if (k.obs.rgb && !deferred) {
                 float* q = k.obs.rgb + ag * 3 * Ro + ro;
                 q[0] = __fmul_rn(v0, inv); q[Ro] = __fmul_rn(v1, inv); q[2 * Ro] = __fmul_rn(v2, inv);
             }
-            if (k.obs.depth) k.obs.depth[ag * Ro + ro] = __fmul_rn(v3, inv);
+            if (k.obs.depth) (k.obs.depth + ag * Ro)[ro] = __fmul_rn(v3, inv);
         }
     }
 }
@@ -948,6 +951,7 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_
     }
     if (tid == 0) {
         m.mrad[0] = 0;
+        *m.next_item = 0;
         mbar_init(m.bar, 1);
         if (nb > 0) {
             const int64_t b0 = __ldg(k.s.box_starts + n);
@@ -1005,10 +1009,14 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_
         }
     }
     __syncthreads();
+    // (agent, block of rays) items: the first is the warp's own, the following ones come off a shared counter — items
+    // differ in cost by what they see, and the CTA holds its registers and shared memory until its last warp is done
     const int RB = k.ray_blocks, rbs = k.rb_shift;          // rb_shift >= 0: RB is that power of two
-    for (int w = warp; w < A * RB; w += nwarps) {
+    for (int w = warp; w < A * RB;) {
         const int a = rbs >= 0 ? w >> rbs : w / RB;
         view_agent<NCH, STATS>(k, m, n, g0, L, W, nb, a, w - a * RB, m.scr + warp * 128, lane);
+        if (lane == 0) w = nwarps + atomicAdd(m.next_item, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
     }
     if (k.has_obs && k.obs.imu) {
         for (int a = tid; a < A; a += blockDim.x) {
@@ -1289,7 +1297,7 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
                     v2 = __fadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
                 }
                 if (have && lane == gl) {
-                    const int Ro = R / sub, ro = (r0 + lane) / sub;
+                    const int Ro = R >> k.sub_shift, ro = (r0 + lane) >> k.sub_shift;
                     float* q = k.obs.rgb + ag * 3 * Ro + ro;
                     q[0] = __fmul_rn(v0, k.inv_sub); q[Ro] = __fmul_rn(v1, k.inv_sub); q[2 * Ro] = __fmul_rn(v2, k.inv_sub);
                 }
@@ -1761,6 +1769,7 @@ static void set_obs(KArgs& k, const msb_obs_out* obs) {
     k.inv_speed = 1.0f / obs->speed_scale;
     k.inv_ang = 1.0f / obs->ang_scale;
     k.inv_sub = 1.0f / (float)obs->subsample;
+    k.sub_shift = __builtin_ctz((unsigned)obs->subsample);
 }
 
 static int check_obs(const msb_params* p, const msb_obs_out* obs) {

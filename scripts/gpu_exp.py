@@ -49,6 +49,22 @@ if __name__ == '__main__':
             del step, c
         print(json.dumps(out)); sys.exit(0)
     c = setup()
+    if mode == 'quick':
+        out = {}
+        torch.manual_seed(0)
+        acts = torch.randint(0, 7, (4096, 4), dtype=torch.int32, device='cuda')
+        step = modules.FusedStep(c, subsample=1, raw=True)
+        for _ in range(20): step(acts)
+        for rep in range(2):
+            out[f'step_us/{rep}'] = round(timeit(lambda: step(acts), iters=300), 1)
+            out[f'render_us/{rep}'] = round(timeit(lambda: c.render(), iters=300), 1)
+            cuda.set_option('debug_skip_dyn', 1); out[f'main_us/{rep}'] = round(timeit(lambda: c.render(), iters=300), 1); cuda.set_option('debug_skip_dyn', 0)
+        out['physics_us'] = round(timeit(lambda: c.physics(), iters=300), 1)
+        cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0)
+        c.render(); torch.cuda.synchronize()
+        for k in ('stat_tests', 'stat_groups', 'stat_dyn_iters', 'stat_dyn_scans', 'stat_dyn_entries', 'stat_replays'): out[k] = cuda.get_option(k)
+        cuda.set_option('stats', 0)
+        print(json.dumps(out)); sys.exit(0)
     if mode == 'ncu':
         for _ in range(3): c.render()
         torch.cuda.synchronize()
