@@ -198,25 +198,34 @@ class FusedStep:
                                    speed_scale=speed_scale, ang_scale=ang_scale)
         self.space = spaces.MultiDiscrete(core.n_agents, 7)
         self._graph = None
+        self.actions_host = self.progress_host = None
         if graph:
             self._capture()
 
-    def _capture(self):
-        """Capture the launch in a CUDA graph so a step costs one graph replay on the host."""
+    def _capture(self, host_io=False):
+        """Capture the launch in a CUDA graph so a step costs one graph replay on the host. With `host_io` the graph
+        also holds the copy of the actions from a pinned host buffer (`actions_host`) and of `progress` back into one
+        (`progress_host`): a whole host-to-host tick is then ONE launch (see `step_host`)."""
+        if host_io:
+            self.actions_host = torch.zeros(tuple(self.actions.shape), dtype=torch.int32).pin_memory()
+            self.progress_host = torch.zeros(tuple(self._plan.progress.shape), dtype=torch.float32).pin_memory()
+        agents = (self.core.agents.angles, self.core.agents.positions, self.core.agents.angvelocity, self.core.agents.velocity)
+        snapshot = [t.clone() for t in agents]                 # the warm-up below advances the state once: undone at the end
         side = torch.cuda.Stream(device=self.core.device)
         side.wait_stream(torch.cuda.current_stream(self.core.device))
         with torch.cuda.stream(side):
             self._plan()           # warm-up outside capture (first-launch attribute set-up)
         torch.cuda.current_stream(self.core.device).wait_stream(side)
         torch.cuda.synchronize(self.core.device)
-        snapshot = [t.clone() for t in (self.core.agents.angles, self.core.agents.positions,
-                                        self.core.agents.angvelocity, self.core.agents.velocity)]
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
+            if host_io:
+                self.actions.copy_(self.actions_host, non_blocking=True)
             self._plan()
+            if host_io:
+                self.progress_host.copy_(self._plan.progress, non_blocking=True)
         # capture does not execute, but the warm-up advanced the state once: restore it
-        for dst, src in zip((self.core.agents.angles, self.core.agents.positions, self.core.agents.angvelocity,
-                             self.core.agents.velocity), snapshot):
+        for dst, src in zip(agents, snapshot):
             dst.copy_(src)
 
     def __call__(self, actions=None):
@@ -228,6 +237,18 @@ class FusedStep:
             self._plan()
         p = self._plan
         return arrdict(obs=arrdict(rgb=p.rgb, d=p.depth, imu=p.imu), progress=p.progress, render=p.render)
+
+    def step_host(self, actions=None):
+        """One tick driven from the host (needs `_capture(host_io=True)`): `actions` — a host tensor / array, or None
+        if the caller filled `self.actions_host` itself — go up, the tick runs, `progress` comes back into
+        `self.progress_host`; all inside one graph launch, then the stream is synchronised. Observations stay on the
+        device, as in `__call__`."""
+        if actions is not None and actions is not self.actions_host:
+            self.actions_host.copy_(torch.as_tensor(actions))
+        self._graph.replay()
+        torch.cuda.current_stream(self.core.device).synchronize()
+        p = self._plan
+        return arrdict(obs=arrdict(rgb=p.rgb, d=p.depth, imu=p.imu), progress=self.progress_host, render=p.render)
 
 
 def random_empty_positions(geometries, n_agents, n_points, random=np.random):

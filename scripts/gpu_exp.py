@@ -49,6 +49,33 @@ if __name__ == '__main__':
             del step, c
         print(json.dumps(out)); sys.exit(0)
     c = setup()
+    if mode == 'e2e':
+        out = {}
+        N, A = 4096, 4
+        acts_host = torch.as_tensor(np.random.RandomState(3).randint(0, 7, (400, N, A)).astype(np.int32)).pin_memory()
+        step = modules.FusedStep(c, subsample=1, raw=True)
+        step._capture(host_io=True)
+        stream = torch.cuda.current_stream()
+        for i in range(50): step.step_host(acts_host[i])
+        t = {'stage': 0., 'replay': 0., 'sync': 0.}
+        t0 = time.perf_counter()
+        for i in range(300):
+            a = time.perf_counter(); step.actions_host.copy_(acts_host[50 + i]); b = time.perf_counter()
+            step._graph.replay(); c_ = time.perf_counter()
+            stream.synchronize(); d = time.perf_counter()
+            t['stage'] += b - a; t['replay'] += c_ - b; t['sync'] += d - c_
+        out['host_io_total_us'] = round((time.perf_counter() - t0) / 300 * 1e6, 1)
+        for k_, v in t.items(): out[f'host_io_{k_}_us'] = round(v / 300 * 1e6, 1)
+        # device time of the same graph alone
+        out['graph_device_us'] = round(timeit(lambda: step._graph.replay(), iters=300), 1)
+        # plain: separate copies
+        step2 = modules.FusedStep(c, subsample=1, raw=True, graph=True)
+        res = torch.empty((N, A), dtype=torch.float32).pin_memory()
+        t0 = time.perf_counter()
+        for i in range(300):
+            step2.actions.copy_(acts_host[50 + i], non_blocking=True); step2._graph.replay(); res.copy_(step2._plan.progress, non_blocking=True); stream.synchronize()
+        out['separate_total_us'] = round((time.perf_counter() - t0) / 300 * 1e6, 1)
+        print(json.dumps(out)); sys.exit(0)
     if mode == 'quick':
         out = {}
         torch.manual_seed(0)

@@ -212,6 +212,34 @@ def test_fused_step_equals_modules_pipeline(A, res, fov, sub):
         common.load_state(c2, common.read_state(c1))
 
 
+def test_graph_replay_with_host_io_equals_plain_launches():
+    """FusedStep as plain launches, as a CUDA-graph replay, and as ONE graph launch holding the host copies too
+    (step_host) must walk the same trajectory: the programmatic-dependent launches and the streaming queue between
+    view_kernel and dyn_kernel are captured as such."""
+    from megastep_b200 import modules
+    gs, arrays, st = make('box', 6, 4, seed=91)
+    st['positions'] = (3.5 + np.random.RandomState(0).uniform(-.8, .8, st['positions'].shape)).astype(np.float32)
+    acts = torch.as_tensor(np.random.RandomState(5).randint(0, 7, (6, 6, 4)).astype(np.int32))
+    recs = []
+    for mode in ('plain', 'graph', 'host'):
+        c = common.to_device(arrays, st, 128, 100.)
+        step = modules.FusedStep(c, subsample=2, raw=True, graph=mode == 'graph')
+        if mode == 'host':
+            step._capture(host_io=True)
+        rec = []
+        for t in range(6):
+            out = step.step_host(acts[t]) if mode == 'host' else step(acts[t].cuda())
+            torch.cuda.synchronize()
+            rec.append([torch.as_tensor(out.progress).cpu().clone(), out.obs.rgb.cpu().clone(), out.obs.d.cpu().clone(),
+                        out.obs.imu.cpu().clone(), out.render.screen.cpu().clone(), out.render.indices.cpu().clone()])
+        recs.append(rec)
+    n_dyn = int(((recs[0][0][5] >= 0) & (recs[0][0][5] < 32)).sum())
+    assert n_dyn > 20
+    for other in recs[1:]:
+        for a, b in zip(recs[0], other):
+            assert all(_same(x, y) for x, y in zip(a, b))
+
+
 def downsampled_all(mask, sub):
     return mask.reshape(*mask.shape[:-1], mask.shape[-1] // sub, sub).all(-1)
 
