@@ -56,6 +56,7 @@ struct KArgs {
     unsigned long long* stats;  // optional diagnostics counters (may be null)
     int32_t debug_skip_dyn;     // timing experiments only: leave agent-hit rays unlit
     int32_t debug_no_vis;       // tests: ignore the visibility grid (same results, more shadow scans)
+    int32_t prefetch_view;      // physics_kernel: prefetch each env's table into L2 for the view_kernel that follows
     // queue of ray chunks whose agent-hit pixels are lit by dyn_kernel (load-balanced second pass)
     int* dyn_ctrl;              // [0] entries reserved, [1] CTAs of dyn_kernel done, [2] entries handed out beyond each CTA's first,
                                 // [3] CTAs of view_kernel done
@@ -255,6 +256,12 @@ __global__ void __launch_bounds__(128) physics_kernel(const __grid_constant__ KA
     const int64_t b0 = __ldg(k.s.box_starts + n);
     const float4* occ = reinterpret_cast<const float4*>(k.s.occ_lines) + VRUN * b0;
     const float4* boxes = reinterpret_cast<const float4*>(k.s.occ_boxes) + b0;
+    // msb_step: view_kernel is next and will stage this env's whole table — start it on its way from HBM to L2 now
+    if (k.prefetch_view && tid == 0 && nb > 0) {
+        bulk_prefetch_l2(occ, (uint32_t)nb * VRUN * 16u);
+        bulk_prefetch_l2(k.s.occ_rec + 4 * VRUN * b0, (uint32_t)nb * VRUN * 16u);
+        bulk_prefetch_l2(boxes, (uint32_t)nb * 16u);
+    }
     const float rF = rcp(k.p.fps);
     const float r2 = fmul(k.p.agent_radius, 2.0020000934600830078f);
     const float r1 = fmul(k.p.agent_radius, 1.0010000467300415039f);
@@ -692,12 +699,10 @@ __device__ __forceinline__ void shade_chunk(const KArgs& k, const VSmem& m, int 
             }
             // publish: dyn_kernel may already be running (it is launched as a programmatic dependent and consumes the
             // queue while this grid drains). The window's lanes have written; one of them raises the entry's flag.
-            __threadfence();
+            // (release at GPU scope by one lane, after a warp barrier: cumulative over the other lanes' stores; no
+            // acquire side here — __threadfence() would also invalidate the SM's L1 under the other CTAs' texel gathers)
             __syncwarp();
-            if (mine && lane == wl) {
-                __threadfence();
-                *reinterpret_cast<volatile int*>(e + DYN_FLAG) = 1;
-            }
+            if (mine && lane == wl) st_release(reinterpret_cast<int*>(e + DYN_FLAG), 1);
         }
         if (!queued) intensity = dyn_inline(seg, Lrows, AF, m.meta[1], k.s.lights + 3 * (int64_t)m.meta[2], dm, Cx, Cy, intensity);
         deferred = queued && gmask != 0;                                  // dyn_kernel writes this group's screen / rgb
@@ -1033,10 +1038,7 @@ __global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_
     // tell dyn_kernel that this CTA will publish nothing more (its last act: dyn_kernel outlives the grid)
     if (k.dyn_entries) {
         __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(k.dyn_ctrl + 3, 1);
-        }
+        if (tid == 0) red_release_add(k.dyn_ctrl + 3, 1);
     }
 }
 
@@ -1451,6 +1453,7 @@ static long long g_opt_nch = 0;          // 0 = auto
 static long long g_opt_threads = 0;      // 0 = auto
 static long long g_opt_skip_dyn = 0;     // debug
 static long long g_opt_no_vis = 0;       // tests: ignore the visibility grid
+static long long g_opt_no_prefetch = 0;  // A/B: physics_kernel does not prefetch view_kernel's tables
 static long long g_opt_dyn_window = 0;   // 0 = default (DYN_MIN_WINDOW); 1, 2, 4, 8: pixels per queue entry when subsample is smaller
 static long long g_opt_dyn_warps = 0;    // warps sharing one queue entry in dyn_kernel (default 2)
 static long long g_opt_fused_step = 0;   // 1: msb_step runs physics inside view_kernel (measured slower: the physics latency
@@ -1550,6 +1553,7 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "dyn_warps")) { g_opt_dyn_warps = value; return 0; }
     if (!strcmp(name, "pdl")) { g_opt_pdl = value; return 0; }
     if (!strcmp(name, "no_vis")) { g_opt_no_vis = value; return 0; }
+    if (!strcmp(name, "no_prefetch")) { g_opt_no_prefetch = value; return 0; }
     if (!strcmp(name, "timing")) {
         timing_flush();
         g_opt_timing = value;
@@ -1830,6 +1834,7 @@ extern "C" int msb_step(const msb_params* p, const msb_scenery* s, const msb_age
         if (launch_view(k, true, nch, threads, (cudaStream_t)cuda_stream)) return 1;
     } else {
         // physics (with the movement prologue) at its own, higher occupancy; then render with the heads
+        k.prefetch_view = g_opt_no_prefetch ? 0 : 1;
         if (launch_physics(k, (cudaStream_t)cuda_stream)) return 1;
         if (launch_view(k, false, nch, threads, (cudaStream_t)cuda_stream)) return 1;
     }

@@ -114,8 +114,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// hint: bring `bytes` (a multiple of 16, from a 16-byte aligned address) into L2; one instruction for the whole range
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 // hint: bring the 128-byte line at p into L2 (no register result, nothing to wait for)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// release-ordered publication at GPU scope: every write that happens-before (this thread's, and those of threads it
+// synchronised with through a warp / CTA barrier) is visible to whoever observes the stored value
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_release_add(int* p, int v) { asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start while the
 // kernel ahead of it in the stream is still running; it must not touch anything that kernel writes before
