@@ -103,8 +103,8 @@ def render_kernel_bytes(cfg, arrays, raw=True):
 
 def profiled_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of view_kernel, from the committed ncu --set full
-    capture of the same workload (profiles/r01_view_kernel_full_summary.json)."""
-    path = os.path.join(ROOT, 'profiles', 'r01_view_kernel_full_summary.json')
+    capture of the same workload (profiles/r01_kernels_full_summary.json)."""
+    path = os.path.join(ROOT, 'profiles', 'r01_kernels_full_summary.json')
     try:
         recs = [r for r in json.load(open(path)) if 'view_kernel' in r['Kernel Name']]
         mb = [float(r['dram__bytes_read.sum']) + float(r['dram__bytes_write.sum']) for r in recs]
@@ -483,7 +483,7 @@ def main():
                     'kernel_share_of_step': km['render'] / sum(km.values()), 'algorithmic_bytes_per_launch': rb,
                     'traffic_source': traffic_src, 'all_kernels_ms': km, 'peak_source': peak_src,
                     'whole_step': {'achieved': step_achieved, 'frac': step_achieved / peak, 'algorithmic_bytes_per_step': out['bytes_per_step']},
-                    'note': 'not HBM-bound yet: issue/latency-bound (ncu: issue-active 60%, DRAM throughput ~10% of peak); see DESIGN.md'}
+                    'note': 'not HBM-bound: issue/latency-bound (ncu: issue-active 62%, DRAM ~15% of peak). Kernels are timed apart here (events between them); in the step dyn_kernel overlaps the tail of view_kernel, so all_kernels_ms sums to more than ms_per_step. See DESIGN.md'}
     else:
         roofline = {'bound': 'hbm', 'achieved': step_achieved, 'peak': peak, 'unit': 'GB/s', 'frac': step_achieved / peak, 'traffic': None,
                     'kernel': 'whole step (physics + render + ~40 ATen launches)', 'algorithmic_bytes_per_step': out['bytes_per_step'],
@@ -503,7 +503,7 @@ def main():
     if reference:
         line['cpu_baseline'] = {'value': value, 'unit': 'agent-frames/s', 'cores': 0, 'kind': 'reference',
                                 'sample': 'the reference\'s own CUDA build (oracle/_ref) on one B200 of this box: megastep has no CPU step path'}
-    elif not args.no_cpu_baseline:
+    elif not args.no_cpu_baseline and world == 1:                # rank 0 at N = 1 only (torchrun pins OMP_NUM_THREADS=1)
         line['cpu_baseline'] = cpu_baseline(cfg, out['arrays'], out['pos'], out['ang'])
     print(json.dumps(line))
     if world > 1 and not reference:
