@@ -63,10 +63,11 @@ typedef struct msb_scenery {
     const float* model;         /* (F, 4) */
     int64_t n_lines;            /* sum L */
     int64_t n_texels;           /* sum T */
-    /* Optional spatial table (all NULL to disable): a copy of every env's STATIC segments sorted along a Morton
-     * curve, in runs of occ_run = 16 with one bounding box per run; each env's rows are padded to a whole number of
-     * runs (so every env's block is 16-byte aligned for bulk copies). Built once per scenery. Used to skip work only:
-     * shadow tests and collisions are order-free, and render() restores the reference's line-order rule exactly. */
+    /* The spatial table, required by msb_physics / msb_render / msb_step: a copy of every env's STATIC segments packed
+     * sort-tile-recursive into runs of occ_run = 16 with one bounding box per run; each env's rows are padded to a
+     * whole number of runs (so every env's block is 16-byte aligned for bulk copies). The caller allocates the arrays
+     * and fills box_starts (exclusive prefix sum of nb); msb_build_table fills the rest, once per scenery. Used to skip
+     * work only: shadow tests and collisions are order-free, and render() restores the reference's line-order rule. */
     const float* occ_lines;     /* (16 * sum nb, 4) sorted static segments; nb = ceil((line_widths[n] - A*F) / 16) per env */
     const int32_t* occ_starts;  /* (N) start of env n's rows in occ_lines (= 16 * box_starts[n]) */
     const float* occ_boxes;     /* (sum nb, 4) {xmin, ymin, xmax, ymax} of each run */
@@ -138,6 +139,10 @@ int msb_params_init(msb_params* p, float agent_radius, int32_t res, float fov, f
 
 /* bake(scenery) — megastep/src/wrappers.cpp:61, kernels.cu:270-293. Writes scenery->baked for every texel. */
 int msb_bake(const msb_params* p, const msb_scenery* s, void* cuda_stream);
+
+/* Fills the spatial table (s->occ_lines, occ_rec, occ_boxes, occ_meta, occ_starts — written through the const pointers)
+ * from s->lines, the texture metadata and s->box_starts. One-off; rerun it if the static lines change. */
+int msb_build_table(const msb_scenery* s, void* cuda_stream);
 
 /* Fills s->vis (see msb_scenery) from the static segments (spatial table) and lights. One-off, like msb_bake. */
 int msb_build_visibility(const msb_scenery* s, void* cuda_stream);

@@ -1335,6 +1335,116 @@ __global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// table_kernel: the spatial table (msb_build_table). One CTA per env; two bitonic sorts of 64-bit keys in shared memory.
+// Sort-tile-recursive packing: the static segments are ranked by the x of their midpoints, cut into ~sqrt(nb) strips of
+// whole runs, each strip sorted by y; consecutive 16 form a run. Ties break by line index (a stable sort).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sortable(float f) {          // bit pattern that orders like the float
+    const uint32_t u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
+__device__ __forceinline__ void bitonic_sort(uint64_t* keys, int n2) {
+    for (int kk = 2; kk <= n2; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int o = i ^ j;
+                if (o > i) {
+                    const uint64_t a = keys[i], b = keys[o];
+                    if ((a > b) == ((i & kk) == 0)) { keys[i] = b; keys[o] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) table_kernel(const __grid_constant__ KArgs k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+    __shared__ float red[8][5];
+    const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int AF = k.s.n_agents * k.s.n_model;
+    const int L = __ldg(k.s.line_widths + n);
+    const int64_t g0 = (int64_t)__ldg(k.s.line_starts + n) + AF;
+    const int W = L > AF ? L - AF : 0;
+    const int nb = (W + VRUN - 1) / VRUN;
+    const int64_t b0 = __ldg(k.s.box_starts + n);
+    const float4* lines = reinterpret_cast<const float4*>(k.s.lines) + g0;
+    float4* occ = const_cast<float4*>(reinterpret_cast<const float4*>(k.s.occ_lines)) + VRUN * b0;
+    int4* rec = const_cast<int4*>(reinterpret_cast<const int4*>(k.s.occ_rec)) + VRUN * b0;
+    float4* boxes = const_cast<float4*>(reinterpret_cast<const float4*>(k.s.occ_boxes)) + b0;
+    int n2 = 1;
+    while (n2 < W) n2 <<= 1;
+    // 1. by (mid x, line)
+    float vmax = 0.f, lox = CUDART_INF_F, loy = CUDART_INF_F, hix = -CUDART_INF_F, hiy = -CUDART_INF_F;
+    for (int i = tid; i < n2; i += blockDim.x) {
+        uint64_t key = ~0ull;
+        if (i < W) {
+            const float4 s4 = __ldg(lines + i);
+            key = ((uint64_t)sortable((s4.x + s4.z) * .5f) << 32) | (uint32_t)i;
+            vmax = fmaxf(vmax, fmaxf(fabsf(s4.z - s4.x), fabsf(s4.w - s4.y)));
+            lox = fminf(lox, fminf(s4.x, s4.z)); hix = fmaxf(hix, fmaxf(s4.x, s4.z));
+            loy = fminf(loy, fminf(s4.y, s4.w)); hiy = fmaxf(hiy, fmaxf(s4.y, s4.w));
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    bitonic_sort(keys, n2);
+    // 2. by (strip of the x ranking, mid y, line): 10 + 32 + 14 bits (msb_build_table refuses more than 16383 lines)
+    const int strips = nb > 0 ? (int)ceil(sqrt((double)nb)) : 1;
+    const int per_strip = ((nb + strips - 1) / strips) * VRUN;
+    for (int r = tid; r < W; r += blockDim.x) {
+        const uint32_t i = (uint32_t)keys[r];
+        const float4 s4 = __ldg(lines + i);
+        const uint32_t strip = (uint32_t)(r / (per_strip > 0 ? per_strip : 1));
+        keys[r] = ((uint64_t)strip << 46) | ((uint64_t)sortable((s4.y + s4.w) * .5f) << 14) | i;
+    }
+    __syncthreads();
+    bitonic_sort(keys, n2);
+    // 3. rows (padding: a far, zero-length segment with line index -1), run boxes, per-env summary
+    for (int p = tid; p < nb * VRUN; p += blockDim.x) {
+        float4 s4 = make_float4(1e30f, 1e30f, 1e30f, 1e30f);
+        int4 rc = make_int4(0, 0, 0, -1);
+        if (p < W) {
+            const int i = (int)(keys[p] & 0x3fffu);
+            s4 = __ldg(lines + i);
+            const int64_t ts = __ldg(k.s.tex_starts + g0 + i);
+            rc = make_int4((int)(uint32_t)ts, (int)(uint32_t)((uint64_t)ts >> 32), __ldg(k.s.tex_widths + g0 + i), AF + i);
+        }
+        occ[p] = s4;
+        rec[p] = rc;
+    }
+    for (int b = tid; b < nb; b += blockDim.x) {
+        float x0 = CUDART_INF_F, y0 = CUDART_INF_F, x1 = -CUDART_INF_F, y1 = -CUDART_INF_F;
+        for (int p = b * VRUN; p < (b + 1) * VRUN && p < W; p++) {
+            const float4 s4 = __ldg(lines + (int)(keys[p] & 0x3fffu));
+            x0 = fminf(x0, fminf(s4.x, s4.z)); x1 = fmaxf(x1, fmaxf(s4.x, s4.z));
+            y0 = fminf(y0, fminf(s4.y, s4.w)); y1 = fmaxf(y1, fmaxf(s4.y, s4.w));
+        }
+        boxes[b] = make_float4(x0, y0, x1, y1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+        loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+    }
+    if (lane == 0) { red[warp][0] = vmax; red[warp][1] = lox; red[warp][2] = loy; red[warp][3] = hix; red[warp][4] = hiy; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
+            vmax = fmaxf(vmax, red[w][0]); lox = fminf(lox, red[w][1]); loy = fminf(loy, red[w][2]);
+            hix = fmaxf(hix, red[w][3]); hiy = fmaxf(hiy, red[w][4]);
+        }
+        float* meta = const_cast<float*>(k.s.occ_meta) + 2 * n;
+        meta[0] = vmax;
+        meta[1] = W > 0 ? fmaxf(hix - lox, hiy - loy) : 0.f;
+        const_cast<int32_t*>(k.s.occ_starts)[n] = (int32_t)(VRUN * b0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // vis_kernel: the light-visibility grid (msb_scenery::vis). One CTA per env, one warp per cell, lane = light.
 // A light is vouched for when NO static segment comes within `thr` of the segment light -> cell centre, where
 //   thr = mg + half the cell's diagonal + slack,   mg = delta * (|U| + vmax) + 0.01,   delta = 4e-4 * vmax * (diam + |U|)
@@ -1839,6 +1949,31 @@ extern "C" int msb_step(const msb_params* p, const msb_scenery* s, const msb_age
         if (launch_view(k, false, nch, threads, (cudaStream_t)cuda_stream)) return 1;
     }
     return launch_dyn(k, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int msb_build_table(const msb_scenery* s, void* cuda_stream) {
+    if (!s) return fail("%s", "msb_build_table: null scenery");
+    if (s->n_envs < 0 || s->n_agents < 1 || s->n_model < 0) return fail("%s", "bad scenery dimensions");
+    if (s->max_lines > 14000) return fail("%s", "scene too large: more than 14000 segments in one environment");
+    if (!s->occ_lines || !s->occ_boxes || !s->box_starts || !s->occ_rec || !s->occ_meta || !s->occ_starts || s->occ_run != VRUN)
+        return fail("%s", "msb_build_table: the table's arrays (occ_lines, occ_rec, occ_boxes, occ_meta, occ_starts) must be "
+                          "allocated and box_starts filled by the caller, with occ_run = 16");
+    if (!s->lines || !s->line_widths || !s->line_starts || !s->tex_widths || !s->tex_starts)
+        return fail("%s", "msb_build_table: lines / textures metadata missing");
+    if (s->n_envs == 0) return 0;
+    msb_params p;
+    memset(&p, 0, sizeof(p));
+    KArgs k;
+    fill(k, &p, s, nullptr);
+    int n2 = 1;
+    while (n2 < s->max_lines) n2 <<= 1;
+    const size_t sm = (size_t)n2 * 8;
+    if (sm > 48 * 1024 &&
+        check(cudaFuncSetAttribute(table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "cudaFuncSetAttribute"))
+        return 1;
+    table_kernel<<<s->n_envs, 256, sm, (cudaStream_t)cuda_stream>>>(k);
+    g_launches++;
+    return check(cudaGetLastError(), "table_kernel launch");
 }
 
 extern "C" int msb_build_visibility(const msb_scenery* s, void* cuda_stream) {

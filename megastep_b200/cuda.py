@@ -85,6 +85,7 @@ def _load():
     lib.msb_params_init.argtypes = [P(Params), ctypes.c_float, ctypes.c_int32, ctypes.c_float, ctypes.c_float]
     lib.msb_bake.argtypes = [P(Params), P(_Scenery), ctypes.c_void_p]
     lib.msb_build_visibility.argtypes = [P(_Scenery), ctypes.c_void_p]
+    lib.msb_build_table.argtypes = [P(_Scenery), ctypes.c_void_p]
     lib.msb_physics.argtypes = [P(Params), P(_Scenery), P(_Agents), ctypes.c_void_p, ctypes.c_void_p]
     lib.msb_render.argtypes = [P(Params), P(_Scenery), P(_Agents), P(_RenderOut), P(_ObsOut), P(_Workspace), ctypes.c_void_p]
     lib.msb_step.argtypes = [P(Params), P(_Scenery), P(_Agents), P(_Movement), ctypes.c_void_p, P(_RenderOut),
@@ -276,10 +277,17 @@ class Scenery:
                 tex_starts=self._tex_starts.data_ptr(), baked=self._baked.vals.data_ptr(), model=self._model.data_ptr(),
                 n_lines=self._lines.vals.size(0), n_texels=self._textures.vals.size(0))
             if self._lines.vals.size(0) > 0:
-                self._occ = _occluder_table(self._lines, self._n_agents * self._model.size(0), OCCLUDER_RUN,
-                                            self._textures.widths, self._tex_starts)
+                n_dynamic = self._n_agents * self._model.size(0)
+                if TABLE_ORDER == 'str' and OCCLUDER_RUN == 16:
+                    # the library's own builder (msb_build_table); the caller's part is the allocation
+                    self._occ = _empty_table(lw, n_dynamic)
+                else:
+                    self._occ = _occluder_table(self._lines, n_dynamic, OCCLUDER_RUN, self._textures.widths, self._tex_starts)
                 (self._c.occ_lines, self._c.occ_starts, self._c.occ_boxes, self._c.box_starts,
                  self._c.occ_meta, self._c.occ_rec) = (t.data_ptr() for t in self._occ)
+                if TABLE_ORDER == 'str' and OCCLUDER_RUN == 16:
+                    with _on_device(self._model) as stream:
+                        _check(_lib.msb_build_table(ctypes.byref(self._c), stream))
                 if USE_VISIBILITY_GRID and self._n_agents > 1:      # only rays that hit ANOTHER agent ask for dynamic light
                     self._vis = _visibility_grid(self._occ[2], self._occ[3], self._lines.widths, self._n_agents * self._model.size(0))
                     self._c.vis, self._c.vis_starts, self._c.vis_meta = (t.data_ptr() for t in self._vis)
@@ -317,12 +325,28 @@ def _morton16(x, y):
 
 
 @torch.no_grad()
+def _empty_table(line_widths, n_dynamic, run=16):
+    """The spatial table's arrays, allocated and with box_starts filled, for msb_build_table to fill: (occ_lines,
+    occ_starts, occ_boxes, box_starts, occ_meta, occ_rec) of include/megastep_b200.h."""
+    dev = line_widths.device
+    W = (line_widths.long() - n_dynamic).clamp(min=0)
+    nb = (W + run - 1) // run
+    box_starts = (nb.cumsum(0) - nb).int().contiguous()
+    nbox = int(nb.sum().item())
+    n = line_widths.size(0)
+    return (torch.empty((nbox * run, 4), dtype=torch.float32, device=dev), torch.empty(n, dtype=torch.int32, device=dev),
+            torch.empty((nbox, 4), dtype=torch.float32, device=dev), box_starts,
+            torch.empty((n, 2), dtype=torch.float32, device=dev), torch.empty((nbox * run, 4), dtype=torch.int32, device=dev))
+
+
+@torch.no_grad()
 def _occluder_table(lines, n_dynamic, run=16, tex_widths=None, tex_starts=None):
-    """(occ_lines, occ_starts, occ_boxes, box_starts, occ_meta, occ_rec) of include/megastep_b200.h: every env's
-    static segments sorted along a Morton curve in runs of `run`, each env padded to a whole number of runs, plus the
-    bounding box of each run and, per row, its line's texel offset / count and original line index. Shadow tests and
-    collisions ask order-free questions (any occluder / nearest obstacle); render() uses the line indices to restore
-    the reference's line-order rule."""
+    """(occ_lines, occ_starts, occ_boxes, box_starts, occ_meta, occ_rec) of include/megastep_b200.h in plain PyTorch
+    — the restatement msb_build_table is tested against (and the only builder for the 'morton' order / other run
+    lengths): every env's static segments packed into runs of `run`, each env padded to a whole number of runs, plus
+    the bounding box of each run and, per row, its line's texel offset / count and original line index. Shadow tests
+    and collisions ask order-free questions (any occluder / nearest obstacle); render() uses the line indices to
+    restore the reference's line-order rule."""
     vals, widths = lines.vals.reshape(-1, 4), lines.widths.long()
     dev = vals.device
     env = lines.inverse.long()

@@ -347,6 +347,30 @@ def test_second_pass_inline_and_overflow_paths_agree(sub):
         assert _same(outs[0][0], other[0]) and _same(outs[0][1], other[1])
 
 
+def test_native_table_builder_equals_the_torch_restatement():
+    """msb_build_table (sort-tile-recursive packing by two shared-memory sorts) against cuda._occluder_table, bit for
+    bit: rows, records, run boxes, per-env summary; ragged envs including ones with no static line at all."""
+    from megastep_b200 import cuda, scene
+    gs, arrays = common.synthetic_scene(9, 3, seed=77, bake=False)
+    s = scene.upload(arrays)
+    # an env with nothing but the agents' lines, and one with a single static line
+    lw = s.lines.widths.clone()
+    AF = 3 * s.model.size(0)
+    keep = torch.ones(s.lines.vals.size(0), dtype=torch.bool, device='cuda')
+    for n, left in ((2, 0), (5, 1)):
+        lo, hi = int(s.lines.starts[n]) + AF + left, int(s.lines.ends[n])
+        keep[lo:hi] = False
+        lw[n] = AF + left
+    lines = cuda.Ragged3D(s.lines.vals[keep].contiguous(), lw)
+    tex = cuda.Ragged2D(s.textures.vals[keep[s.textures.inverse.long()]].contiguous(), s.textures.widths[keep].contiguous())
+    s2 = cuda.Scenery(3, s.lights, lines, tex, s.model)
+    got = s2._struct() and s2._occ
+    want = cuda._occluder_table(lines, AF, 16, tex.widths, tex._long_starts())
+    names = ('occ_lines', 'occ_starts', 'occ_boxes', 'box_starts', 'occ_meta', 'occ_rec')
+    for name, a, b in zip(names, got, want):
+        assert a.shape == b.shape and torch.equal(a, b), name
+
+
 def test_visibility_grid_is_conservative_and_changes_nothing():
     """The light-visibility grid (msb_scenery::vis) may only vouch for lights that no static segment comes near, and
     using it may not change a single output bit. Checked on a box scene with packed agents (lit by the room's light)

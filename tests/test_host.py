@@ -85,7 +85,7 @@ def test_render_result_exposes_exactly_the_reference_attributes():
 def test_library_exports_every_symbol_the_header_declares():
     header = open(os.path.join(common.ROOT, 'include', 'megastep_b200.h')).read()
     declared = set(re.findall(r'\b(msb_[a-z_]+)\s*\(', header))
-    assert {'msb_physics', 'msb_render', 'msb_step', 'msb_bake', 'msb_build_visibility', 'msb_params_init'} <= declared
+    assert {'msb_physics', 'msb_render', 'msb_step', 'msb_bake', 'msb_build_table', 'msb_build_visibility', 'msb_params_init'} <= declared
     lib = ctypes.CDLL(cuda.library_path())
     for name in declared:
         assert hasattr(lib, name), f'{name} is declared in the header but not exported'
