@@ -66,8 +66,9 @@ struct KArgs {
     int* dyn_cache;             // [N][A][32] last occluder of each light as seen from (around) each agent; a hint
 };
 
-#ifndef MSB_MIN_BLOCKS
-#define MSB_MIN_BLOCKS 4      // 256 threads x 4 blocks -> at most 64 registers per thread
+#ifndef MSB_VIEW_THREADS
+#define MSB_VIEW_THREADS 256   // 256 threads x 4 blocks -> at most 64 registers per thread (launched with 128: 8 CTAs/SM)
+#define MSB_VIEW_BLOCKS 4
 #endif
 enum { ST_ANG = 0, ST_PX = 1, ST_PY = 2, ST_AV = 3, ST_VX = 4, ST_VY = 5, ST_SN = 6, ST_CS = 7, ST_STRIDE = 8 };   // SN, CS: view_kernel only
 enum { STAT_TESTS = 0, STAT_GROUPS = 1, STAT_DYN_RAYS = 2, STAT_DYN_ITERS = 3, STAT_DYN_ENTRIES = 4, STAT_REPLAYS = 5,
@@ -930,7 +931,7 @@ __device__ __forceinline__ void view_agent(const KArgs& k, const VSmem& m, int n
 }
 
 template <int NCH, bool PHYS, bool STATS>
-__global__ void __launch_bounds__(256, MSB_MIN_BLOCKS) view_kernel(const __grid_constant__ KArgs k) {
+__global__ void __launch_bounds__(MSB_VIEW_THREADS, MSB_VIEW_BLOCKS) view_kernel(const __grid_constant__ KArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = blockIdx.x;
     const int A = k.s.n_agents, AF = A * k.s.n_model;

@@ -274,14 +274,18 @@ class RandomSpawns:
         self._spawns = torchify(arrdict(positions=positions, angles=angles)).to(core.device)
 
     def __call__(self, reset):
-        """`reset`: (n_envs, n_agents) bool mask of agents to respawn; their velocities are zeroed."""
+        """`reset`: (n_envs, n_agents) bool mask of agents to respawn; their velocities are zeroed.
+
+        Same effect as the reference (modules.py:312-326) without its `nonzero()` — a device-to-host sync in the middle
+        of every step: a spawn is drawn for every agent and blended in under the mask, all on the device."""
         core = self.core
-        required = reset.nonzero(as_tuple=True)
-        choices = torch.randint_like(required[0], 0, self._spawns.angles.shape[-1])
-        core.agents.angles[required] = self._spawns.angles[(*required, choices)]
-        core.agents.positions[required] = self._spawns.positions[(*required, choices)]
-        core.agents.velocity[required] = 0.
-        core.agents.angvelocity[required] = 0.
+        choices = torch.randint(0, self._spawns.angles.shape[-1], reset.shape, device=reset.device)
+        angles = self._spawns.angles.gather(-1, choices[..., None]).squeeze(-1)
+        positions = self._spawns.positions.gather(2, choices[..., None, None].expand(-1, -1, 1, 2)).squeeze(2)
+        core.agents.angles.copy_(torch.where(reset, angles, core.agents.angles))
+        core.agents.positions.copy_(torch.where(reset[..., None], positions, core.agents.positions))
+        core.agents.velocity.masked_fill_(reset[..., None], 0.)
+        core.agents.angvelocity.masked_fill_(reset, 0.)
 
 
 class RandomLifespans:

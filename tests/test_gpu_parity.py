@@ -212,6 +212,27 @@ def test_fused_step_equals_modules_pipeline(A, res, fov, sub):
         common.load_state(c2, common.read_state(c1))
 
 
+def test_random_spawns_respawn_only_the_flagged_agents_on_the_device():
+    """modules.RandomSpawns (reference modules.py:295-326): flagged agents land on one of their pre-computed free
+    spawn points with zeroed velocities, the others are untouched — without the reference's host sync."""
+    from megastep_b200 import modules
+    gs, arrays, st = make('box', 6, 3, seed=41)               # toy geometries carry the free-space masks spawns are drawn from
+    c = common.to_device(arrays, st, 64, 90.)
+    spawner = modules.RandomSpawns(gs, c, n_spawns=20)
+    before = common.read_state(c)
+    reset = torch.as_tensor(np.random.RandomState(1).rand(6, 3) < .5).cuda()
+    spawner(reset)
+    after = common.read_state(c)
+    m = _np(reset)
+    for k in before:
+        assert np.array_equal(before[k][~m], after[k][~m]), k
+    assert (after['velocity'][m] == 0).all() and (after['angvelocity'][m] == 0).all()
+    spawns = _np(spawner._spawns.positions)                  # (N, A, n_spawns, 2)
+    for n, a in zip(*m.nonzero()):
+        assert (np.abs(spawns[n, a] - after['positions'][n, a]).sum(-1) == 0).any()
+        assert -180 <= after['angles'][n, a] <= 180
+
+
 def test_graph_replay_with_host_io_equals_plain_launches():
     """FusedStep as plain launches, as a CUDA-graph replay, and as ONE graph launch holding the host copies too
     (step_host) must walk the same trajectory: the programmatic-dependent launches and the streaming queue between
@@ -482,6 +503,40 @@ def test_full_size_render_properties(full):
         want = oracle.render(one, sub, res=128, fov=70.)
         differ, really = common.index_agreement(_np(r1.indices[n:n + 1]), want['indices'], _np(r1.distances[n:n + 1]), want['distances'])
         assert really == 0. and differ < 5e-3
+
+
+def test_full_size_trajectory_bit_exact_against_reference_build(ref, full):
+    """BASELINE.json's configuration (4096 envs x 4 agents x 128 rays), several ticks of kick -> physics -> render through
+    both libraries from the same start: every output of every tick bit-identical, agents' states included."""
+    if ref is None:
+        pytest.skip('oracle/_ref not built (needs /root/reference at build time)')
+    c, gs, arrays = full
+    st0 = common.read_state(c)
+    try:
+        ref.initialize(common.AGENT_RADIUS, 128, 70., 10.)
+        rs = common.reference_scenery(ref, arrays)
+        rs.baked.vals.copy_(c.scenery.baked.vals)
+        ra = common.reference_agents(ref, st0)
+        rng = np.random.RandomState(4)
+        for tick in range(4):
+            kick = torch.as_tensor((2.5 * rng.normal(size=st0['velocity'].shape)).astype(np.float32)).cuda()
+            spin = torch.as_tensor((150 * rng.normal(size=st0['angles'].shape)).astype(np.float32)).cuda()
+            for agents in (c.agents, ra):
+                agents.velocity.add_(kick)
+                agents.angvelocity.add_(spin)
+            p, rp = c.physics(), ref.physics(rs, ra)
+            r, rr = c.render(), ref.render(rs, ra)
+            torch.cuda.synchronize()
+            assert torch.equal(p.progress, rp.progress), f'tick {tick}: progress'
+            for k in ('positions', 'angles', 'velocity', 'angvelocity'):
+                assert torch.equal(getattr(c.agents, k), getattr(ra, k)), f'tick {tick}: {k}'
+            assert torch.equal(r.indices, rr.indices), f'tick {tick}: {(r.indices != rr.indices).float().mean():.4%} hit indices differ'
+            for k in ('locations', 'dots', 'distances', 'screen'):
+                assert _same(getattr(r, k), getattr(rr, k)), f'tick {tick}: {k}'
+            assert torch.equal(c.scenery.lines.vals, rs.lines.vals), f'tick {tick}: drawn lines'
+        assert float((p.progress < 1).float().mean()) > .02, 'the kicks should make some agents collide'
+    finally:
+        common.load_state(c, st0)
 
 
 def test_full_size_physics_properties(full):
