@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MSB_ABI_VERSION 3
+#define MSB_ABI_VERSION 4
 
 /* Replaces initialize(agent_radius, res, fov, fps) — megastep/src/wrappers.cpp:53, kernels.cu:18-27. */
 typedef struct msb_params {
@@ -83,6 +83,9 @@ typedef struct msb_scenery {
     uint32_t* vis;              /* (sum gx*gy) */
     const int64_t* vis_starts;  /* (N) first cell of env n */
     const float* vis_meta;      /* (N, 4) {x0, y0, gx, gy}: the grid's origin in metres and its dimensions (whole numbers) */
+    /* Optional launch order (NULL: env n is CTA n): a permutation of 0..N-1, costliest envs first, so that the grid's
+     * last CTAs are its cheapest. Speed only. */
+    const int32_t* env_order;   /* (N) */
 } msb_scenery;
 
 /* The Agents struct of megastep/src/common.h:162-177. Updated in place by msb_physics. */

@@ -56,6 +56,7 @@ struct KArgs {
     unsigned long long* stats;  // optional diagnostics counters (may be null)
     int32_t debug_skip_dyn;     // timing experiments only: leave agent-hit rays unlit
     int32_t debug_no_vis;       // tests: ignore the visibility grid (same results, more shadow scans)
+    const int32_t* env_order;   // view_kernel: env of CTA b (null: b)
     int32_t prefetch_view;      // physics_kernel: prefetch each env's table into L2 for the view_kernel that follows
     // queue of ray chunks whose agent-hit pixels are lit by dyn_kernel (load-balanced second pass)
     int* dyn_ctrl;              // [0] entries reserved, [1] CTAs of dyn_kernel done, [2] entries handed out beyond each CTA's first,
@@ -66,6 +67,9 @@ struct KArgs {
     int* dyn_cache;             // [N][A][32] last occluder of each light as seen from (around) each agent; a hint
 };
 
+#ifndef MSB_DYN_BLOCKS
+#define MSB_DYN_BLOCKS 7        // 72 registers
+#endif
 #ifndef MSB_VIEW_THREADS
 #define MSB_VIEW_THREADS 256   // 256 threads x 4 blocks -> at most 64 registers per thread (launched with 128: 8 CTAs/SM)
 #define MSB_VIEW_BLOCKS 4
@@ -933,7 +937,7 @@ __device__ __forceinline__ void view_agent(const KArgs& k, const VSmem& m, int n
 template <int NCH, bool PHYS, bool STATS>
 __global__ void __launch_bounds__(MSB_VIEW_THREADS, MSB_VIEW_BLOCKS) view_kernel(const __grid_constant__ KArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = blockIdx.x;
+    const int n = k.env_order ? __ldg(k.env_order + blockIdx.x) : (int)blockIdx.x;   // costliest envs first: a short tail
     const int A = k.s.n_agents, AF = A * k.s.n_model;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const VSmem m = vcarve(smem_raw, k.wcap, nwarps, A, AF);
@@ -1064,7 +1068,7 @@ __global__ void __launch_bounds__(MSB_VIEW_THREADS, MSB_VIEW_BLOCKS) view_kernel
 __device__ __forceinline__ bool occludes(const Hit h) { return (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f); }
 
 template <bool STATS>
-__global__ void __launch_bounds__(128) dyn_kernel(const __grid_constant__ KArgs k) {
+__global__ void __launch_bounds__(128, MSB_DYN_BLOCKS) dyn_kernel(const __grid_constant__ KArgs k) {
     __shared__ unsigned s_lit[4][32];                          // per warp: the lights it found unoccluded, per pixel lane
     __shared__ int s_next, s_ready;                            // the CTA's next entry; whether the current one was published
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
@@ -1564,6 +1568,7 @@ static long long g_opt_nch = 0;          // 0 = auto
 static long long g_opt_threads = 0;      // 0 = auto
 static long long g_opt_skip_dyn = 0;     // debug
 static long long g_opt_no_vis = 0;       // tests: ignore the visibility grid
+static long long g_opt_no_env_order = 0; // A/B: CTA b takes env b
 static long long g_opt_no_prefetch = 0;  // A/B: physics_kernel does not prefetch view_kernel's tables
 static long long g_opt_dyn_window = 0;   // 0 = default (DYN_MIN_WINDOW); 1, 2, 4, 8: pixels per queue entry when subsample is smaller
 static long long g_opt_dyn_warps = 0;    // warps sharing one queue entry in dyn_kernel (default 2)
@@ -1665,6 +1670,7 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "pdl")) { g_opt_pdl = value; return 0; }
     if (!strcmp(name, "no_vis")) { g_opt_no_vis = value; return 0; }
     if (!strcmp(name, "no_prefetch")) { g_opt_no_prefetch = value; return 0; }
+    if (!strcmp(name, "no_env_order")) { g_opt_no_env_order = value; return 0; }
     if (!strcmp(name, "timing")) {
         timing_flush();
         g_opt_timing = value;
@@ -1748,6 +1754,7 @@ static void fill(KArgs& k, const msb_params* p, const msb_scenery* s, const msb_
     k.stats = g_stats;
     k.debug_skip_dyn = (int32_t)g_opt_skip_dyn;
     k.debug_no_vis = (int32_t)g_opt_no_vis;
+    k.env_order = g_opt_no_env_order ? nullptr : s->env_order;
     k.xclip = 0.5f * p->agent_radius / sqrtf(1.f + p->half_screen * p->half_screen);
 }
 

@@ -44,7 +44,8 @@ class _Scenery(ctypes.Structure):
                 ('n_lines', ctypes.c_int64), ('n_texels', ctypes.c_int64),
                 ('occ_lines', ctypes.c_void_p), ('occ_starts', ctypes.c_void_p), ('occ_boxes', ctypes.c_void_p),
                 ('box_starts', ctypes.c_void_p), ('occ_meta', ctypes.c_void_p), ('occ_rec', ctypes.c_void_p),
-                ('vis', ctypes.c_void_p), ('vis_starts', ctypes.c_void_p), ('vis_meta', ctypes.c_void_p)]
+                ('vis', ctypes.c_void_p), ('vis_starts', ctypes.c_void_p), ('vis_meta', ctypes.c_void_p),
+                ('env_order', ctypes.c_void_p)]
 
 
 class _Agents(ctypes.Structure):
@@ -95,8 +96,8 @@ def _load():
     lib.msb_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
     lib.msb_get_option.argtypes = [ctypes.c_char_p]
     lib.msb_get_option.restype = ctypes.c_int64
-    if lib.msb_abi_version() != 3:
-        raise ImportError(f'{_LIBPATH} has ABI version {lib.msb_abi_version()}, expected 3; rebuild it')
+    if lib.msb_abi_version() != 4:
+        raise ImportError(f'{_LIBPATH} has ABI version {lib.msb_abi_version()}, expected 4; rebuild it')
     return lib
 
 
@@ -288,6 +289,9 @@ class Scenery:
                 if TABLE_ORDER == 'str' and OCCLUDER_RUN == 16:
                     with _on_device(self._model) as stream:
                         _check(_lib.msb_build_table(ctypes.byref(self._c), stream))
+                # launch order: the envs with the most lines first (their CTAs take longest), so the grid tails off on cheap ones
+                self._env_order = torch.argsort(lw, descending=True, stable=True).int().contiguous()
+                self._c.env_order = self._env_order.data_ptr()
                 if USE_VISIBILITY_GRID and self._n_agents > 1:      # only rays that hit ANOTHER agent ask for dynamic light
                     self._vis = _visibility_grid(self._occ[2], self._occ[3], self._lines.widths, self._n_agents * self._model.size(0))
                     self._c.vis, self._c.vis_starts, self._c.vis_meta = (t.data_ptr() for t in self._vis)
