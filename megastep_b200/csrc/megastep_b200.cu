@@ -43,6 +43,8 @@ struct KArgs {
     msb_obs_out obs;
     msb_movement mv;
     int32_t has_obs;
+    int32_t idx32;          // every output index (3 * N * A * R at most) fits 32 bits
+    int32_t out_mask;       // which outputs are wanted (OUT_* bits): one uniform test instead of a 64-bit pointer compare each
     int32_t sub_shift;      // log2(obs.subsample)
     int32_t has_mv;
     int32_t ray_blocks;     // RB: warps per agent in view_kernel
@@ -77,6 +79,7 @@ struct KArgs {
 enum { ST_ANG = 0, ST_PX = 1, ST_PY = 2, ST_AV = 3, ST_VX = 4, ST_VY = 5, ST_SN = 6, ST_CS = 7, ST_STRIDE = 8 };   // SN, CS: view_kernel only
 enum { STAT_TESTS = 0, STAT_GROUPS = 1, STAT_DYN_RAYS = 2, STAT_DYN_ITERS = 3, STAT_DYN_ENTRIES = 4, STAT_REPLAYS = 5,
        STAT_DYN_CYCLES = 6, STAT_DYN_MAXCYC = 7, STAT_DYN_WARPMAX = 8, STAT_DYN_SLOW = 9, STAT_DYN_KERNEL = 10, STAT_DYN_SCANS = 11, STAT_DYN_SCANS_LIT = 12, STAT_DYN_ITERS_LIT = 13, STAT_SLOTS = 16 };
+enum { OUT_INDICES = 1, OUT_LOCATIONS = 2, OUT_DOTS = 4, OUT_DISTANCES = 8, OUT_SCREEN = 16, OUT_RGB = 32, OUT_DEPTH = 64, OUT_IMU = 128 };
 enum { VRUN = 16 };                       // segments per run of the spatial table
 enum { DYN_MIN_WINDOW = 4 };               // pixels per queue entry: max(4, subsample) adjacent pixels (a 'window')
 constexpr float VIS_CELL = 0.25f, VIS_INV_CELL = 4.f;   // the light-visibility grid's cell, metres
@@ -721,12 +724,21 @@ __device__ __forceinline__ void shade_chunk(const KArgs& k, const VSmem& m, int 
     }
     const int64_t ag = (int64_t)n * A + a;                 // warp-uniform: the 64-bit part of every address below
     const int64_t o0 = ag * R;
-    if (live) {
-        if (k.out.indices) (k.out.indices + o0)[r] = l0;
-        if (k.out.locations) (k.out.locations + o0)[r] = locv;
-        if (k.out.dots) (k.out.dots + o0)[r] = dotv;
-        if (k.out.distances) (k.out.distances + o0)[r] = dist;
-        if (k.out.screen && !(queued && isdyn)) { float* sc = k.out.screen + 3 * o0 + 3 * r; sc[0] = s0; sc[1] = s1; sc[2] = s2; }
+    const int om = k.out_mask;
+    const uint32_t o32 = (uint32_t)ag * (uint32_t)R + (uint32_t)r;      // the same index when everything fits 32 bits (k.idx32)
+    if (live && k.idx32) {
+        // (one IMAD.WIDE.U32 per store; with 64-bit indices the compiler re-derives the whole product at every store)
+        if (om & OUT_INDICES) k.out.indices[o32] = l0;
+        if (om & OUT_LOCATIONS) k.out.locations[o32] = locv;
+        if (om & OUT_DOTS) k.out.dots[o32] = dotv;
+        if (om & OUT_DISTANCES) k.out.distances[o32] = dist;
+        if ((om & OUT_SCREEN) && !(queued && isdyn)) { float* sc = k.out.screen + 3u * o32; sc[0] = s0; sc[1] = s1; sc[2] = s2; }
+    } else if (live) {
+        if (om & OUT_INDICES) (k.out.indices + o0)[r] = l0;
+        if (om & OUT_LOCATIONS) (k.out.locations + o0)[r] = locv;
+        if (om & OUT_DOTS) (k.out.dots + o0)[r] = dotv;
+        if (om & OUT_DISTANCES) (k.out.distances + o0)[r] = dist;
+        if ((om & OUT_SCREEN) && !(queued && isdyn)) { float* sc = k.out.screen + 3 * o0 + 3 * r; sc[0] = s0; sc[1] = s1; sc[2] = s2; }
     }
     // fused observation heads: Depth (modules.py:181-183) and RGB (:222-223), mean over `subsample` pixels
     if (k.has_obs) {
@@ -745,11 +757,20 @@ __device__ __forceinline__ void shade_chunk(const KArgs& k, const VSmem& m, int 
         if (live && lane == gl) {
             const int Ro = R >> k.sub_shift, ro = r >> k.sub_shift;         // subsample is a power of two
             const float inv = k.inv_sub;
-            if (k.obs.rgb && !deferred) {
-                float* q = k.obs.rgb + ag * 3 * Ro + ro;
-                q[0] = __fmul_rn(v0, inv); q[Ro] = __fmul_rn(v1, inv); q[2 * Ro] = __fmul_rn(v2, inv);
+            if (k.idx32) {
+                const uint32_t od = (uint32_t)ag * (uint32_t)Ro + (uint32_t)ro;
+                if ((om & OUT_RGB) && !deferred) {
+                    float* q = k.obs.rgb + (3u * (uint32_t)ag * (uint32_t)Ro + (uint32_t)ro);
+                    q[0] = __fmul_rn(v0, inv); q[Ro] = __fmul_rn(v1, inv); q[2 * Ro] = __fmul_rn(v2, inv);
+                }
+                if (om & OUT_DEPTH) k.obs.depth[od] = __fmul_rn(v3, inv);
+            } else {
+                if ((om & OUT_RGB) && !deferred) {
+                    float* q = k.obs.rgb + ag * 3 * Ro + ro;
+                    q[0] = __fmul_rn(v0, inv); q[Ro] = __fmul_rn(v1, inv); q[2 * Ro] = __fmul_rn(v2, inv);
+                }
+                if (om & OUT_DEPTH) (k.obs.depth + ag * Ro)[ro] = __fmul_rn(v3, inv);
             }
-            if (k.obs.depth) (k.obs.depth + ag * Ro)[ro] = __fmul_rn(v3, inv);
         }
     }
 }
@@ -937,7 +958,9 @@ __device__ __forceinline__ void view_agent(const KArgs& k, const VSmem& m, int n
 template <int NCH, bool PHYS, bool STATS>
 __global__ void __launch_bounds__(MSB_VIEW_THREADS, MSB_VIEW_BLOCKS) view_kernel(const __grid_constant__ KArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = k.env_order ? __ldg(k.env_order + blockIdx.x) : (int)blockIdx.x;   // costliest envs first: a short tail
+    // costliest envs first: a short tail. (Through REDUX so that n — and every address part derived from it — lives in
+    // a uniform register.)
+    const int n = k.env_order ? __reduce_max_sync(0xffffffffu, __ldg(k.env_order + blockIdx.x)) : (int)blockIdx.x;
     const int A = k.s.n_agents, AF = A * k.s.n_model;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const VSmem m = vcarve(smem_raw, k.wcap, nwarps, A, AF);
@@ -1025,8 +1048,9 @@ __global__ void __launch_bounds__(MSB_VIEW_THREADS, MSB_VIEW_BLOCKS) view_kernel
     for (int w = warp; w < A * RB;) {
         const int a = rbs >= 0 ? w >> rbs : w / RB;
         view_agent<NCH, STATS>(k, m, n, g0, L, W, nb, a, w - a * RB, m.scr + warp * 128, lane);
-        if (lane == 0) w = nwarps + atomicAdd(m.next_item, 1);
-        w = __shfl_sync(0xffffffffu, w, 0);
+        int next = 0;
+        if (lane == 0) next = nwarps + atomicAdd(m.next_item, 1);
+        w = __reduce_max_sync(0xffffffffu, next);            // (lands in a uniform register: so do the item's address parts)
     }
     if (k.has_obs && k.obs.imu) {
         for (int a = tid; a < A; a += blockDim.x) {
@@ -1095,9 +1119,16 @@ __global__ void __launch_bounds__(128, MSB_DYN_BLOCKS) dyn_kernel(const __grid_c
             volatile int* flag = reinterpret_cast<volatile int*>(e + DYN_FLAG);
             volatile int* done = k.dyn_ctrl + 3;
             int ready = *flag;
-            for (unsigned spins = 0; !ready && spins < (1u << 22); spins++) {       // (bounded: a lost signal must not hang the GPU)
-                if (*done >= k.s.n_envs) { __threadfence(); ready = *flag; break; }
+            bool over = false;
+            for (unsigned spins = 0; !ready && !over && spins < (1u << 17); spins++) {
+                if (*done >= k.s.n_envs) { __threadfence(); ready = *flag; over = true; break; }
                 __nanosleep(100);
+                ready = *flag;
+            }
+            if (!ready && !over) {
+                // polled for tens of milliseconds: stop guessing and block until view_kernel has completed as a grid
+                griddep_wait();
+                __threadfence();
                 ready = *flag;
             }
             if (ready) {
@@ -1795,7 +1826,11 @@ static void plan_view(const msb_params* p, const msb_scenery* s, int* nch, int* 
     *threads = t;
 }
 
-static int launch_view(const KArgs& k, bool phys, int nch, int threads, cudaStream_t st) {
+static int launch_view(KArgs& k, bool phys, int nch, int threads, cudaStream_t st) {
+    k.idx32 = 3ll * k.s.n_envs * k.s.n_agents * (long long)k.p.res < (1ll << 32) ? 1 : 0;
+    k.out_mask = (k.out.indices ? OUT_INDICES : 0) | (k.out.locations ? OUT_LOCATIONS : 0) | (k.out.dots ? OUT_DOTS : 0) |
+                 (k.out.distances ? OUT_DISTANCES : 0) | (k.out.screen ? OUT_SCREEN : 0) |
+                 (k.has_obs && k.obs.rgb ? OUT_RGB : 0) | (k.has_obs && k.obs.depth ? OUT_DEPTH : 0) | (k.has_obs && k.obs.imu ? OUT_IMU : 0);
     const size_t sm = vsmem_bytes(k.wcap, threads / 32, k.s.n_agents, k.s.n_agents * k.s.n_model);
     if (sm > 227 * 1024) return fail("%s", "scene too large: an env's segments do not fit in shared memory (227 KB)");
 #define MSB_LAUNCH(N)                                                                                            \
