@@ -874,7 +874,7 @@ __device__ __forceinline__ void view_agent(const KArgs& k, const VSmem& m, int n
 #pragma unroll
                 for (int c = 1; c < NCH; c++) cmaxall = fmaxf(cmaxall, ry.cmax[c]);
                 const float Bn = v.B0 - (float)NCH * v.dB;
-                const float sec0 = sqrtf(1.f + v.B0 * v.B0), secn = sqrtf(1.f + Bn * Bn);
+                const float sec0 = 1.0001f * sqrt_(1.f + v.B0 * v.B0), secn = 1.0001f * sqrt_(1.f + Bn * Bn);   // (rounded up: culling only)
                 bool vis = false;
                 for (int a2 = lane; a2 < A; a2 += 32) {
                     if (a2 == a) { vis = vis || !(mrad * 1.001f + 1e-4f < k.p.agent_radius); continue; }
