@@ -6,17 +6,22 @@
 //   msb_step() = MomentumMovement (modules.py:106-118) + physics + render + RGB/Depth/IMU heads -> the same three launches
 //   bake()     = baking_kernel (:270-284)                                                       -> bake_kernel
 //
+// One-off, per scenery: table_kernel (msb_build_table), vis_kernel (msb_build_visibility), bake_kernel (msb_bake).
+//
 // Layout / mapping:
-//   * every scenery carries a SPATIAL TABLE built once: each env's static segments sorted along a Morton curve in runs
+//   * every scenery carries a SPATIAL TABLE built once: each env's static segments packed sort-tile-recursive into runs
 //     of 16 with one bounding box per run, padded per env, plus per row the texel offset / count and line index;
 //   * view_kernel: one CTA per env stages the env's table with three 1-D bulk (TMA) copies on one mbarrier; one warp
 //     per (agent, block of rays) visits the run boxes nearest first, bins 32 segments at a time (lane = segment),
 //     tests them lane = ray on the candidates a ballot yields, and never opens boxes hidden behind what it already
 //     hit; the reference's order-dependent nearest-hit rule is restored exactly by replaying near-tied rays;
 //   * the ray/line cosine and its sqrt are computed for the winning line only (the reference does it for every line);
-//   * rays that hit another agent need the dynamic light at the hit point (I lights x W occluders): queued per ray
-//     chunk for dyn_kernel, which spreads them over the whole GPU and scans only the runs near each light ray;
-//   * physics_kernel: one warp per agent, box-culled over the same table, fused movement / integration.
+//   * rays that hit another agent need the dynamic light at the hit point (I lights x W occluders): queued as windows
+//     of 4 pixels for dyn_kernel, which spreads them over the whole GPU, consumes the queue while view_kernel still
+//     fills it (programmatic dependent launch) and scans only the runs near each light ray that neither the
+//     light-visibility grid nor the remembered occluders settle;
+//   * physics_kernel: one warp per agent, box-culled over the same table, fused movement / integration; it also
+//     prefetches each env's table into L2 for the view_kernel behind it.
 //
 // No tensor cores: nothing on this path is a dense contraction.
 #include <cuda_runtime.h>
@@ -385,7 +390,7 @@ __device__ __forceinline__ float light_intensity_thread(const float4* seg, int A
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// view_kernel: render over the env's spatial table (Morton-sorted static segments in runs of 16 with bounding boxes).
+// view_kernel: render over the env's spatial table (static segments packed into runs of 16 with bounding boxes).
 //
 // One CTA per env, one warp per (agent, block of 32*NCH rays). Thread 0 stages the env's table — sorted segments,
 // their line ids and the run boxes — with three 1-D bulk (TMA) copies on one mbarrier. Each warp then
