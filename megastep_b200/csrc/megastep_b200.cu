@@ -48,6 +48,7 @@ struct KArgs {
     msb_obs_out obs;
     msb_movement mv;
     int32_t has_obs;
+    int32_t stage_rec;      // view_kernel stages the rows' records too (worth their shared memory when there are many rays per env)
     int32_t idx32;          // every output index (3 * N * A * R at most) fits 32 bits
     int32_t out_mask;       // which outputs are wanted (OUT_* bits): one uniform test instead of a 64-bit pointer compare each
     int32_t sub_shift;      // log2(obs.subsample)
@@ -416,7 +417,8 @@ constexpr float CULL_EPS = 4.e-4f;
 struct VSmem {
     float4* seg;            // [AF + wcap]: [0, AF) the agents' model lines at their current poses; then the sorted static rows
     float4* boxes;          // [wcap / 16]
-    int4* rec;              // [wcap] per sorted row: {texel offset lo, hi, texel count, line id}
+    int4* rec;              // [wcap] per sorted row: {texel offset lo, hi, texel count, line id} — only when KArgs::stage_rec
+    const int4* rec_g;      // the same rows in global memory
     float4* scr;            // [nwarps][128] per warp: 64 candidate records while casting, then the chunk results
     float* st_in;           // [A][8]
     float* st_out;          // [A][8]
@@ -427,12 +429,13 @@ struct VSmem {
                             //      {bits of vis_meta x0, y0, gx, gy, vis_starts lo, hi, -, -}
 };
 
-__device__ __forceinline__ VSmem vcarve(unsigned char* base, int wcap, int nwarps, int A, int AF) {
+__device__ __forceinline__ VSmem vcarve(unsigned char* base, int wcap, int nwarps, int A, int AF, bool stage_rec) {
     VSmem m;
     m.seg = reinterpret_cast<float4*>(base);
     m.boxes = m.seg + AF + wcap;
     m.rec = reinterpret_cast<int4*>(m.boxes + wcap / VRUN);
-    m.scr = reinterpret_cast<float4*>(m.rec + wcap);
+    m.rec_g = nullptr;
+    m.scr = reinterpret_cast<float4*>(m.rec + (stage_rec ? wcap : 0));
     m.st_in = reinterpret_cast<float*>(m.scr + nwarps * 128);
     m.st_out = m.st_in + A * ST_STRIDE;
     m.mrad = reinterpret_cast<int*>(m.st_out + A * ST_STRIDE);
@@ -444,8 +447,8 @@ __device__ __forceinline__ VSmem vcarve(unsigned char* base, int wcap, int nwarp
     return m;
 }
 
-static size_t vsmem_bytes(int wcap, int nwarps, int A, int AF) {
-    size_t b = (size_t)(AF + wcap) * 16 + (size_t)(wcap / VRUN) * 16 + (size_t)nwarps * 128 * 16 + (size_t)wcap * 16 +
+static size_t vsmem_bytes(int wcap, int nwarps, int A, int AF, bool stage_rec) {
+    size_t b = (size_t)(AF + wcap) * 16 + (size_t)(wcap / VRUN) * 16 + (size_t)nwarps * 128 * 16 + (stage_rec ? (size_t)wcap * 16 : 0) +
                (size_t)A * ST_STRIDE * 4 * 2 + (size_t)A * 4;
     b = (b + 15) & ~size_t(15);
     return b + 16 + 64;
@@ -595,7 +598,8 @@ __device__ __forceinline__ ShadeIn shade_prepare(const KArgs& k, const VSmem& m,
     if (in.hitany) {
         const int row = packed >> 16;
         if (row >= AF && row != ROW_UNKNOWN) {
-            const int4 rc = m.rec[row - AF];
+            const int4 rc = k.stage_rec ? m.rec[row - AF] : __ldg(m.rec_g + (row - AF));
+            in.l0 = rc.w;
             in.w = rc.z;
             in.ts = (int64_t)(((uint64_t)(uint32_t)rc.y << 32) | (uint32_t)rc.x);
         } else {                                            // an agent's model line, or a replayed ray: rare
@@ -915,7 +919,7 @@ __device__ __forceinline__ void view_agent(const KArgs& k, const VSmem& m, int n
             const float4 s4 = m.seg[row];
             const float Vx = fsub(s4.z, s4.x), Vy = fsub(s4.w, s4.y);
             dotv = fmul(dot2(ry.rux[c], Vx, ry.ruy[c], Vy), rcp(ffma(rlen, sqrt_(ffma(Vx, Vx, fmul(Vy, Vy))), 1.e-6f)));
-            packed = (row << 16) | (row < AF ? row : m.rec[row - AF].w);
+            packed = (row << 16) | (row < AF ? row : 0);              // a static row's line index comes with its record, at shading
         }
         float best = ry.best[c], loc = ry.loc[c];
         unsigned am = __ballot_sync(0xffffffffu, (ry.tie[c] - ry.best[c] <= AMB_EPS) && r < R);
@@ -968,12 +972,13 @@ __global__ void __launch_bounds__(MSB_VIEW_THREADS, MSB_VIEW_BLOCKS) view_kernel
     const int n = k.env_order ? __reduce_max_sync(0xffffffffu, __ldg(k.env_order + blockIdx.x)) : (int)blockIdx.x;
     const int A = k.s.n_agents, AF = A * k.s.n_model;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const VSmem m = vcarve(smem_raw, k.wcap, nwarps, A, AF);
+    VSmem m = vcarve(smem_raw, k.wcap, nwarps, A, AF, k.stage_rec != 0);
     const int L = __ldg(k.s.line_widths + n);
     const int64_t g0 = __ldg(k.s.line_starts + n);
     const int W = L - AF;
     const int nb = (W + VRUN - 1) / VRUN;
-    // stage this env's table: three bulk (TMA) copies, ragged-packed HBM -> shared memory, one mbarrier
+    m.rec_g = reinterpret_cast<const int4*>(k.s.occ_rec) + VRUN * (int64_t)__ldg(k.s.box_starts + n);
+    // stage this env's table: two or three bulk (TMA) copies, ragged-packed HBM -> shared memory, one mbarrier
     if (tid == 32 % blockDim.x) {
         m.meta[0] = W; m.meta[1] = __ldg(k.s.light_widths + n); m.meta[2] = __ldg(k.s.light_starts + n);
         m.meta[3] = __ldg(k.s.box_starts + n);
@@ -993,9 +998,9 @@ __global__ void __launch_bounds__(MSB_VIEW_THREADS, MSB_VIEW_BLOCKS) view_kernel
         mbar_init(m.bar, 1);
         if (nb > 0) {
             const int64_t b0 = __ldg(k.s.box_starts + n);
-            mbar_expect_tx(m.bar, (uint32_t)nb * (VRUN * 32u + 16u));
+            mbar_expect_tx(m.bar, (uint32_t)nb * (VRUN * (k.stage_rec ? 32u : 16u) + 16u));
             bulk_g2s(m.seg + AF, k.s.occ_lines + 4 * VRUN * b0, (uint32_t)nb * VRUN * 16u, m.bar);
-            bulk_g2s(m.rec, k.s.occ_rec + 4 * VRUN * b0, (uint32_t)nb * VRUN * 16u, m.bar);
+            if (k.stage_rec) bulk_g2s(m.rec, k.s.occ_rec + 4 * VRUN * b0, (uint32_t)nb * VRUN * 16u, m.bar);
             bulk_g2s(m.boxes, k.s.occ_boxes + 4 * b0, (uint32_t)nb * 16u, m.bar);
         }
     }
@@ -1604,6 +1609,7 @@ static long long g_opt_nch = 0;          // 0 = auto
 static long long g_opt_threads = 0;      // 0 = auto
 static long long g_opt_skip_dyn = 0;     // debug
 static long long g_opt_no_vis = 0;       // tests: ignore the visibility grid
+static long long g_opt_stage_rec = 0;    // 0: auto (when n_agents * res >= 256), 1: always, 2: never
 static long long g_opt_no_env_order = 0; // A/B: CTA b takes env b
 static long long g_opt_no_prefetch = 0;  // A/B: physics_kernel does not prefetch view_kernel's tables
 static long long g_opt_dyn_window = 0;   // 0 = default (DYN_MIN_WINDOW); 1, 2, 4, 8: pixels per queue entry when subsample is smaller
@@ -1707,6 +1713,7 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "no_vis")) { g_opt_no_vis = value; return 0; }
     if (!strcmp(name, "no_prefetch")) { g_opt_no_prefetch = value; return 0; }
     if (!strcmp(name, "no_env_order")) { g_opt_no_env_order = value; return 0; }
+    if (!strcmp(name, "stage_rec")) { g_opt_stage_rec = value; return 0; }
     if (!strcmp(name, "timing")) {
         timing_flush();
         g_opt_timing = value;
@@ -1832,11 +1839,16 @@ static void plan_view(const msb_params* p, const msb_scenery* s, int* nch, int* 
 }
 
 static int launch_view(KArgs& k, bool phys, int nch, int threads, cudaStream_t st) {
+    k.stage_rec = g_opt_stage_rec ? (g_opt_stage_rec == 1) : (k.s.n_agents * k.p.res >= 256);
     k.idx32 = 3ll * k.s.n_envs * k.s.n_agents * (long long)k.p.res < (1ll << 32) ? 1 : 0;
     k.out_mask = (k.out.indices ? OUT_INDICES : 0) | (k.out.locations ? OUT_LOCATIONS : 0) | (k.out.dots ? OUT_DOTS : 0) |
                  (k.out.distances ? OUT_DISTANCES : 0) | (k.out.screen ? OUT_SCREEN : 0) |
                  (k.has_obs && k.obs.rgb ? OUT_RGB : 0) | (k.has_obs && k.obs.depth ? OUT_DEPTH : 0) | (k.has_obs && k.obs.imu ? OUT_IMU : 0);
-    const size_t sm = vsmem_bytes(k.wcap, threads / 32, k.s.n_agents, k.s.n_agents * k.s.n_model);
+    size_t sm = vsmem_bytes(k.wcap, threads / 32, k.s.n_agents, k.s.n_agents * k.s.n_model, k.stage_rec != 0);
+    if (sm > 227 * 1024 && k.stage_rec) {                      // a very large env: leave the records in global memory
+        k.stage_rec = 0;
+        sm = vsmem_bytes(k.wcap, threads / 32, k.s.n_agents, k.s.n_agents * k.s.n_model, false);
+    }
     if (sm > 227 * 1024) return fail("%s", "scene too large: an env's segments do not fit in shared memory (227 KB)");
 #define MSB_LAUNCH(N)                                                                                            \
     {                                                                                                            \

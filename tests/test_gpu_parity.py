@@ -288,17 +288,20 @@ def test_every_kernel_variant_gives_identical_results(res):
     c = common.to_device(arrays, st, res, 70.)
     base = c.render()
     try:
-        for nch in (1, 2, 4):
-            for threads in (32, 64, 128, 256):
-                cuda.set_option('nch', nch)
-                cuda.set_option('threads', threads)
-                r = c.render()
-                for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
-                    a, b = getattr(r, k), getattr(base, k)
-                    assert ((a == b) | (a != a) & (b != b)).all(), f'nch={nch} threads={threads}: {k} differs'
+        for stage_rec in (1, 2):                               # the rows' records staged in shared memory / left in global
+            for nch in (1, 2, 4):
+                for threads in (32, 64, 128, 256):
+                    cuda.set_option('stage_rec', stage_rec)
+                    cuda.set_option('nch', nch)
+                    cuda.set_option('threads', threads)
+                    r = c.render()
+                    for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
+                        a, b = getattr(r, k), getattr(base, k)
+                        assert ((a == b) | (a != a) & (b != b)).all(), f'stage_rec={stage_rec} nch={nch} threads={threads}: {k} differs'
     finally:
         cuda.set_option('nch', 0)
         cuda.set_option('threads', 0)
+        cuda.set_option('stage_rec', 0)
 
 
 def _same(a, b):
