@@ -87,6 +87,7 @@ if __name__ == '__main__':
             out[f'render_us/{rep}'] = round(timeit(lambda: c.render(), iters=300), 1)
             cuda.set_option('debug_skip_dyn', 1); out[f'main_us/{rep}'] = round(timeit(lambda: c.render(), iters=300), 1); cuda.set_option('debug_skip_dyn', 0)
         out['physics_us'] = round(timeit(lambda: c.physics(), iters=300), 1)
+        out['bake_ms'] = round(timeit(lambda: cuda.bake(c.scenery, params=c.params), iters=3, warm=1) / 1e3, 1)
         cuda.set_option('stats', 1); cuda.set_option('stats_reset', 0)
         c.render(); torch.cuda.synchronize()
         for k in ('stat_tests', 'stat_groups', 'stat_dyn_iters', 'stat_dyn_scans', 'stat_dyn_entries', 'stat_replays'): out[k] = cuda.get_option(k)
