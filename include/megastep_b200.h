@@ -119,7 +119,7 @@ typedef struct msb_obs_out {
 
 /* MomentumMovement (megastep/modules.py:68-118), fused into msb_step ahead of the physics. */
 typedef struct msb_movement {
-    const int32_t* actions; /* (N, A) in [0, 7): noop, forward, back, strafe right(+x local y?) … see modules.py:95-96 */
+    const int32_t* actions; /* (N, A) in [0, 7): 0 noop, 1 +y, 2 -y, 3 +x, 4 -x (agent-local metres), 5 turn +, 6 turn - (modules.py:95-96) */
     float accel;            /* m/s^2, default 5 */
     float ang_accel;        /* deg/s^2, default 180 */
     float decay;            /* default 0.125 */
@@ -127,8 +127,10 @@ typedef struct msb_movement {
 
 /* Scratch for the second pass that lights the rays which hit agents (their light is dynamic: kernels.cu:434-436).
  * Caller-owned device memory, 16-byte aligned, zero-filled once before first use; sized by msb_workspace_bytes
- * (any size works — what does not fit is resolved inline by the first pass, same results, longer tail). One
- * workspace per concurrent stream. NULL disables the second pass. */
+ * (any size works — what does not fit is resolved inline by the first pass, same results, longer tail). Holds the
+ * queue of agent-hit pixel windows (filled by the first pass while the second — a programmatic dependent launch —
+ * already drains it), its counters and the per-(env, agent) occluder hints, which persist from step to step.
+ * One workspace per concurrent stream. NULL disables the second pass. */
 typedef struct msb_workspace {
     void* ptr;
     int64_t bytes;
