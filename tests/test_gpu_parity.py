@@ -25,6 +25,7 @@ CASES = [
     ('synthetic-deathmatch', 'synthetic', 16, 4, 128, 70.),
     ('synthetic-ragged-res', 'synthetic', 5, 3, 48, 100.),     # res not a multiple of 32
     ('synthetic-wide', 'synthetic', 4, 2, 512, 70.),
+    ('synthetic-six-agents', 'synthetic', 6, 6, 96, 90.),       # more agents than warps in a CTA
 ]
 
 
@@ -161,6 +162,44 @@ def test_physics_bit_exact_against_reference_build(ref, name, kind, N, A, res, f
         kick = torch.as_tensor(rng.normal(size=st['velocity'].shape).astype(np.float32) * 2).cuda()
         c.agents.velocity.add_(kick)
         ra.velocity.add_(kick)
+
+
+def test_more_lights_than_lanes_bit_exact_against_reference_build(ref):
+    """An env with 40 lights: dynamic lighting of agent-hit rays leaves the 32-lights-per-warp fast path (dyn_kernel's
+    and the inline fallback's), baking sums all of them. Agents packed close so that many rays hit agents."""
+    if ref is None:
+        pytest.skip('oracle/_ref not built (needs /root/reference at build time)')
+    from megastep_b200 import cuda, scene, toys
+    from megastep_b200.arrdict import arrdict
+    g = toys.box()
+    rng = np.random.RandomState(5)
+    g = arrdict(walls=g.walls, lights=rng.uniform(1.5, 5.5, (40, 2)), masks=g.masks, res=g.res)
+    gs = [g] * 3
+    arrays = scene.scene_arrays(gs, 4, np.random.RandomState(6))
+    arrays['baked'] = oracle.bake(arrays)
+    st = common.random_state(gs, 4, seed=7)
+    st['positions'] = (3.5 + rng.uniform(-.6, .6, st['positions'].shape)).astype(np.float32)
+    ref.initialize(common.AGENT_RADIUS, 128, 100., 10.)
+    rs, ra = common.reference_scenery(ref, arrays), common.reference_agents(ref, st)
+    rr = ref.render(rs, ra)
+    for use_ws in (True, False):
+        cuda.USE_WORKSPACE = use_ws
+        try:
+            c = common.to_device(arrays, st, 128, 100.)
+            r = c.render()
+            torch.cuda.synchronize()
+        finally:
+            cuda.USE_WORKSPACE = True
+        assert int(((r.indices >= 0) & (r.indices < 32)).sum()) > 50
+        assert torch.equal(r.indices, rr.indices)
+        assert _same(r.screen, rr.screen), f'workspace={use_ws}: {(r.screen != rr.screen).float().mean():.4%} of screen differs'
+    # and the baked light map with 40 lights
+    s = scene.upload(arrays)
+    cuda.bake(s, params=cuda.make_params(common.AGENT_RADIUS, 128, 100., 10.))
+    rs2 = common.reference_scenery(ref, arrays)
+    ref.bake(rs2)
+    torch.cuda.synchronize()
+    assert torch.equal(s.baked.vals, rs2.baked.vals)
 
 
 def test_bake_bit_exact_against_reference_build(ref):
