@@ -1609,6 +1609,7 @@ static long long g_opt_nch = 0;          // 0 = auto
 static long long g_opt_threads = 0;      // 0 = auto
 static long long g_opt_skip_dyn = 0;     // debug
 static long long g_opt_no_vis = 0;       // tests: ignore the visibility grid
+static long long g_opt_idx64 = 0;        // tests: 64-bit output indexing even when 32 bits would do
 static long long g_opt_stage_rec = 0;    // 0: auto (when n_agents * res >= 256), 1: always, 2: never
 static long long g_opt_no_env_order = 0; // A/B: CTA b takes env b
 static long long g_opt_no_prefetch = 0;  // A/B: physics_kernel does not prefetch view_kernel's tables
@@ -1714,6 +1715,7 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "no_prefetch")) { g_opt_no_prefetch = value; return 0; }
     if (!strcmp(name, "no_env_order")) { g_opt_no_env_order = value; return 0; }
     if (!strcmp(name, "stage_rec")) { g_opt_stage_rec = value; return 0; }
+    if (!strcmp(name, "idx64")) { g_opt_idx64 = value; return 0; }
     if (!strcmp(name, "timing")) {
         timing_flush();
         g_opt_timing = value;
@@ -1840,7 +1842,7 @@ static void plan_view(const msb_params* p, const msb_scenery* s, int* nch, int* 
 
 static int launch_view(KArgs& k, bool phys, int nch, int threads, cudaStream_t st) {
     k.stage_rec = g_opt_stage_rec ? (g_opt_stage_rec == 1) : (k.s.n_agents * k.p.res >= 256);
-    k.idx32 = 3ll * k.s.n_envs * k.s.n_agents * (long long)k.p.res < (1ll << 32) ? 1 : 0;
+    k.idx32 = (!g_opt_idx64 && 3ll * k.s.n_envs * k.s.n_agents * (long long)k.p.res < (1ll << 32)) ? 1 : 0;
     k.out_mask = (k.out.indices ? OUT_INDICES : 0) | (k.out.locations ? OUT_LOCATIONS : 0) | (k.out.dots ? OUT_DOTS : 0) |
                  (k.out.distances ? OUT_DISTANCES : 0) | (k.out.screen ? OUT_SCREEN : 0) |
                  (k.has_obs && k.obs.rgb ? OUT_RGB : 0) | (k.has_obs && k.obs.depth ? OUT_DEPTH : 0) | (k.has_obs && k.obs.imu ? OUT_IMU : 0);

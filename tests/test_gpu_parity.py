@@ -281,17 +281,22 @@ def test_graph_replay_with_host_io_equals_plain_launches():
     st['positions'] = (3.5 + np.random.RandomState(0).uniform(-.8, .8, st['positions'].shape)).astype(np.float32)
     acts = torch.as_tensor(np.random.RandomState(5).randint(0, 7, (6, 6, 4)).astype(np.int32))
     recs = []
-    for mode in ('plain', 'graph', 'host'):
+    from megastep_b200 import cuda
+    for mode in ('plain', 'graph', 'host', 'idx64'):            # idx64: plain launches with 64-bit output indexing
         c = common.to_device(arrays, st, 128, 100.)
         step = modules.FusedStep(c, subsample=2, raw=True, graph=mode == 'graph')
         if mode == 'host':
             step._capture(host_io=True)
+        cuda.set_option('idx64', int(mode == 'idx64'))
         rec = []
-        for t in range(6):
-            out = step.step_host(acts[t]) if mode == 'host' else step(acts[t].cuda())
-            torch.cuda.synchronize()
-            rec.append([torch.as_tensor(out.progress).cpu().clone(), out.obs.rgb.cpu().clone(), out.obs.d.cpu().clone(),
-                        out.obs.imu.cpu().clone(), out.render.screen.cpu().clone(), out.render.indices.cpu().clone()])
+        try:
+            for t in range(6):
+                out = step.step_host(acts[t]) if mode == 'host' else step(acts[t].cuda())
+                torch.cuda.synchronize()
+                rec.append([torch.as_tensor(out.progress).cpu().clone(), out.obs.rgb.cpu().clone(), out.obs.d.cpu().clone(),
+                            out.obs.imu.cpu().clone(), out.render.screen.cpu().clone(), out.render.indices.cpu().clone()])
+        finally:
+            cuda.set_option('idx64', 0)
         recs.append(rec)
     n_dyn = int(((recs[0][0][5] >= 0) & (recs[0][0][5] < 32)).sum())
     assert n_dyn > 20
@@ -337,10 +342,19 @@ def test_every_kernel_variant_gives_identical_results(res):
                     for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
                         a, b = getattr(r, k), getattr(base, k)
                         assert ((a == b) | (a != a) & (b != b)).all(), f'stage_rec={stage_rec} nch={nch} threads={threads}: {k} differs'
+        cuda.set_option('nch', 0)
+        cuda.set_option('threads', 0)
+        cuda.set_option('stage_rec', 0)
+        cuda.set_option('idx64', 1)                            # the 64-bit output indexing of very large batches
+        r = c.render()
+        for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
+            a, b = getattr(r, k), getattr(base, k)
+            assert ((a == b) | (a != a) & (b != b)).all(), f'idx64: {k} differs'
     finally:
         cuda.set_option('nch', 0)
         cuda.set_option('threads', 0)
         cuda.set_option('stage_rec', 0)
+        cuda.set_option('idx64', 0)
 
 
 def _same(a, b):
