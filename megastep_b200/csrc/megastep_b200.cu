@@ -1108,10 +1108,9 @@ __global__ void __launch_bounds__(128, MSB_DYN_BLOCKS) dyn_kernel(const __grid_c
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
     const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
     unsigned dyn_rays = 0, dyn_iters = 0, dyn_entries = 0;
-    // One entry per CTA at a time, entries strided over the grid (every entry is an independent unit of work; a shared
-    // counter would serialise thousands of CTAs on one address). The CTA's warps split the entry's LIGHTS between them:
-    // the kernel lasts as long as its slowest entry (an agent in a large open room: ~20 lights to scan one after the
-    // other), so the per-entry chain is what has to be short.
+    // One entry per CTA at a time (every entry is an independent unit of work). The CTA's warps split the entry's LIGHTS
+    // between them: the kernel lasts as long as its slowest entry (an agent in a large open room: ~20 lights to scan one
+    // after the other), so the per-entry chain is what has to be short.
     const long long t_start = STATS ? clock64() : 0;
     long long t_entries = 0;
     // the first entry is the CTA's own index; the following ones come off a shared counter (ctrl[2]) — CTAs that drew
