@@ -286,3 +286,23 @@ def test_spatial_table_is_a_padded_permutation_with_tight_boxes():
             bx = boxes[int(box_starts[n]) + b]
             assert bx[0] == seg[:, [0, 2]].min() and bx[2] == seg[:, [0, 2]].max()
             assert bx[1] == seg[:, [1, 3]].min() and bx[3] == seg[:, [1, 3]].max()
+
+
+def test_caller_side_allocations_of_the_side_tables():
+    """What the caller owes msb_build_table / msb_build_visibility (cuda._empty_table, cuda._visibility_grid): array
+    sizes, the exclusive prefix sums, a grid that covers each env's static geometry in 0.25 m cells; envs without a
+    static line get no boxes and no cells."""
+    widths = torch.tensor([16 + 40, 16, 16 + 1, 16 + 33], dtype=torch.int32)      # 16 = the agents' lines
+    occ, occ_starts, boxes, box_starts, meta, rec = cuda._empty_table(widths, 16)
+    assert box_starts.tolist() == [0, 3, 3, 4] and boxes.shape == (7, 4)
+    assert occ.shape == (7 * 16, 4) and rec.shape == (7 * 16, 4) and rec.dtype == torch.int32
+    assert occ_starts.shape == (4,) and meta.shape == (4, 2)
+    boxes = torch.tensor([[1., 1., 3., 2.], [2., 0., 6.1, 2.], [0., 0., 1., 1.],        # env 0: x 0..6.1, y 0..2
+                          [5., 5., 5., 9.],                                                # env 2: a vertical sliver
+                          [0., 0., 1., 1.], [1., 1., 2., 2.], [2., 2., 3., 3.]])          # env 3
+    vis, starts, vmeta = cuda._visibility_grid(boxes, box_starts, widths, 16)
+    gx, gy = vmeta[:, 2].long(), vmeta[:, 3].long()
+    assert gx.tolist() == [25, 0, 1, 12] and gy.tolist() == [8, 0, 16, 12]
+    assert vmeta[0, :2].tolist() == [0., 0.] and vmeta[2, :2].tolist() == [5., 5.]
+    assert starts.tolist() == [0, 200, 200, 216] and vis.numel() == 200 + 16 + 144 and vis.dtype == torch.int32
+    assert float(vmeta[0, 0] + gx[0] * cuda.VIS_CELL) >= 6.1 and float(vmeta[3, 1] + gy[3] * cuda.VIS_CELL) >= 3.   # reaches the far corner
