@@ -306,3 +306,49 @@ def test_caller_side_allocations_of_the_side_tables():
     assert vmeta[0, :2].tolist() == [0., 0.] and vmeta[2, :2].tolist() == [5., 5.]
     assert starts.tolist() == [0, 200, 200, 216] and vis.numel() == 200 + 16 + 144 and vis.dtype == torch.int32
     assert float(vmeta[0, 0] + gx[0] * cuda.VIS_CELL) >= 6.1 and float(vmeta[3, 1] + gy[3] * cuda.VIS_CELL) >= 3.   # reaches the far corner
+
+
+def test_geometry_cache_round_trip_and_reference_format(tmp_path):
+    """megastep_b200.cubicasa against the reference's cache format (cubicasa.py:149-174: gzip(np.savez(flat)) with
+    members "<id>/walls|lights|masks|res"): a file written the reference's way loads here, a file written here loads
+    the reference's way (np.load on the unzipped bytes), and sample() splits and cycles as the reference does."""
+    import gzip
+    from io import BytesIO
+    from megastep_b200 import cubicasa, toys, synthetic
+    gs = {str(100 + i): g for i, g in enumerate([toys.box(), toys.column()] + synthetic.sample(18, seed=5))}
+    for g in gs.values():
+        if 'masks' not in g:
+            g['masks'] = np.zeros((3, 4), np.int16)
+    # written the reference's way
+    flat = {f'{k}/{f}': np.asarray(g[f]) for k, g in gs.items() for f in cubicasa.FIELDS}
+    bs = BytesIO()
+    np.savez(bs, **flat)
+    theirs = tmp_path / 'theirs.npz.gz'
+    theirs.write_bytes(gzip.compress(bs.getvalue()))
+    got = cubicasa.load_geometries(theirs)
+    assert sorted(got) == sorted(gs)
+    for k, g in gs.items():
+        for f in cubicasa.FIELDS:
+            assert np.array_equal(got[k][f], np.asarray(g[f])) and got[k][f].dtype == np.asarray(g[f]).dtype
+    # written here, read the reference's way
+    ours = cubicasa.save_geometries(gs, tmp_path / 'ours.npz.gz')
+    back = np.load(BytesIO(gzip.decompress(ours.read_bytes())))
+    assert sorted(back.files) == sorted(flat)
+    assert all(np.array_equal(back[name], flat[name]) for name in flat)
+    # flatten / unflatten
+    tree = {'a': {'b': 1, 'c': {'d': 2}}, 'e': 3}
+    assert cubicasa.flatten(tree) == {'a/b': 1, 'a/c/d': 2, 'e': 3} and cubicasa.unflatten(cubicasa.flatten(tree)) == tree
+    # sample(): sorted ids shuffled by the seed, first 90 % training, cycled
+    order = np.random.RandomState(7).permutation(sorted(gs))
+    train = cubicasa.sample(40, 'training', seed=7, path=ours)
+    assert [g.id for g in train] == [order[:18][i % 18] for i in range(40)]
+    assert [g.id for g in cubicasa.sample(3, 'test', seed=7, path=ours)] == [order[18], order[19], order[18]]
+    assert len(cubicasa.sample(5, 'all', seed=7, path=ours)) == 5
+    with pytest.raises(ValueError):
+        cubicasa.sample(1, 'validation', path=ours)
+    with pytest.raises(FileNotFoundError):
+        cubicasa.load_geometries(tmp_path / 'missing.npz.gz')
+    # and the geometries feed the scene builder unchanged
+    from megastep_b200 import scene
+    arrays = scene.scene_arrays(train[:3], 2, np.random.RandomState(0))
+    assert len(arrays['line_widths']) == 3
