@@ -55,6 +55,7 @@ def parse():
     ap.add_argument('--no-raw', action='store_true', help='skip materialising the five Render tensors (obs heads only)')
     ap.add_argument('--gather', action='store_true', help='all-gather the observations to every rank each step (NCCL)')
     ap.add_argument('--no-graph', action='store_true', help='e2e leg: plain launches instead of a CUDA-graph replay')
+    ap.add_argument('--e2e', default='native', choices=['native', 'torch'], help='e2e leg: the library\'s own host-driven graph (one call per tick) or a torch CUDA graph between PyTorch copies')
     ap.add_argument('--dry-run', action='store_true', help='build the scene and the CPU baseline only (no GPU)')
     return ap.parse_args()
 
@@ -218,11 +219,23 @@ class Ours:
         self.graphed = False
         self.fused = False                   # physics and render are separate launches: each stages the segments
 
-    def use_graph(self):
-        """The public API's CUDA-graph mode (modules.FusedStep(graph=True)): one graph replay per step on the host.
-        (FusedStep.step_host — the two host copies inside the graph as well — measured no faster: 179 vs 170 us.)"""
-        self.stepper._capture()
+    def use_graph(self, native=True):
+        """The public API's CUDA-graph modes. native: FusedStep.enable_host_graph() — the tick captured inside the
+        library and driven by ONE foreign call per tick (actions up, graph launch, progress down, stream sync);
+        otherwise FusedStep(graph=True): a torch.cuda.CUDAGraph replay between PyTorch copies."""
+        self.host_graph = False
+        if native:
+            try:
+                self.stepper.enable_host_graph()
+                self.host_graph = True
+            except RuntimeError as e:
+                print(f'native host graph unavailable ({e}); falling back to the torch graph', file=sys.stderr)
+        if not self.host_graph:
+            self.stepper._capture()
         self.graphed = True
+
+    def step_host(self, actions_host):
+        return self.stepper.step_host(actions_host).progress
 
     def step(self):
         self.stepper()                       # movement+physics | render+heads | agent-hit lighting: 3 launches, no host sync
@@ -366,9 +379,9 @@ def run_gpu(args, cfg, arm_cls, rank, world, local_rank):
 
     # ---- e2e: host actions in pinned memory -> H2D -> step through the public API -> D2H of the step's result -----
     if hasattr(arm, 'use_graph') and not args.no_graph:
-        arm.use_graph()
+        arm.use_graph(native=args.e2e == 'native')
     result_host = torch.empty((N, A), dtype=torch.float32).pin_memory()
-    one_launch = getattr(arm, 'graphed', False) and hasattr(arm, 'step_host')
+    one_launch = getattr(arm, 'host_graph', False)
 
     def tick(i):
         if one_launch:                                     # H2D + kernels + D2H in one graph launch, then a stream sync
@@ -494,7 +507,7 @@ def main():
         'data': 'synthetic', 'config': base_cfg, 'impl': args.impl,
         'e2e': {'value': e2e, 'unit': 'agent-frames/s', 'h2d_bytes_per_step': out['N'] * out['A'] * 4,
                 'd2h_bytes_per_step': out['N'] * out['A'] * 4, 'ms_per_step': out['e2e_ms'] / K,
-                'what': 'pinned-host actions -> H2D -> step via the public API (modules.FusedStep' + (', CUDA-graph replay' if getattr(out.get('arm'), 'graphed', False) else '') + ') -> D2H of progress (the physics result) + stream sync, every step; observations stay on the device as in the reference'},
+                'what': 'pinned-host actions -> H2D -> step via the public API (modules.FusedStep' + ('.step_host: one foreign call per tick around a CUDA graph captured inside the library' if getattr(out.get('arm'), 'host_graph', False) else ', CUDA-graph replay' if getattr(out.get('arm'), 'graphed', False) else '') + ') -> D2H of progress (the physics result) + stream sync, every step; observations stay on the device as in the reference'},
         'gpu_launches': out['launches'],
         'roofline': roofline,
         'clocks': out['clocks'],

@@ -168,6 +168,18 @@ int msb_step(const msb_params* p, const msb_scenery* s, const msb_agents* a, con
              float* progress, const msb_render_out* out, const msb_obs_out* obs, const msb_workspace* ws,
              void* cuda_stream);
 
+/* The same tick captured once as a CUDA graph (its programmatic dependencies included) and driven from the host in
+ * ONE call: msb_step_graph_run uploads the actions from pinned host memory (NULL: already on the device), replays
+ * the graph, downloads `progress` into pinned host memory (NULL: leave it on the device) and, if `sync`, waits for the
+ * stream. All pointers given to msb_step_graph_create are baked in and must outlive the graph. The step's kernels
+ * must have run at least once before (msb_step), and per-kernel timing must be off. */
+typedef struct msb_graph msb_graph;
+int msb_step_graph_create(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_movement* mv,
+                          float* progress, const msb_render_out* out, const msb_obs_out* obs, const msb_workspace* ws,
+                          msb_graph** handle);
+int msb_step_graph_run(msb_graph* g, const int32_t* actions_host, float* progress_host, void* cuda_stream, int32_t sync);
+int msb_step_graph_destroy(msb_graph* g);
+
 /* [host] Recommended workspace size in bytes for this scene and observation subsample (1 when obs is NULL). */
 int64_t msb_workspace_bytes(const msb_params* p, const msb_scenery* s, int32_t subsample);
 

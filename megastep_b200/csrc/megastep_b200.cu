@@ -2012,6 +2012,76 @@ extern "C" int msb_step(const msb_params* p, const msb_scenery* s, const msb_age
     return launch_dyn(k, (cudaStream_t)cuda_stream);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// A whole host-to-host tick as one call: the step's three launches captured once in a CUDA graph (programmatic
+// dependencies included), replayed between the upload of the actions and the download of `progress`.
+// ---------------------------------------------------------------------------------------------------------------
+struct msb_graph {
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    int32_t* actions_dev;
+    float* progress_dev;
+    size_t n;               // N * A
+};
+
+extern "C" int msb_step_graph_create(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_movement* mv,
+                                     float* progress, const msb_render_out* out, const msb_obs_out* obs,
+                                     const msb_workspace* ws, msb_graph** handle) {
+    if (!handle) return fail("%s", "msb_step_graph_create: null handle");
+    *handle = nullptr;
+    if (g_opt_timing) return fail("%s", "msb_step_graph_create: per-kernel timing is on (events cannot be captured)");
+    if (!s || s->n_envs <= 0) return fail("%s", "msb_step_graph_create: empty scenery");
+    cudaStream_t cs;
+    if (check(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking), "cudaStreamCreate")) return 1;
+    msb_graph* g = new msb_graph();
+    g->graph = nullptr; g->exec = nullptr;
+    g->actions_dev = mv ? const_cast<int32_t*>(mv->actions) : nullptr;
+    g->progress_dev = progress;
+    g->n = (size_t)s->n_envs * s->n_agents;
+    int rc = check(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+    if (!rc) {
+        const long long launches = g_launches;
+        rc = msb_step(p, s, a, mv, progress, out, obs, ws, cs);
+        g_launches = launches;                                  // captured, not launched
+        cudaError_t e = cudaStreamEndCapture(cs, &g->graph);
+        if (!rc) rc = check(e, "cudaStreamEndCapture");
+    }
+    if (!rc) rc = check(cudaGraphInstantiate(&g->exec, g->graph, 0), "cudaGraphInstantiate");
+    cudaStreamDestroy(cs);
+    if (rc) {
+        if (g->graph) cudaGraphDestroy(g->graph);
+        delete g;
+        return 1;
+    }
+    *handle = g;
+    return 0;
+}
+
+extern "C" int msb_step_graph_run(msb_graph* g, const int32_t* actions_host, float* progress_host, void* cuda_stream, int32_t sync) {
+    if (!g || !g->exec) return fail("%s", "msb_step_graph_run: null graph");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (actions_host) {
+        if (!g->actions_dev) return fail("%s", "msb_step_graph_run: the step was captured without actions");
+        if (check(cudaMemcpyAsync(g->actions_dev, actions_host, g->n * sizeof(int32_t), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(actions)")) return 1;
+    }
+    if (check(cudaGraphLaunch(g->exec, st), "cudaGraphLaunch")) return 1;
+    g_launches += 3;
+    if (progress_host) {
+        if (!g->progress_dev) return fail("%s", "msb_step_graph_run: the step was captured without progress");
+        if (check(cudaMemcpyAsync(progress_host, g->progress_dev, g->n * sizeof(float), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(progress)")) return 1;
+    }
+    if (sync) return check(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    return 0;
+}
+
+extern "C" int msb_step_graph_destroy(msb_graph* g) {
+    if (!g) return 0;
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+    return 0;
+}
+
 extern "C" int msb_build_table(const msb_scenery* s, void* cuda_stream) {
     if (!s) return fail("%s", "msb_build_table: null scenery");
     if (s->n_envs < 0 || s->n_agents < 1 || s->n_model < 0) return fail("%s", "bad scenery dimensions");

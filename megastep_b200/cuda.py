@@ -91,6 +91,10 @@ def _load():
     lib.msb_render.argtypes = [P(Params), P(_Scenery), P(_Agents), P(_RenderOut), P(_ObsOut), P(_Workspace), ctypes.c_void_p]
     lib.msb_step.argtypes = [P(Params), P(_Scenery), P(_Agents), P(_Movement), ctypes.c_void_p, P(_RenderOut),
                              P(_ObsOut), P(_Workspace), ctypes.c_void_p]
+    lib.msb_step_graph_create.argtypes = [P(Params), P(_Scenery), P(_Agents), P(_Movement), ctypes.c_void_p, P(_RenderOut),
+                                          P(_ObsOut), P(_Workspace), P(ctypes.c_void_p)]
+    lib.msb_step_graph_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
+    lib.msb_step_graph_destroy.argtypes = [ctypes.c_void_p]
     lib.msb_workspace_bytes.argtypes = [P(Params), P(_Scenery), ctypes.c_int32]
     lib.msb_workspace_bytes.restype = ctypes.c_int64
     lib.msb_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
@@ -595,6 +599,34 @@ class StepPlan:
                                  ctypes.byref(self._ws) if self._ws is not None else None, stream))
 
     __call__ = step
+
+    def graph_create(self):
+        """Captures step() once as a CUDA graph inside the library (msb_step_graph_create); step() must have run before."""
+        self.graph_destroy()
+        h = ctypes.c_void_p()
+        with _on_device(self.progress):
+            _check(_lib.msb_step_graph_create(ctypes.byref(self.params), ctypes.byref(self._s), ctypes.byref(self.agents._c),
+                                              ctypes.byref(self._mv) if self._mv is not None else None, self.progress.data_ptr(),
+                                              ctypes.byref(self._out) if self._out is not None else None,
+                                              ctypes.byref(self._obs) if self._obs is not None else None,
+                                              ctypes.byref(self._ws) if self._ws is not None else None, ctypes.byref(h)))
+        self._graph = h
+
+    def graph_run(self, actions_host_ptr, progress_host_ptr, sync=True):
+        """actions (pinned host, or 0) up, the captured step, progress (pinned host, or 0) down, stream sync: one call"""
+        with _on_device(self.progress) as stream:
+            _check(_lib.msb_step_graph_run(self._graph, actions_host_ptr or None, progress_host_ptr or None, stream, int(sync)))
+
+    def graph_destroy(self):
+        if getattr(self, '_graph', None):
+            _lib.msb_step_graph_destroy(self._graph)
+        self._graph = None
+
+    def __del__(self):
+        try:
+            self.graph_destroy()
+        except Exception:       # noqa: BLE001  (interpreter shutdown)
+            pass
 
     def render_only(self):
         """render + heads, one launch; the agents are not moved"""

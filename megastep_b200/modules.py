@@ -238,16 +238,41 @@ class FusedStep:
         p = self._plan
         return arrdict(obs=arrdict(rgb=p.rgb, d=p.depth, imu=p.imu), progress=p.progress, render=p.render)
 
+    def enable_host_graph(self):
+        """The tick as a CUDA graph captured inside the library, driven by `step_host` with ONE foreign call per tick
+        (upload of the actions, graph launch, download of `progress`, stream sync: msb_step_graph_run) instead of four
+        PyTorch calls."""
+        agents = (self.core.agents.angles, self.core.agents.positions, self.core.agents.angvelocity, self.core.agents.velocity)
+        snapshot = [t.clone() for t in agents]                 # the warm-up tick is undone below
+        self._plan()                                           # first-launch set-up outside the capture
+        torch.cuda.synchronize(self.core.device)
+        self._plan.graph_create()
+        for dst, src in zip(agents, snapshot):
+            dst.copy_(src)
+        self.actions_host = torch.zeros(tuple(self.actions.shape), dtype=torch.int32).pin_memory()
+        self.progress_host = torch.zeros(tuple(self._plan.progress.shape), dtype=torch.float32).pin_memory()
+        self._native_graph = True
+
     def step_host(self, actions=None):
-        """One tick driven from the host (needs `_capture(host_io=True)`): `actions` — a host tensor / array, or None
-        if the caller filled `self.actions_host` itself — go up, the tick runs, `progress` comes back into
-        `self.progress_host`; all inside one graph launch, then the stream is synchronised. Observations stay on the
-        device, as in `__call__`."""
+        """One tick driven from the host (needs `enable_host_graph()` or `_capture(host_io=True)`): `actions` — a host
+        tensor / array, or None if the caller filled `self.actions_host` itself — go up, the tick runs, `progress`
+        comes back into `self.progress_host`, then the stream is synchronised. Observations stay on the device, as
+        in `__call__`."""
+        p = self._plan
+        if getattr(self, '_native_graph', False):
+            src = self.actions_host
+            if actions is not None and actions is not self.actions_host:
+                a = torch.as_tensor(actions)
+                if a.dtype == torch.int32 and a.is_contiguous() and not a.is_cuda and a.is_pinned() and a.shape == self.actions.shape:
+                    src = a                                     # straight from the caller's pinned buffer
+                else:
+                    self.actions_host.copy_(a)
+            p.graph_run(src.data_ptr(), self.progress_host.data_ptr(), sync=True)
+            return arrdict(obs=arrdict(rgb=p.rgb, d=p.depth, imu=p.imu), progress=self.progress_host, render=p.render)
         if actions is not None and actions is not self.actions_host:
             self.actions_host.copy_(torch.as_tensor(actions))
         self._graph.replay()
         torch.cuda.current_stream(self.core.device).synchronize()
-        p = self._plan
         return arrdict(obs=arrdict(rgb=p.rgb, d=p.depth, imu=p.imu), progress=self.progress_host, render=p.render)
 
 

@@ -282,16 +282,24 @@ def test_graph_replay_with_host_io_equals_plain_launches():
     acts = torch.as_tensor(np.random.RandomState(5).randint(0, 7, (6, 6, 4)).astype(np.int32))
     recs = []
     from megastep_b200 import cuda
-    for mode in ('plain', 'graph', 'host', 'idx64'):            # idx64: plain launches with 64-bit output indexing
+    pinned = acts.pin_memory()
+    for mode in ('plain', 'graph', 'host', 'idx64', 'native', 'native-pinned'):   # idx64: plain launches, 64-bit output indexing
         c = common.to_device(arrays, st, 128, 100.)
         step = modules.FusedStep(c, subsample=2, raw=True, graph=mode == 'graph')
         if mode == 'host':
             step._capture(host_io=True)
+        if mode.startswith('native'):                          # the graph captured inside the library, one call per tick
+            step.enable_host_graph()
         cuda.set_option('idx64', int(mode == 'idx64'))
         rec = []
         try:
             for t in range(6):
-                out = step.step_host(acts[t]) if mode == 'host' else step(acts[t].cuda())
+                if mode in ('host', 'native'):
+                    out = step.step_host(acts[t])
+                elif mode == 'native-pinned':
+                    out = step.step_host(pinned[t])
+                else:
+                    out = step(acts[t].cuda())
                 torch.cuda.synchronize()
                 rec.append([torch.as_tensor(out.progress).cpu().clone(), out.obs.rgb.cpu().clone(), out.obs.d.cpu().clone(),
                             out.obs.imu.cpu().clone(), out.render.screen.cpu().clone(), out.render.indices.cpu().clone()])
