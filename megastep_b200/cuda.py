@@ -614,8 +614,14 @@ class StepPlan:
 
     def graph_run(self, actions_host_ptr, progress_host_ptr, sync=True):
         """actions (pinned host, or 0) up, the captured step, progress (pinned host, or 0) down, stream sync: one call"""
-        with _on_device(self.progress) as stream:
-            _check(_lib.msb_step_graph_run(self._graph, actions_host_ptr or None, progress_host_ptr or None, stream, int(sync)))
+        dev = self.progress.device.index
+        if torch.cuda.current_device() != dev:
+            with _on_device(self.progress) as stream:
+                _check(_lib.msb_step_graph_run(self._graph, actions_host_ptr or None, progress_host_ptr or None, stream, int(sync)))
+            return
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if _lib.msb_step_graph_run(self._graph, actions_host_ptr or None, progress_host_ptr or None, stream, int(sync)):
+            _check(1)
 
     def graph_destroy(self):
         if getattr(self, '_graph', None):

@@ -252,6 +252,18 @@ class FusedStep:
         self.actions_host = torch.zeros(tuple(self.actions.shape), dtype=torch.int32).pin_memory()
         self.progress_host = torch.zeros(tuple(self._plan.progress.shape), dtype=torch.float32).pin_memory()
         self._native_graph = True
+        self._pinned_storages = {}
+        self._progress_host_ptr = self.progress_host.data_ptr()
+        p = self._plan
+        self._host_result = arrdict(obs=arrdict(rgb=p.rgb, d=p.depth, imu=p.imu), progress=self.progress_host, render=p.render)
+
+    def _is_pinned(self, t):
+        """`t.is_pinned()` asks the driver every time (microseconds); the answer per storage does not change."""
+        key = t.untyped_storage().data_ptr()
+        known = self._pinned_storages.get(key)
+        if known is None:
+            known = self._pinned_storages[key] = t.is_pinned()
+        return known
 
     def step_host(self, actions=None):
         """One tick driven from the host (needs `enable_host_graph()` or `_capture(host_io=True)`): `actions` — a host
@@ -262,13 +274,14 @@ class FusedStep:
         if getattr(self, '_native_graph', False):
             src = self.actions_host
             if actions is not None and actions is not self.actions_host:
-                a = torch.as_tensor(actions)
-                if a.dtype == torch.int32 and a.is_contiguous() and not a.is_cuda and a.is_pinned() and a.shape == self.actions.shape:
+                a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(actions)
+                if (a.dtype == torch.int32 and not a.is_cuda and a.shape == self.actions.shape and a.is_contiguous()
+                        and self._is_pinned(a)):
                     src = a                                     # straight from the caller's pinned buffer
                 else:
                     self.actions_host.copy_(a)
-            p.graph_run(src.data_ptr(), self.progress_host.data_ptr(), sync=True)
-            return arrdict(obs=arrdict(rgb=p.rgb, d=p.depth, imu=p.imu), progress=self.progress_host, render=p.render)
+            p.graph_run(src.data_ptr(), self._progress_host_ptr, sync=True)
+            return self._host_result
         if actions is not None and actions is not self.actions_host:
             self.actions_host.copy_(torch.as_tensor(actions))
         self._graph.replay()
