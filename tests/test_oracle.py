@@ -138,3 +138,59 @@ def test_bake_light_falloff_and_occlusion():
 def test_half_screen_matches_reference_formula():
     for fov in (60., 70., 90., 130.):
         assert abs(oracle.half_screen(fov) - np.tan(np.deg2rad(fov) / 2)) < 1e-6
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# properties the domain offers, on random inputs (hypothesis)
+# ----------------------------------------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as hst  # noqa: E402
+
+
+@settings(max_examples=15, deadline=None)
+@given(seed=hst.integers(0, 10 ** 6), speed=hst.floats(0., 40.), n_agents=hst.integers(1, 5))
+def test_physics_properties_on_random_states(seed, speed, n_agents):
+    """progress in [0, 1]; momentum is kept exactly when nothing was hit and zeroed otherwise (kernels.cu:223-227);
+    positions advance by progress * velocity / fps; angles stay in [-180, 180)."""
+    gs, arrays = common.synthetic_scene(3, n_agents, seed=seed % 7, bake=False)
+    st = common.random_state(gs, n_agents, seed=seed, speed=speed, angspeed=400.)
+    before = common.copy_state(st)
+    progress = oracle.physics(arrays, st, fps=10.)
+    assert ((progress >= 0) & (progress <= 1)).all()
+    hit = progress < 1
+    assert (st['velocity'][hit] == 0).all() and (st['angvelocity'][hit] == 0).all()
+    assert np.array_equal(st['velocity'][~hit], before['velocity'][~hit])
+    assert np.array_equal(st['angvelocity'][~hit], before['angvelocity'][~hit])
+    np.testing.assert_allclose(st['positions'], before['positions'] + progress[..., None] * before['velocity'] / 10., atol=1e-5)
+    assert ((st['angles'] >= -180) & (st['angles'] < 180 + 1e-4)).all()
+
+
+@settings(max_examples=10, deadline=None)
+@given(seed=hst.integers(0, 10 ** 6), res=hst.sampled_from([7, 32, 48, 64]), fov=hst.floats(30., 170.))
+def test_render_properties_on_random_states(seed, res, fov):
+    """Every hit lies beyond the near plane (the agent's radius) and on its line; misses are -1 / NaN / +inf / black;
+    rendering twice changes nothing; the screen is within [0, 1]; the agents' lines are drawn at their poses."""
+    n_agents = 2
+    gs, arrays = common.synthetic_scene(2, n_agents, seed=seed % 5, bake=True)
+    st = common.random_state(gs, n_agents, seed=seed)
+    a1 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in arrays.items()}
+    r1 = oracle.render(a1, st, res=res, fov=fov)
+    r2 = oracle.render(a1, st, res=res, fov=fov)
+    for k in r1:
+        assert np.array_equal(r1[k], r2[k], equal_nan=True), k
+    assert np.array_equal(a1['lines'], arrays['lines'])
+    hit = r1['indices'] >= 0
+    assert (r1['distances'][hit] > common.AGENT_RADIUS * .999).all() and np.isinf(r1['distances'][~hit]).all()
+    assert ((r1['locations'][hit] >= 0) & (r1['locations'][hit] <= 1)).all() and np.isnan(r1['locations'][~hit]).all()
+    assert (r1['screen'] >= 0).all() and (r1['screen'] <= 1 + 1e-4).all() and (r1['screen'][~hit] == 0).all()
+    widths = np.asarray(arrays['line_widths'])[:, None, None]
+    assert (r1['indices'] < widths).all()
+    # draw (kernels.cu:297-318): agent a's model lines sit within the model's radius of its position
+    lines = r1['lines'].reshape(-1, 2, 2)                     # the oracle returns the drawn lines, the input is untouched
+    ls = oracle.starts(arrays['line_widths'])
+    F = len(arrays['model'])
+    rad = np.abs(np.asarray(arrays['model'])).reshape(-1, 2)
+    rad = np.hypot(rad[:, 0], rad[:, 1]).max()
+    for n in range(2):
+        for a in range(n_agents):
+            seg = lines[ls[n] + a * F: ls[n] + (a + 1) * F].reshape(-1, 2)
+            assert (np.hypot(*(seg - st['positions'][n, a]).T) <= rad + 1e-4).all()
