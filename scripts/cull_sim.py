@@ -55,8 +55,9 @@ def pack(walls, run, order):
     return rows, boxes
 
 
-def item(rows, boxes, pos, ang, r0, nch, R, hs, run, per_batch, others, model_radius):
-    """One warp-item. Returns (batches of static rows, candidate tests, agent batches, agent tests are not modelled)."""
+def item(rows, boxes, pos, ang, r0, nch, R, hs, run, per_batch, others, model_radius, hint=None):
+    """One warp-item. Returns (batches of static rows, candidate tests on them, agent batches, the rays' hit parameters);
+    the tests on the agents' own lines are not modelled."""
     cs, sn = np.cos(np.deg2rad(ang)), np.sin(np.deg2rad(ang))
     xclip = .5 * AGENT_RADIUS / np.sqrt(1 + hs * hs)
     B0, dB = (R - 2 * r0) * hs / R, 64. * hs / R
@@ -67,6 +68,9 @@ def item(rows, boxes, pos, ang, r0, nch, R, hs, run, per_batch, others, model_ra
     nearp = AGENT_RADIUS / np.hypot(ru[:, 0], ru[:, 1])
     best = np.where(rays < R, np.inf, 0.)
     cmax = np.array([np.inf if r0 + 32 * c < R else 0. for c in range(nch)])
+    if hint is not None:                                        # what a perfect per-ray guess from the previous frame would buy
+        best = np.minimum(best, hint * (1 + 1e-3) + 1e-3)
+        cmax = np.array([best[32 * c:32 * c + 32].max() for c in range(nch)])
 
     def camera(p):
         d = p - pos
@@ -127,7 +131,7 @@ def item(rows, boxes, pos, ang, r0, nch, R, hs, run, per_batch, others, model_ra
         if not (behind or left or right or hidden):
             agent_groups = 1
             break
-    return groups, tests, agent_groups
+    return groups, tests, agent_groups, best
 
 
 def main():
@@ -140,6 +144,7 @@ def main():
     ap.add_argument('--runs-per-batch', type=int, default=2)
     ap.add_argument('--nch', type=int, default=2)
     ap.add_argument('--order', default='str', choices=['str', 'morton'])
+    ap.add_argument('--hint', action='store_true', help='second pass with every ray starting from (just behind) its final hit')
     args = ap.parse_args()
     gs = synthetic.sample(args.envs, seed=1, n_unique=args.envs)
     pos, ang = synthetic.spawns(gs, args.agents, np.random.RandomState(2))
@@ -154,8 +159,12 @@ def main():
         for a in range(args.agents):
             others = [pos[n, b].astype(np.float64) for b in range(args.agents) if b != a]
             for r0 in range(0, args.res, 32 * args.nch):
-                tot += item(rows, boxes, pos[n, a].astype(np.float64), float(ang[n, a]), r0, args.nch, args.res, hs, args.run,
-                            args.runs_per_batch, others, model_radius)
+                common_args = (rows, boxes, pos[n, a].astype(np.float64), float(ang[n, a]), r0, args.nch, args.res, hs, args.run,
+                               args.runs_per_batch, others, model_radius)
+                res = item(*common_args)
+                if args.hint:
+                    res = item(*common_args, hint=res[3])
+                tot += res[:3]
                 items += 1
     g, t, ag = tot / items
     print(f'{vars(args)}\nitems {items}: static batches {g:.2f} + agent batches {ag:.2f} = {g + ag:.2f} per item '
