@@ -4,11 +4,9 @@ Mirrors the behaviour of rebar/arrdict.py:11-162 that the kept API relies on: `d
 `d[idx] = other_arrdict` assigns into every value, binary operators apply value-wise (against a scalar or a
 same-keyed dict), plus the `torchify / numpyify / stack / cat / clone` helpers.
 """
-import operator
 import numpy as np
 import torch
 
-from . import dotdict as _dd
 from .dotdict import dotdict, mapping
 
 __all__ = ['arrdict', 'torchify', 'numpyify', 'stack', 'cat', 'clone']

@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from . import cuda
-from .arrdict import arrdict, clone
+from .arrdict import clone
 from .dotdict import dotdict
 
 AGENT_WIDTH = .15

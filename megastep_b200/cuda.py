@@ -20,7 +20,6 @@ wrappers.cpp:57-59), and texel offsets are 64-bit.
 import ctypes
 import os
 
-import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

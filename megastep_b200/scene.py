@@ -8,7 +8,6 @@ import numpy as np
 import torch
 
 from . import core, cuda
-from .arrdict import arrdict, torchify
 
 # ten bland wall colours (iwanthue), reference scene.py:10-20
 COLORS = ['#c185ae', '#73a171', '#5666a4', '#9f7c4a', '#809cd5', '#566e40', '#8e537b', '#4f9fa4', '#b56d66', '#5a728c']

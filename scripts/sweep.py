@@ -4,7 +4,6 @@ Writes gpurun_out/sweep.json. Cells the reference cannot run (32-bit accessors) 
 import json
 import os
 import sys
-import time
 
 import numpy as np
 import torch
