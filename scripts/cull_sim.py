@@ -27,11 +27,12 @@ CULL_EPS = 4e-4
 
 def pack(walls, run, order):
     """Static segments (W, 4) -> rows in table order, (nb, 4) run boxes. 'str' as msb_build_table, 'morton' as before."""
-    mid = (walls[:, :2] + walls[:, 2:]) * .5
+    w32 = walls.astype(np.float32)
+    mid = (w32[:, :2] + w32[:, 2:]) * np.float32(.5)          # in float32, as the table builder ranks them
     n = len(walls)
     nb = -(-n // run)
     if order == 'morton':
-        cell = np.clip(((mid - mid.min(0)) / .25), 0, 65535).astype(np.int64)
+        cell = np.clip(((mid - mid.min(0)) / np.float32(.25)), 0, 65535).astype(np.int64)
 
         def spread(v):
             v = (v | (v << 8)) & 0x00FF00FF

@@ -352,3 +352,33 @@ def test_geometry_cache_round_trip_and_reference_format(tmp_path):
     from megastep_b200 import scene
     arrays = scene.scene_arrays(train[:3], 2, np.random.RandomState(0))
     assert len(arrays['line_widths']) == 3
+
+
+def test_culling_model_packs_runs_like_the_table_builder():
+    """scripts/cull_sim.py (the CPU model used to plan kernel changes) must pack runs exactly as the spatial table does,
+    or its batch / test counts say nothing about the kernel."""
+    import importlib.util
+    import os
+    from megastep_b200 import scene, synthetic
+    spec = importlib.util.spec_from_file_location('cull_sim', os.path.join(os.path.dirname(os.path.dirname(__file__)), 'scripts', 'cull_sim.py'))
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    gs = synthetic.sample(3, seed=9)
+    arrays = scene.scene_arrays(gs, 2, np.random.RandomState(9))
+    lines = cuda.Ragged3D(torch.as_tensor(arrays['lines']), torch.as_tensor(arrays['line_widths']))
+    AF = 2 * len(arrays['model'])
+    for order in ('str',):                                 # (the model's Morton cells start at each env's own corner)
+        old = cuda.TABLE_ORDER
+        cuda.TABLE_ORDER = order
+        try:
+            occ, occ_starts, boxes, box_starts, meta, rec = cuda._occluder_table(lines, AF, 16)
+        finally:
+            cuda.TABLE_ORDER = old
+        for n in range(3):
+            walls = lines[n].reshape(-1, 4)[AF:].numpy().astype(np.float64)
+            rows, bx = sim.pack(walls, 16, order)
+            W = len(walls)
+            lo = int(occ_starts[n])
+            assert np.array_equal(rows.astype(np.float32), occ[lo:lo + W].numpy()), (order, n)
+            nb = (W + 15) // 16
+            assert np.allclose(bx, boxes[int(box_starts[n]):int(box_starts[n]) + nb].numpy())
