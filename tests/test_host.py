@@ -382,3 +382,118 @@ def test_culling_model_packs_runs_like_the_table_builder():
             assert np.array_equal(rows.astype(np.float32), occ[lo:lo + W].numpy()), (order, n)
             nb = (W + 15) // 16
             assert np.allclose(bx, boxes[int(box_starts[n]):int(box_starts[n]) + nb].numpy())
+
+
+def test_demo_env_rules_on_plain_tensors():
+    """megastep_b200.envs: the game rules of the reference's Explorer (explorer.py:34-58) and Deathmatch
+    (deathmatch.py:54-80) on CPU tensors, against hand-worked cases."""
+    from megastep_b200 import envs
+    # --- Explorer: two envs; env 0 has lines of 3 and 2 texels, env 1 one line of 4 texels
+    line_starts = torch.tensor([0, 2], dtype=torch.int32)
+    tex_widths = torch.tensor([3, 2, 4], dtype=torch.int32)
+    tex_starts = torch.tensor([0, 3, 5], dtype=torch.int32)
+    indices = torch.tensor([[[0, 1, -1, 0]], [[0, 0, 0, -1]]], dtype=torch.int32)               # (N=2, A=1, R=4)
+    locations = torch.tensor([[[0., .99, float('nan'), 1.]], [[.3, .5, 1., float('nan')]]])
+    tex = envs.texel_indices(line_starts, tex_starts, tex_widths, indices, locations)
+    #   env 0: line 0 @0 -> texel 0; line 1 @.99 -> 3 + floor(1.98) = 4; miss; line 0 @1 -> floor(3) clamped to 2
+    #   env 1: global line 2 @.3 -> 5 + 1; @.5 -> 5 + 2; @1 -> clamped to 5 + 3; miss
+    assert tex.tolist() == [[[0, 4, -1, 2]], [[6, 7, 8, -1]]]
+    texel_env = torch.tensor([0, 0, 0, 0, 0, 1, 1, 1, 1])
+    led = envs.ExplorationLedger(texel_env, n_envs=2, rays_per_obs=4)
+    r = led.reward(tex, reset=torch.tensor([False, False]))
+    assert r.tolist() == [3 / 4, 3 / 4] and led.potential.tolist() == [3., 3.]
+    r = led.reward(tex, reset=torch.tensor([False, False]))                                      # nothing new
+    assert r.tolist() == [0., 0.]
+    more = torch.tensor([[[1, 4, -1, 2]], [[5, 7, 8, -1]]])
+    r = led.reward(more, reset=torch.tensor([False, True]))                                      # env 1's reward is void
+    assert r.tolist() == [1 / 4, 0.] and led.potential.tolist() == [4., 4.]
+    led.forget(torch.tensor([True, False]))
+    assert led.potential.tolist() == [0., 4.] and led.seen.tolist() == [False] * 5 + [True] * 4
+    # --- Deathmatch: 1 env, 3 agents, 8 rays pooled by 2 -> 4 pixels; the two middle pixels are the crosshairs
+    F = 8
+    lines = torch.full((1, 3, 1, 8), 40, dtype=torch.int32)                                      # a wall (line 40 >= 3 * F)
+    lines[0, 0, 0, 2:6] = 1 * F + 3            # agent 0 has agent 1 across the middle of its view
+    lines[0, 1, 0, 0:2] = 2 * F                # agent 1 sees agent 2 at the edge only
+    lines[0, 2, 0, 4:6] = 0 * F + 7            # agent 2 has agent 0 in the right middle pixel
+    lines[0, 2, 0, 7] = -1
+    opp = envs.seen_agents(lines, n_model=F, n_agents=3, subsample=2)
+    assert opp.shape == (1, 3, 1, 4)
+    assert opp[0, :, 0].tolist() == [[-1, 1, 1, -1], [2, -1, -1, -1], [-1, -1, 0, -1]]
+    matchings, hits, wounds = envs.shots(opp, 3)
+    assert matchings[0].tolist() == [[False, True, False], [False, False, False], [True, False, False]]
+    assert hits[0].tolist() == [1., 0., 1.] and wounds[0].tolist() == [1., 1., 0.]
+
+
+def test_demo_envs_wiring_on_a_fake_core(monkeypatch):
+    """Explorer / Deathmatch end to end on CPU: the Core, the scenery upload, physics and render are faked (they need a
+    GPU), everything else — observation modules, spawns, ledger, shooting, the reset/step protocol — is the real thing."""
+    from megastep_b200 import envs, modules, scene, toys
+    from megastep_b200.arrdict import arrdict
+
+    class FakeScenery:
+        def __init__(self, geometries, n_agents):
+            a = scene.scene_arrays(geometries, n_agents, np.random.RandomState(0))
+            self.n_agents = n_agents
+            self.lines = cuda.Ragged3D(torch.as_tensor(a['lines']), torch.as_tensor(a['line_widths']))
+            self.textures = cuda.Ragged2D(torch.as_tensor(a['textures']), torch.as_tensor(a['tex_widths']))
+            self.model = torch.as_tensor(a['model'])
+
+    class FakeCore:
+        def __init__(self, scenery, res=64, fov=130, fps=10):
+            self.scenery, self.res, self.fov, self.fps = scenery, res, fov, fps
+            self.n_envs, self.n_agents = len(scenery.lines), scenery.n_agents
+            self.device = torch.device('cpu')
+            self.agent_radius = .1
+            self.random = np.random.RandomState(1)
+            z = lambda *s: torch.zeros((self.n_envs, self.n_agents, *s))
+            self.agents = arrdict(angles=z(), positions=z(2), angvelocity=z(), velocity=z(2))
+
+        def env_full(self, x):
+            return torch.full((self.n_envs,), x)
+
+        def agent_full(self, x):
+            return torch.full((self.n_envs, self.n_agents), x)
+
+        def state(self, e):
+            return arrdict(n_envs=torch.tensor(self.n_envs))
+
+    rng = np.random.RandomState(3)
+
+    def fake_render(core):
+        N, A, R = core.n_envs, core.n_agents, core.res
+        L = int(core.scenery.lines.widths.min())
+        idx = torch.as_tensor(rng.randint(-1, L, (N, A, 1, R)).astype(np.int32))
+        loc = torch.as_tensor(rng.rand(N, A, 1, R).astype(np.float32))
+        loc[idx < 0] = float('nan')
+        dist = torch.as_tensor(rng.uniform(.2, 12., (N, A, 1, R)).astype(np.float32))
+        return arrdict(indices=idx, locations=loc, dots=torch.zeros(N, A, 1, R), distances=dist,
+                       screen=torch.as_tensor(rng.rand(N, A, 3, 1, R).astype(np.float32)))
+
+    monkeypatch.setattr(envs.scene, 'scenery', FakeScenery)
+    monkeypatch.setattr(envs.core_, 'Core', FakeCore)
+    monkeypatch.setattr(modules, '_physics', lambda core: None)
+    monkeypatch.setattr(modules, 'render', fake_render)
+    gs = [toys.box()] * 3
+
+    env = envs.Explorer(gs)
+    out = env.reset()
+    assert out.obs.rgb.shape == (3, 1, 3, 1, 64) and out.obs.d.shape == (3, 1, 1, 1, 64) and out.obs.imu.shape == (3, 1, 3)
+    assert out.reset.all() and (out.reward == 0).all()
+    total = torch.zeros(3)
+    for _ in range(4):
+        out = env.step(arrdict(actions=torch.as_tensor(rng.randint(0, 7, (3, 1)))))
+        assert out.reward.shape == (3,) and (out.reward >= 0).all() and not out.reset.any()
+        total += out.reward
+    assert (total > 0).all() and (total * 64 <= env._ledger.potential + 1e-3).all()      # rewards are new texels / 64 pooled rays
+    assert env.state(1).seen.dtype == torch.bool and int(env.state(1).length) == 4
+
+    dm = envs.Deathmatch(gs, 2)
+    out = dm.reset()
+    assert dm.n_envs == 6 and out.obs.rgb.shape == (6, 1, 3, 1, 128) and out.obs.health.shape == (6, 1, 1)
+    assert out.reset.shape == (6,) and out.reset.all() and out.reward.shape == (6,)
+    for _ in range(3):
+        out = dm.step(arrdict(actions=torch.as_tensor(rng.randint(0, 7, (6, 1)))))
+        assert out.obs.imu.shape == (6, 1, 3) and out.reward.shape == (6,) and torch.isfinite(out.obs.health).all()
+    assert (dm._health <= 1).all() and dm.matchings.shape == (3, 2, 2)
+    # health only ever drops between respawns: by 0.001 per step plus 0.05 per wound
+    assert (dm._health < 1).all()
