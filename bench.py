@@ -253,52 +253,38 @@ class Ours:
 
 
 class Reference:
-    """The reference's own CUDA build through its own API, with the PyTorch ops of its modules.py around it
-    (modules.py:106-118 MomentumMovement, :126-136 render, :181-184 Depth, :222-224 RGB, :268-270 IMU)."""
+    """The reference's own CUDA build (oracle/_ref/megastepcuda*.so) driven by the reference's own, unmodified Python
+    (oracle/_ref/site/megastep: core.Core, modules.MomentumMovement :106-118, modules.render :126-136, Depth :170-184,
+    RGB :211-224, IMU :263-270) — through tests/common.py::reference_package, the same shim the parity tests use.
+    Nothing of this repository's library is on that path (it is not even loaded into the process)."""
     name = 'reference'
 
     def __init__(self, cfg, arrays, pos, ang, device, raw):
         import torch
         import common
         self.torch = torch
-        self.ref = common.reference_module()
-        if self.ref is None:
+        pkg = common.reference_package()
+        if pkg is None:
             raise RuntimeError('oracle/_ref is not built')
-        ref = self.ref
-        ref.initialize(AGENT_RADIUS, cfg['res'], cfg['fov'], FPS)
-        self.scenery = common.reference_scenery(ref, arrays, device)
-        ref.bake(self.scenery)
+        self.pkg = pkg
+        scenery = common.reference_scenery(pkg.cuda, arrays, device)
+        self.core = pkg.core.Core(scenery, res=cfg['res'], fov=cfg['fov'], fps=FPS)     # -> cuda.initialize (core.py:86)
+        pkg.cuda.bake(scenery)
+        self.core.agents.positions.copy_(torch.as_tensor(pos))
+        self.core.agents.angles.copy_(torch.as_tensor(ang))
+        m = pkg.modules
+        self.mover, self.rgb, self.depth, self.imu = (m.MomentumMovement(self.core), m.RGB(self.core, subsample=cfg['subsample']),
+                                                      m.Depth(self.core, subsample=cfg['subsample']), m.IMU(self.core))
         N, A = pos.shape[:2]
-        z = lambda *s: torch.zeros(s, device=device)
-        self.agents = ref.Agents(angles=torch.as_tensor(ang).to(device), positions=torch.as_tensor(pos).to(device),
-                                 angvelocity=z(N, A), velocity=z(N, A, 2))
         self.actions = torch.zeros((N, A), dtype=torch.int32, device=device)
-        vel = torch.tensor([[0., 0.], [0., 1.], [0., -1.], [1., 0.], [-1., 0.], [0., 0.], [0., 0.]], device=device)
-        angv = torch.tensor([0., 0., 0., 0., 0., +1., -1.], device=device)
-        self.set_v, self.set_w = 5 / FPS * vel, 180 / FPS * angv
-        self.sub = cfg['subsample']
+        self.decision = pkg.arrdict.arrdict(actions=self.actions)
         self.fused = False
         self._p = self._obs = None
 
     def step(self):
-        torch, ag = self.torch, self.agents
-        a = self.actions.long()
-        dv, dw = self.set_v[a], self.set_w[a]
-        ag.angvelocity[:] = (1 - .125) * ag.angvelocity + dw
-        rad = np.pi / 180 * ag.angles
-        c, s = torch.cos(rad), torch.sin(rad)
-        ag.velocity[:] = (1 - .125) * ag.velocity + torch.stack([c * dv[..., 0] - s * dv[..., 1], s * dv[..., 0] + c * dv[..., 1]], -1)
-        self._p = self.ref.physics(self.scenery, ag)
-        r = self.ref.render(self.scenery, ag)
-        screen = r.screen.unsqueeze(2).permute(0, 1, 4, 2, 3)
-        dist = r.distances.unsqueeze(2)
-        depth = 1 - ((dist - AGENT_RADIUS) / 10).clamp(0, 1)
-        ds = lambda x: x.view(*x.shape[:-1], x.shape[-1] // self.sub, self.sub).mean(-1)
-        rad = np.pi / 180 * ag.angles
-        c, s = torch.cos(rad), torch.sin(rad)
-        vx, vy = ag.velocity[..., 0], ag.velocity[..., 1]
-        imu = torch.cat([ag.angvelocity[..., None] / 360., torch.stack([c * vx + s * vy, -s * vx + c * vy], -1) / 10.], -1)
-        self._obs = {'rgb': ds(screen), 'd': ds(depth).unsqueeze(3), 'imu': imu}
+        self._p = self.mover(self.decision)
+        r = self.pkg.modules.render(self.core)
+        self._obs = {'rgb': self.rgb(r), 'd': self.depth(r), 'imu': self.imu()}
 
     def result(self):
         return self._p.progress
@@ -424,7 +410,8 @@ def peaks():
 
 
 def main():
-    os.environ['NCCL_DEBUG'] = 'WARN'      # NCCL's version banner would otherwise land on stdout next to the JSON line
+    # NCCL's own log lines (rank / channel banner under NCCL_DEBUG=INFO) stay as the launcher set them; the JSON line is
+    # the LAST line rank 0 prints, after the process group is gone
     args = parse()
     cfg = dict(WORKLOADS[args.workload])
     if args.res:
@@ -508,7 +495,9 @@ def main():
         'data': 'synthetic', 'config': base_cfg, 'impl': args.impl,
         'e2e': {'value': e2e, 'unit': 'agent-frames/s', 'h2d_bytes_per_step': out['N'] * out['A'] * 4,
                 'd2h_bytes_per_step': out['N'] * out['A'] * 4, 'ms_per_step': out['e2e_ms'] / K,
-                'what': 'pinned-host actions -> H2D -> step via the public API (modules.FusedStep' + ('.step_host: one foreign call per tick around a CUDA graph captured inside the library' if getattr(out.get('arm'), 'host_graph', False) else ', CUDA-graph replay' if getattr(out.get('arm'), 'graphed', False) else '') + ') -> D2H of progress (the physics result) + stream sync, every step; observations stay on the device as in the reference'},
+                'what': ('pinned-host actions -> H2D -> the reference\'s own modules.MomentumMovement / render / RGB / Depth / IMU on its own CUDA build' if reference else
+                         'pinned-host actions -> H2D -> step via the public API (modules.FusedStep' + ('.step_host: one foreign call per tick around a CUDA graph captured inside the library' if getattr(out.get('arm'), 'host_graph', False) else ', CUDA-graph replay' if getattr(out.get('arm'), 'graphed', False) else '') + ')')
+                        + ' -> D2H of progress (the physics result) + stream sync, every step; observations (33 MB/step at the default workload) stay on the device in both arms, as the reference\'s policy networks consume them there'},
         'gpu_launches': out['launches'],
         'roofline': roofline,
         'clocks': out['clocks'],
@@ -519,10 +508,13 @@ def main():
                                 'sample': 'the reference\'s own CUDA build (oracle/_ref) on one B200 of this box: megastep has no CPU step path'}
     elif not args.no_cpu_baseline and world == 1:                # rank 0 at N = 1 only (torchrun pins OMP_NUM_THREADS=1)
         line['cpu_baseline'] = cpu_baseline(cfg, out['arrays'], out['pos'], out['ang'])
-    print(json.dumps(line))
     if world > 1 and not reference:
         import torch.distributed as dist
         dist.destroy_process_group()
+        time.sleep(1.)                      # let the other ranks' NCCL teardown lines (NCCL_DEBUG=INFO) drain first
+    sys.stdout.flush()
+    sys.stdout.write('\n' + json.dumps(line) + '\n')      # the LAST line of stdout, on a line of its own
+    sys.stdout.flush()
 
 
 if __name__ == '__main__':

@@ -13,7 +13,7 @@ import importlib
 __version__ = '0.1.0'
 
 _SUBMODULES = ('cuda', 'core', 'ragged', 'modules', 'spaces', 'scene', 'toys', 'geometry', 'synthetic', 'sharding',
-               'arrdict', 'dotdict', 'build')
+               'arrdict', 'dotdict', 'build', 'envs', 'cubicasa', 'constants')
 
 
 def __getattr__(name):

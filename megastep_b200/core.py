@@ -10,20 +10,7 @@ from . import cuda
 from .arrdict import clone
 from .dotdict import dotdict
 
-AGENT_WIDTH = .15
-TEXTURE_RES = .05
-# radius of the disc containing the agent: collision radius and near camera plane
-AGENT_RADIUS = 1 / 2 ** .5 * AGENT_WIDTH
-
-
-def gamma_encode(x):
-    """linear -> viewable RGB"""
-    return x ** (1 / 2.2)
-
-
-def gamma_decode(x):
-    """viewable -> linear (interpolatable) RGB"""
-    return x ** 2.2
+from .constants import AGENT_RADIUS, AGENT_WIDTH, TEXTURE_RES, gamma_decode, gamma_encode  # noqa: F401  (core.py:10-22)
 
 
 def _init_agents(n_envs, n_agents, device='cuda'):

@@ -67,7 +67,8 @@ class Explorer:
     """One agent per env, rewarded for every texel of wall it sees for the first time (explorer.py:8-107)."""
 
     def __init__(self, geometries, *args, **kwargs):
-        """`geometries`: a list of geometries (`cubicasa.sample(n)` in the reference, `synthetic.sample(n)` here)."""
+        """`geometries`: a list of geometries (`cubicasa.sample(n)` in the reference; here e.g.
+        `synthetic.sample(n, with_masks=True)` — without the masks, spawn points are drawn inside the room rectangles)."""
         s = scene.scenery(geometries, 1)
         self.core = core_.Core(s, *args, res=4 * 64, fov=130, **kwargs)
         self._rgb = modules.RGB(self.core, n_agents=1, subsample=4)
@@ -140,6 +141,14 @@ def seen_agents(indices, n_model, n_agents, subsample):
     return torch.where((lines >= 0) & (agent < n_agents), agent, torch.full_like(lines, -1)).long()
 
 
+def _extent(g):
+    """(height, width) of the geometry's mask grid in metres (deathmatch.py:44); from the walls when there is no grid."""
+    if 'masks' in g:
+        return np.asarray(g.masks.shape) * g.res
+    from . import geometry
+    return np.asarray(geometry.mask_shape(np.asarray(g.walls, dtype=float))) * g.res
+
+
 class Deathmatch:
     """Several agents per env shooting at whoever is in their crosshairs (deathmatch.py:20-119). The env is flattened
     to `n_envs * n_agents` single-agent environments at the interface, as in the reference."""
@@ -154,7 +163,7 @@ class Deathmatch:
         self._spawner = modules.RandomSpawns(geometries, self.core)
         self.action_space = self._movement.space
         self.obs_space = dotdict(rgb=self._rgb.space, d=self._depth.space, imu=self._imu.space, health=spaces.MultiVector(1, 1))
-        self._bounds = torchify(np.stack([np.asarray(g.masks.shape) * g.res for g in geometries])).to(self.core.device)
+        self._bounds = torchify(np.stack([_extent(g) for g in geometries])).to(self.core.device)
         self._health = self.core.agent_full(np.nan)
         self._damage = self.core.agent_full(np.nan)
         self.n_envs = self.core.n_envs * self.core.n_agents

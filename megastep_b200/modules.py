@@ -293,6 +293,13 @@ def random_empty_positions(geometries, n_agents, n_points, random=np.random):
     """(n_geometries, n_agents, n_points, 2) random free-space points, in metres (modules.py:272-293)."""
     points = []
     for g in geometries:
+        if 'masks' not in g:
+            # a geometry without the rasterised free-space grid (synthetic.sample(n) builds it only on request): draw
+            # the points inside its room rectangles instead
+            from . import synthetic
+            pts = [synthetic.spawns([g], n_agents, random)[0][0] for _ in range(n_points)]
+            points.append(np.stack(pts, 1).astype(float))
+            continue
         free = np.stack((g.masks > 0).nonzero(), -1)
         n_possible = min(len(free) // n_agents, n_points)
         sample = free[random.choice(np.arange(len(free)), (n_possible, n_agents), replace=True)]

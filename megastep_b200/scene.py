@@ -5,9 +5,8 @@
 without a GPU; `scenery` uploads its result and bakes the static lighting.
 """
 import numpy as np
-import torch
 
-from . import core, cuda
+from . import constants as core      # (the CPU half must not load the native library: bench.py's reference arm builds scenes too)
 
 # ten bland wall colours (iwanthue), reference scene.py:10-20
 COLORS = ['#c185ae', '#73a171', '#5666a4', '#9f7c4a', '#809cd5', '#566e40', '#8e537b', '#4f9fa4', '#b56d66', '#5a728c']
@@ -105,6 +104,8 @@ def scene_arrays(geometries, n_agents=1, random=np.random):
 
 def upload(arrays, device='cuda'):
     """scene_arrays(...) -> cuda.Scenery on `device` (not yet baked)."""
+    import torch
+    from . import cuda
     t = lambda k, dtype: torch.as_tensor(arrays[k], dtype=dtype).contiguous().to(device)
     return cuda.Scenery(
         n_agents=arrays['n_agents'],
@@ -114,9 +115,9 @@ def upload(arrays, device='cuda'):
         model=t('model', torch.float32))
 
 
-@torch.no_grad()
 def scenery(geometries, n_agents=1, device='cuda', random=np.random):
     """Geometries -> baked `cuda.Scenery` (reference scene.py:75-100)."""
+    from . import cuda
     s = upload(scene_arrays(geometries, n_agents, random), device)
     cuda.bake(s, params=cuda.make_params(core.AGENT_RADIUS, 64, 130., 10.))   # bake uses no per-Core parameter
     return s

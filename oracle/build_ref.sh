@@ -17,6 +17,18 @@ if [ ! -f "$SRC/kernels.cu" ]; then
 fi
 mkdir -p "$OUT"
 PY=${PYTHON:-python}
+# The reference's PYTHON package (megastep/, rebar/), installed — not copied into the repo — next to the extension:
+# the parity tests and `bench.py --impl reference` drive the reference's own unmodified modules.py / core.py / scene.py
+# / demo envs through it (tests/common.py::reference_package). pip builds in the source tree, so install from a copy.
+if [ ! -f "$OUT/site/megastep/modules.py" ] || [ "$REF/megastep/modules.py" -nt "$OUT/site/megastep/modules.py" ]; then
+    TMP=$(mktemp -d)
+    cp -r "$REF" "$TMP/reference"
+    rm -rf "$OUT/site"
+    $PY -m pip install --quiet --no-index --no-build-isolation --no-deps --find-links /opt/wheelhouse \
+        --target "$OUT/site" "$TMP/reference" >/dev/null 2>&1 && echo "build_ref: installed the reference package into $OUT/site" \
+        || echo "build_ref: pip install of the reference package failed (tests that drive its Python will skip)" >&2
+    rm -rf "$TMP"
+fi
 TORCH_INC=$($PY - <<'EOF'
 import warnings, logging
 logging.disable(logging.CRITICAL)

@@ -113,3 +113,95 @@ def index_agreement(a, b, dist_a, dist_b, tol=2e-3):
         far = np.abs(da - db) > tol * np.maximum(1., np.minimum(np.abs(da), np.abs(db)))
     far |= np.isinf(da) != np.isinf(db)
     return float(diff.mean()), float((diff & far).mean())
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The reference's own PYTHON package as a checker: megastep/{core,modules,scene,ragged}.py and the demo
+# envs, unmodified, as pip-installed by oracle/build_ref.sh into oracle/_ref/site (git-ignored, travels to the GPU box),
+# running on the reference's own extension build (oracle/_ref/megastepcuda*.so). The package's __init__ (a JIT build
+# with -std=c++14 that torch >= 2 rejects) is bypassed; matplotlib / rasterio / shapely / bs4, absent from this image
+# and used by none of the code the checker runs, are stubbed.
+# ----------------------------------------------------------------------------------------------------------------------
+_REFPKG = None
+
+
+def _stub_absent_modules():
+    import sys
+    import types
+    from unittest import mock
+
+    def absent(name):
+        if name in sys.modules:
+            return False
+        try:
+            return importlib.util.find_spec(name) is None
+        except (ImportError, ValueError):
+            return True
+
+    if absent('matplotlib'):
+        from megastep_b200.scene import to_rgb               # '#rrggbb', 'g' / 'r', '.25': all reference scene.py asks of it
+        mpl = types.ModuleType('matplotlib')
+        mpl.__path__ = []
+        mpl.colors = types.ModuleType('matplotlib.colors')
+        mpl.colors.to_rgb = to_rgb
+        sys.modules['matplotlib'] = mpl
+        sys.modules['matplotlib.colors'] = mpl.colors
+        for sub in ('pyplot', 'tight_bbox', 'collections', 'patches', 'cm'):
+            m = mock.MagicMock(name=f'matplotlib.{sub}')
+            setattr(mpl, sub, m)
+            sys.modules[f'matplotlib.{sub}'] = m
+    stubs = {'rasterio': ('features', 'transform'), 'shapely': ('ops', 'geometry'), 'bs4': ()}
+    for top, subs in stubs.items():
+        if absent(top):
+            m = mock.MagicMock(name=top)
+            m.__path__ = []
+            sys.modules[top] = m
+            for sub in subs:
+                sys.modules[f'{top}.{sub}'] = getattr(m, sub)
+
+
+def reference_package():
+    """Namespace with the reference's own `core`, `modules`, `scene`, `ragged`, `spaces`, `cuda` (its extension) and
+    `envs` (explorer / deathmatch modules), or None when oracle/_ref (extension + site) is not built."""
+    global _REFPKG
+    if _REFPKG is not None:
+        return _REFPKG or None
+    import sys
+    import types
+    site = os.path.join(ROOT, 'oracle', '_ref', 'site')
+    ext = reference_module()
+    if ext is None or not os.path.exists(os.path.join(site, 'megastep', 'modules.py')):
+        _REFPKG = False
+        return None
+    _stub_absent_modules()
+    if site not in sys.path:
+        sys.path.insert(0, site)                               # for `rebar` (arrdict / dotdict)
+    pkg = types.ModuleType('megastep')
+    pkg.__path__ = [os.path.join(site, 'megastep')]            # submodules come from the installed reference ...
+    pkg.cuda = ext                                             # ... but `megastep.cuda` is the pre-built extension
+    sys.modules['megastep'] = pkg
+    sys.modules['megastep.cuda'] = ext
+    ns = types.SimpleNamespace(cuda=ext)
+    for name in ('ragged', 'core', 'spaces', 'scene', 'modules', 'cubicasa'):
+        setattr(ns, name, importlib.import_module(f'megastep.{name}'))
+    demo = types.ModuleType('megastep.demo')                   # (its __init__ pulls in the RL learner)
+    demo.__path__ = [os.path.join(site, 'megastep', 'demo')]
+    sys.modules['megastep.demo'] = demo
+    envs = types.ModuleType('megastep.demo.envs')
+    envs.__path__ = [os.path.join(site, 'megastep', 'demo', 'envs')]
+    sys.modules['megastep.demo.envs'] = envs
+    ns.explorer = importlib.import_module('megastep.demo.envs.explorer')
+    ns.deathmatch = importlib.import_module('megastep.demo.envs.deathmatch')
+    import rebar.arrdict
+    import rebar.dotdict
+    ns.arrdict, ns.dotdict = rebar.arrdict, rebar.dotdict
+    _REFPKG = ns
+    return ns
+
+
+def reference_core(pkg, arrays, st, res, fov, fps=10., device='cuda'):
+    """A reference `core.Core` (its own Python, its own extension) over the same scene arrays and agent state."""
+    s = reference_scenery(pkg.cuda, arrays, device)
+    c = pkg.core.Core(s, res=res, fov=fov, fps=fps)
+    load_state(c, st)
+    return c

@@ -143,7 +143,7 @@ def test_render_bit_exact_against_reference_build(ref, name, kind, N, A, res, fo
     assert torch.equal(c.scenery.lines.vals, rs.lines.vals)
 
 
-@pytest.mark.parametrize('name,kind,N,A,res,fov', CASES[:4])
+@pytest.mark.parametrize('name,kind,N,A,res,fov', CASES)
 def test_physics_bit_exact_against_reference_build(ref, name, kind, N, A, res, fov):
     if ref is None:
         pytest.skip('oracle/_ref not built (needs /root/reference at build time)')
