@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MSB_ABI_VERSION 4
+#define MSB_ABI_VERSION 5
 
 /* Replaces initialize(agent_radius, res, fov, fps) — megastep/src/wrappers.cpp:53, kernels.cu:18-27. */
 typedef struct msb_params {

@@ -30,6 +30,8 @@
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
+#include <atomic>
+#include <mutex>
 
 #include "../../include/megastep_b200.h"
 #include "msb_math.cuh"
@@ -73,6 +75,13 @@ struct KArgs {
     int32_t dyn_cap;            // entries that fit
     int32_t dyn_window;         // PS: pixels per entry = max(DYN_MIN_WINDOW, subsample); entry = DYN_HDR + 32 * PS bytes
     int* dyn_cache;             // [N][A][32] last occluder of each light as seen from (around) each agent; a hint
+    int32_t view_ctas;          // CTAs of the kernel that fills the queue (each signs off on dyn_ctrl[3] when it will publish no more)
+    // tick_kernel (the persistent form of view_kernel)
+    int* sched;                 // [0] envs handed out beyond every CTA's first p_stages, [1] CTAs out; null: envs are dealt round-robin
+    int32_t p_stages;           // S: envs staged per CTA at a time (ring of shared-memory stages)
+    int32_t p_stage_bytes;      // bytes of one stage
+    int32_t p_items;            // (agent, ray block) items per env = n_agents * ray_blocks
+    int32_t dyn_groups;         // merged second pass: warps (tickets) sharing one queue entry, each owning the lights i = g (mod groups)
 };
 
 #ifndef MSB_DYN_BLOCKS
@@ -699,7 +708,7 @@ __device__ __forceinline__ void shade_chunk(const KArgs& k, const VSmem& m, int 
                     if (queued && gmask && live) {
                         // the lights that are certainly unoccluded from the hit point's cell of the visibility grid
                         unsigned sure = 0;
-                        if (isdyn) {
+                        if (isdyn && !k.debug_no_vis) {
                             const int ix = __float2int_rd((Cx - __int_as_float(m.meta[8])) * VIS_INV_CELL);
                             const int iy = __float2int_rd((Cy - __int_as_float(m.meta[9])) * VIS_INV_CELL);
                             const int gx = m.meta[10], gy = m.meta[11];
@@ -1101,12 +1110,236 @@ __global__ void __launch_bounds__(MSB_VIEW_THREADS, MSB_VIEW_BLOCKS) view_kernel
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool occludes(const Hit h) { return (h.t > 0.f) && (h.t < 1.f) && (h.s > 0.f) && (h.s < .999f); }
 
+// One queue entry as every lane of a warp holds it after dyn_scan: the header's fields (warp-uniform), this lane's pixel
+// (lane < PS) and this lane's light (lane < nlights), plus what the scan found.
+struct DynEntry {
+    int n, sub, tgt, nlights, R0;      // env; pooling factor; hit agent; lights of the env (0: empty slot); agent * R + first ray
+    unsigned mask;                     // the window's agent-hit pixels
+    bool have, isdyn;                  // my pixel's records were filled in; my pixel hit an agent
+    float4 ra, rb;                     // my pixel: {texel rgb, 1 - dot^2}, {hit point, static intensity, bits vouched for by the grid}
+    float lx, ly, li;                  // my light
+    unsigned mylit;                    // lights (of this warp's share) with nothing between them and my pixel
+    float intensity;                   // my pixel's light when it does not come from `mylit` (static pixel; > 32 lights)
+};
+
+// Steps 1 and 2 of the second pass for one entry, by one warp that owns the lights i = part (mod parts). Leaves in
+// d.mylit the owned lights found unoccluded per pixel lane; with more than 32 lights part 0 alone computes d.intensity.
+template <bool STATS>
+__device__ __forceinline__ void dyn_scan(const KArgs& k, const unsigned char* e, int part, int parts, int lane, DynEntry& d,
+                                         unsigned& dyn_iters) {
+    const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
+    const int PS = k.dyn_window;
+    // (entries are read past L1: a neighbour's line fetched earlier by this SM may hold this entry's bytes from
+    // before they were written)
+    const int4 hdr = __ldcg(reinterpret_cast<const int4*>(e));
+    const int4 hdr1 = __ldcg(reinterpret_cast<const int4*>(e + 16));      // {W, lights, first light, first box} of the env
+    const float2 hdr2 = __ldcg(reinterpret_cast<const float2*>(e + 32));   // occ_meta of the env
+    const unsigned mask = (unsigned)hdr.z;                          // 0: slot reserved by a chunk that fell back inline
+    const int sub = hdr.w & 0xff, tgt = hdr.w >> 8;
+    const int n = hdr.x, ar = hdr.y;                       // env; agent * R + first ray of the window
+    const int r0 = ar % R;
+    const int gl = lane & ~(sub - 1);
+    const unsigned subm = sub == 32 ? 0xffffffffu : ((1u << sub) - 1u);
+    const unsigned gmask = lane < PS ? (mask >> gl) & subm : 0u;   // my pooling group's agent-hit pixels
+    const bool have = lane < PS && gmask != 0 && (r0 + lane < R);       // my pixel's records were filled in
+    const bool isdyn = lane < PS && ((mask >> lane) & 1u);
+    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (have) {
+        const float4* rec = reinterpret_cast<const float4*>(e + DYN_HDR) + 2 * lane;
+        ra = __ldcg(rec);
+        rb = __ldcg(rec + 1);
+    }
+    const float Cx = rb.x, Cy = rb.y;
+    const unsigned sure = (isdyn && !k.debug_no_vis) ? __float_as_uint(rb.w) : 0u;   // lights the visibility grid vouches for
+    const int W = hdr1.x, L = W + AF, nb = (W + VRUN - 1) / VRUN;
+    const int nlights = mask ? hdr1.y : 0;
+    const float* lt = k.s.lights + 3 * (int64_t)hdr1.z;
+    float intensity = rb.z;
+    unsigned mylit = 0;
+    float lx = 0.f, ly = 0.f, li = 0.f;
+    if (nlights > 32) {
+        // rare: more lights than lanes. Part 0 alone, one pixel at a time over the env's lines in their original order.
+        if (part == 0) {
+            const float4* seg = reinterpret_cast<const float4*>(k.s.lines) + __ldg(k.s.line_starts + n);
+            LaneLight ll;
+            ll.occ = -1;
+            ll.x = __ldg(lt + 3 * lane); ll.y = __ldg(lt + 3 * lane + 1); ll.i = __ldg(lt + 3 * lane + 2);
+            for (unsigned m = mask; m; m &= m - 1) {
+                const int p = __ffs(m) - 1;
+                const float cx = __shfl_sync(0xffffffffu, Cx, p), cy = __shfl_sync(0xffffffffu, Cy, p);
+                const float v = light_intensity_cached<STATS>(seg, L, AF, nlights, lt, cx, cy, lane, ll, dyn_iters);
+                if (lane == p) intensity = v;
+            }
+        }
+    } else if (nlights > 0) {
+        const int64_t b0 = hdr1.w;
+        const float4* occ = reinterpret_cast<const float4*>(k.s.occ_lines) + VRUN * b0;
+        const float4* boxes = reinterpret_cast<const float4*>(k.s.occ_boxes) + b0;
+        const float vmax = hdr2.x, diam = hdr2.y;
+        // lights one per lane, each with the occluder remembered for this (env, agent that was hit)
+        int* cache = k.dyn_cache + ((size_t)n * A + (tgt < A ? tgt : 0)) * 32;
+        int hint = cache[lane];
+        if (lane < nlights) { lx = __ldg(lt + 3 * lane); ly = __ldg(lt + 3 * lane + 1); li = __ldg(lt + 3 * lane + 2); }
+        const int hint_before = hint;
+        const unsigned resident = nlights == 32 ? 0xffffffffu : ((1u << nlights) - 1u);
+        float4 bx0 = make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+        if (lane < nb) bx0 = __ldg(boxes + lane);
+        // 1. the remembered occluders (every warp, redundantly: one test per pixel)
+        const bool has_hint = lane < nlights && hint >= 0 && hint < W;
+        float4 hseg = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_hint) hseg = __ldg(occ + hint);
+        unsigned mytodo = 0;
+        for (unsigned m = mask; m; m &= m - 1) {
+            const int p = __ffs(m) - 1;
+            const float cx = __shfl_sync(0xffffffffu, Cx, p), cy = __shfl_sync(0xffffffffu, Cy, p);
+            bool ob = false;
+            if (has_hint) ob = occludes(intersect(lx, ly, fsub(cx, lx), fsub(cy, ly), hseg));
+            const unsigned todo = resident & ~__ballot_sync(0xffffffffu, ob);
+            if (lane == p) mytodo = todo & ~sure;
+        }
+        if (STATS) dyn_iters++;
+        // the box around the entry's hit points
+        float cx0 = isdyn ? Cx : CUDART_INF_F, cx1 = isdyn ? Cx : -CUDART_INF_F;
+        float cy0 = isdyn ? Cy : CUDART_INF_F, cy1 = isdyn ? Cy : -CUDART_INF_F;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cx0 = fminf(cx0, __shfl_xor_sync(0xffffffffu, cx0, o)); cx1 = fmaxf(cx1, __shfl_xor_sync(0xffffffffu, cx1, o));
+            cy0 = fminf(cy0, __shfl_xor_sync(0xffffffffu, cy0, o)); cy1 = fmaxf(cy1, __shfl_xor_sync(0xffffffffu, cy1, o));
+        }
+        // 2. scans, light by light; part w owns the lights i = w (mod parts). (Ownership must not depend on which lights
+        // still need a scan: the hints are shared with other warps and may change between two warps' reads.)
+        unsigned owned = 0x11111111u;                                   // parts = 4
+        if (parts == 1) owned = 0xffffffffu; else if (parts == 2) owned = 0x55555555u; else if (parts == 3) owned = 0x49249249u;
+        unsigned todo_any = __reduce_or_sync(0xffffffffu, isdyn ? mytodo : 0u) & (owned << part);
+        const int slot = lane / VRUN, within = lane - slot * VRUN;
+        while (todo_any) {
+            const int i = __ffs(todo_any) - 1;
+            todo_any &= todo_any - 1;
+            const float Ix = __shfl_sync(0xffffffffu, lx, i), Iy = __shfl_sync(0xffffffffu, ly, i);
+            unsigned need = __ballot_sync(0xffffffffu, isdyn && ((mytodo >> i) & 1u));
+            const unsigned iters0 = dyn_iters;
+            // conservative query (see DESIGN.md "shadow cull"): rounding can move the computed crossing by at most
+            // delta (a fraction of each segment's length) along either segment. A run can only hold an occluder if
+            // its box comes within mg (+ the spread of the hit points) of the segment from the light to the middle
+            // of the hit points: slab test of that segment against the grown box.
+            const float ulen = fmaxf(fmaxf(fabsf(cx0 - Ix), fabsf(cx1 - Ix)), fmaxf(fabsf(cy0 - Iy), fabsf(cy1 - Iy)));
+            const float delta = 4e-4f * vmax * (diam + ulen);
+            const float mg = delta * (ulen + vmax) + 0.01f + fmaxf(cx1 - cx0, cy1 - cy0);
+            const float mx_ = 0.5f * (cx0 + cx1) - Ix, my_ = 0.5f * (cy0 + cy1) - Iy;      // light -> middle of the hit points
+            const float irx = 1.f / mx_, iry = 1.f / my_;                                  // +-inf when axis-parallel
+            int found = -1;
+            for (int bb = 0; bb < nb && need; bb += 32) {
+                float4 bx = bx0;
+                if (bb) bx = (bb + lane < nb) ? __ldg(boxes + bb + lane) : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+                // parameters at which the segment is inside each slab of the grown box; NaN (0 * inf: the segment runs
+                // along a slab boundary) compares false below, i.e. errs on the side of visiting
+                const float tx0 = (bx.x - mg - Ix) * irx, tx1 = (bx.z + mg - Ix) * irx;
+                const float ty0 = (bx.y - mg - Iy) * iry, ty1 = (bx.w + mg - Iy) * iry;
+                const float tlo = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), 0.f);
+                const float thi = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), 1.f);
+                const bool visit = (bb + lane < nb) && !(tlo > thi);
+                unsigned runs = __ballot_sync(0xffffffffu, visit);
+                // lanes [0, 16) take the first run still to visit, lanes [16, 32) the second; the next pair's
+                // segments are requested before this pair's are tested (one L2 round trip per light, not per pair)
+                int l = W;
+                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (runs) {
+                    const unsigned rest = runs & (runs - 1);
+                    const int nth = slot == 0 ? __ffs(runs) - 1 : (rest ? __ffs(rest) - 1 : -1);
+                    l = nth >= 0 ? VRUN * (bb + nth) + within : W;
+                    if (l < W) s4 = __ldg(occ + l);
+                }
+                while (runs && need) {
+                    const unsigned rest = runs & (runs - 1);
+                    const unsigned after = rest & (rest - 1);
+                    int l_next = W;
+                    float4 s4_next = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (after) {
+                        const unsigned rest2 = after & (after - 1);
+                        const int nth = slot == 0 ? __ffs(after) - 1 : (rest2 ? __ffs(rest2) - 1 : -1);
+                        l_next = nth >= 0 ? VRUN * (bb + nth) + within : W;
+                        if (l_next < W) s4_next = __ldg(occ + l_next);
+                    }
+                    const bool real = l < W;
+                    float Vx = 0.f, Vy = 0.f, PQx = 0.f, PQy = 0.f, snum = 0.f;
+                    if (real) {
+                        Vx = fsub(s4.z, s4.x); Vy = fsub(s4.w, s4.y);
+                        PQx = fsub(s4.x, Ix); PQy = fsub(s4.y, Iy);
+                        snum = cross2(Vy, PQx, Vx, PQy);
+                    }
+                    for (unsigned q = need; q; q &= q - 1) {
+                        const int p = __ffs(q) - 1;
+                        const float ux = fsub(__shfl_sync(0xffffffffu, Cx, p), Ix), uy = fsub(__shfl_sync(0xffffffffu, Cy, p), Iy);
+                        const bool o = real && occludes(intersect_pre(ux, uy, Vx, Vy, PQx, PQy, snum));
+                        const unsigned bal = __ballot_sync(0xffffffffu, o);
+                        if (bal) { need &= ~(1u << p); found = __shfl_sync(0xffffffffu, l, __ffs(bal) - 1); }
+                    }
+                    if (STATS) dyn_iters++;
+                    runs = after; l = l_next; s4 = s4_next;
+                }
+            }
+            if (found >= 0 && lane == i) hint = found;
+            if ((need >> lane) & 1u) mylit |= 1u << i;         // nothing in the way of light i for my pixel
+            if (STATS && k.stats && lane == 0) {
+                atomicAdd(k.stats + STAT_DYN_SCANS, 1ull);
+                if (need) { atomicAdd(k.stats + STAT_DYN_SCANS_LIT, 1ull); atomicAdd(k.stats + STAT_DYN_ITERS_LIT, (unsigned long long)(dyn_iters - iters0)); }
+            }
+        }
+        if (hint != hint_before) cache[lane] = hint;   // racy on purpose: any stored value is only a hint
+    }
+    d.n = n; d.sub = sub; d.tgt = tgt; d.nlights = nlights; d.R0 = ar; d.mask = mask;
+    d.have = have; d.isdyn = isdyn; d.ra = ra; d.rb = rb; d.lx = lx; d.ly = ly; d.li = li;
+    d.mylit = mylit; d.intensity = intensity;
+}
+
+// Step 3 of the second pass, lane = pixel: the unoccluded lights (`lit`: every part's finds plus what the visibility grid
+// vouches for) summed in light order (kernels.cu:261-264), then the pixel's screen value and its pooled RGB.
+__device__ __forceinline__ void dyn_finish(const KArgs& k, const DynEntry& d, unsigned lit_mine, int lane) {
+    const int A = k.s.n_agents, R = k.p.res;
+    const int av = d.R0 / R, r0 = d.R0 - av * R;
+    const int64_t ag = (int64_t)d.n * A + av;
+    const int sub = d.sub, gl = lane & ~(sub - 1);
+    float intensity = d.intensity;
+    if (d.nlights <= 32) {
+        const float Cx = d.rb.x, Cy = d.rb.y;
+        float acc = 0.1f;                                  // AMBIENT (kernels.cu:9)
+        for (unsigned lit = __reduce_or_sync(0xffffffffu, lit_mine); lit; lit &= lit - 1) {
+            const int i = __ffs(lit) - 1;
+            const float Ix = __shfl_sync(0xffffffffu, d.lx, i), Iy = __shfl_sync(0xffffffffu, d.ly, i);
+            const float Ii = __shfl_sync(0xffffffffu, d.li, i);
+            if ((lit_mine >> i) & 1u) {
+                const float dx = fsub(Ix, Cx), dy = fsub(Iy, Cy);
+                acc = ffma(fadd(Ii, Ii), rcp(fmaxf(ffma(dx, dx, fmul(dy, dy)), 1.f)), acc);   // LUMINANCE = 2 (:240)
+            }
+        }
+        if (d.isdyn) intensity = fminf(acc, 1.f);
+    }
+    const float kk = fmul(d.ra.w, intensity);
+    const float s0 = fmul(kk, d.ra.x), s1 = fmul(kk, d.ra.y), s2 = fmul(kk, d.ra.z);
+    if (k.out.screen && d.isdyn) {
+        float* sc = k.out.screen + 3 * (ag * R + r0 + lane);
+        sc[0] = s0; sc[1] = s1; sc[2] = s2;
+    }
+    if (k.has_obs && k.obs.rgb) {
+        float v0 = d.have ? s0 : 0.f, v1 = d.have ? s1 : 0.f, v2 = d.have ? s2 : 0.f;
+        for (int o = 1; o < sub; o <<= 1) {
+            v0 = __fadd_rn(v0, __shfl_xor_sync(0xffffffffu, v0, o));
+            v1 = __fadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+            v2 = __fadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
+        }
+        if (d.have && lane == gl) {
+            const int Ro = R >> k.sub_shift, ro = (r0 + lane) >> k.sub_shift;
+            float* q = k.obs.rgb + ag * 3 * Ro + ro;
+            q[0] = __fmul_rn(v0, k.inv_sub); q[Ro] = __fmul_rn(v1, k.inv_sub); q[2 * Ro] = __fmul_rn(v2, k.inv_sub);
+        }
+    }
+}
+
 template <bool STATS>
 __global__ void __launch_bounds__(128, MSB_DYN_BLOCKS) dyn_kernel(const __grid_constant__ KArgs k) {
     __shared__ unsigned s_lit[4][32];                          // per warp: the lights it found unoccluded, per pixel lane
     __shared__ int s_next, s_ready;                            // the CTA's next entry; whether the current one was published
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
-    const int A = k.s.n_agents, AF = A * k.s.n_model, R = k.p.res;
     unsigned dyn_rays = 0, dyn_iters = 0, dyn_entries = 0;
     // One entry per CTA at a time (every entry is an independent unit of work). The CTA's warps split the entry's LIGHTS
     // between them: the kernel lasts as long as its slowest entry (an agent in a large open room: ~20 lights to scan one
@@ -1130,7 +1363,7 @@ __global__ void __launch_bounds__(128, MSB_DYN_BLOCKS) dyn_kernel(const __grid_c
             int ready = *flag;
             bool over = false;
             for (unsigned spins = 0; !ready && !over && spins < (1u << 17); spins++) {
-                if (*done >= k.s.n_envs) { __threadfence(); ready = *flag; over = true; break; }
+                if (*done >= k.view_ctas) { __threadfence(); ready = *flag; over = true; break; }
                 __nanosleep(100);
                 ready = *flag;
             }
@@ -1149,206 +1382,19 @@ __global__ void __launch_bounds__(128, MSB_DYN_BLOCKS) dyn_kernel(const __grid_c
         }
         __syncthreads();
         if (!s_ready) break;
-        // (entries are read past L1: a neighbour's line fetched earlier by this SM may hold this entry's bytes from
-        // before they were written)
-        const int4 hdr = __ldcg(reinterpret_cast<const int4*>(e));
-        const int4 hdr1 = __ldcg(reinterpret_cast<const int4*>(e + 16));      // {W, lights, first light, first box} of the env
-        const float2 hdr2 = __ldcg(reinterpret_cast<const float2*>(e + 32));   // occ_meta of the env
-        const unsigned mask = (unsigned)hdr.z;                          // 0: slot reserved by a chunk that fell back inline
-        const int sub = hdr.w & 0xff, tgt = hdr.w >> 8;
-        const int n = hdr.x, ar = hdr.y;                       // env; agent * R + first ray of the window
-        const int av = ar / R, r0 = ar - av * R;
-        const int64_t ag = (int64_t)n * A + av;
-        const int gl = lane & ~(sub - 1);
-        const unsigned subm = sub == 32 ? 0xffffffffu : ((1u << sub) - 1u);
-        const unsigned gmask = lane < PS ? (mask >> gl) & subm : 0u;   // my pooling group's agent-hit pixels
-        const bool have = lane < PS && gmask != 0 && (r0 + lane < R);       // my pixel's records were filled in
-        const bool isdyn = lane < PS && ((mask >> lane) & 1u);
-        float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (have) {
-            const float4* rec = reinterpret_cast<const float4*>(e + DYN_HDR) + 2 * lane;
-            ra = __ldcg(rec);
-            rb = __ldcg(rec + 1);
-        }
-        const float Cx = rb.x, Cy = rb.y;
-        const unsigned sure = (isdyn && !k.debug_no_vis) ? __float_as_uint(rb.w) : 0u;   // lights the visibility grid vouches for
-        const int W = hdr1.x, L = W + AF, nb = (W + VRUN - 1) / VRUN;
-        const int nlights = mask ? hdr1.y : 0;
-        const float* lt = k.s.lights + 3 * (int64_t)hdr1.z;
-        float intensity = rb.z;
-        if (STATS && warp == 0 && mask) { dyn_rays += __popc(mask); dyn_entries++; }
-        unsigned mylit = 0;
-        float lx = 0.f, ly = 0.f, li = 0.f;
-        if (nlights > 32) {
-            // rare: more lights than lanes. Warp 0 alone, one pixel at a time over the env's lines in their original order.
-            if (warp == 0) {
-                const float4* seg = reinterpret_cast<const float4*>(k.s.lines) + __ldg(k.s.line_starts + n);
-                LaneLight ll;
-                ll.occ = -1;
-                ll.x = __ldg(lt + 3 * lane); ll.y = __ldg(lt + 3 * lane + 1); ll.i = __ldg(lt + 3 * lane + 2);
-                for (unsigned m = mask; m; m &= m - 1) {
-                    const int p = __ffs(m) - 1;
-                    const float cx = __shfl_sync(0xffffffffu, Cx, p), cy = __shfl_sync(0xffffffffu, Cy, p);
-                    const float v = light_intensity_cached<STATS>(seg, L, AF, nlights, lt, cx, cy, lane, ll, dyn_iters);
-                    if (lane == p) intensity = v;
-                }
-            }
-        } else {
-            const int64_t b0 = hdr1.w;
-            const float4* occ = reinterpret_cast<const float4*>(k.s.occ_lines) + VRUN * b0;
-            const float4* boxes = reinterpret_cast<const float4*>(k.s.occ_boxes) + b0;
-            const float vmax = hdr2.x, diam = hdr2.y;
-            // lights one per lane, each with the occluder remembered for this (env, agent that was hit)
-            int* cache = k.dyn_cache + ((size_t)n * A + (tgt < A ? tgt : 0)) * 32;
-            int hint = mask ? cache[lane] : -1;
-            if (lane < nlights) { lx = __ldg(lt + 3 * lane); ly = __ldg(lt + 3 * lane + 1); li = __ldg(lt + 3 * lane + 2); }
-            const int hint_before = hint;
-            const unsigned resident = nlights == 32 ? 0xffffffffu : ((1u << nlights) - 1u);
-            float4 bx0 = make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-            if (lane < nb) bx0 = __ldg(boxes + lane);
-            // 1. the remembered occluders (every warp, redundantly: one test per pixel)
-            const bool has_hint = lane < nlights && hint >= 0 && hint < W;
-            float4 hseg = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_hint) hseg = __ldg(occ + hint);
-            unsigned mytodo = 0;
-            for (unsigned m = mask; m; m &= m - 1) {
-                const int p = __ffs(m) - 1;
-                const float cx = __shfl_sync(0xffffffffu, Cx, p), cy = __shfl_sync(0xffffffffu, Cy, p);
-                bool ob = false;
-                if (has_hint) ob = occludes(intersect(lx, ly, fsub(cx, lx), fsub(cy, ly), hseg));
-                const unsigned todo = resident & ~__ballot_sync(0xffffffffu, ob);
-                if (lane == p) mytodo = todo & ~sure;
-            }
-            if (STATS) dyn_iters++;
-            // the box around the entry's hit points
-            float cx0 = isdyn ? Cx : CUDART_INF_F, cx1 = isdyn ? Cx : -CUDART_INF_F;
-            float cy0 = isdyn ? Cy : CUDART_INF_F, cy1 = isdyn ? Cy : -CUDART_INF_F;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                cx0 = fminf(cx0, __shfl_xor_sync(0xffffffffu, cx0, o)); cx1 = fmaxf(cx1, __shfl_xor_sync(0xffffffffu, cx1, o));
-                cy0 = fminf(cy0, __shfl_xor_sync(0xffffffffu, cy0, o)); cy1 = fmaxf(cy1, __shfl_xor_sync(0xffffffffu, cy1, o));
-            }
-            // 2. scans, light by light; warp w owns the lights i = w (mod NW). (Ownership must not depend on which lights
-            // still need a scan: the hints are shared with other CTAs and may change between two warps' reads.)
-            unsigned owned = 0x11111111u;                                   // NW = 4
-            if (NW == 1) owned = 0xffffffffu; else if (NW == 2) owned = 0x55555555u; else if (NW == 3) owned = 0x49249249u;
-            unsigned todo_any = __reduce_or_sync(0xffffffffu, isdyn ? mytodo : 0u) & (owned << warp);
-            const int slot = lane / VRUN, within = lane - slot * VRUN;
-            while (todo_any) {
-                const int i = __ffs(todo_any) - 1;
-                todo_any &= todo_any - 1;
-                const float Ix = __shfl_sync(0xffffffffu, lx, i), Iy = __shfl_sync(0xffffffffu, ly, i);
-                unsigned need = __ballot_sync(0xffffffffu, isdyn && ((mytodo >> i) & 1u));
-                const unsigned iters0 = dyn_iters;
-                // conservative query (see DESIGN.md "shadow cull"): rounding can move the computed crossing by at most
-                // delta (a fraction of each segment's length) along either segment. A run can only hold an occluder if
-                // its box comes within mg (+ the spread of the hit points) of the segment from the light to the middle
-                // of the hit points: slab test of that segment against the grown box.
-                const float ulen = fmaxf(fmaxf(fabsf(cx0 - Ix), fabsf(cx1 - Ix)), fmaxf(fabsf(cy0 - Iy), fabsf(cy1 - Iy)));
-                const float delta = 4e-4f * vmax * (diam + ulen);
-                const float mg = delta * (ulen + vmax) + 0.01f + fmaxf(cx1 - cx0, cy1 - cy0);
-                const float mx_ = 0.5f * (cx0 + cx1) - Ix, my_ = 0.5f * (cy0 + cy1) - Iy;      // light -> middle of the hit points
-                const float irx = 1.f / mx_, iry = 1.f / my_;                                  // +-inf when axis-parallel
-                int found = -1;
-                for (int bb = 0; bb < nb && need; bb += 32) {
-                    float4 bx = bx0;
-                    if (bb) bx = (bb + lane < nb) ? __ldg(boxes + bb + lane) : make_float4(CUDART_INF_F, CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-                    // parameters at which the segment is inside each slab of the grown box; NaN (0 * inf: the segment runs
-                    // along a slab boundary) compares false below, i.e. errs on the side of visiting
-                    const float tx0 = (bx.x - mg - Ix) * irx, tx1 = (bx.z + mg - Ix) * irx;
-                    const float ty0 = (bx.y - mg - Iy) * iry, ty1 = (bx.w + mg - Iy) * iry;
-                    const float tlo = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), 0.f);
-                    const float thi = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), 1.f);
-                    const bool visit = (bb + lane < nb) && !(tlo > thi);
-                    unsigned runs = __ballot_sync(0xffffffffu, visit);
-                    // lanes [0, 16) take the first run still to visit, lanes [16, 32) the second; the next pair's
-                    // segments are requested before this pair's are tested (one L2 round trip per light, not per pair)
-                    int l = W;
-                    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (runs) {
-                        const unsigned rest = runs & (runs - 1);
-                        const int nth = slot == 0 ? __ffs(runs) - 1 : (rest ? __ffs(rest) - 1 : -1);
-                        l = nth >= 0 ? VRUN * (bb + nth) + within : W;
-                        if (l < W) s4 = __ldg(occ + l);
-                    }
-                    while (runs && need) {
-                        const unsigned rest = runs & (runs - 1);
-                        const unsigned after = rest & (rest - 1);
-                        int l_next = W;
-                        float4 s4_next = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (after) {
-                            const unsigned rest2 = after & (after - 1);
-                            const int nth = slot == 0 ? __ffs(after) - 1 : (rest2 ? __ffs(rest2) - 1 : -1);
-                            l_next = nth >= 0 ? VRUN * (bb + nth) + within : W;
-                            if (l_next < W) s4_next = __ldg(occ + l_next);
-                        }
-                        const bool real = l < W;
-                        float Vx = 0.f, Vy = 0.f, PQx = 0.f, PQy = 0.f, snum = 0.f;
-                        if (real) {
-                            Vx = fsub(s4.z, s4.x); Vy = fsub(s4.w, s4.y);
-                            PQx = fsub(s4.x, Ix); PQy = fsub(s4.y, Iy);
-                            snum = cross2(Vy, PQx, Vx, PQy);
-                        }
-                        for (unsigned q = need; q; q &= q - 1) {
-                            const int p = __ffs(q) - 1;
-                            const float ux = fsub(__shfl_sync(0xffffffffu, Cx, p), Ix), uy = fsub(__shfl_sync(0xffffffffu, Cy, p), Iy);
-                            const bool o = real && occludes(intersect_pre(ux, uy, Vx, Vy, PQx, PQy, snum));
-                            const unsigned bal = __ballot_sync(0xffffffffu, o);
-                            if (bal) { need &= ~(1u << p); found = __shfl_sync(0xffffffffu, l, __ffs(bal) - 1); }
-                        }
-                        if (STATS) dyn_iters++;
-                        runs = after; l = l_next; s4 = s4_next;
-                    }
-                }
-                if (found >= 0 && lane == i) hint = found;
-                if ((need >> lane) & 1u) mylit |= 1u << i;         // nothing in the way of light i for my pixel
-                if (STATS && k.stats && lane == 0) {
-                    atomicAdd(k.stats + STAT_DYN_SCANS, 1ull);
-                    if (need) { atomicAdd(k.stats + STAT_DYN_SCANS_LIT, 1ull); atomicAdd(k.stats + STAT_DYN_ITERS_LIT, (unsigned long long)(dyn_iters - iters0)); }
-                }
-            }
-            if (mask && hint != hint_before) cache[lane] = hint;   // racy on purpose: any stored value is only a hint
-        }
-        s_lit[warp][lane] = mylit;
+        DynEntry d;
+        dyn_scan<STATS>(k, e, warp, NW, lane, d, dyn_iters);
+        if (STATS && warp == 0 && d.mask) { dyn_rays += __popc(d.mask); dyn_entries++; }
+        s_lit[warp][lane] = d.mylit;
         if (threadIdx.x == 0) s_next = nxt;
         __syncthreads();
         const int ei_next = s_next;
         if (warp == 0) {
-            if (nlights <= 32) {
-                // 3. lane = pixel: sum the unoccluded lights in light order (:261-264)
-                for (int w = 1; w < NW; w++) mylit |= s_lit[w][lane];
-                mylit |= sure & (nlights == 32 ? 0xffffffffu : ((1u << nlights) - 1u));
-                float acc = 0.1f;                                  // AMBIENT (kernels.cu:9)
-                for (unsigned lit = __reduce_or_sync(0xffffffffu, mylit); lit; lit &= lit - 1) {
-                    const int i = __ffs(lit) - 1;
-                    const float Ix = __shfl_sync(0xffffffffu, lx, i), Iy = __shfl_sync(0xffffffffu, ly, i);
-                    const float Ii = __shfl_sync(0xffffffffu, li, i);
-                    if ((mylit >> i) & 1u) {
-                        const float dx = fsub(Ix, Cx), dy = fsub(Iy, Cy);
-                        acc = ffma(fadd(Ii, Ii), rcp(fmaxf(ffma(dx, dx, fmul(dy, dy)), 1.f)), acc);   // LUMINANCE = 2 (:240)
-                    }
-                }
-                if (isdyn) intensity = fminf(acc, 1.f);
-            }
-            const float kk = fmul(ra.w, intensity);
-            const float s0 = fmul(kk, ra.x), s1 = fmul(kk, ra.y), s2 = fmul(kk, ra.z);
-            if (k.out.screen && isdyn) {
-                float* sc = k.out.screen + 3 * (ag * R + r0 + lane);
-                sc[0] = s0; sc[1] = s1; sc[2] = s2;
-            }
-            if (k.has_obs && k.obs.rgb) {
-                float v0 = have ? s0 : 0.f, v1 = have ? s1 : 0.f, v2 = have ? s2 : 0.f;
-                for (int o = 1; o < sub; o <<= 1) {
-                    v0 = __fadd_rn(v0, __shfl_xor_sync(0xffffffffu, v0, o));
-                    v1 = __fadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, o));
-                    v2 = __fadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
-                }
-                if (have && lane == gl) {
-                    const int Ro = R >> k.sub_shift, ro = (r0 + lane) >> k.sub_shift;
-                    float* q = k.obs.rgb + ag * 3 * Ro + ro;
-                    q[0] = __fmul_rn(v0, k.inv_sub); q[Ro] = __fmul_rn(v1, k.inv_sub); q[2 * Ro] = __fmul_rn(v2, k.inv_sub);
-                }
-            }
+            unsigned lit = d.mylit;
+            for (int w = 1; w < NW; w++) lit |= s_lit[w][lane];
+            const unsigned sure = (d.isdyn && !k.debug_no_vis) ? __float_as_uint(d.rb.w) : 0u;
+            lit |= sure & (d.nlights >= 32 ? 0xffffffffu : ((1u << d.nlights) - 1u));
+            dyn_finish(k, d, lit, lane);
         }
         __syncthreads();                                       // s_lit and s_next are reused by the next entry
         if (STATS && k.stats && threadIdx.x == 0) {
@@ -1376,6 +1422,336 @@ __global__ void __launch_bounds__(128, MSB_DYN_BLOCKS) dyn_kernel(const __grid_c
     if (threadIdx.x == 0) {
         __threadfence();
         if (atomicAdd(k.dyn_ctrl + 1, 1) == (int)gridDim.x - 1) { k.dyn_ctrl[0] = 0; k.dyn_ctrl[1] = 0; k.dyn_ctrl[2] = 0; k.dyn_ctrl[3] = 0; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tick_kernel: view_kernel as a persistent grid — one CTA per resident slot, looping over environments — with the
+// second pass (dyn_kernel's work) taken on by the same warps.
+//
+// Why: a one-shot CTA per env spends its first microseconds waiting (table copy, agent state, draw: three barriers) and
+// its last ones with most warps parked at the final barrier while the slowest (agent, ray block) item finishes, holding
+// registers and shared memory all the while (ncu, round 1: 25 % of the stall samples in 9 % of the instructions; stall
+// `barrier` 1.9 per issue; 15 % of the SM cycles idle in the grid's tail). Here
+//   * each CTA keeps a ring of S shared-memory STAGES, one env each. The warp that finishes the last item of the env in
+//     stage s refills it: takes the next env off a global counter (costliest first), starts the three bulk (TMA) copies
+//     of its table, loads and draws its agents, waits for the copies' mbarrier and publishes the stage — while the other
+//     warps are busy with the envs in the other stages. No CTA-wide barrier anywhere after the first;
+//   * items are handed out by one ticket counter per CTA, env after env: a warp that runs out of items of one env moves
+//     on to the next staged one instead of waiting for its siblings;
+//   * the queue of agent-hit pixel windows is drained by the same warps: every warp holds a TICKET for one (entry,
+//     light group) and looks at that entry's flag between two ray items — a published entry is lit right away by the
+//     `dyn_groups` warps holding its tickets (their finds OR-ed into the entry, the last one sums the lights and writes
+//     the pixels); once the rays are done the warps drain what is left. No second kernel, no tail of idle CTAs.
+// Results are those of view_kernel + dyn_kernel, bit for bit (same item code, same per-entry scan).
+// ---------------------------------------------------------------------------------------------------------------
+enum { PMAXS = 4, META_N = 16, META_G0 = 17, META_L = 19, META_PAR = 20, META_INTS = 24 };
+enum { SPIN_LIMIT = 1 << 22 };
+
+struct PCtl {
+    uint64_t full_bar[PMAXS];   // per stage: the bulk copies of its env's table have landed
+    int ready_seq[PMAXS];       // per stage: 1 + sequence number of the env staged and drawn there (0x7fffffff: none will come)
+    int done_cnt[PMAXS];        // per stage: items of its env finished
+    int fills[PMAXS];           // per stage: bulk-copy rounds so far (the mbarrier's phase)
+    int next_ticket;            // items handed out
+    int dead;                   // stages that will not be refilled
+    int rays_out;               // warps that have left the ray loop
+    int all_out;                // warps that have left the kernel
+    int mrad;                   // bits of the agent model's radius
+    int error;                  // a bounded wait ran out (a bug): results are void, nothing hangs
+    int pad[2];
+};
+
+__device__ __forceinline__ size_t pctl_bytes() { return (sizeof(PCtl) + 15) & ~size_t(15); }
+
+static size_t pstage_bytes(int wcap, int A, int AF, bool stage_rec) {
+    size_t b = (size_t)(AF + wcap) * 16 + (size_t)(wcap / VRUN) * 16 + (stage_rec ? (size_t)wcap * 16 : 0) +
+               (size_t)A * ST_STRIDE * 4 + (size_t)META_INTS * 4;
+    return (b + 15) & ~size_t(15);
+}
+
+__device__ __forceinline__ VSmem pstage(unsigned char* base, PCtl* ctl, const KArgs& k, int A, int AF) {
+    VSmem m;
+    m.seg = reinterpret_cast<float4*>(base);
+    m.boxes = m.seg + AF + k.wcap;
+    m.rec = reinterpret_cast<int4*>(m.boxes + k.wcap / VRUN);
+    m.rec_g = nullptr;
+    m.scr = nullptr;
+    m.st_in = m.st_out = reinterpret_cast<float*>(m.rec + (k.stage_rec ? k.wcap : 0));
+    m.meta = reinterpret_cast<int*>(m.st_out + A * ST_STRIDE);
+    m.mrad = &ctl->mrad;
+    m.bar = nullptr;
+    m.next_item = nullptr;
+    return m;
+}
+
+__device__ __forceinline__ int ld_volatile_shared(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ int ld_volatile_global(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+// First half of staging an env (static scenery only: may run ahead of griddep_wait): which env, its metadata into the
+// stage's meta block, its table on its way by three bulk copies. Returns the env, or -1 when there is none left.
+__device__ __forceinline__ int stage_fill(const KArgs& k, PCtl* ctl, const VSmem& m, int s, int q, int lane, int AF) {
+    int n = -1;
+    if (lane == 0) {
+        long long e;
+        if (q < k.p_stages || !k.sched) e = (long long)blockIdx.x + (long long)q * gridDim.x;     // every CTA's first envs: dealt
+        else e = (long long)k.p_stages * gridDim.x + atomicAdd(k.sched, 1);                       // then first come, first served
+        if (e < k.s.n_envs) n = k.env_order ? __ldg(k.env_order + e) : (int)e;
+    }
+    n = __shfl_sync(0xffffffffu, n, 0);
+    if (n < 0) return -1;
+    if (lane == 0) {
+        const int L = __ldg(k.s.line_widths + n);
+        const int64_t g0 = __ldg(k.s.line_starts + n);
+        const int b0 = __ldg(k.s.box_starts + n);
+        const int W = L - AF, nb = (W + VRUN - 1) / VRUN;
+        m.meta[0] = W; m.meta[3] = b0;
+        m.meta[META_N] = n; m.meta[META_G0] = (int)(uint32_t)g0; m.meta[META_G0 + 1] = (int)(uint32_t)((uint64_t)g0 >> 32);
+        m.meta[META_L] = L;
+        m.meta[META_PAR] = ctl->fills[s] & 1;
+        if (nb > 0) {
+            ctl->fills[s]++;
+            // the stage's previous tenant was read through the generic proxy: order those reads (synchronised with by the
+            // done counter) before the async-proxy writes of the copies
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&ctl->full_bar[s], (uint32_t)nb * (VRUN * (k.stage_rec ? 32u : 16u) + 16u));
+            bulk_g2s(m.seg + AF, k.s.occ_lines + 4 * VRUN * (int64_t)b0, (uint32_t)nb * VRUN * 16u, &ctl->full_bar[s]);
+            if (k.stage_rec) bulk_g2s(m.rec, k.s.occ_rec + 4 * VRUN * (int64_t)b0, (uint32_t)nb * VRUN * 16u, &ctl->full_bar[s]);
+            bulk_g2s(m.boxes, k.s.occ_boxes + 4 * (int64_t)b0, (uint32_t)nb * 16u, &ctl->full_bar[s]);
+        }
+    } else if (lane == 1) {
+        m.meta[1] = __ldg(k.s.light_widths + n); m.meta[2] = __ldg(k.s.light_starts + n);
+    } else if (lane == 2) {
+        m.meta[4] = __float_as_int(__ldg(k.s.occ_meta + 2 * n)); m.meta[5] = __float_as_int(__ldg(k.s.occ_meta + 2 * n + 1));
+        m.meta[6] = 0; m.meta[7] = 0;
+    } else if (lane == 3) {
+        m.meta[10] = 0; m.meta[11] = 0;                                  // no grid: every lookup falls outside
+        if (k.s.vis) {
+            const float4 vm = __ldg(reinterpret_cast<const float4*>(k.s.vis_meta) + n);
+            const int64_t vs = __ldg(k.s.vis_starts + n);
+            m.meta[8] = __float_as_int(vm.x); m.meta[9] = __float_as_int(vm.y); m.meta[10] = (int)vm.z; m.meta[11] = (int)vm.w;
+            m.meta[12] = (int)(uint32_t)vs; m.meta[13] = (int)(uint32_t)((uint64_t)vs >> 32);
+        }
+    }
+    return n;
+}
+
+// Second half (needs the kernels ahead in the stream: call after griddep_wait): the agents' state and their model lines
+// at their current poses (draw_kernel, kernels.cu:297-318), the IMU head; then wait for the table and publish the stage.
+__device__ __forceinline__ void stage_publish(const KArgs& k, PCtl* ctl, const VSmem& m, int s, int q, int n, int lane, int A) {
+    const int F = k.s.n_model;
+    for (int a = lane; a < A; a += 32) {
+        const int64_t i = (int64_t)n * A + a;
+        const float2 pos = reinterpret_cast<const float2*>(k.a.positions)[i];
+        const float2 vel = reinterpret_cast<const float2*>(k.a.velocity)[i];
+        const float ang = k.a.angles[i];
+        const float av = k.a.angvelocity[i];
+        float* st = m.st_out + a * ST_STRIDE;
+        st[ST_ANG] = ang; st[ST_PX] = pos.x; st[ST_PY] = pos.y; st[ST_AV] = av; st[ST_VX] = vel.x; st[ST_VY] = vel.y;
+        sincos_deg(ang, st[ST_SN], st[ST_CS]);                  // once per agent (kernels.cu:304-306, 335-337 redo it per thread)
+        if (k.has_obs && k.obs.imu) {                             // IMU (modules.py:263-270)
+            const float rad = __fmul_rn(0.017453292519943295f, ang);
+            const float c = cosf(rad), sn = sinf(rad);
+            float* q3 = k.obs.imu + 3 * i;
+            q3[0] = __fmul_rn(av, k.inv_ang);
+            q3[1] = __fmul_rn(__fadd_rn(__fmul_rn(c, vel.x), __fmul_rn(sn, vel.y)), k.inv_speed);
+            q3[2] = __fmul_rn(__fadd_rn(__fmul_rn(-sn, vel.x), __fmul_rn(c, vel.y)), k.inv_speed);
+        }
+    }
+    __syncwarp();
+    const int64_t g0 = (int64_t)(((uint64_t)(uint32_t)m.meta[META_G0 + 1] << 32) | (uint32_t)m.meta[META_G0]);
+    for (int t = lane; t < 2 * F * A; t += 32) {                // t = 2 * (agent's model line) + endpoint, over all agents
+        const int a = t / (2 * F), tt = t - a * 2 * F;
+        const float* st = m.st_out + a * ST_STRIDE;
+        const float sn = st[ST_SN], cs = st[ST_CS];
+        const float2 mp = __ldg(reinterpret_cast<const float2*>(k.s.model) + tt);
+        const float2 pt = make_float2(fadd(st[ST_PX], cross2(cs, mp.x, sn, mp.y)), fadd(st[ST_PY], dot2(sn, mp.x, cs, mp.y)));
+        reinterpret_cast<float2*>(m.seg)[t] = pt;
+        reinterpret_cast<float2*>(k.s.lines)[2 * g0 + t] = pt;
+    }
+    if (m.meta[0] > 0) mbar_wait(&ctl->full_bar[s], (uint32_t)m.meta[META_PAR]);
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        *reinterpret_cast<volatile int*>(&ctl->ready_seq[s]) = q + 1;
+    }
+}
+
+__device__ __forceinline__ void stage_dead(PCtl* ctl, int s, int lane) {
+    if (lane == 0) {
+        atomicAdd(&ctl->dead, 1);
+        __threadfence_block();
+        *reinterpret_cast<volatile int*>(&ctl->ready_seq[s]) = 0x7fffffff;
+    }
+}
+
+// One ticket of the merged second pass: entry T / groups, lights i = T % groups (mod groups). Returns after the entry's
+// share is done; the last of the entry's `groups` warps to finish sums the lights and writes the pixels.
+template <bool STATS>
+__device__ __noinline__ void dyn_ticket_run(const KArgs& k, int T, int lane) {
+    const int G = k.dyn_groups, PS = k.dyn_window;
+    const int ei = T / G, part = T - ei * G;
+    unsigned char* e = k.dyn_entries + (size_t)ei * (DYN_HDR + 32 * PS);
+    DynEntry d;
+    unsigned iters = 0;
+    dyn_scan<STATS>(k, e, part, G, lane, d, iters);
+    float4* rec = reinterpret_cast<float4*>(e + DYN_HDR) + 2 * lane;
+    int* parts_done = reinterpret_cast<int*>(e + 40);
+    if (G > 1) {
+        // my finds join the entry: OR-ed into the word that already holds the lights the visibility grid vouches for
+        if (d.isdyn) {
+            if (d.nlights <= 32) { if (d.mylit) atomicOr(reinterpret_cast<unsigned*>(&rec[1].w), d.mylit); }
+            else if (part == 0) __stcg(&rec[1].z, d.intensity);
+        }
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) { __threadfence(); last = atomicAdd(parts_done, 1) == G - 1; __threadfence(); }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) return;
+        if (d.isdyn) {
+            d.rb.w = __ldcg(&rec[1].w);
+            if (d.nlights > 32) d.intensity = __ldcg(&rec[1].z);
+        }
+    }
+    unsigned lit = d.mylit;
+    if (d.isdyn) {
+        const unsigned bits = __float_as_uint(d.rb.w);                       // the grid's lights (+ the other parts' finds)
+        lit |= bits & (d.nlights >= 32 ? 0xffffffffu : ((1u << d.nlights) - 1u));
+    }
+    dyn_finish(k, d, lit, lane);
+    __syncwarp();
+    if (lane == 0) {
+        *parts_done = 0;
+        *reinterpret_cast<volatile int*>(e + DYN_FLAG) = 0;                  // re-armed for the next step
+    }
+}
+
+template <int NCH, bool MERGE, bool STATS>
+__global__ void __launch_bounds__(MSB_VIEW_THREADS, MSB_VIEW_BLOCKS) tick_kernel(const __grid_constant__ KArgs k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int A = k.s.n_agents, AF = A * k.s.n_model;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int S = k.p_stages, IPE = k.p_items;
+    PCtl* ctl = reinterpret_cast<PCtl*>(smem_raw);
+    unsigned char* stages = smem_raw + pctl_bytes();
+    float4* scr = reinterpret_cast<float4*>(stages + (size_t)S * k.p_stage_bytes) + warp * (32 * NCH < 64 ? 64 : 32 * NCH);
+    if (tid == 0) {
+        for (int s = 0; s < PMAXS; s++) { ctl->ready_seq[s] = 0; ctl->done_cnt[s] = 0; ctl->fills[s] = 0; }
+        ctl->next_ticket = 0; ctl->dead = 0; ctl->rays_out = 0; ctl->all_out = 0; ctl->error = 0;
+        float r = 0.f;
+        for (int t = 0; t < 2 * k.s.n_model; t++) {                          // the model's radius: lets a warp skip agents it cannot see
+            const float2 mp = __ldg(reinterpret_cast<const float2*>(k.s.model) + t);
+            r = fmaxf(r, sqrtf(mp.x * mp.x + mp.y * mp.y));
+        }
+        ctl->mrad = __float_as_int(r);
+        for (int s = 0; s < S; s++) mbar_init(&ctl->full_bar[s], 1);
+    }
+    __syncthreads();
+    // the first S envs: their tables start moving before the kernels ahead in the stream are known to be done
+    int n0 = -1;
+    VSmem m0;
+    if (warp < S) {
+        m0 = pstage(stages + (size_t)warp * k.p_stage_bytes, ctl, k, A, AF);
+        n0 = stage_fill(k, ctl, m0, warp, warp, lane, AF);
+    }
+    griddep_wait();
+    griddep_launch();
+    if (warp < S) {
+        if (n0 >= 0) stage_publish(k, ctl, m0, warp, warp, n0, lane, A);
+        else stage_dead(ctl, warp, lane);
+    }
+    const bool merge = MERGE && k.dyn_entries != nullptr;
+    const int esize = DYN_HDR + 32 * k.dyn_window;
+    int T = -1, fl = 0;                                             // my ticket of the second pass; its entry's flag at the last look
+    auto take_ticket = [&]() {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(k.dyn_ctrl + 2, 1);
+        T = __shfl_sync(0xffffffffu, t, 0);
+    };
+    auto peek = [&]() -> int {                                      // (every lane reads the same word: one transaction, no shuffle)
+        const int ei = T / k.dyn_groups;
+        return ei < k.dyn_cap ? ld_volatile_global(reinterpret_cast<const int*>(k.dyn_entries + (size_t)ei * esize + DYN_FLAG)) : 0;
+    };
+    if (merge) { take_ticket(); fl = peek(); }
+    bool rays = true;
+    unsigned spins = 0;
+    for (;;) {
+        if (merge && __any_sync(0xffffffffu, fl != 0)) {
+            dyn_ticket_run<STATS>(k, T, lane);
+            take_ticket();
+            fl = peek();
+            continue;
+        }
+        if (rays) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&ctl->next_ticket, 1);
+            t = __reduce_max_sync(0xffffffffu, t);                  // (lands in a uniform register: so do the item's address parts)
+            const int q = t / IPE, it = t - q * IPE, s = q % S;
+            int v;
+            while ((v = ld_volatile_shared(&ctl->ready_seq[s])) < q + 1) {
+                __nanosleep(64);
+                if (++spins > SPIN_LIMIT) { ctl->error = 1; v = 0x7fffffff; break; }
+            }
+            __threadfence_block();
+            if (v == 0x7fffffff) {
+                // nothing will be staged here any more; when that goes for every stage, the rays are done
+                if (ld_volatile_shared(&ctl->dead) >= S || ld_volatile_shared(&ctl->error)) {
+                    rays = false;
+                    __syncwarp();
+                    if (lane == 0) {
+                        __threadfence();
+                        // the CTA's last warp out tells the second pass that this CTA will publish nothing more
+                        if (atomicAdd(&ctl->rays_out, 1) == nwarps - 1 && k.dyn_entries) { __threadfence(); red_release_add(k.dyn_ctrl + 3, 1); }
+                    }
+                    if (!merge) break;
+                }
+                continue;
+            }
+            VSmem m = pstage(stages + (size_t)s * k.p_stage_bytes, ctl, k, A, AF);
+            const int fl_next = merge ? peek() : 0;                 // asked for now, looked at after the item
+            {
+                const int n = __reduce_max_sync(0xffffffffu, m.meta[META_N]);
+                const int64_t g0 = (int64_t)(((uint64_t)(uint32_t)m.meta[META_G0 + 1] << 32) | (uint32_t)m.meta[META_G0]);
+                const int L = m.meta[META_L], W = m.meta[0], nb = (W + VRUN - 1) / VRUN;
+                m.rec_g = reinterpret_cast<const int4*>(k.s.occ_rec) + VRUN * (int64_t)m.meta[3];
+                const int RB = k.ray_blocks, rbs = k.rb_shift;
+                const int a = rbs >= 0 ? it >> rbs : it / RB;
+                view_agent<NCH, STATS>(k, m, n, g0, L, W, nb, a, it - a * RB, scr, lane);
+            }
+            fl = fl_next;
+            __syncwarp();
+            int last = 0;
+            if (lane == 0) { __threadfence_block(); last = atomicAdd(&ctl->done_cnt[s], 1) == IPE - 1; }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                // the env in stage s is finished: stage the next one there
+                if (lane == 0) ctl->done_cnt[s] = 0;
+                const int n = stage_fill(k, ctl, m, s, q + S, lane, AF);
+                if (n >= 0) stage_publish(k, ctl, m, s, q + S, n, lane, A);
+                else stage_dead(ctl, s, lane);
+            }
+        } else {
+            // drain: my entry will be published, or every CTA has signed off and it never will be
+            fl = peek();
+            if (__any_sync(0xffffffffu, fl != 0)) continue;
+            if (ld_volatile_global(k.dyn_ctrl + 3) >= (int)gridDim.x) {
+                __threadfence();
+                fl = peek();
+                if (!__any_sync(0xffffffffu, fl != 0)) break;
+                continue;
+            }
+            __nanosleep(200);
+            if (++spins > SPIN_LIMIT) break;
+        }
+    }
+    // the last warp of the last CTA out re-arms the counters for the next launch
+    __syncwarp();
+    if (lane == 0 && atomicAdd(&ctl->all_out, 1) == nwarps - 1 && k.sched) {
+        __threadfence();
+        if (atomicAdd(k.sched + 1, 1) == (int)gridDim.x - 1) {
+            k.sched[0] = 0; k.sched[1] = 0;
+            if (merge) { k.dyn_ctrl[0] = 0; k.dyn_ctrl[1] = 0; k.dyn_ctrl[2] = 0; k.dyn_ctrl[3] = 0; }
+        }
     }
 }
 
@@ -1603,7 +1979,7 @@ __global__ void __launch_bounds__(256) bake_kernel(const __grid_constant__ KArgs
 // host side: C ABI
 // ---------------------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-static long long g_launches = 0;
+static std::atomic<long long> g_launches{0};
 static long long g_opt_nch = 0;          // 0 = auto
 static long long g_opt_threads = 0;      // 0 = auto
 static long long g_opt_skip_dyn = 0;     // debug
@@ -1616,6 +1992,11 @@ static long long g_opt_dyn_window = 0;   // 0 = default (DYN_MIN_WINDOW); 1, 2, 
 static long long g_opt_dyn_warps = 0;    // warps sharing one queue entry in dyn_kernel (default 2)
 static long long g_opt_fused_step = 0;   // 1: msb_step runs physics inside view_kernel (measured slower: the physics latency
                                          // chain adds to every CTA's life instead of running at its own high occupancy)
+static long long g_opt_persist = 0;      // 0: auto (tick_kernel when an env has >= 4 items), 1: whenever possible, 2: never (view_kernel + dyn_kernel)
+static long long g_opt_merge_dyn = 0;    // tick_kernel lights the agent-hit windows itself — 0 / 1: yes, 2: no (dyn_kernel follows)
+static long long g_opt_dyn_groups = 0;   // merged second pass: tickets per queue entry (1, 2 or 4; default 4)
+static long long g_opt_stages = 0;       // tick_kernel: envs staged per CTA (2..4; 0: auto)
+static long long g_opt_no_sched = 0;     // tick_kernel: deal the envs round-robin instead of first come, first served
 static unsigned long long* g_stats = nullptr;   // device counters, enabled by option "stats"
 
 // Optional per-kernel timing with CUDA events on the launching stream (option "timing" = 1): bench.py uses it to
@@ -1686,7 +2067,7 @@ static int check(cudaError_t e, const char* what) {
 
 extern "C" int msb_abi_version(void) { return MSB_ABI_VERSION; }
 extern "C" const char* msb_last_error(void) { return g_err; }
-extern "C" int64_t msb_launch_count(void) { return g_launches; }
+extern "C" int64_t msb_launch_count(void) { return g_launches.load(); }
 
 extern "C" int msb_params_init(msb_params* p, float agent_radius, int32_t res, float fov, float fps) {
     if (!p) return fail("%s", "msb_params_init: null params");
@@ -1715,6 +2096,11 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "no_env_order")) { g_opt_no_env_order = value; return 0; }
     if (!strcmp(name, "stage_rec")) { g_opt_stage_rec = value; return 0; }
     if (!strcmp(name, "idx64")) { g_opt_idx64 = value; return 0; }
+    if (!strcmp(name, "persist")) { g_opt_persist = value; return 0; }
+    if (!strcmp(name, "merge_dyn")) { g_opt_merge_dyn = value; return 0; }
+    if (!strcmp(name, "dyn_groups")) { g_opt_dyn_groups = value; return 0; }
+    if (!strcmp(name, "stages")) { g_opt_stages = value; return 0; }
+    if (!strcmp(name, "no_sched")) { g_opt_no_sched = value; return 0; }
     if (!strcmp(name, "timing")) {
         timing_flush();
         g_opt_timing = value;
@@ -1879,7 +2265,9 @@ static int dyn_window(int sub) {
     return sub > w ? sub : w;
 }
 
-// workspace layout: int ctrl[4] (16 bytes) | occluder cache int[N][A][32] | queue entries of DYN_HDR + 32 * PS bytes
+// workspace layout: int ctrl[4] (queue) | int sched[4] (tick_kernel's env counter) | occluder cache int[N][A][32] |
+// queue entries of DYN_HDR + 32 * PS bytes
+enum { WS_HEAD = 32 };
 static int64_t cache_bytes(const msb_scenery* s) { return (int64_t)s->n_envs * s->n_agents * 32 * 4; }
 
 static int set_workspace(KArgs& k, const msb_workspace* ws) {
@@ -1887,43 +2275,139 @@ static int set_workspace(KArgs& k, const msb_workspace* ws) {
     k.dyn_entries = nullptr;
     k.dyn_cache = nullptr;
     k.dyn_cap = 0;
+    k.sched = nullptr;
     if (!ws || !ws->ptr) return 0;
     if (((uintptr_t)ws->ptr & 15) != 0) return fail("%s", "workspace must be 16-byte aligned");
+    if (ws->bytes < WS_HEAD) return 0;
+    k.dyn_ctrl = reinterpret_cast<int*>(ws->ptr);
+    k.sched = g_opt_no_sched ? nullptr : reinterpret_cast<int*>(ws->ptr) + 4;
     if (k.s.n_agents == 1) return 0;    // a lone agent can only ever hit its own model (if at all): no second pass to launch
     const int sub = k.has_obs ? k.obs.subsample : 1;
     k.dyn_window = dyn_window(sub);
-    const int64_t head = 16 + cache_bytes(&k.s);
+    const int64_t head = WS_HEAD + cache_bytes(&k.s);
     const int64_t cap = (ws->bytes - head) / (DYN_HDR + 32 * k.dyn_window);
     if (cap < 1) return 0;
-    k.dyn_ctrl = reinterpret_cast<int*>(ws->ptr);
-    k.dyn_cache = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws->ptr) + 16);
+    k.dyn_cache = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(ws->ptr) + WS_HEAD);
     k.dyn_entries = reinterpret_cast<unsigned char*>(ws->ptr) + head;
     k.dyn_cap = cap > 0x7fffffff ? 0x7fffffff : (int32_t)cap;
     return 0;
 }
 
+// resident CTAs per SM of a kernel at a given shape, per device (a process may drive several GPUs)
+static int occupancy(const void* fn, int threads, size_t smem, int* sms_out) {
+    struct Key { const void* fn; int dev, threads; size_t smem; int per_sm, sms; };
+    static std::mutex mu;
+    static Key cache[64];
+    static int n_cached = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < n_cached; i++)
+        if (cache[i].fn == fn && cache[i].dev == dev && cache[i].threads == threads && cache[i].smem == smem) {
+            if (sms_out) *sms_out = cache[i].sms;
+            return cache[i].per_sm;
+        }
+    Key key = {fn, dev, threads, smem, 0, 0};
+    cudaDeviceGetAttribute(&key.sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&key.per_sm, fn, threads, smem);
+    if (key.per_sm < 1) key.per_sm = 1;
+    if (n_cached < 64) cache[n_cached++] = key;
+    if (sms_out) *sms_out = key.sms;
+    return key.per_sm;
+}
+
 static int launch_dyn(const KArgs& k, cudaStream_t st) {
     if (!k.dyn_entries) return 0;
-    static int per_sm[2] = {0, 0};          // resident CTAs per SM of dyn_kernel<false/true>: exactly one wave
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], dyn_kernel<false>, 128, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], dyn_kernel<true>, 128, 0);
-        if (per_sm[0] < 1) per_sm[0] = 1;
-        if (per_sm[1] < 1) per_sm[1] = 1;
-    }
     {
         TimedLaunch timed(TK_DYN, st);
         const int threads = (g_opt_dyn_warps >= 1 && g_opt_dyn_warps <= 4) ? 32 * (int)g_opt_dyn_warps : 64;   // measured: 2 warps per entry
         const int scale = 128 / threads;            // same number of resident threads whatever the CTA size
-        if (k.stats) launch(dyn_kernel<true>, sms * per_sm[1] * scale, threads, 0, st, true, k);
-        else launch(dyn_kernel<false>, sms * per_sm[0] * scale, threads, 0, st, true, k);
+        int sms = 0;
+        if (k.stats) {
+            const int per_sm = occupancy((const void*)dyn_kernel<true>, 128, 0, &sms);       // exactly one wave
+            launch(dyn_kernel<true>, sms * per_sm * scale, threads, 0, st, true, k);
+        } else {
+            const int per_sm = occupancy((const void*)dyn_kernel<false>, 128, 0, &sms);
+            launch(dyn_kernel<false>, sms * per_sm * scale, threads, 0, st, true, k);
+        }
     }
     g_launches++;
     return check(cudaGetLastError(), "dyn_kernel launch");
+}
+
+// tick_kernel: the persistent form of view_kernel (+ dyn_kernel). *merged: the second pass ran inside it.
+static bool want_tick(const KArgs& k, int rb) {
+    if (g_opt_persist == 2 || g_opt_fused_step) return false;
+    const int items = k.s.n_agents * rb;
+    return g_opt_persist == 1 ? items >= 1 : items >= 4;
+}
+
+static int launch_tick(KArgs& k, int nch, cudaStream_t st, bool* merged) {
+    const int A = k.s.n_agents, AF = A * k.s.n_model;
+    k.idx32 = (!g_opt_idx64 && 3ll * k.s.n_envs * k.s.n_agents * (long long)k.p.res < (1ll << 32)) ? 1 : 0;
+    k.out_mask = (k.out.indices ? OUT_INDICES : 0) | (k.out.locations ? OUT_LOCATIONS : 0) | (k.out.dots ? OUT_DOTS : 0) |
+                 (k.out.distances ? OUT_DISTANCES : 0) | (k.out.screen ? OUT_SCREEN : 0) |
+                 (k.has_obs && k.obs.rgb ? OUT_RGB : 0) | (k.has_obs && k.obs.depth ? OUT_DEPTH : 0) | (k.has_obs && k.obs.imu ? OUT_IMU : 0);
+    k.p_items = A * k.ray_blocks;
+    const int threads = (g_opt_threads >= 64 && g_opt_threads <= 256) ? (int)(g_opt_threads / 32) * 32 : 256;
+    const int nwarps = threads / 32;
+    const size_t scr = (size_t)nwarps * (32 * nch < 64 ? 64 : 32 * nch) * 16;
+    const size_t ctl = (sizeof(PCtl) + 15) & ~size_t(15);
+    // stages and whether the rows' records are staged too: as much as keeps four CTAs on an SM
+    const size_t budget = (227 * 1024 - MSB_VIEW_BLOCKS * 1024) / MSB_VIEW_BLOCKS;
+    int S = 2;
+    bool rec = g_opt_stage_rec != 2;
+    if (g_opt_stages >= 2 && g_opt_stages <= PMAXS) S = (int)g_opt_stages;
+    auto total = [&](int stages, bool r) { return ctl + stages * pstage_bytes(k.wcap, A, AF, r) + scr; };
+    if (rec && g_opt_stage_rec != 1 && total(S, true) > budget) rec = false;
+    while (S > 2 && !g_opt_stages && total(S, rec) > budget) S--;
+    if (S > nwarps) S = nwarps;
+    if (total(S, rec) > 227 * 1024 && rec) rec = false;
+    if (total(S, rec) > 227 * 1024) return fail("%s", "scene too large: an env's segments do not fit in shared memory (227 KB)");
+    k.stage_rec = rec ? 1 : 0;
+    k.p_stages = S;
+    k.p_stage_bytes = (int32_t)pstage_bytes(k.wcap, A, AF, rec);
+    k.dyn_groups = (g_opt_dyn_groups == 1 || g_opt_dyn_groups == 2 || g_opt_dyn_groups == 4) ? (int)g_opt_dyn_groups : 4;
+    const size_t sm = total(S, rec);
+    const bool merge = g_opt_merge_dyn != 2 && k.dyn_entries != nullptr && k.sched != nullptr;
+    *merged = merge;
+#define MSB_LAUNCH(N)                                                                                            \
+    {                                                                                                            \
+        auto fn = merge ? (k.stats ? tick_kernel<N, true, true> : tick_kernel<N, true, false>)                   \
+                        : (k.stats ? tick_kernel<N, false, true> : tick_kernel<N, false, false>);                \
+        if (sm > 48 * 1024 && check(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), \
+                                    "cudaFuncSetAttribute"))                                                     \
+            return 1;                                                                                            \
+        int sms = 0;                                                                                             \
+        const int per_sm = occupancy((const void*)fn, threads, sm, &sms);                                       \
+        int grid = sms * per_sm;                                                                                 \
+        if (grid > k.s.n_envs) grid = k.s.n_envs;                                                               \
+        k.view_ctas = grid;                                                                                      \
+        launch(fn, grid, threads, sm, st, true, k);                                                              \
+    }
+    {
+        TimedLaunch timed(TK_RENDER, st);
+        switch (nch) {
+            case 1: MSB_LAUNCH(1); break;
+            case 2: MSB_LAUNCH(2); break;
+            default: MSB_LAUNCH(4); break;
+        }
+    }
+#undef MSB_LAUNCH
+    g_launches++;
+    return check(cudaGetLastError(), "tick_kernel launch");
+}
+
+// render (+ heads) after the agents have been moved: the persistent kernel where an env has enough items, else one CTA per env
+static int launch_render(KArgs& k, int nch, int rb, int threads, cudaStream_t st) {
+    if (want_tick(k, rb)) {
+        bool merged = false;
+        if (launch_tick(k, nch, st, &merged)) return 1;
+        return merged ? 0 : launch_dyn(k, st);
+    }
+    k.view_ctas = k.s.n_envs;
+    if (launch_view(k, false, nch, threads, st)) return 1;
+    return launch_dyn(k, st);
 }
 
 extern "C" int64_t msb_workspace_bytes(const msb_params* p, const msb_scenery* s, int32_t subsample) {
@@ -1933,7 +2417,7 @@ extern "C" int64_t msb_workspace_bytes(const msb_params* p, const msb_scenery* s
     // room for a quarter of all pixel windows to contain an agent-hit ray (overflow falls back to inline, still exact)
     int64_t cap = windows / 4;
     if (cap < 16384) cap = windows < 16384 ? windows : 16384;
-    return 16 + cache_bytes(s) + cap * (DYN_HDR + 32 * PS);
+    return WS_HEAD + cache_bytes(s) + cap * (DYN_HDR + 32 * PS);
 }
 
 static void set_obs(KArgs& k, const msb_obs_out* obs) {
@@ -1979,8 +2463,7 @@ extern "C" int msb_render(const msb_params* p, const msb_scenery* s, const msb_a
     plan_view(p, s, &nch, &rb, &threads);
     k.ray_blocks = rb;
     k.rb_shift = (rb & (rb - 1)) ? -1 : __builtin_ctz((unsigned)rb);
-    if (launch_view(k, false, nch, threads, (cudaStream_t)cuda_stream)) return 1;
-    return launch_dyn(k, (cudaStream_t)cuda_stream);
+    return launch_render(k, nch, rb, threads, (cudaStream_t)cuda_stream);
 }
 
 extern "C" int msb_step(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_movement* mv,
@@ -2002,14 +2485,17 @@ extern "C" int msb_step(const msb_params* p, const msb_scenery* s, const msb_age
     k.ray_blocks = rb;
     k.rb_shift = (rb & (rb - 1)) ? -1 : __builtin_ctz((unsigned)rb);
     if (g_opt_fused_step) {
+        k.view_ctas = k.s.n_envs;
         if (launch_view(k, true, nch, threads, (cudaStream_t)cuda_stream)) return 1;
-    } else {
-        // physics (with the movement prologue) at its own, higher occupancy; then render with the heads
-        k.prefetch_view = g_opt_no_prefetch ? 0 : 1;
-        if (launch_physics(k, (cudaStream_t)cuda_stream)) return 1;
-        if (launch_view(k, false, nch, threads, (cudaStream_t)cuda_stream)) return 1;
+        return launch_dyn(k, (cudaStream_t)cuda_stream);
     }
-    return launch_dyn(k, (cudaStream_t)cuda_stream);
+    // physics (with the movement prologue) at its own, higher occupancy; then render with the heads. One CTA per env
+    // stages its table right at its start: physics sends it on its way from HBM to L2; the persistent kernel stages an
+    // env ahead, which hides that latency by itself.
+    k.prefetch_view = (g_opt_no_prefetch || want_tick(k, rb)) ? 0 : 1;
+    if (launch_physics(k, (cudaStream_t)cuda_stream)) return 1;
+    k.prefetch_view = 0;
+    return launch_render(k, nch, rb, threads, (cudaStream_t)cuda_stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -2022,6 +2508,7 @@ struct msb_graph {
     int32_t* actions_dev;
     float* progress_dev;
     size_t n;               // N * A
+    int launches;           // kernels in the captured step
 };
 
 extern "C" int msb_step_graph_create(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_movement* mv,
@@ -2040,9 +2527,10 @@ extern "C" int msb_step_graph_create(const msb_params* p, const msb_scenery* s, 
     g->n = (size_t)s->n_envs * s->n_agents;
     int rc = check(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
     if (!rc) {
-        const long long launches = g_launches;
+        const long long launches = g_launches.load();
         rc = msb_step(p, s, a, mv, progress, out, obs, ws, cs);
-        g_launches = launches;                                  // captured, not launched
+        g->launches = (int)(g_launches.load() - launches);      // captured, not launched
+        g_launches = launches;
         cudaError_t e = cudaStreamEndCapture(cs, &g->graph);
         if (!rc) rc = check(e, "cudaStreamEndCapture");
     }
@@ -2065,7 +2553,7 @@ extern "C" int msb_step_graph_run(msb_graph* g, const int32_t* actions_host, flo
         if (check(cudaMemcpyAsync(g->actions_dev, actions_host, g->n * sizeof(int32_t), cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(actions)")) return 1;
     }
     if (check(cudaGraphLaunch(g->exec, st), "cudaGraphLaunch")) return 1;
-    g_launches += 3;
+    g_launches += g->launches;
     if (progress_host) {
         if (!g->progress_dev) return fail("%s", "msb_step_graph_run: the step was captured without progress");
         if (check(cudaMemcpyAsync(progress_host, g->progress_dev, g->n * sizeof(float), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(progress)")) return 1;

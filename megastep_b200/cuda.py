@@ -99,8 +99,8 @@ def _load():
     lib.msb_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
     lib.msb_get_option.argtypes = [ctypes.c_char_p]
     lib.msb_get_option.restype = ctypes.c_int64
-    if lib.msb_abi_version() != 4:
-        raise ImportError(f'{_LIBPATH} has ABI version {lib.msb_abi_version()}, expected 4; rebuild it')
+    if lib.msb_abi_version() != 5:
+        raise ImportError(f'{_LIBPATH} has ABI version {lib.msb_abi_version()}, expected 5; rebuild it')
     return lib
 
 
@@ -300,6 +300,9 @@ class Scenery:
                     self._c.vis, self._c.vis_starts, self._c.vis_meta = (t.data_ptr() for t in self._vis)
                     with _on_device(self._model) as stream:
                         _check(_lib.msb_build_visibility(ctypes.byref(self._c), stream))
+                # the kernels read these tables ahead of their programmatic-dependency wait (they are static): make sure
+                # the one-off builders are done before anything is launched behind them
+                torch.cuda.current_stream(self._model.device).synchronize()
         return self._c
 
 

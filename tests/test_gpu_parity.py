@@ -331,38 +331,54 @@ def test_rgbd_head_equals_rgb_and_depth_modules():
     torch.testing.assert_close(obs.imu, want_imu, rtol=0, atol=1e-6)
 
 
+OPTIONS = ('nch', 'threads', 'stage_rec', 'idx64', 'persist', 'merge_dyn', 'dyn_groups', 'stages', 'no_sched', 'dyn_warps')
+
+
+def _reset_options():
+    from megastep_b200 import cuda
+    for name in OPTIONS:
+        cuda.set_option(name, 0)
+
+
 @pytest.mark.parametrize('res', [48, 64, 128, 512])
 def test_every_kernel_variant_gives_identical_results(res):
-    """The chunking / thread-count options change which boxes a warp opens, which segments it skips and who runs
-    what, never results."""
+    """One CTA per env (view_kernel + dyn_kernel) or the persistent grid (tick_kernel, second pass merged in or not); the
+    chunking / thread-count / staging options: they change which boxes a warp opens, which segments it skips and who
+    runs what, never results."""
     from megastep_b200 import cuda
     gs, arrays, st = make('synthetic', 10, 4, seed=51)
     c = common.to_device(arrays, st, res, 70.)
+    cuda.set_option('persist', 2)
     base = c.render()
+
+    def check(what):
+        r = c.render()
+        for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
+            a, b = getattr(r, k), getattr(base, k)
+            assert ((a == b) | (a != a) & (b != b)).all(), f'{what}: {k} differs'
+
     try:
         for stage_rec in (1, 2):                               # the rows' records staged in shared memory / left in global
             for nch in (1, 2, 4):
                 for threads in (32, 64, 128, 256):
-                    cuda.set_option('stage_rec', stage_rec)
-                    cuda.set_option('nch', nch)
-                    cuda.set_option('threads', threads)
-                    r = c.render()
-                    for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
-                        a, b = getattr(r, k), getattr(base, k)
-                        assert ((a == b) | (a != a) & (b != b)).all(), f'stage_rec={stage_rec} nch={nch} threads={threads}: {k} differs'
-        cuda.set_option('nch', 0)
-        cuda.set_option('threads', 0)
-        cuda.set_option('stage_rec', 0)
-        cuda.set_option('idx64', 1)                            # the 64-bit output indexing of very large batches
-        r = c.render()
-        for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
-            a, b = getattr(r, k), getattr(base, k)
-            assert ((a == b) | (a != a) & (b != b)).all(), f'idx64: {k} differs'
+                    for name, v in (('persist', 2), ('stage_rec', stage_rec), ('nch', nch), ('threads', threads)):
+                        cuda.set_option(name, v)
+                    check(f'view_kernel stage_rec={stage_rec} nch={nch} threads={threads}')
+                for threads in (64, 256):
+                    for stages in (2, 3):
+                        for name, v in (('persist', 1), ('stage_rec', stage_rec), ('nch', nch), ('threads', threads), ('stages', stages)):
+                            cuda.set_option(name, v)
+                        check(f'tick_kernel stage_rec={stage_rec} nch={nch} threads={threads} stages={stages}')
+        _reset_options()
+        for opts in ({'persist': 1, 'merge_dyn': 2}, {'persist': 1, 'dyn_groups': 1}, {'persist': 1, 'dyn_groups': 2},
+                     {'persist': 1, 'no_sched': 1}, {'persist': 1, 'stages': 4, 'threads': 128}, {'idx64': 1}, {'persist': 2, 'idx64': 1}, {}):
+            _reset_options()
+            for name, v in opts.items():
+                cuda.set_option(name, v)
+            for _ in range(2):                                 # twice: the counters must re-arm themselves
+                check(str(opts))
     finally:
-        cuda.set_option('nch', 0)
-        cuda.set_option('threads', 0)
-        cuda.set_option('stage_rec', 0)
-        cuda.set_option('idx64', 0)
+        _reset_options()
 
 
 def _same(a, b):
@@ -398,38 +414,43 @@ def test_step_with_physics_inside_the_render_kernel_agrees():
 
 @pytest.mark.parametrize('sub', [1, 4])
 def test_second_pass_inline_and_overflow_paths_agree(sub):
-    """Agent-hit rays are lit by dyn_kernel (workspace; its warps share each entry's lights 2, 1 or 4 ways), inline by
-    the first pass (no workspace), or by a mix (workspace too small): all must give identical screens and observations. Agents are packed close so many rays
-    hit agents."""
+    """Agent-hit rays are lit by the persistent kernel itself (tickets: 4, 2 or 1 warps per queue entry), by dyn_kernel
+    behind it or behind view_kernel (its warps share each entry's lights 2, 1 or 4 ways), inline by the first pass (no
+    workspace), or by a mix (workspace too small): all must give identical screens and observations. Agents are packed
+    close so many rays hit agents."""
     from megastep_b200 import cuda
     gs, arrays, st = make('box', 6, 4, seed=61)
     rng = np.random.RandomState(0)
     st['positions'] = (3.5 + rng.uniform(-.6, .6, st['positions'].shape)).astype(np.float32)
     res = 128
     outs = []
-    for mode in ('workspace', 'inline', 'overflow', 'workspace-1warp', 'workspace-4warps'):
-        cuda.USE_WORKSPACE = mode != 'inline'
-        cuda.set_option('dyn_warps', {'workspace-1warp': 1, 'workspace-4warps': 4}.get(mode, 0))
+    modes = {'tick': {}, 'tick-2-per-entry': {'dyn_groups': 2}, 'tick-1-per-entry': {'dyn_groups': 1}, 'tick+dyn_kernel': {'merge_dyn': 2},
+             'tick-inline': {}, 'tick-overflow': {}, 'tick+dyn_kernel-overflow': {'merge_dyn': 2},
+             'view+dyn': {'persist': 2}, 'view-inline': {'persist': 2}, 'view-overflow': {'persist': 2},
+             'view+dyn-1warp': {'persist': 2, 'dyn_warps': 1}, 'view+dyn-4warps': {'persist': 2, 'dyn_warps': 4}}
+    for mode, opts in modes.items():
+        cuda.USE_WORKSPACE = 'inline' not in mode
+        _reset_options()
+        for name, v in opts.items():
+            cuda.set_option(name, v)
         try:
             c = common.to_device(arrays, st, res, 100.)
             plan = cuda.StepPlan(c.scenery, c.agents, c.params, actions=None, raw=True, subsample=sub)
-        finally:
-            cuda.USE_WORKSPACE = True
-        if mode == 'overflow':
-            small = 16 + 6 * 4 * 32 * 4 + 3 * (48 + 32 * max(4, sub))   # ctrl + occluder cache + room for three pixel windows only
-            plan._wsbuf = torch.zeros(small, dtype=torch.uint8, device='cuda')
-            plan._ws = cuda._Workspace(plan._wsbuf.data_ptr(), small)
-        try:
-            for _ in range(2):                                          # twice: the queue must re-arm itself
+            if 'overflow' in mode:
+                small = 32 + 6 * 4 * 32 * 4 + 3 * (48 + 32 * max(4, sub))   # counters + occluder cache + room for three pixel windows only
+                plan._wsbuf = torch.zeros(small, dtype=torch.uint8, device='cuda')
+                plan._ws = cuda._Workspace(plan._wsbuf.data_ptr(), small)
+            for _ in range(3):                                          # several times: the queue must re-arm itself
                 plan.render_only()
             torch.cuda.synchronize()
         finally:
-            cuda.set_option('dyn_warps', 0)
-        outs.append((plan.render.screen.clone(), plan.rgb.clone(), plan.render.indices.clone()))
-    n_dyn = int(((outs[0][2] >= 0) & (outs[0][2] < 32)).sum())
+            cuda.USE_WORKSPACE = True
+            _reset_options()
+        outs.append((mode, plan.render.screen.clone(), plan.rgb.clone(), plan.render.indices.clone()))
+    n_dyn = int(((outs[0][3] >= 0) & (outs[0][3] < 32)).sum())
     assert n_dyn > 50, 'the scene should have plenty of agent-hit rays'
-    for other in outs[1:]:
-        assert _same(outs[0][0], other[0]) and _same(outs[0][1], other[1])
+    for mode, screen, rgb, _ in outs[1:]:
+        assert _same(outs[0][1], screen) and _same(outs[0][2], rgb), mode
 
 
 def test_native_table_builder_equals_the_torch_restatement():

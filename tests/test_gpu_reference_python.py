@@ -162,7 +162,7 @@ def _geometries(n, with_masks=True):
     from megastep_b200 import synthetic
     gs = synthetic.sample(n, seed=9, n_unique=n, with_masks=with_masks)
     for g in gs:
-        g['res'] = np.float64(g['res'])          # the reference multiplies a shape tuple by it (deathmatch.py:44)
+        g['res'] = np.array(g['res'])            # a 0-d array, as np.load gives the reference: it multiplies a shape TUPLE by it (deathmatch.py:44)
     return gs
 
 

@@ -89,7 +89,7 @@ def test_library_exports_every_symbol_the_header_declares():
     lib = ctypes.CDLL(cuda.library_path())
     for name in declared:
         assert hasattr(lib, name), f'{name} is declared in the header but not exported'
-    assert lib.msb_abi_version() == 4
+    assert lib.msb_abi_version() == 5
 
 
 def test_params_init_matches_reference_formula_and_validates():
