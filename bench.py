@@ -53,7 +53,8 @@ def parse():
     ap.add_argument('--unique', type=int, default=256, help='distinct floorplans, tiled cyclically')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-raw', action='store_true', help='skip materialising the five Render tensors (obs heads only)')
-    ap.add_argument('--gather', action='store_true', help='all-gather the observations to every rank each step (NCCL)')
+    ap.add_argument('--gather', action='store_true', help='all-gather the observations to every rank each step (NCCL, side stream, overlapping the next step)')
+    ap.add_argument('--obs-dtype', default='float32', choices=['float32', 'float16'], help='precision of the gathered observations')
     ap.add_argument('--no-graph', action='store_true', help='e2e leg: plain launches instead of a CUDA-graph replay')
     ap.add_argument('--e2e', default='torch', choices=['native', 'torch'], help='e2e leg: the library\'s own host-driven graph (one call per tick) or a torch CUDA graph between PyTorch copies')
     ap.add_argument('--dry-run', action='store_true', help='build the scene and the CPU baseline only (no GPU)')
@@ -316,7 +317,9 @@ def run_gpu(args, cfg, arm_cls, rank, world, local_rank):
         from megastep_b200 import sharding
         arm.actions.copy_(acts_dev[0])
         arm.step()
-        gather = sharding.ObsGather(arm.obs())
+        # ShardedCore's collective: rows packed per env, ONE all_gather_into_tensor on a side stream, double-buffered
+        packing = sharding.PackedObs(A, cfg['res'] // cfg['subsample'], getattr(torch, args.obs_dtype))
+        gather = sharding.RowGather(packing, N, device)
 
     def barrier():
         if world > 1:
@@ -342,9 +345,12 @@ def run_gpu(args, cfg, arm_cls, rank, world, local_rank):
         starts[i].record()
         arm.step()
         if gather is not None:
+            # pack + start the all-gather of this step's observations; it runs on the side stream under the next step
+            # (its buffers are reused two steps later: if the gathers cannot keep up, that wait lands in the step's time)
             gather.start(arm.obs())
-            gather.wait()
         stops[i].record()
+    if gather is not None:
+        gather.wait()
     barrier()
     wall = time.perf_counter() - t0
     launches = arm.launches() - launches0
@@ -397,7 +403,7 @@ def run_gpu(args, cfg, arm_cls, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     step_ms, e2e_ms = t.tolist()
     total_bytes, mean_w = algorithmic_bytes(cfg, arrays, arm.fused, raw)
-    return dict(arm=arm, kernel_ms=kernel_ms, N=N, A=A, step_ms=step_ms, e2e_ms=e2e_ms, wall_s=wall, launches=launches, clocks=clocks,
+    return dict(arm=arm, gather_bytes=gather.bytes_received() if gather is not None else None, kernel_ms=kernel_ms, N=N, A=A, step_ms=step_ms, e2e_ms=e2e_ms, wall_s=wall, launches=launches, clocks=clocks,
                 bytes_per_step=total_bytes, mean_walls=mean_w, arrays=arrays, pos=pos, ang=ang,
                 per_step_ms=per_step_ms)
 
@@ -503,6 +509,9 @@ def main():
         'clocks': out['clocks'],
         'step_ms_percentiles': {p: float(np.percentile(out['per_step_ms'], p)) for p in (5, 50, 95)},
     }
+    if out.get('gather_bytes') is not None:
+        line['gather'] = {'what': 'observations packed per env, one NCCL all_gather_into_tensor per step on a side stream (overlaps the next step), every rank receives the whole batch', 'dtype': args.obs_dtype, 'bytes_received_per_rank_per_step': out['gather_bytes'],
+                          'achieved_GBps_per_rank': out['gather_bytes'] / (out['step_ms'] / K * 1e-3) / 1e9}
     if reference:
         line['cpu_baseline'] = {'value': value, 'unit': 'agent-frames/s', 'cores': 0, 'kind': 'reference',
                                 'sample': 'the reference\'s own CUDA build (oracle/_ref) on one B200 of this box: megastep has no CPU step path'}

@@ -30,6 +30,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <math.h>
+#include <stdlib.h>
 #include <atomic>
 #include <mutex>
 
@@ -75,9 +76,9 @@ struct KArgs {
     int32_t dyn_cap;            // entries that fit
     int32_t dyn_window;         // PS: pixels per entry = max(DYN_MIN_WINDOW, subsample); entry = DYN_HDR + 32 * PS bytes
     int* dyn_cache;             // [N][A][32] last occluder of each light as seen from (around) each agent; a hint
-    int32_t view_ctas;          // CTAs of the kernel that fills the queue (each signs off on dyn_ctrl[3] when it will publish no more)
+    int32_t view_ctas;          // what dyn_ctrl[3] counts up to: envs (= CTAs of view_kernel) that will publish nothing more
     // tick_kernel (the persistent form of view_kernel)
-    int* sched;                 // [0] envs handed out beyond every CTA's first p_stages, [1] CTAs out; null: envs are dealt round-robin
+    int* sched;                 // [0] envs handed out beyond every CTA's first p_stages, [1] CTAs out, [2] a bounded wait ran out (bug); null: envs are dealt round-robin
     int32_t p_stages;           // S: envs staged per CTA at a time (ring of shared-memory stages)
     int32_t p_stage_bytes;      // bytes of one stage
     int32_t p_items;            // (agent, ray block) items per env = n_agents * ray_blocks
@@ -93,7 +94,11 @@ struct KArgs {
 #endif
 enum { ST_ANG = 0, ST_PX = 1, ST_PY = 2, ST_AV = 3, ST_VX = 4, ST_VY = 5, ST_SN = 6, ST_CS = 7, ST_STRIDE = 8 };   // SN, CS: view_kernel only
 enum { STAT_TESTS = 0, STAT_GROUPS = 1, STAT_DYN_RAYS = 2, STAT_DYN_ITERS = 3, STAT_DYN_ENTRIES = 4, STAT_REPLAYS = 5,
-       STAT_DYN_CYCLES = 6, STAT_DYN_MAXCYC = 7, STAT_DYN_WARPMAX = 8, STAT_DYN_SLOW = 9, STAT_DYN_KERNEL = 10, STAT_DYN_SCANS = 11, STAT_DYN_SCANS_LIT = 12, STAT_DYN_ITERS_LIT = 13, STAT_SLOTS = 16 };
+       STAT_DYN_CYCLES = 6, STAT_DYN_MAXCYC = 7, STAT_DYN_WARPMAX = 8, STAT_DYN_SLOW = 9, STAT_DYN_KERNEL = 10, STAT_DYN_SCANS = 11, STAT_DYN_SCANS_LIT = 12, STAT_DYN_ITERS_LIT = 13,
+       // tick_kernel, warp-cycles summed over the grid: in ray items, waiting for a stage, in second-pass tickets, idle in the
+       // drain, staging envs, whole kernel; counts of tickets run and items; the longest warp; waits that actually spun
+       STAT_T_ITEMS = 16, STAT_T_WAIT = 17, STAT_T_DYN = 18, STAT_T_DRAIN = 19, STAT_T_PREP = 20, STAT_T_TOTAL = 21, STAT_N_DYN = 22,
+       STAT_N_ITEMS = 23, STAT_T_MAXWARP = 24, STAT_N_SPUN = 25, STAT_T_FETCH = 26, STAT_SLOTS = 32 };
 enum { OUT_INDICES = 1, OUT_LOCATIONS = 2, OUT_DOTS = 4, OUT_DISTANCES = 8, OUT_SCREEN = 16, OUT_RGB = 32, OUT_DEPTH = 64, OUT_IMU = 128 };
 enum { VRUN = 16 };                       // segments per run of the spatial table
 enum { DYN_MIN_WINDOW = 4 };               // pixels per queue entry: max(4, subsample) adjacent pixels (a 'window')
@@ -1445,7 +1450,7 @@ __global__ void __launch_bounds__(128, MSB_DYN_BLOCKS) dyn_kernel(const __grid_c
 //     the pixels); once the rays are done the warps drain what is left. No second kernel, no tail of idle CTAs.
 // Results are those of view_kernel + dyn_kernel, bit for bit (same item code, same per-entry scan).
 // ---------------------------------------------------------------------------------------------------------------
-enum { PMAXS = 4, META_N = 16, META_G0 = 17, META_L = 19, META_PAR = 20, META_INTS = 24 };
+enum { PMAXS = 8, META_N = 16, META_G0 = 17, META_L = 19, META_PAR = 20, META_INTS = 24 };
 enum { SPIN_LIMIT = 1 << 22 };
 
 struct PCtl {
@@ -1453,13 +1458,14 @@ struct PCtl {
     int ready_seq[PMAXS];       // per stage: 1 + sequence number of the env staged and drawn there (0x7fffffff: none will come)
     int done_cnt[PMAXS];        // per stage: items of its env finished
     int fills[PMAXS];           // per stage: bulk-copy rounds so far (the mbarrier's phase)
+    int nseq[PMAXS];            // per stage: 1 + sequence number of the env whose descriptor waits in nmeta (its next tenant)
+    int nmeta[PMAXS][META_INTS];// per stage: that descriptor, fetched while the current tenant is being worked on
     int next_ticket;            // items handed out
     int dead;                   // stages that will not be refilled
-    int rays_out;               // warps that have left the ray loop
     int all_out;                // warps that have left the kernel
     int mrad;                   // bits of the agent model's radius
     int error;                  // a bounded wait ran out (a bug): results are void, nothing hangs
-    int pad[2];
+    int pad[3];
 };
 
 __device__ __forceinline__ size_t pctl_bytes() { return (sizeof(PCtl) + 15) & ~size_t(15); }
@@ -1488,26 +1494,56 @@ __device__ __forceinline__ VSmem pstage(unsigned char* base, PCtl* ctl, const KA
 __device__ __forceinline__ int ld_volatile_shared(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 __device__ __forceinline__ int ld_volatile_global(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
-// First half of staging an env (static scenery only: may run ahead of griddep_wait): which env, its metadata into the
-// stage's meta block, its table on its way by three bulk copies. Returns the env, or -1 when there is none left.
-__device__ __forceinline__ int stage_fill(const KArgs& k, PCtl* ctl, const VSmem& m, int s, int q, int lane, int AF) {
+// An env's DESCRIPTOR: which env comes next and everything static the stage needs to know about it, into `meta`
+// ([META_N] = -1: there is none left). Three dependent global reads — why it is fetched one tenancy ahead of its use —
+// plus an L2 prefetch of the env's table, so that the bulk copies that will stage it find it on chip.
+__device__ __forceinline__ void desc_fetch(const KArgs& k, int* meta, int q, int lane, int AF) {
     int n = -1;
     if (lane == 0) {
         long long e;
         if (q < k.p_stages || !k.sched) e = (long long)blockIdx.x + (long long)q * gridDim.x;     // every CTA's first envs: dealt
         else e = (long long)k.p_stages * gridDim.x + atomicAdd(k.sched, 1);                       // then first come, first served
         if (e < k.s.n_envs) n = k.env_order ? __ldg(k.env_order + e) : (int)e;
+        meta[META_N] = n;
     }
     n = __shfl_sync(0xffffffffu, n, 0);
-    if (n < 0) return -1;
+    if (n >= 0) {
+        if (lane == 0) {
+            const int L = __ldg(k.s.line_widths + n);
+            const int64_t g0 = __ldg(k.s.line_starts + n);
+            const int b0 = __ldg(k.s.box_starts + n);
+            const int W = L - AF, nb = (W + VRUN - 1) / VRUN;
+            meta[0] = W; meta[3] = b0;
+            meta[META_G0] = (int)(uint32_t)g0; meta[META_G0 + 1] = (int)(uint32_t)((uint64_t)g0 >> 32);
+            meta[META_L] = L;
+            if (nb > 0 && q >= k.p_stages) {
+                bulk_prefetch_l2(k.s.occ_lines + 4 * VRUN * (int64_t)b0, (uint32_t)nb * VRUN * 16u);
+                if (k.stage_rec) bulk_prefetch_l2(k.s.occ_rec + 4 * VRUN * (int64_t)b0, (uint32_t)nb * VRUN * 16u);
+                bulk_prefetch_l2(k.s.occ_boxes + 4 * (int64_t)b0, (uint32_t)nb * 16u);
+            }
+        } else if (lane == 1) {
+            meta[1] = __ldg(k.s.light_widths + n); meta[2] = __ldg(k.s.light_starts + n);
+        } else if (lane == 2) {
+            meta[4] = __float_as_int(__ldg(k.s.occ_meta + 2 * n)); meta[5] = __float_as_int(__ldg(k.s.occ_meta + 2 * n + 1));
+            meta[6] = 0; meta[7] = 0;
+        } else if (lane == 3) {
+            meta[10] = 0; meta[11] = 0;                                  // no grid: every lookup falls outside
+            if (k.s.vis) {
+                const float4 vm = __ldg(reinterpret_cast<const float4*>(k.s.vis_meta) + n);
+                const int64_t vs = __ldg(k.s.vis_starts + n);
+                meta[8] = __float_as_int(vm.x); meta[9] = __float_as_int(vm.y); meta[10] = (int)vm.z; meta[11] = (int)vm.w;
+                meta[12] = (int)(uint32_t)vs; meta[13] = (int)(uint32_t)((uint64_t)vs >> 32);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// The env described in the stage's meta block: its table on its way into the stage by three bulk copies (static scenery
+// only: may run ahead of griddep_wait).
+__device__ __forceinline__ void stage_load(const KArgs& k, PCtl* ctl, const VSmem& m, int s, int lane, int AF) {
     if (lane == 0) {
-        const int L = __ldg(k.s.line_widths + n);
-        const int64_t g0 = __ldg(k.s.line_starts + n);
-        const int b0 = __ldg(k.s.box_starts + n);
-        const int W = L - AF, nb = (W + VRUN - 1) / VRUN;
-        m.meta[0] = W; m.meta[3] = b0;
-        m.meta[META_N] = n; m.meta[META_G0] = (int)(uint32_t)g0; m.meta[META_G0 + 1] = (int)(uint32_t)((uint64_t)g0 >> 32);
-        m.meta[META_L] = L;
+        const int W = m.meta[0], b0 = m.meta[3], nb = (W + VRUN - 1) / VRUN;
         m.meta[META_PAR] = ctl->fills[s] & 1;
         if (nb > 0) {
             ctl->fills[s]++;
@@ -1519,21 +1555,8 @@ __device__ __forceinline__ int stage_fill(const KArgs& k, PCtl* ctl, const VSmem
             if (k.stage_rec) bulk_g2s(m.rec, k.s.occ_rec + 4 * VRUN * (int64_t)b0, (uint32_t)nb * VRUN * 16u, &ctl->full_bar[s]);
             bulk_g2s(m.boxes, k.s.occ_boxes + 4 * (int64_t)b0, (uint32_t)nb * 16u, &ctl->full_bar[s]);
         }
-    } else if (lane == 1) {
-        m.meta[1] = __ldg(k.s.light_widths + n); m.meta[2] = __ldg(k.s.light_starts + n);
-    } else if (lane == 2) {
-        m.meta[4] = __float_as_int(__ldg(k.s.occ_meta + 2 * n)); m.meta[5] = __float_as_int(__ldg(k.s.occ_meta + 2 * n + 1));
-        m.meta[6] = 0; m.meta[7] = 0;
-    } else if (lane == 3) {
-        m.meta[10] = 0; m.meta[11] = 0;                                  // no grid: every lookup falls outside
-        if (k.s.vis) {
-            const float4 vm = __ldg(reinterpret_cast<const float4*>(k.s.vis_meta) + n);
-            const int64_t vs = __ldg(k.s.vis_starts + n);
-            m.meta[8] = __float_as_int(vm.x); m.meta[9] = __float_as_int(vm.y); m.meta[10] = (int)vm.z; m.meta[11] = (int)vm.w;
-            m.meta[12] = (int)(uint32_t)vs; m.meta[13] = (int)(uint32_t)((uint64_t)vs >> 32);
-        }
     }
-    return n;
+    __syncwarp();
 }
 
 // Second half (needs the kernels ahead in the stream: call after griddep_wait): the agents' state and their model lines
@@ -1626,8 +1649,8 @@ __device__ __noinline__ void dyn_ticket_run(const KArgs& k, int T, int lane) {
     }
 }
 
-template <int NCH, bool MERGE, bool STATS>
-__global__ void __launch_bounds__(MSB_VIEW_THREADS, MSB_VIEW_BLOCKS) tick_kernel(const __grid_constant__ KArgs k) {
+template <int NCH, bool MERGE, bool STATS, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) tick_kernel(const __grid_constant__ KArgs k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int A = k.s.n_agents, AF = A * k.s.n_model;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -1636,8 +1659,8 @@ __global__ void __launch_bounds__(MSB_VIEW_THREADS, MSB_VIEW_BLOCKS) tick_kernel
     unsigned char* stages = smem_raw + pctl_bytes();
     float4* scr = reinterpret_cast<float4*>(stages + (size_t)S * k.p_stage_bytes) + warp * (32 * NCH < 64 ? 64 : 32 * NCH);
     if (tid == 0) {
-        for (int s = 0; s < PMAXS; s++) { ctl->ready_seq[s] = 0; ctl->done_cnt[s] = 0; ctl->fills[s] = 0; }
-        ctl->next_ticket = 0; ctl->dead = 0; ctl->rays_out = 0; ctl->all_out = 0; ctl->error = 0;
+        for (int s = 0; s < PMAXS; s++) { ctl->ready_seq[s] = 0; ctl->done_cnt[s] = 0; ctl->fills[s] = 0; ctl->nseq[s] = 0; }
+        ctl->next_ticket = 0; ctl->dead = 0; ctl->all_out = 0; ctl->error = 0;
         float r = 0.f;
         for (int t = 0; t < 2 * k.s.n_model; t++) {                          // the model's radius: lets a warp skip agents it cannot see
             const float2 mp = __ldg(reinterpret_cast<const float2*>(k.s.model) + t);
@@ -1652,13 +1675,18 @@ __global__ void __launch_bounds__(MSB_VIEW_THREADS, MSB_VIEW_BLOCKS) tick_kernel
     VSmem m0;
     if (warp < S) {
         m0 = pstage(stages + (size_t)warp * k.p_stage_bytes, ctl, k, A, AF);
-        n0 = stage_fill(k, ctl, m0, warp, warp, lane, AF);
+        desc_fetch(k, m0.meta, warp, lane, AF);
+        n0 = m0.meta[META_N];
+        if (n0 >= 0) stage_load(k, ctl, m0, warp, lane, AF);
     }
     griddep_wait();
     griddep_launch();
     if (warp < S) {
         if (n0 >= 0) stage_publish(k, ctl, m0, warp, warp, n0, lane, A);
         else stage_dead(ctl, warp, lane);
+        // and the descriptor of the stage's next tenant
+        desc_fetch(k, ctl->nmeta[warp], warp + S, lane, AF);
+        if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(&ctl->nseq[warp]) = warp + S + 1; }
     }
     const bool merge = MERGE && k.dyn_entries != nullptr;
     const int esize = DYN_HDR + 32 * k.dyn_window;
@@ -1675,11 +1703,15 @@ __global__ void __launch_bounds__(MSB_VIEW_THREADS, MSB_VIEW_BLOCKS) tick_kernel
     if (merge) { take_ticket(); fl = peek(); }
     bool rays = true;
     unsigned spins = 0;
+    long long c_items = 0, c_wait = 0, c_dyn = 0, c_drain = 0, c_prep = 0, c_fetch = 0, n_dyn = 0, n_items = 0, n_spun = 0;
+    const long long c_start = STATS ? clock64() : 0;
     for (;;) {
         if (merge && __any_sync(0xffffffffu, fl != 0)) {
+            const long long c0 = STATS ? clock64() : 0;
             dyn_ticket_run<STATS>(k, T, lane);
             take_ticket();
             fl = peek();
+            if (STATS) { c_dyn += clock64() - c0; n_dyn++; }
             continue;
         }
         if (rays) {
@@ -1688,22 +1720,22 @@ __global__ void __launch_bounds__(MSB_VIEW_THREADS, MSB_VIEW_BLOCKS) tick_kernel
             t = __reduce_max_sync(0xffffffffu, t);                  // (lands in a uniform register: so do the item's address parts)
             const int q = t / IPE, it = t - q * IPE, s = q % S;
             int v;
+            const long long c0 = STATS ? clock64() : 0;
+            if (STATS && ld_volatile_shared(&ctl->ready_seq[s]) < q + 1) n_spun++;
             while ((v = ld_volatile_shared(&ctl->ready_seq[s])) < q + 1) {
-                __nanosleep(64);
-                if (++spins > SPIN_LIMIT) { ctl->error = 1; v = 0x7fffffff; break; }
+                __nanosleep(200);
+                if (++spins > SPIN_LIMIT) { ctl->error = 1; if (k.sched) k.sched[2] = 1; v = 0x7fffffff; break; }
             }
             __threadfence_block();
+            const long long c1 = STATS ? clock64() : 0;
+            if (STATS) c_wait += c1 - c0;
             if (v == 0x7fffffff) {
                 // nothing will be staged here any more; when that goes for every stage, the rays are done
                 if (ld_volatile_shared(&ctl->dead) >= S || ld_volatile_shared(&ctl->error)) {
                     rays = false;
-                    __syncwarp();
-                    if (lane == 0) {
-                        __threadfence();
-                        // the CTA's last warp out tells the second pass that this CTA will publish nothing more
-                        if (atomicAdd(&ctl->rays_out, 1) == nwarps - 1 && k.dyn_entries) { __threadfence(); red_release_add(k.dyn_ctrl + 3, 1); }
-                    }
                     if (!merge) break;
+                } else {
+                    __nanosleep(500);       // the other stages' last envs are still being worked on: no item for me, no hurry
                 }
                 continue;
             }
@@ -1720,29 +1752,63 @@ __global__ void __launch_bounds__(MSB_VIEW_THREADS, MSB_VIEW_BLOCKS) tick_kernel
             }
             fl = fl_next;
             __syncwarp();
+            const long long c2 = STATS ? clock64() : 0;
+            if (STATS) { c_items += c2 - c1; n_items++; }
             int last = 0;
             if (lane == 0) { __threadfence_block(); last = atomicAdd(&ctl->done_cnt[s], 1) == IPE - 1; }
             last = __shfl_sync(0xffffffffu, last, 0);
             if (last) {
-                // the env in stage s is finished: stage the next one there
-                if (lane == 0) ctl->done_cnt[s] = 0;
-                const int n = stage_fill(k, ctl, m, s, q + S, lane, AF);
-                if (n >= 0) stage_publish(k, ctl, m, s, q + S, n, lane, A);
-                else stage_dead(ctl, s, lane);
+                // the env in stage s is finished (nothing more will be queued for it: the second pass counts envs, so
+                // that it depends on no CTA that is yet to be scheduled): stage the next one there
+                if (lane == 0) {
+                    ctl->done_cnt[s] = 0;
+                    if (k.dyn_entries) { __threadfence(); red_release_add(k.dyn_ctrl + 3, 1); }
+                }
+                // its descriptor was fetched while this env was being worked on
+                while (ld_volatile_shared(&ctl->nseq[s]) != q + S + 1) {
+                    __nanosleep(100);
+                    if (++spins > SPIN_LIMIT) { ctl->error = 1; if (k.sched) k.sched[2] = 1; break; }
+                }
+                __threadfence_block();
+                if (lane < META_INTS) m.meta[lane] = ctl->nmeta[s][lane];
+                __syncwarp();
+                const int n = m.meta[META_N];
+                if (n >= 0) {
+                    stage_load(k, ctl, m, s, lane, AF);
+                    stage_publish(k, ctl, m, s, q + S, n, lane, A);
+                    const long long c3 = STATS ? clock64() : 0;
+                    desc_fetch(k, ctl->nmeta[s], q + 2 * S, lane, AF);
+                    if (STATS) { c_fetch += clock64() - c3; c_prep -= clock64() - c3; }
+                    if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(&ctl->nseq[s]) = q + 2 * S + 1; }
+                } else {
+                    stage_dead(ctl, s, lane);
+                }
+                if (STATS) c_prep += clock64() - c2;
             }
         } else {
-            // drain: my entry will be published, or every CTA has signed off and it never will be
+            // drain: my entry will be published, or every env is done and it never will be
+            const long long c0 = STATS ? clock64() : 0;
             fl = peek();
             if (__any_sync(0xffffffffu, fl != 0)) continue;
-            if (ld_volatile_global(k.dyn_ctrl + 3) >= (int)gridDim.x) {
+            if (ld_volatile_global(k.dyn_ctrl + 3) >= k.s.n_envs) {
                 __threadfence();
                 fl = peek();
                 if (!__any_sync(0xffffffffu, fl != 0)) break;
                 continue;
             }
             __nanosleep(200);
-            if (++spins > SPIN_LIMIT) break;
+            if (STATS) c_drain += clock64() - c0;
+            if (++spins > 16u * SPIN_LIMIT) { if (k.sched) k.sched[2] = 1; break; }         // (seconds: a bug, not a wait)
         }
+    }
+    if (STATS && k.stats && lane == 0) {
+        const long long total = clock64() - c_start;
+        atomicAdd(k.stats + STAT_T_ITEMS, (unsigned long long)c_items); atomicAdd(k.stats + STAT_T_WAIT, (unsigned long long)c_wait);
+        atomicAdd(k.stats + STAT_T_DYN, (unsigned long long)c_dyn); atomicAdd(k.stats + STAT_T_DRAIN, (unsigned long long)c_drain);
+        atomicAdd(k.stats + STAT_T_PREP, (unsigned long long)c_prep); atomicAdd(k.stats + STAT_T_TOTAL, (unsigned long long)total);
+        atomicAdd(k.stats + STAT_N_DYN, (unsigned long long)n_dyn); atomicAdd(k.stats + STAT_N_ITEMS, (unsigned long long)n_items);
+        atomicMax(k.stats + STAT_T_MAXWARP, (unsigned long long)total); atomicAdd(k.stats + STAT_N_SPUN, (unsigned long long)n_spun);
+        atomicAdd(k.stats + STAT_T_FETCH, (unsigned long long)c_fetch);
     }
     // the last warp of the last CTA out re-arms the counters for the next launch
     __syncwarp();
@@ -2141,6 +2207,7 @@ extern "C" int64_t msb_get_option(const char* name) {
     if (!strncmp(name, "stat", 4) && g_stats) {
         unsigned long long h[STAT_SLOTS];
         if (cudaMemcpy(h, g_stats, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        if (name[5] >= '0' && name[5] <= '9') { const int i = atoi(name + 5); return i < STAT_SLOTS ? (int64_t)h[i] : -1; }
         if (!strcmp(name, "stat_tests")) return (int64_t)h[STAT_TESTS];
         if (!strcmp(name, "stat_groups")) return (int64_t)h[STAT_GROUPS];
         if (!strcmp(name, "stat_dyn_rays")) return (int64_t)h[STAT_DYN_RAYS];
@@ -2349,20 +2416,27 @@ static int launch_tick(KArgs& k, int nch, cudaStream_t st, bool* merged) {
                  (k.out.distances ? OUT_DISTANCES : 0) | (k.out.screen ? OUT_SCREEN : 0) |
                  (k.has_obs && k.obs.rgb ? OUT_RGB : 0) | (k.has_obs && k.obs.depth ? OUT_DEPTH : 0) | (k.has_obs && k.obs.imu ? OUT_IMU : 0);
     k.p_items = A * k.ray_blocks;
-    const int threads = (g_opt_threads >= 64 && g_opt_threads <= 256) ? (int)(g_opt_threads / 32) * 32 : 256;
+    int threads = 256;
+    if (g_opt_threads >= 64 && g_opt_threads <= 1024) threads = (int)(g_opt_threads / 32) * 32;
+    const int bound = threads <= 256 ? 256 : (threads <= 512 ? 512 : 1024);     // the instantiation: bound x (1024 / bound) CTAs fill an SM's registers
+    const int per_sm_target = 1024 / bound;
     const int nwarps = threads / 32;
     const size_t scr = (size_t)nwarps * (32 * nch < 64 ? 64 : 32 * nch) * 16;
     const size_t ctl = (sizeof(PCtl) + 15) & ~size_t(15);
-    // stages and whether the rows' records are staged too: as much as keeps four CTAs on an SM
-    const size_t budget = (227 * 1024 - MSB_VIEW_BLOCKS * 1024) / MSB_VIEW_BLOCKS;
-    int S = 2;
+    // stages and whether the rows' records are staged too: as much as keeps the SM's registers in use
+    const size_t budget = (227 * 1024 - per_sm_target * 1024) / per_sm_target;
     bool rec = g_opt_stage_rec != 2;
-    if (g_opt_stages >= 2 && g_opt_stages <= PMAXS) S = (int)g_opt_stages;
     auto total = [&](int stages, bool r) { return ctl + stages * pstage_bytes(k.wcap, A, AF, r) + scr; };
+    // enough stages for every warp to have an item, plus one being refilled
+    int S = (nwarps + k.p_items - 1) / k.p_items + 1;
+    if (S < 2) S = 2;
+    if (g_opt_stages >= 2 && g_opt_stages <= PMAXS) S = (int)g_opt_stages;
+    if (S > PMAXS) S = PMAXS;
     if (rec && g_opt_stage_rec != 1 && total(S, true) > budget) rec = false;
     while (S > 2 && !g_opt_stages && total(S, rec) > budget) S--;
     if (S > nwarps) S = nwarps;
     if (total(S, rec) > 227 * 1024 && rec) rec = false;
+    while (S > 2 && total(S, rec) > 227 * 1024) S--;
     if (total(S, rec) > 227 * 1024) return fail("%s", "scene too large: an env's segments do not fit in shared memory (227 KB)");
     k.stage_rec = rec ? 1 : 0;
     k.p_stages = S;
@@ -2371,10 +2445,8 @@ static int launch_tick(KArgs& k, int nch, cudaStream_t st, bool* merged) {
     const size_t sm = total(S, rec);
     const bool merge = g_opt_merge_dyn != 2 && k.dyn_entries != nullptr && k.sched != nullptr;
     *merged = merge;
-#define MSB_LAUNCH(N)                                                                                            \
+#define MSB_GO(fn)                                                                                               \
     {                                                                                                            \
-        auto fn = merge ? (k.stats ? tick_kernel<N, true, true> : tick_kernel<N, true, false>)                   \
-                        : (k.stats ? tick_kernel<N, false, true> : tick_kernel<N, false, false>);                \
         if (sm > 48 * 1024 && check(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), \
                                     "cudaFuncSetAttribute"))                                                     \
             return 1;                                                                                            \
@@ -2382,8 +2454,19 @@ static int launch_tick(KArgs& k, int nch, cudaStream_t st, bool* merged) {
         const int per_sm = occupancy((const void*)fn, threads, sm, &sms);                                       \
         int grid = sms * per_sm;                                                                                 \
         if (grid > k.s.n_envs) grid = k.s.n_envs;                                                               \
-        k.view_ctas = grid;                                                                                      \
         launch(fn, grid, threads, sm, st, true, k);                                                              \
+    }
+#define MSB_LAUNCH(N)                                                                                            \
+    {                                                                                                            \
+        if (bound == 256) {                                                                                      \
+            if (merge) { if (k.stats) MSB_GO((tick_kernel<N, true, true, 256>)) else MSB_GO((tick_kernel<N, true, false, 256>)) }   \
+            else { if (k.stats) MSB_GO((tick_kernel<N, false, true, 256>)) else MSB_GO((tick_kernel<N, false, false, 256>)) }       \
+        } else if (bound == 512) {                                                                               \
+            if (merge) MSB_GO((tick_kernel<N, true, false, 512>)) else MSB_GO((tick_kernel<N, false, false, 512>))                  \
+        } else {                                                                                                 \
+            if (merge) { if (k.stats) MSB_GO((tick_kernel<N, true, true, 1024>)) else MSB_GO((tick_kernel<N, true, false, 1024>)) } \
+            else { if (k.stats) MSB_GO((tick_kernel<N, false, true, 1024>)) else MSB_GO((tick_kernel<N, false, false, 1024>)) }     \
+        }                                                                                                        \
     }
     {
         TimedLaunch timed(TK_RENDER, st);
@@ -2394,18 +2477,19 @@ static int launch_tick(KArgs& k, int nch, cudaStream_t st, bool* merged) {
         }
     }
 #undef MSB_LAUNCH
+#undef MSB_GO
     g_launches++;
     return check(cudaGetLastError(), "tick_kernel launch");
 }
 
 // render (+ heads) after the agents have been moved: the persistent kernel where an env has enough items, else one CTA per env
 static int launch_render(KArgs& k, int nch, int rb, int threads, cudaStream_t st) {
+    k.view_ctas = k.s.n_envs;       // what the second pass counts up to: envs whose rays are done
     if (want_tick(k, rb)) {
         bool merged = false;
         if (launch_tick(k, nch, st, &merged)) return 1;
         return merged ? 0 : launch_dyn(k, st);
     }
-    k.view_ctas = k.s.n_envs;
     if (launch_view(k, false, nch, threads, st)) return 1;
     return launch_dyn(k, st);
 }

@@ -87,3 +87,182 @@ class ObsGather:
 def gathered_bytes(example, world_size):
     """Bytes each rank receives per gather (cost model: / ~725 GB/s measured all-gather bus bandwidth)."""
     return sum(v.numel() * v.element_size() for v in example.values()) * (world_size - 1)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# ShardedCore: one process per GPU, each stepping its own contiguous range of the batch's environments
+# ----------------------------------------------------------------------------------------------------------------------
+def initialize(device=None, devices=None, backend=None):
+    """Single-host process group, as the reference sets it up for its learner (rebar/processes.py:18-29): rendezvous on
+    127.0.0.1, port 29500 + the first device, rank = this process's position in `devices`. Under torchrun (RANK /
+    WORLD_SIZE / MASTER_* in the environment) those are used instead. No-op if a group already exists."""
+    import os
+    if dist.is_initialized():
+        return
+    backend = backend or ('nccl' if torch.cuda.is_available() else 'gloo')
+    if 'RANK' in os.environ and 'WORLD_SIZE' in os.environ:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29500')
+        dist.init_process_group(backend)
+        return
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    if device is None:
+        os.environ['MASTER_PORT'] = str(29500)
+        dist.init_process_group(backend, rank=0, world_size=1)
+    else:
+        os.environ['MASTER_PORT'] = str(29500 + devices[0])
+        dist.init_process_group(backend, rank=devices.index(device), world_size=len(devices))
+
+
+class PackedObs:
+    """The observation heads of one rank packed per environment — one row [rgb | d | imu] per env — so that ONE
+    all-gather of the rows gives every rank the whole batch, and each observation of the whole batch is a plain strided
+    view of the gathered rows (no unpacking pass). Optionally carried at reduced precision.
+
+    layout(n_agents, ro) -> column ranges; views(rows) -> arrdict(rgb (N,A,3,1,ro), d (N,A,1,1,ro), imu (N,A,3))."""
+
+    def __init__(self, n_agents, ro, dtype=torch.float32):
+        self.A, self.ro, self.dtype = n_agents, ro, dtype
+        self.cols = {'rgb': (0, n_agents * 3 * ro), 'd': (n_agents * 3 * ro, n_agents * 4 * ro),
+                     'imu': (n_agents * 4 * ro, n_agents * 4 * ro + n_agents * 3)}
+        self.width = self.cols['imu'][1]
+
+    def empty(self, n_envs, device):
+        return torch.empty((n_envs, self.width), dtype=self.dtype, device=device)
+
+    def pack(self, obs, out):
+        """obs: arrdict(rgb, d, imu) of one rank (float32) -> out (n_local, width); three strided copies (with the cast)."""
+        n = out.shape[0]
+        for k, (a, b) in self.cols.items():
+            out[:, a:b].copy_(obs[k].reshape(n, -1))
+        return out
+
+    def views(self, rows):
+        from .arrdict import arrdict
+        n, A, ro = rows.shape[0], self.A, self.ro
+        c = self.cols
+        return arrdict(rgb=rows[:, c['rgb'][0]:c['rgb'][1]].unflatten(1, (A, 3, 1, ro)),
+                       d=rows[:, c['d'][0]:c['d'][1]].unflatten(1, (A, 1, 1, ro)),
+                       imu=rows[:, c['imu'][0]:c['imu'][1]].unflatten(1, (A, 3)))
+
+
+class ShardedCore:
+    """This rank's share of a batch of environments, behind one object.
+
+        sharding.initialize(device, devices)                 # or torchrun
+        sc = ShardedCore(arrays, n_envs_total, res=128, fov=70, subsample=1)
+        out = sc.step(actions_local)                         # FusedStep on this rank's envs [sc.lo, sc.hi): no communication
+        full = sc.gather()                                   # optional: every rank gets the whole batch's observations
+
+    `arrays` is either the whole batch's `scene.scene_arrays` dict (each rank keeps its slice) or a callable
+    `(lo, hi) -> arrays` that builds only this rank's envs. Envs are split into contiguous ranges (`shard_range`); each
+    rank owns its scenery, agents and parameters. The only collective is `gather()`: the observation heads are packed
+    one row per env (`PackedObs`) and all-gathered with ONE `all_gather_into_tensor` on a side stream, so that it
+    overlaps the next `step()`; `gather_start()` / `gather_wait()` split it. `obs_dtype=torch.float16` halves the bytes
+    on the wire.
+    """
+
+    def __init__(self, arrays, n_envs, n_agents=None, res=64, fov=130., fps=10., subsample=1, raw=False, obs_dtype=torch.float32,
+                 group=None, device=None, graph=False, positions=None, angles=None):
+        from . import core as core_, cuda, modules, scene
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n_envs = n_envs
+        self.lo, self.hi = shard_range(n_envs, self.rank, self.world)
+        assert n_envs % self.world == 0, 'the all-gather needs equally sized shards: n_envs must be a multiple of the world size'
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
+        self.device = torch.device(device)
+        local = arrays(self.lo, self.hi) if callable(arrays) else shard_arrays(arrays, self.lo, self.hi)
+        s = scene.upload(local, self.device)
+        if 'baked' in local:
+            s.baked.vals.copy_(torch.as_tensor(local['baked']))
+        else:
+            cuda.bake(s, params=cuda.make_params(core_.AGENT_RADIUS, res, fov, fps))
+        self.core = core_.Core(s, res=res, fov=fov, fps=fps)
+        if positions is not None:
+            self.core.agents.positions.copy_(torch.as_tensor(positions[self.lo:self.hi]))
+        if angles is not None:
+            self.core.agents.angles.copy_(torch.as_tensor(angles[self.lo:self.hi]))
+        self.stepper = modules.FusedStep(self.core, subsample=subsample, raw=raw, graph=graph)
+        self.packing = PackedObs(self.core.n_agents, res // subsample, obs_dtype)
+        self._gatherer = None
+        self._out = None
+
+    @property
+    def n_local(self):
+        return self.hi - self.lo
+
+    def step(self, actions=None):
+        """One tick of this rank's envs; `actions` (n_local, A) int. Returns FusedStep's arrdict (obs, progress, render)."""
+        self._out = self.stepper(actions)
+        return self._out
+
+    def gather_start(self):
+        """Pack the latest observations and start all-gathering them on the side stream."""
+        if self._gatherer is None:
+            self._gatherer = RowGather(self.packing, self.n_local, self.device, self.group)
+        self._gatherer.start(self._out.obs)
+
+    def gather_wait(self):
+        """The whole batch's observations (env-major, rank 0's envs first): arrdict(rgb, d, imu) of strided views."""
+        return self._gatherer.wait()
+
+    def gather(self):
+        self.gather_start()
+        return self.gather_wait()
+
+
+class RowGather:
+    """One `all_gather_into_tensor` of per-env packed rows, double-buffered so that the gather of tick t may still be in
+    flight (side stream) while tick t+1 runs and packs into the other buffer."""
+
+    def __init__(self, packing, n_local, device, group=None):
+        self.packing, self.group = packing, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.cuda = torch.device(device).type == 'cuda'
+        self.rows = [packing.empty(n_local, device) for _ in range(2)]
+        self.full = [packing.empty(n_local * self.world, device) for _ in range(2)]
+        self.stream = torch.cuda.Stream(device=device, priority=-1) if self.cuda else None
+        self.done = [None, None]
+        self.tick = 0
+        self._work = None
+
+    def start(self, obs):
+        i = self.tick & 1
+        if self.cuda:
+            main = torch.cuda.current_stream()
+            if self.done[i] is not None:
+                main.wait_event(self.done[i])                  # the gather that last read rows[i] / wrote full[i]
+            self.packing.pack(obs, self.rows[i])
+            self.stream.wait_stream(main)
+            with torch.cuda.stream(self.stream):
+                if self.world > 1:
+                    dist.all_gather_into_tensor(self.full[i], self.rows[i], group=self.group)
+                else:
+                    self.full[i].copy_(self.rows[i])
+                self.done[i] = torch.cuda.Event()
+                self.done[i].record(self.stream)
+        else:
+            self.packing.pack(obs, self.rows[i])
+            if self.world > 1:
+                self._work = dist.all_gather_into_tensor(self.full[i], self.rows[i], group=self.group, async_op=True) \
+                    if dist.get_backend(self.group) != 'gloo' else \
+                    dist.all_gather(list(self.full[i].chunk(self.world, 0)), self.rows[i], group=self.group, async_op=True)
+            else:
+                self.full[i].copy_(self.rows[i])
+        self._pending = i
+        self.tick += 1
+
+    def wait(self):
+        i = self._pending
+        if self.cuda:
+            torch.cuda.current_stream().wait_event(self.done[i])
+        elif self._work is not None:
+            self._work.wait()
+            self._work = None
+        return self.packing.views(self.full[i])
+
+    def bytes_received(self):
+        return self.rows[0].numel() * self.rows[0].element_size() * (self.world - 1)

@@ -29,6 +29,7 @@ def main():
     ap.add_argument('--envs', type=int, default=None)
     ap.add_argument('--steps', type=int, default=300)
     ap.add_argument('--no-raw', action='store_true')
+    ap.add_argument('--stats', action='store_true', help='one extra step with the device counters on: where tick_kernel\'s warp-cycles go')
     ap.add_argument('sets', nargs='*', default=[''])
     args = ap.parse_args()
     cfg = dict(bench.WORKLOADS[args.workload])
@@ -72,7 +73,20 @@ def main():
         km = {kind: round(cuda.get_option(f'time_ns_{kind}') / 1e3 / max(cuda.get_option(f'time_count_{kind}'), 1), 1)
               for kind in ('physics', 'render', 'dyn') if cuda.get_option(f'time_count_{kind}') > 0}
         cuda.set_option('timing', 0)
-        print(json.dumps({'options': spec, 'workload': args.workload, 'envs': N, 'step_us': round(float(ms.mean()) * 1e3, 1),
+        st = None
+        if args.stats:
+            cuda.set_option('stats', 1)
+            cuda.set_option('stats_reset', 0)
+            step._plan()
+            torch.cuda.synchronize()
+            names = ('items', 'wait', 'dyn', 'drain', 'prep', 'total', 'n_dyn', 'n_items', 'max_warp', 'n_spun', 'fetch')
+            raw = {n: cuda.get_option(f'stat_{16 + i}') for i, n in enumerate(names)}
+            tot = max(raw['total'], 1)
+            st = {n: round(raw[n] / tot, 4) for n in ('items', 'wait', 'dyn', 'drain', 'prep', 'fetch')}
+            st.update(n_dyn=raw['n_dyn'], n_items=raw['n_items'], n_spun=raw['n_spun'], max_warp_cycles=raw['max_warp'],
+                      tests=cuda.get_option('stat_tests'), groups=cuda.get_option('stat_groups'), total_cycles=tot)
+            cuda.set_option('stats', 0)
+        print(json.dumps({'options': spec, 'stats': st, 'workload': args.workload, 'envs': N, 'step_us': round(float(ms.mean()) * 1e3, 1),
                           'p50': round(float(np.percentile(ms, 50)) * 1e3, 1), 'p95': round(float(np.percentile(ms, 95)) * 1e3, 1),
                           'kernels_apart_us': km, 'checksum': float(step._plan.rgb.double().sum())}), flush=True)
         del step, c
