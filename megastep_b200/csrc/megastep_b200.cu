@@ -1455,12 +1455,15 @@ enum { SPIN_LIMIT = 1 << 22 };
 
 struct PCtl {
     uint64_t full_bar[PMAXS];   // per stage: the bulk copies of its env's table have landed
-    int ready_seq[PMAXS];       // per stage: 1 + sequence number of the env staged and drawn there (0x7fffffff: none will come)
+    int ready_seq[PMAXS];       // per stage: 0 while it is being (re)staged; else the publication number of the env staged and
+                                // drawn there (older envs first); 0x7fffffff: none will come
+    int item_next[PMAXS];       // per stage: items of its env handed out
     int done_cnt[PMAXS];        // per stage: items of its env finished
     int fills[PMAXS];           // per stage: bulk-copy rounds so far (the mbarrier's phase)
-    int nseq[PMAXS];            // per stage: 1 + sequence number of the env whose descriptor waits in nmeta (its next tenant)
+    int nseq[PMAXS];            // per stage: nmeta holds the descriptor of its next tenant
     int nmeta[PMAXS][META_INTS];// per stage: that descriptor, fetched while the current tenant is being worked on
-    int next_ticket;            // items handed out
+    int fetches;                // descriptors fetched by this CTA
+    int pubs;                   // envs published by this CTA
     int dead;                   // stages that will not be refilled
     int all_out;                // warps that have left the kernel
     int mrad;                   // bits of the agent model's radius
@@ -1561,7 +1564,7 @@ __device__ __forceinline__ void stage_load(const KArgs& k, PCtl* ctl, const VSme
 
 // Second half (needs the kernels ahead in the stream: call after griddep_wait): the agents' state and their model lines
 // at their current poses (draw_kernel, kernels.cu:297-318), the IMU head; then wait for the table and publish the stage.
-__device__ __forceinline__ void stage_publish(const KArgs& k, PCtl* ctl, const VSmem& m, int s, int q, int n, int lane, int A) {
+__device__ __forceinline__ void stage_publish(const KArgs& k, PCtl* ctl, const VSmem& m, int s, int n, int lane, int A) {
     const int F = k.s.n_model;
     for (int a = lane; a < A; a += 32) {
         const int64_t i = (int64_t)n * A + a;
@@ -1595,8 +1598,9 @@ __device__ __forceinline__ void stage_publish(const KArgs& k, PCtl* ctl, const V
     if (m.meta[0] > 0) mbar_wait(&ctl->full_bar[s], (uint32_t)m.meta[META_PAR]);
     __syncwarp();
     if (lane == 0) {
+        const int pub = atomicAdd(&ctl->pubs, 1) + 1;
         __threadfence_block();
-        *reinterpret_cast<volatile int*>(&ctl->ready_seq[s]) = q + 1;
+        *reinterpret_cast<volatile int*>(&ctl->ready_seq[s]) = pub;
     }
 }
 
@@ -1659,8 +1663,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) tick_kernel(const __g
     unsigned char* stages = smem_raw + pctl_bytes();
     float4* scr = reinterpret_cast<float4*>(stages + (size_t)S * k.p_stage_bytes) + warp * (32 * NCH < 64 ? 64 : 32 * NCH);
     if (tid == 0) {
-        for (int s = 0; s < PMAXS; s++) { ctl->ready_seq[s] = 0; ctl->done_cnt[s] = 0; ctl->fills[s] = 0; ctl->nseq[s] = 0; }
-        ctl->next_ticket = 0; ctl->dead = 0; ctl->all_out = 0; ctl->error = 0;
+        for (int s = 0; s < PMAXS; s++) { ctl->ready_seq[s] = 0; ctl->item_next[s] = 0; ctl->done_cnt[s] = 0; ctl->fills[s] = 0; ctl->nseq[s] = 0; }
+        ctl->fetches = S; ctl->pubs = 0; ctl->dead = 0; ctl->all_out = 0; ctl->error = 0;
         float r = 0.f;
         for (int t = 0; t < 2 * k.s.n_model; t++) {                          // the model's radius: lets a warp skip agents it cannot see
             const float2 mp = __ldg(reinterpret_cast<const float2*>(k.s.model) + t);
@@ -1682,11 +1686,13 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) tick_kernel(const __g
     griddep_wait();
     griddep_launch();
     if (warp < S) {
-        if (n0 >= 0) stage_publish(k, ctl, m0, warp, warp, n0, lane, A);
+        if (n0 >= 0) stage_publish(k, ctl, m0, warp, n0, lane, A);
         else stage_dead(ctl, warp, lane);
         // and the descriptor of the stage's next tenant
-        desc_fetch(k, ctl->nmeta[warp], warp + S, lane, AF);
-        if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(&ctl->nseq[warp]) = warp + S + 1; }
+        int f = 0;
+        if (lane == 0) f = atomicAdd(&ctl->fetches, 1);
+        desc_fetch(k, ctl->nmeta[warp], __shfl_sync(0xffffffffu, f, 0), lane, AF);
+        if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(&ctl->nseq[warp]) = 1; }
     }
     const bool merge = MERGE && k.dyn_entries != nullptr;
     const int esize = DYN_HDR + 32 * k.dyn_window;
@@ -1715,30 +1721,41 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) tick_kernel(const __g
             continue;
         }
         if (rays) {
-            int t = 0;
-            if (lane == 0) t = atomicAdd(&ctl->next_ticket, 1);
-            t = __reduce_max_sync(0xffffffffu, t);                  // (lands in a uniform register: so do the item's address parts)
-            const int q = t / IPE, it = t - q * IPE, s = q % S;
-            int v;
+            // an item of the staged env that was published first and still has items to hand out. (The stages are a pool,
+            // not a ring: an item that takes long keeps ITS stage; the others go on being refilled around it.)
             const long long c0 = STATS ? clock64() : 0;
-            if (STATS && ld_volatile_shared(&ctl->ready_seq[s]) < q + 1) n_spun++;
-            while ((v = ld_volatile_shared(&ctl->ready_seq[s])) < q + 1) {
+            int s = -1, alive = 0, oldest = 0x7fffffff;
+            for (int i = 0; i < S; i++) {
+                const int v = ld_volatile_shared(&ctl->ready_seq[i]);
+                if (v == 0x7fffffff) continue;
+                alive++;
+                if (v > 0 && v < oldest && ld_volatile_shared(&ctl->item_next[i]) < IPE) { oldest = v; s = i; }
+            }
+            if (s < 0) {
+                if (alive == 0 || ld_volatile_shared(&ctl->error)) {        // nothing is staged and nothing will be: the rays are done
+                    rays = false;
+                    if (!merge) break;
+                    continue;
+                }
+                __nanosleep(200);
+                if (STATS) { c_wait += clock64() - c0; n_spun++; }
+                if (++spins > SPIN_LIMIT) { ctl->error = 1; if (k.sched) k.sched[2] = 1; }
+                continue;
+            }
+            int it = 0;
+            if (lane == 0) it = atomicAdd(&ctl->item_next[s], 1);
+            it = __reduce_max_sync(0xffffffffu, it);                // (lands in a uniform register: so do the item's address parts)
+            if (it >= IPE) continue;                                // another warp was quicker
+            // (the stage may have been finished and taken down for restaging since I looked: my item is then one of its
+            // next tenant's, or void)
+            int v;
+            while ((v = ld_volatile_shared(&ctl->ready_seq[s])) == 0) {
                 __nanosleep(200);
                 if (++spins > SPIN_LIMIT) { ctl->error = 1; if (k.sched) k.sched[2] = 1; v = 0x7fffffff; break; }
             }
+            if (v == 0x7fffffff) continue;
             __threadfence_block();
             const long long c1 = STATS ? clock64() : 0;
-            if (STATS) c_wait += c1 - c0;
-            if (v == 0x7fffffff) {
-                // nothing will be staged here any more; when that goes for every stage, the rays are done
-                if (ld_volatile_shared(&ctl->dead) >= S || ld_volatile_shared(&ctl->error)) {
-                    rays = false;
-                    if (!merge) break;
-                } else {
-                    __nanosleep(500);       // the other stages' last envs are still being worked on: no item for me, no hurry
-                }
-                continue;
-            }
             VSmem m = pstage(stages + (size_t)s * k.p_stage_bytes, ctl, k, A, AF);
             const int fl_next = merge ? peek() : 0;                 // asked for now, looked at after the item
             {
@@ -1759,13 +1776,16 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) tick_kernel(const __g
             last = __shfl_sync(0xffffffffu, last, 0);
             if (last) {
                 // the env in stage s is finished (nothing more will be queued for it: the second pass counts envs, so
-                // that it depends on no CTA that is yet to be scheduled): stage the next one there
+                // that it depends on no CTA that is yet to be scheduled): take the stage down and stage the next env there
                 if (lane == 0) {
+                    *reinterpret_cast<volatile int*>(&ctl->ready_seq[s]) = 0;
+                    __threadfence_block();
                     ctl->done_cnt[s] = 0;
+                    *reinterpret_cast<volatile int*>(&ctl->item_next[s]) = 0;
                     if (k.dyn_entries) { __threadfence(); red_release_add(k.dyn_ctrl + 3, 1); }
                 }
                 // its descriptor was fetched while this env was being worked on
-                while (ld_volatile_shared(&ctl->nseq[s]) != q + S + 1) {
+                while (ld_volatile_shared(&ctl->nseq[s]) == 0) {
                     __nanosleep(100);
                     if (++spins > SPIN_LIMIT) { ctl->error = 1; if (k.sched) k.sched[2] = 1; break; }
                 }
@@ -1774,12 +1794,15 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) tick_kernel(const __g
                 __syncwarp();
                 const int n = m.meta[META_N];
                 if (n >= 0) {
+                    if (lane == 0) ctl->nseq[s] = 0;
                     stage_load(k, ctl, m, s, lane, AF);
-                    stage_publish(k, ctl, m, s, q + S, n, lane, A);
+                    stage_publish(k, ctl, m, s, n, lane, A);
                     const long long c3 = STATS ? clock64() : 0;
-                    desc_fetch(k, ctl->nmeta[s], q + 2 * S, lane, AF);
+                    int f = 0;
+                    if (lane == 0) f = atomicAdd(&ctl->fetches, 1);
+                    desc_fetch(k, ctl->nmeta[s], __shfl_sync(0xffffffffu, f, 0), lane, AF);
                     if (STATS) { c_fetch += clock64() - c3; c_prep -= clock64() - c3; }
-                    if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(&ctl->nseq[s]) = q + 2 * S + 1; }
+                    if (lane == 0) { __threadfence_block(); *reinterpret_cast<volatile int*>(&ctl->nseq[s]) = 1; }
                 } else {
                     stage_dead(ctl, s, lane);
                 }
@@ -2042,6 +2065,81 @@ __global__ void __launch_bounds__(256) bake_kernel(const __grid_constant__ KArgs
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// bake over the spatial table: the same light_intensity() per texel, but a light's shadow test only opens the runs whose
+// (conservatively grown) box the segment light -> texel passes through — the slab test and margin of dyn_scan — instead
+// of every static line of the env. Which segments get tested varies; occluded / unoccluded per (texel, light) does not,
+// and the lights are summed in light order: bit-identical to bake_kernel (and to the reference's baking_kernel).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bake_table_kernel(const __grid_constant__ KArgs k) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = blockIdx.x;
+    const int A = k.s.n_agents, AF = A * k.s.n_model;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    float4* seg = reinterpret_cast<float4*>(smem_raw);                   // [wcap] sorted static rows
+    float4* boxes = seg + k.wcap;                                        // [wcap / 16]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(boxes + k.wcap / VRUN);
+    const int L = __ldg(k.s.line_widths + n);
+    const int64_t g0 = __ldg(k.s.line_starts + n);
+    const int W = L > AF ? L - AF : 0, nb = (W + VRUN - 1) / VRUN;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        if (nb > 0) {
+            const int64_t b0 = __ldg(k.s.box_starts + n);
+            mbar_expect_tx(bar, (uint32_t)nb * (VRUN * 16u + 16u));
+            bulk_g2s(seg, k.s.occ_lines + 4 * VRUN * b0, (uint32_t)nb * VRUN * 16u, bar);
+            bulk_g2s(boxes, k.s.occ_boxes + 4 * b0, (uint32_t)nb * 16u, bar);
+        }
+    }
+    __syncthreads();
+    if (nb > 0) mbar_wait(bar, 0);
+    const int I = __ldg(k.s.light_widths + n);
+    const float* lt = k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n);
+    const float vmax = __ldg(k.s.occ_meta + 2 * n), diam = __ldg(k.s.occ_meta + 2 * n + 1);
+    const float4* lines = reinterpret_cast<const float4*>(k.s.lines) + g0;
+    for (int l = warp; l < L; l += nwarps) {
+        const int w = __ldg(k.s.tex_widths + g0 + l);
+        const int64_t ts = __ldg(k.s.tex_starts + g0 + l);
+        const float4 s4 = __ldg(lines + l);
+        const float rw = rcp((float)w);
+        for (int t = lane; t < w; t += 32) {
+            const float loc = fmul(fadd((float)(unsigned)t, 0.5f), rw);                     // kernels.cu:278
+            const float om = fsub(1.f, loc);
+            const float Cx = ffma(s4.x, om, fmul(loc, s4.z)), Cy = ffma(s4.y, om, fmul(loc, s4.w));   // :279
+            float acc = 0.1f;                                                               // AMBIENT
+            for (int i = 0; i < I; i++) {
+                const float Ix = __ldg(lt + 3 * i), Iy = __ldg(lt + 3 * i + 1), Ii = __ldg(lt + 3 * i + 2);
+                const float Ux = fsub(Cx, Ix), Uy = fsub(Cy, Iy);
+                // conservative query, as dyn_scan's (DESIGN.md "shadow cull")
+                const float ulen = fmaxf(fabsf(Ux), fabsf(Uy));
+                const float delta = 4e-4f * vmax * (diam + ulen);
+                const float mg = delta * (ulen + vmax) + 0.01f;
+                const float irx = 1.f / Ux, iry = 1.f / Uy;                                 // +-inf when axis-parallel
+                bool occluded = false;
+                for (int b = 0; b < nb && !occluded; b++) {
+                    const float4 bx = boxes[b];
+                    const float tx0 = (bx.x - mg - Ix) * irx, tx1 = (bx.z + mg - Ix) * irx;
+                    const float ty0 = (bx.y - mg - Iy) * iry, ty1 = (bx.w + mg - Iy) * iry;
+                    const float tlo = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), 0.f);
+                    const float thi = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), 1.f);
+                    if (!(tlo > thi)) {                                                     // (NaN: visit)
+                        const float4* run = seg + VRUN * b;
+#pragma unroll 4
+                        for (int r = 0; r < VRUN; r++) {
+                            if (occludes(intersect(Ix, Iy, Ux, Uy, run[r]))) { occluded = true; break; }
+                        }
+                    }
+                }
+                if (!occluded) {
+                    const float dx = fsub(Ix, Cx), dy = fsub(Iy, Cy);
+                    acc = ffma(fadd(Ii, Ii), rcp(fmaxf(ffma(dx, dx, fmul(dy, dy)), 1.f)), acc);
+                }
+            }
+            k.s.baked[ts + t] = fminf(acc, 1.f);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side: C ABI
 // ---------------------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -2058,7 +2156,8 @@ static long long g_opt_dyn_window = 0;   // 0 = default (DYN_MIN_WINDOW); 1, 2, 
 static long long g_opt_dyn_warps = 0;    // warps sharing one queue entry in dyn_kernel (default 2)
 static long long g_opt_fused_step = 0;   // 1: msb_step runs physics inside view_kernel (measured slower: the physics latency
                                          // chain adds to every CTA's life instead of running at its own high occupancy)
-static long long g_opt_persist = 0;      // 0: auto (tick_kernel when an env has >= 4 items), 1: whenever possible, 2: never (view_kernel + dyn_kernel)
+static long long g_opt_bake_brute = 0;  // 1: bake tests every static line per (texel, light) like the reference, even when the spatial table exists
+static long long g_opt_persist = 0;      // 1: render with tick_kernel (persistent grid) instead of view_kernel + dyn_kernel
 static long long g_opt_merge_dyn = 0;    // tick_kernel lights the agent-hit windows itself — 0 / 1: yes, 2: no (dyn_kernel follows)
 static long long g_opt_dyn_groups = 0;   // merged second pass: tickets per queue entry (1, 2 or 4; default 4)
 static long long g_opt_stages = 0;       // tick_kernel: envs staged per CTA (2..4; 0: auto)
@@ -2163,6 +2262,7 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "stage_rec")) { g_opt_stage_rec = value; return 0; }
     if (!strcmp(name, "idx64")) { g_opt_idx64 = value; return 0; }
     if (!strcmp(name, "persist")) { g_opt_persist = value; return 0; }
+    if (!strcmp(name, "bake_brute")) { g_opt_bake_brute = value; return 0; }
     if (!strcmp(name, "merge_dyn")) { g_opt_merge_dyn = value; return 0; }
     if (!strcmp(name, "dyn_groups")) { g_opt_dyn_groups = value; return 0; }
     if (!strcmp(name, "stages")) { g_opt_stages = value; return 0; }
@@ -2404,9 +2504,12 @@ static int launch_dyn(const KArgs& k, cudaStream_t st) {
 
 // tick_kernel: the persistent form of view_kernel (+ dyn_kernel). *merged: the second pass ran inside it.
 static bool want_tick(const KArgs& k, int rb) {
-    if (g_opt_persist == 2 || g_opt_fused_step) return false;
-    const int items = k.s.n_agents * rb;
-    return g_opt_persist == 1 ? items >= 1 : items >= 4;
+    // Opt-in (option "persist" = 1). Measured on the benchmark (4096 envs x 4 agents x 128 rays, B200): 112-121 us against
+    // view_kernel's 102 — with ~7 envs per persistent CTA the pipeline's look-ahead (staged envs) costs more in the grid's
+    // tail than the barriers it removes; see DESIGN.md.
+    (void)rb;
+    if (g_opt_fused_step) return false;
+    return g_opt_persist == 1;
 }
 
 static int launch_tick(KArgs& k, int nch, cudaStream_t st, bool* merged) {
@@ -2707,14 +2810,16 @@ extern "C" int msb_bake(const msb_params* p, const msb_scenery* s, void* cuda_st
     if (s->n_envs == 0) return 0;
     KArgs k;
     fill(k, p, s, nullptr);
-    const size_t sm = (size_t)k.seg_cap * 16 + 16;
+    const bool table = !g_opt_bake_brute && s->occ_lines && s->occ_boxes && s->box_starts && s->occ_meta && s->occ_run == VRUN;
+    const size_t sm = table ? (size_t)k.wcap * 16 + (size_t)(k.wcap / VRUN) * 16 + 16 : (size_t)k.seg_cap * 16 + 16;
     if (sm > 227 * 1024) return fail("%s", "scene too large: an env's segments do not fit in shared memory (227 KB)");
     if (sm > 48 * 1024 &&
-        check(cudaFuncSetAttribute(bake_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "cudaFuncSetAttribute"))
+        check(cudaFuncSetAttribute(table ? bake_table_kernel : bake_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm), "cudaFuncSetAttribute"))
         return 1;
     {
         TimedLaunch timed(TK_BAKE, (cudaStream_t)cuda_stream);
-        bake_kernel<<<s->n_envs, 256, sm, (cudaStream_t)cuda_stream>>>(k);
+        if (table) bake_table_kernel<<<s->n_envs, 256, sm, (cudaStream_t)cuda_stream>>>(k);
+        else bake_kernel<<<s->n_envs, 256, sm, (cudaStream_t)cuda_stream>>>(k);
     }
     g_launches++;
     return check(cudaGetLastError(), "bake launch");

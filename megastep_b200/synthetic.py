@@ -97,19 +97,24 @@ def sample(n_geometries, seed=1, n_unique=1024, with_masks=False):
 
 def spawns(geometries, n_agents, random, clearance=.35):
     """Random collision-free-ish poses: positions (N, A, 2) uniform inside rooms (kept `clearance` from the room's
-    walls), angles (N, A) uniform in [-180, 180). Plays the role of RandomSpawns without needing masks."""
+    walls), angles (N, A) uniform in [-180, 180). Plays the role of RandomSpawns without needing masks. Envs that share
+    a geometry object (`sample` cycles through its distinct floorplans) are drawn together, so that very large batches
+    take seconds."""
     N = len(geometries)
     pos = np.zeros((N, n_agents, 2), np.float32)
+    groups = {}
     for n, g in enumerate(geometries):
+        groups.setdefault(id(g), (g, []))[1].append(n)
+    for g, envs in groups.values():
         rooms = g['rooms']
         inner = np.stack([rooms[:, 0] + clearance, rooms[:, 1] + clearance, rooms[:, 2] - clearance, rooms[:, 3] - clearance], -1)
         ok = (inner[:, 2] > inner[:, 0]) & (inner[:, 3] > inner[:, 1])
         inner = inner[ok] if ok.any() else inner
         areas = np.maximum(inner[:, 2] - inner[:, 0], 1e-3) * np.maximum(inner[:, 3] - inner[:, 1], 1e-3)
-        which = random.choice(len(inner), size=n_agents, p=areas / areas.sum())
-        u = random.uniform(size=(n_agents, 2))
-        pos[n, :, 0] = inner[which, 0] + u[:, 0] * (inner[which, 2] - inner[which, 0])
-        pos[n, :, 1] = inner[which, 1] + u[:, 1] * (inner[which, 3] - inner[which, 1])
+        which = random.choice(len(inner), size=(len(envs), n_agents), p=areas / areas.sum())
+        u = random.uniform(size=(len(envs), n_agents, 2))
+        pos[envs, :, 0] = inner[which, 0] + u[..., 0] * (inner[which, 2] - inner[which, 0])
+        pos[envs, :, 1] = inner[which, 1] + u[..., 1] * (inner[which, 3] - inner[which, 1])
     ang = random.uniform(-180, 180, (N, n_agents)).astype(np.float32)
     return pos, ang
 
@@ -119,18 +124,17 @@ def tile_arrays(arrays, n_envs):
     u = len(arrays['line_widths'])
     if n_envs == u:
         return arrays
-    idx = np.arange(n_envs) % u
+    reps, rest = divmod(n_envs, u)
     lw, iw, tw = arrays['line_widths'], arrays['light_widths'], arrays['tex_widths']
-    ls, is_ = np.cumsum(lw) - lw, np.cumsum(iw) - iw
-    ts = np.cumsum(tw.astype(np.int64)) - tw
-    # per-env texel extents
-    env_tex_lo = ts[ls]
-    env_tex_hi = np.append(ts, tw.astype(np.int64).sum())[ls + lw]
-    take = lambda vals, s, w: np.concatenate([vals[s[i]:s[i] + w[i]] for i in idx])
+    l_rest, i_rest = int(lw[:rest].sum()), int(iw[:rest].sum())
+    t_rest = int(tw[:l_rest].astype(np.int64).sum())
+
+    def cyc(vals, n_rest):                                  # the whole array `reps` times, then its first `n_rest` rows
+        return np.concatenate([np.tile(vals, (reps,) + (1,) * (vals.ndim - 1)), vals[:n_rest]])
+
     return dict(
         n_agents=arrays['n_agents'], model=arrays['model'],
-        lines=take(arrays['lines'], ls, lw), line_widths=lw[idx],
-        lights=take(arrays['lights'], is_, iw), light_widths=iw[idx],
-        textures=np.concatenate([arrays['textures'][env_tex_lo[i]:env_tex_hi[i]] for i in idx]),
-        tex_widths=take(tw, ls, lw),
-        **({'baked': np.concatenate([arrays['baked'][env_tex_lo[i]:env_tex_hi[i]] for i in idx])} if 'baked' in arrays else {}))
+        lines=cyc(arrays['lines'], l_rest), line_widths=cyc(lw, rest),
+        lights=cyc(arrays['lights'], i_rest), light_widths=cyc(iw, rest),
+        textures=cyc(arrays['textures'], t_rest), tex_widths=cyc(tw, l_rest),
+        **({'baked': cyc(arrays['baked'], t_rest)} if 'baked' in arrays else {}))

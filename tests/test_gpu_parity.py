@@ -202,6 +202,29 @@ def test_more_lights_than_lanes_bit_exact_against_reference_build(ref):
     assert torch.equal(s.baked.vals, rs2.baked.vals)
 
 
+def test_bake_over_the_spatial_table_equals_brute_force():
+    """msb_bake's two kernels — every static line per (texel, light) like the reference, or only the runs of the spatial
+    table the light ray passes — must agree bit for bit (the cull is conservative), ragged envs and 40 lights included."""
+    from megastep_b200 import cuda, scene
+    gs, arrays = common.synthetic_scene(9, 3, seed=23, bake=False)
+    rng = np.random.RandomState(5)
+    extra = rng.uniform(2., 9., (40 - int(arrays['light_widths'][0]), 3)).astype(np.float32)      # env 0 gets 40 lights
+    arrays['lights'] = np.concatenate([arrays['lights'][:arrays['light_widths'][0]], extra, arrays['lights'][arrays['light_widths'][0]:]])
+    arrays['light_widths'][0] = 40
+    outs = []
+    for brute in (1, 0):
+        cuda.set_option('bake_brute', brute)
+        try:
+            s = scene.upload(arrays)
+            cuda.bake(s, params=cuda.make_params(common.AGENT_RADIUS, 64, 130., 10.))
+            torch.cuda.synchronize()
+        finally:
+            cuda.set_option('bake_brute', 0)
+        outs.append(s.baked.vals.clone())
+    assert torch.equal(outs[0], outs[1]), f'{(outs[0] != outs[1]).float().mean():.4%} of baked texels differ'
+    assert float(outs[0].min()) >= .1 and float(outs[0].max()) <= 1. and float(outs[0].std()) > .05
+
+
 def test_bake_bit_exact_against_reference_build(ref):
     if ref is None:
         pytest.skip('oracle/_ref not built (needs /root/reference at build time)')
