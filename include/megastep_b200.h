@@ -156,6 +156,11 @@ int msb_build_visibility(const msb_scenery* s, void* cuda_stream);
  * progress: (N, A) out. Agents are advanced in place (positions, angles) and stopped where progress < 1. */
 int msb_physics(const msb_params* p, const msb_scenery* s, const msb_agents* a, float* progress, void* cuda_stream);
 
+/* MomentumMovement.__call__ — megastep/modules.py:106-118 — as ONE launch: the velocities decay and take the chosen
+ * actions' impulses, then physics() as above (the reference: ~10 PyTorch launches, then physics). */
+int msb_move(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_movement* mv, float* progress,
+             void* cuda_stream);
+
 /* render(scenery, agents) -> Render — wrappers.cpp:82, kernels.cu:297-475. Also rewrites the agents' model
  * lines inside s->lines (the reference's draw_kernel side effect). obs may be NULL. */
 int msb_render(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_render_out* out,
@@ -186,6 +191,35 @@ int64_t msb_workspace_bytes(const msb_params* p, const msb_scenery* s, int32_t s
 /* Tuning/diagnostics: selects kernel variants (0 = default). Affects speed only, never results. */
 int msb_set_option(const char* name, int64_t value);
 int64_t msb_get_option(const char* name);
+
+/* ---- Environment rules on the device (the game logic of the reference's demo envs). Each is one small
+ * launch on the caller's stream, no host round trip; `indices` / `locations` are msb_render_out tensors. ----------------- */
+
+/* Explorer's reward bookkeeping — megastep/demo/envs/explorer.py:34-58. `seen`: one bit per texel of the whole scene
+ * (ceil(n_texels / 32) words, zeroed once); every ray's texel (min(floor(width * location), width - 1) on the line it hit)
+ * is marked, and the number of bits NEWLY set per env is added to potential[n] (the env's seen-texel count, what the
+ * reference recomputes with a scatter_add over every texel each step) and to gained[n] (zero it before the call). */
+int msb_env_ledger_mark(const msb_scenery* s, const int32_t* indices, const float* locations, int32_t n_agents, int32_t res,
+                        uint32_t* seen, int32_t* potential, int32_t* gained, void* cuda_stream);
+
+/* explorer.py:73-77: envs with reset[n] != 0 forget what they have seen (their bit range is cleared, potential[n] = 0). */
+int msb_env_ledger_clear(const msb_scenery* s, const uint8_t* reset, uint32_t* seen, int32_t* potential, void* cuda_stream);
+
+/* Deathmatch's crosshair rule and its consequences — megastep/demo/envs/deathmatch.py:54-72, 75-80. For every agent: the
+ * agents whose model shows at the centre ray of one of its two middle pooled pixels (pooling = `subsample`) are hit.
+ * matchings (N, A, A) uint8 [shooter][target]; hits (N, A) = targets hit by each agent; damage += .05 hits;
+ * health += -.05 (times hit + outside the floorplan by more than `clearance`) - .001. bounds (N, 2) as the reference's. */
+int msb_env_shoot(const msb_scenery* s, const msb_agents* a, const int32_t* indices, int32_t res, int32_t subsample,
+                  const float* bounds, float clearance, uint8_t* matchings, float* hits, float* health, float* damage,
+                  void* cuda_stream);
+
+/* RandomSpawns — megastep/modules.py:312-326 — without its nonzero() (a device-to-host sync per step): agents with
+ * reset[n][a] != 0 move to spawn `choices[n][a] % n_spawns` (or, choices NULL, to one drawn by a counter-based hash of
+ * (seed, tick, agent)) of their precomputed spawn_positions (N, A, n_spawns, 2) / spawn_angles (N, A, n_spawns), with
+ * their velocities zeroed. */
+int msb_env_respawn(const msb_scenery* s, const msb_agents* a, const uint8_t* reset, const float* spawn_positions,
+                    const float* spawn_angles, int32_t n_spawns, uint32_t seed, uint32_t tick, const int32_t* choices,
+                    void* cuda_stream);
 
 /* Number of kernels launched by this library since load (bench.py's `gpu_launches`). */
 int64_t msb_launch_count(void);

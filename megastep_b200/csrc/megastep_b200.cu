@@ -2140,6 +2140,119 @@ __global__ void __launch_bounds__(256) bake_table_kernel(const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Environment rules on the device: the game logic the reference's demo envs run as chains of PyTorch
+// ops around physics()/render(), each as one small launch with no host round trip.
+//   ledger_mark_kernel   Explorer's reward bookkeeping (demo/envs/explorer.py:34-58): which texel every ray landed on, one
+//                        bit per texel of the whole scene; the count of bits newly set per env IS the step's potential
+//                        gain — instead of a scatter_add over every texel of every env (28 M elements) each step
+//   ledger_clear_kernel  envs that reset forget what they have seen (explorer.py:73-77)
+//   shoot_kernel         Deathmatch's crosshair rule (demo/envs/deathmatch.py:54-72, 75-80) + the health / damage updates
+//   respawn_kernel       RandomSpawns (modules.py:312-326) with the draw on the device (a counter-based hash: no
+//                        nonzero(), i.e. no device-to-host sync in the middle of every step)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ledger_mark_kernel(const int32_t* __restrict__ indices, const float* __restrict__ locations,
+                                                          const int32_t* __restrict__ line_starts, const int32_t* __restrict__ tex_widths,
+                                                          const int64_t* __restrict__ tex_starts, uint32_t* seen, int32_t* potential,
+                                                          int32_t* gained, int64_t n_rays, int32_t rays_per_env) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool fresh = false;
+    int n = -1;
+    if (i < n_rays) {
+        n = (int)(i / rays_per_env);
+        const int idx = __ldg(indices + i);
+        if (idx >= 0) {
+            const int64_t g = (int64_t)__ldg(line_starts + n) + idx;
+            const float w = (float)__ldg(tex_widths + g);
+            // explorer.py:40: min(floor(width * location), width - 1)
+            const int64_t texel = __ldg(tex_starts + g) + (int64_t)fminf(floorf(__fmul_rn(w, __ldg(locations + i))), w - 1.f);
+            const uint32_t bit = 1u << (texel & 31);
+            fresh = !(atomicOr(seen + (texel >> 5), bit) & bit);
+        }
+    }
+    // one add per env and warp (a warp's rays belong to one env, or two at an env boundary)
+    const unsigned active = __activemask();
+    const int n0 = __shfl_sync(active, n, __ffs(active) - 1);
+    const unsigned first = __ballot_sync(active, fresh && n == n0), second = __ballot_sync(active, fresh && n != n0);
+    const int lane = threadIdx.x & 31;
+    if (lane == __ffs(active) - 1 && first) { atomicAdd(potential + n0, __popc(first)); atomicAdd(gained + n0, __popc(first)); }
+    if (second && lane == __ffs(second) - 1) { atomicAdd(potential + n, __popc(second)); atomicAdd(gained + n, __popc(second)); }
+}
+
+// one CTA per env: if the env resets, its texels' bits — a range of the scene-wide bit array, not word-aligned — are cleared
+__global__ void __launch_bounds__(128) ledger_clear_kernel(const uint8_t* __restrict__ reset, const int32_t* __restrict__ line_starts,
+                                                           const int32_t* __restrict__ line_widths, const int32_t* __restrict__ tex_widths,
+                                                           const int64_t* __restrict__ tex_starts, uint32_t* seen, int32_t* potential) {
+    const int n = blockIdx.x;
+    if (!reset[n]) return;
+    const int64_t g0 = line_starts[n], g1 = g0 + line_widths[n];
+    if (g1 == g0) return;
+    const int64_t t0 = tex_starts[g0], t1 = tex_starts[g1 - 1] + tex_widths[g1 - 1];
+    const int64_t w0 = t0 >> 5, w1 = (t1 + 31) >> 5;
+    for (int64_t w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
+        uint32_t keep = 0;                                               // bits of the word that belong to neighbouring envs
+        if (w == w0 && (t0 & 31)) keep |= (1u << (t0 & 31)) - 1u;
+        if (w == w1 - 1 && (t1 & 31)) keep |= ~((1u << (t1 & 31)) - 1u);
+        if (keep) atomicAnd(seen + w, keep); else seen[w] = 0u;
+    }
+    if (threadIdx.x == 0) potential[n] = 0;
+}
+
+// one thread per (env, agent): who is in my crosshairs — the centre rays of the two middle pooled pixels (deathmatch.py:56,
+// 76-79) — then damage / health (deathmatch.py:62-70). matchings[n][shooter][target]; hits = targets hit, wounds = shooters.
+__global__ void __launch_bounds__(128) shoot_kernel(const int32_t* __restrict__ indices, const float* __restrict__ positions,
+                                                    const float* __restrict__ bounds, uint8_t* matchings, float* hits, float* health,
+                                                    float* damage, int32_t n_envs, int32_t A, int32_t R, int32_t sub, int32_t F,
+                                                    float clearance) {
+    const int n = blockIdx.x;
+    extern __shared__ int wounds[];                                    // [A]
+    for (int a = threadIdx.x; a < A; a += blockDim.x) wounds[a] = 0;
+    __syncthreads();
+    const int Ro = R / sub;
+    for (int a = threadIdx.x; a < A; a += blockDim.x) {
+        const int32_t* row = indices + ((int64_t)n * A + a) * R;
+        int h = 0;
+        uint8_t* mrow = matchings + ((int64_t)n * A + a) * A;
+        for (int t = 0; t < A; t++) mrow[t] = 0;
+        for (int px = Ro / 2 - 1; px <= Ro / 2; px++) {
+            if (px < 0 || px >= Ro) continue;
+            const int line = __ldg(row + px * sub + sub / 2);
+            const int who = line >= 0 ? line / F : -1;
+            if (who >= 0 && who < A && !mrow[who]) { mrow[who] = 1; h++; atomicAdd(&wounds[who], 1); }
+        }
+        hits[(int64_t)n * A + a] = (float)h;
+        damage[(int64_t)n * A + a] = __fadd_rn(damage[(int64_t)n * A + a], __fmul_rn(.05f, (float)h));      // (torch: two roundings)
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < A; a += blockDim.x) {
+        const int64_t i = (int64_t)n * A + a;
+        const float px = positions[2 * i], py = positions[2 * i + 1];
+        // bounds are (height, width) of the mask grid in metres, compared against (x, y) as the reference does (deathmatch.py:66)
+        const bool outside = px < -clearance || py < -clearance || px > bounds[2 * n] + clearance || py > bounds[2 * n + 1] + clearance;
+        health[i] = __fadd_rn(health[i], __fsub_rn(__fmul_rn(-.05f, (float)wounds[a] + (outside ? 1.f : 0.f)), .001f));
+    }
+}
+
+__device__ __forceinline__ uint32_t hash3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return h;
+}
+
+// one thread per (env, agent): flagged agents go to one of their precomputed spawn points, velocities zeroed
+__global__ void __launch_bounds__(256) respawn_kernel(const uint8_t* __restrict__ reset, const float* __restrict__ spawn_positions,
+                                                      const float* __restrict__ spawn_angles, msb_agents ag, int64_t n_agents_total,
+                                                      int32_t n_spawns, uint32_t seed, uint32_t tick, int32_t* choices) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_agents_total || !reset[i]) return;
+    const int c = choices ? choices[i] % n_spawns : (int)(hash3(seed, tick, (uint32_t)i) % (uint32_t)n_spawns);
+    ag.angles[i] = spawn_angles[i * n_spawns + c];
+    ag.positions[2 * i] = spawn_positions[2 * (i * n_spawns + c)];
+    ag.positions[2 * i + 1] = spawn_positions[2 * (i * n_spawns + c) + 1];
+    ag.velocity[2 * i] = 0.f; ag.velocity[2 * i + 1] = 0.f;
+    ag.angvelocity[i] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side: C ABI
 // ---------------------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -2636,6 +2749,19 @@ extern "C" int msb_physics(const msb_params* p, const msb_scenery* s, const msb_
     return launch_physics(k, (cudaStream_t)cuda_stream);
 }
 
+extern "C" int msb_move(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_movement* mv, float* progress,
+                        void* cuda_stream) {
+    if (validate(p, s, true)) return 1;
+    if (!a || !a->angles || !a->positions || !a->angvelocity || !a->velocity) return fail("%s", "msb_move: null agents");
+    if (!mv || !mv->actions) return fail("%s", "msb_move: movement without actions");
+    if (s->n_envs == 0) return 0;
+    KArgs k;
+    fill(k, p, s, a);
+    k.progress = progress;
+    set_movement(k, p, mv);
+    return launch_physics(k, (cudaStream_t)cuda_stream);
+}
+
 extern "C" int msb_render(const msb_params* p, const msb_scenery* s, const msb_agents* a, const msb_render_out* out,
                           const msb_obs_out* obs, const msb_workspace* ws, void* cuda_stream) {
     if (validate(p, s, true) || check_obs(p, obs)) return 1;
@@ -2823,4 +2949,52 @@ extern "C" int msb_bake(const msb_params* p, const msb_scenery* s, void* cuda_st
     }
     g_launches++;
     return check(cudaGetLastError(), "bake launch");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// environment rules (see the kernels' banner)
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int msb_env_ledger_mark(const msb_scenery* s, const int32_t* indices, const float* locations, int32_t n_agents, int32_t res,
+                                   uint32_t* seen, int32_t* potential, int32_t* gained, void* cuda_stream) {
+    if (!s || !indices || !locations || !seen || !potential || !gained) return fail("%s", "msb_env_ledger_mark: null argument");
+    if (s->n_envs == 0) return 0;
+    const int64_t rays = (int64_t)s->n_envs * n_agents * res;
+    const int64_t blocks = (rays + 255) / 256;
+    ledger_mark_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>(indices, locations, s->line_starts, s->tex_widths, s->tex_starts,
+                                                                             seen, potential, gained, rays, n_agents * res);
+    g_launches++;
+    return check(cudaGetLastError(), "ledger_mark_kernel launch");
+}
+
+extern "C" int msb_env_ledger_clear(const msb_scenery* s, const uint8_t* reset, uint32_t* seen, int32_t* potential, void* cuda_stream) {
+    if (!s || !reset || !seen || !potential) return fail("%s", "msb_env_ledger_clear: null argument");
+    if (s->n_envs == 0) return 0;
+    ledger_clear_kernel<<<s->n_envs, 128, 0, (cudaStream_t)cuda_stream>>>(reset, s->line_starts, s->line_widths, s->tex_widths, s->tex_starts,
+                                                                       seen, potential);
+    g_launches++;
+    return check(cudaGetLastError(), "ledger_clear_kernel launch");
+}
+
+extern "C" int msb_env_shoot(const msb_scenery* s, const msb_agents* a, const int32_t* indices, int32_t res, int32_t subsample,
+                             const float* bounds, float clearance, uint8_t* matchings, float* hits, float* health, float* damage,
+                             void* cuda_stream) {
+    if (!s || !a || !indices || !bounds || !matchings || !hits || !health || !damage) return fail("%s", "msb_env_shoot: null argument");
+    if (subsample < 1 || res % subsample || s->n_model < 1) return fail("%s", "msb_env_shoot: subsample must divide res");
+    if (s->n_envs == 0) return 0;
+    shoot_kernel<<<s->n_envs, 128, (size_t)s->n_agents * sizeof(int), (cudaStream_t)cuda_stream>>>(
+        indices, a->positions, bounds, matchings, hits, health, damage, s->n_envs, s->n_agents, res, subsample, s->n_model, clearance);
+    g_launches++;
+    return check(cudaGetLastError(), "shoot_kernel launch");
+}
+
+extern "C" int msb_env_respawn(const msb_scenery* s, const msb_agents* a, const uint8_t* reset, const float* spawn_positions,
+                               const float* spawn_angles, int32_t n_spawns, uint32_t seed, uint32_t tick, const int32_t* choices,
+                               void* cuda_stream) {
+    if (!s || !a || !reset || !spawn_positions || !spawn_angles || n_spawns < 1) return fail("%s", "msb_env_respawn: bad argument");
+    const int64_t total = (int64_t)s->n_envs * s->n_agents;
+    if (total == 0) return 0;
+    respawn_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(reset, spawn_positions, spawn_angles, *a, total, n_spawns,
+                                                                                       seed, tick, const_cast<int32_t*>(choices));
+    g_launches++;
+    return check(cudaGetLastError(), "respawn_kernel launch");
 }

@@ -87,6 +87,7 @@ def _load():
     lib.msb_build_visibility.argtypes = [P(_Scenery), ctypes.c_void_p]
     lib.msb_build_table.argtypes = [P(_Scenery), ctypes.c_void_p]
     lib.msb_physics.argtypes = [P(Params), P(_Scenery), P(_Agents), ctypes.c_void_p, ctypes.c_void_p]
+    lib.msb_move.argtypes = [P(Params), P(_Scenery), P(_Agents), P(_Movement), ctypes.c_void_p, ctypes.c_void_p]
     lib.msb_render.argtypes = [P(Params), P(_Scenery), P(_Agents), P(_RenderOut), P(_ObsOut), P(_Workspace), ctypes.c_void_p]
     lib.msb_step.argtypes = [P(Params), P(_Scenery), P(_Agents), P(_Movement), ctypes.c_void_p, P(_RenderOut),
                              P(_ObsOut), P(_Workspace), ctypes.c_void_p]
@@ -96,6 +97,13 @@ def _load():
     lib.msb_step_graph_destroy.argtypes = [ctypes.c_void_p]
     lib.msb_workspace_bytes.argtypes = [P(Params), P(_Scenery), ctypes.c_int32]
     lib.msb_workspace_bytes.restype = ctypes.c_int64
+    lib.msb_env_ledger_mark.argtypes = [P(_Scenery), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.msb_env_ledger_clear.argtypes = [P(_Scenery), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.msb_env_shoot.argtypes = [P(_Scenery), P(_Agents), ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_float,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.msb_env_respawn.argtypes = [P(_Scenery), P(_Agents), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                    ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
     lib.msb_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
     lib.msb_get_option.argtypes = [ctypes.c_char_p]
     lib.msb_get_option.restype = ctypes.c_int64
@@ -145,14 +153,21 @@ class _Ragged:
             ends = widths.cumsum(0).to(torch.int32)
             self._vals, self._widths = vals, widths
             self._starts, self._ends = ends - widths, ends
-            self._inverse = _inverses(widths, total)
+        self._total = total
+        self._inverse = None                                    # computed on first use: one int32 per value (GBs for the texels of a big batch)
         self._starts64 = None
 
     vals = property(lambda self: self._vals)
     widths = property(lambda self: self._widths)
     starts = property(lambda self: self._starts)
     ends = property(lambda self: self._ends)
-    inverse = property(lambda self: self._inverse)
+
+    @property
+    def inverse(self):
+        if self._inverse is None:
+            with torch.no_grad():
+                self._inverse = _inverses(self._widths, self._total)
+        return self._inverse
 
     def _long_starts(self):
         """64-bit exclusive prefix sum of the widths (the kernels' texel offsets); int32 `starts` wraps at 2^31."""
@@ -636,6 +651,12 @@ class StepPlan:
         except Exception:       # noqa: BLE001  (interpreter shutdown)
             pass
 
+    def move_only(self):
+        """movement + physics, one launch (msb_move); the agents are not rendered"""
+        with _on_device(self.progress) as stream:
+            _check(_lib.msb_move(ctypes.byref(self.params), ctypes.byref(self._s), ctypes.byref(self.agents._c), ctypes.byref(self._mv),
+                                 self.progress.data_ptr(), stream))
+
     def render_only(self):
         """render + heads, one launch; the agents are not moved"""
         with _on_device(self.progress) as stream:
@@ -643,6 +664,53 @@ class StepPlan:
                                    ctypes.byref(self._out) if self._out is not None else None,
                                    ctypes.byref(self._obs) if self._obs is not None else None,
                                    ctypes.byref(self._ws) if self._ws is not None else None, stream))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# environment rules on the device (include/megastep_b200.h, "Environment rules")
+# --------------------------------------------------------------------------------------------------------------
+def ledger_words(scenery):
+    """Length of the int32 tensor that holds one 'seen' bit per texel of the scenery."""
+    return (scenery.textures.vals.size(0) + 31) // 32
+
+
+def env_ledger_mark(scenery, indices, locations, seen, potential, gained):
+    """Explorer's bookkeeping (explorer.py:34-58): marks the texel under every ray in `seen` (int32 words, one bit per
+    texel) and adds the number of newly seen texels per env to `potential` and `gained` (int32 (N,))."""
+    s = scenery._struct()
+    n, a, r = indices.shape
+    _require(indices.dtype == torch.int32 and indices.is_contiguous() and locations.is_contiguous(), 'indices / locations must be contiguous (N, A, R) tensors')
+    with _on_device(indices) as stream:
+        _check(_lib.msb_env_ledger_mark(ctypes.byref(s), indices.data_ptr(), locations.data_ptr(), a, r, seen.data_ptr(), potential.data_ptr(),
+                                        gained.data_ptr(), stream))
+
+
+def env_ledger_clear(scenery, reset, seen, potential):
+    """explorer.py:73-77: the envs flagged in `reset` (uint8 / bool (N,)) forget what they have seen."""
+    s = scenery._struct()
+    reset = reset.to(torch.uint8) if reset.dtype != torch.uint8 else reset
+    with _on_device(seen) as stream:
+        _check(_lib.msb_env_ledger_clear(ctypes.byref(s), reset.data_ptr(), seen.data_ptr(), potential.data_ptr(), stream))
+
+
+def env_shoot(scenery, agents, indices, subsample, bounds, clearance, matchings, hits, health, damage):
+    """Deathmatch's crosshair rule + health / damage updates (deathmatch.py:54-72, 75-80), one launch."""
+    s = scenery._struct()
+    n, a, r = indices.shape
+    _require(indices.dtype == torch.int32 and indices.is_contiguous(), 'indices must be a contiguous int32 (N, A, R) tensor')
+    with _on_device(indices) as stream:
+        _check(_lib.msb_env_shoot(ctypes.byref(s), ctypes.byref(agents._c), indices.data_ptr(), r, int(subsample), bounds.data_ptr(),
+                                  float(clearance), matchings.data_ptr(), hits.data_ptr(), health.data_ptr(), damage.data_ptr(), stream))
+
+
+def env_respawn(scenery, agents, reset, spawn_positions, spawn_angles, seed, tick, choices=None):
+    """RandomSpawns (modules.py:312-326) on the device: no nonzero(), no host sync."""
+    s = scenery._struct()
+    reset = reset.to(torch.uint8) if reset.dtype != torch.uint8 else reset
+    with _on_device(reset) as stream:
+        _check(_lib.msb_env_respawn(ctypes.byref(s), ctypes.byref(agents._c), reset.contiguous().data_ptr(), spawn_positions.data_ptr(),
+                                    spawn_angles.data_ptr(), spawn_angles.shape[-1], int(seed) & 0xffffffff, int(tick) & 0xffffffff,
+                                    choices.data_ptr() if choices is not None else None, stream))
 
 
 def set_option(name, value):

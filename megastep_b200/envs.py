@@ -63,28 +63,81 @@ class ExplorationLedger:
         self.potential[reset] = 0.
 
 
-class Explorer:
-    """One agent per env, rewarded for every texel of wall it sees for the first time (explorer.py:8-107)."""
+class BitLedger:
+    """`ExplorationLedger` on the device: one bit per texel of the whole scene and a running count per env, kept by two
+    small kernels (`cuda.env_ledger_mark` / `env_ledger_clear`) — a step touches the texels its rays landed on instead
+    of summing a flag for every texel of every env (the reference's `scatter_add_`, explorer.py:49-50: 28 M elements at
+    4096 envs). Same rewards, potentials and `seen` set as `ExplorationLedger`."""
 
-    def __init__(self, geometries, *args, **kwargs):
+    def __init__(self, scenery, n_envs, rays_per_obs):
+        from . import cuda
+        dev = scenery.model.device
+        self._cuda, self.scenery = cuda, scenery
+        self._bits = torch.zeros(cuda.ledger_words(scenery), dtype=torch.int32, device=dev)
+        self._count = torch.zeros(n_envs, dtype=torch.int32, device=dev)
+        self._gained = torch.zeros(n_envs, dtype=torch.int32, device=dev)
+        self.rays_per_obs = rays_per_obs
+
+    @property
+    def potential(self):
+        return self._count.float()
+
+    @property
+    def seen(self):
+        """(T,) bool, as ExplorationLedger.seen (unpacked on demand: plotting / tests)."""
+        shifts = torch.arange(32, device=self._bits.device, dtype=torch.int32)
+        bits = ((self._bits[:, None] >> shifts[None, :]) & 1).bool().reshape(-1)
+        return bits[:self.scenery.textures.vals.size(0)]
+
+    def reward(self, indices, locations, reset):
+        """indices / locations: (N, A, R) outputs of render(); reset (N,) bool envs whose reward is void."""
+        self._gained.zero_()
+        self._cuda.env_ledger_mark(self.scenery, indices, locations, self._bits, self._count, self._gained)
+        gained = self._gained.float() / self.rays_per_obs
+        return torch.where(reset, torch.zeros_like(gained), gained)
+
+    def forget(self, reset):
+        self._cuda.env_ledger_clear(self.scenery, reset, self._bits, self._count)
+
+
+class Explorer:
+    """One agent per env, rewarded for every texel of wall it sees for the first time (explorer.py:8-107).
+
+    `fused` (default on a CUDA device): movement + physics in one launch (`modules.FusedMovement`), render + RGB / Depth /
+    IMU heads in one pass (`modules.RGBD`), the reward ledger as bits kept by two small kernels (`BitLedger`), respawns
+    drawn on the device — about a dozen launches per step and no host round trip, where the reference's env runs ~70
+    PyTorch ops, a `nonzero()` and a scatter over every texel of the scene. `fused=False` is the op-for-op restatement."""
+
+    def __init__(self, geometries, *args, fused=None, **kwargs):
         """`geometries`: a list of geometries (`cubicasa.sample(n)` in the reference; here e.g.
         `synthetic.sample(n, with_masks=True)` — without the masks, spawn points are drawn inside the room rectangles)."""
         s = scene.scenery(geometries, 1)
         self.core = core_.Core(s, *args, res=4 * 64, fov=130, **kwargs)
+        self.fused = (self.core.device.type == 'cuda') if fused is None else fused
         self._rgb = modules.RGB(self.core, n_agents=1, subsample=4)
         self._depth = modules.Depth(self.core, n_agents=1, subsample=4)
-        self._mover = modules.MomentumMovement(self.core)
+        self._mover = modules.FusedMovement(self.core) if self.fused else modules.MomentumMovement(self.core)
         self._imu = modules.IMU(self.core)
-        self._respawner = modules.RandomSpawns(geometries, self.core)
+        self._respawner = modules.RandomSpawns(geometries, self.core, fused=self.fused)
         self.action_space = self._mover.space
         self.obs_space = dotdict(rgb=self._rgb.space, d=self._depth.space, imu=self._imu.space)
         sc = self.core.scenery
-        texel_env = sc.lines.inverse[sc.textures.inverse.long()]
-        self._ledger = ExplorationLedger(texel_env, self.core.n_envs, self.core.res // self._rgb.subsample)
+        rays_per_obs = self.core.res // self._rgb.subsample
+        if self.fused:
+            self._rgbd = modules.RGBD(self.core, subsample=4, raw=True)
+            self._ledger = BitLedger(sc, self.core.n_envs, rays_per_obs)
+        else:
+            texel_env = sc.lines.inverse[sc.textures.inverse.long()]
+            self._ledger = ExplorationLedger(texel_env, self.core.n_envs, rays_per_obs)
         self._lengths = torch.zeros(self.core.n_envs, device=self.core.device, dtype=torch.int)
         self.device = self.core.device
 
     def _observe(self, reset):
+        if self.fused:
+            obs = self._rgbd()                                  # render + the three heads, one pass
+            r = self._rgbd.render
+            self._rgb._last_obs, self._depth._last_obs = obs.rgb, obs.d
+            return arrdict(rgb=obs.rgb, d=obs.d, imu=obs.imu), self._ledger.reward(r.indices, r.locations, reset)
         r = modules.render(self.core)
         obs = arrdict(rgb=self._rgb(r), d=self._depth(r), imu=self._imu())
         sc = self.core.scenery
@@ -114,8 +167,10 @@ class Explorer:
 
     def state(self, e=0):
         led = self._ledger
+        sc = self.core.scenery
+        texel_env = led.texel_env if hasattr(led, 'texel_env') else sc.lines.inverse[sc.textures.inverse.long()].long()
         return arrdict(core=self.core.state(e), rgb=self._rgb.state(e), d=self._depth.state(e),
-                       potential=led.potential[e].clone(), seen=led.seen[led.texel_env == e].clone(),
+                       potential=led.potential[e].clone(), seen=led.seen[texel_env == e].clone(),
                        length=self._lengths[e].clone(), max_length=led.potential[e].add(200).clone())
 
 
@@ -153,17 +208,26 @@ class Deathmatch:
     """Several agents per env shooting at whoever is in their crosshairs (deathmatch.py:20-119). The env is flattened
     to `n_envs * n_agents` single-agent environments at the interface, as in the reference."""
 
-    def __init__(self, geometries, n_agents, *args, **kwargs):
+    def __init__(self, geometries, n_agents, *args, fused=None, **kwargs):
+        """`fused` (default on a CUDA device): as `Explorer` — movement + physics in one launch, render + heads in one pass,
+        the crosshair rule with its health / damage updates as one kernel (`cuda.env_shoot`), respawns drawn on the
+        device."""
         s = scene.scenery(geometries, n_agents)
         self.core = core_.Core(s, *args, res=4 * 128, fov=70, **kwargs)
+        self.fused = (self.core.device.type == 'cuda') if fused is None else fused
         self._rgb = modules.RGB(self.core, n_agents=1, subsample=4)
         self._depth = modules.Depth(self.core, n_agents=1, subsample=4)
         self._imu = modules.IMU(self.core, n_agents=1)
-        self._movement = modules.MomentumMovement(self.core, n_agents=1)
-        self._spawner = modules.RandomSpawns(geometries, self.core)
+        self._movement = modules.FusedMovement(self.core, n_agents=1) if self.fused else modules.MomentumMovement(self.core, n_agents=1)
+        self._spawner = modules.RandomSpawns(geometries, self.core, fused=self.fused)
+        if self.fused:
+            self._rgbd = modules.RGBD(self.core, subsample=4, raw=True)
+            N, A = self.core.n_envs, self.core.n_agents
+            self._matchings = torch.zeros((N, A, A), dtype=torch.uint8, device=self.core.device)
+            self._hits = torch.zeros((N, A), dtype=torch.float32, device=self.core.device)
         self.action_space = self._movement.space
         self.obs_space = dotdict(rgb=self._rgb.space, d=self._depth.space, imu=self._imu.space, health=spaces.MultiVector(1, 1))
-        self._bounds = torchify(np.stack([_extent(g) for g in geometries])).to(self.core.device)
+        self._bounds = torchify(np.stack([_extent(g) for g in geometries])).to(self.core.device).contiguous()
         self._health = self.core.agent_full(np.nan)
         self._damage = self.core.agent_full(np.nan)
         self.n_envs = self.core.n_envs * self.core.n_agents
@@ -193,6 +257,14 @@ class Deathmatch:
         return hits.reshape(-1)
 
     def _observe(self):
+        if self.fused:
+            from . import cuda
+            obs = self._rgbd()
+            cuda.env_shoot(self.core.scenery, self.core.agents, self._rgbd.render.indices, self._rgb.subsample, self._bounds, CLEARANCE,
+                           self._matchings, self._hits, self._health, self._damage)
+            self.matchings = self._matchings.bool()
+            self._rgb._last_obs, self._depth._last_obs = obs.rgb, obs.d
+            return arrdict(rgb=obs.rgb, d=obs.d, imu=obs.imu, health=self._health.unsqueeze(-1).clone()), self._hits.reshape(-1).clone()
         r = modules.render(self.core)
         opponents = seen_agents(r.indices, len(self.core.scenery.model), self.core.n_agents, self._rgb.subsample)
         hits = self._shoot(opponents)

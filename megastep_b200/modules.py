@@ -73,6 +73,23 @@ class MomentumMovement:
         return _physics(core)
 
 
+class FusedMovement:
+    """`MomentumMovement` as one launch (msb_move): the decay, the action impulses and physics() in the same kernel,
+    bit-identical to `MomentumMovement(core)(decision)` (and to the reference's, tests/test_gpu_reference_python.py)."""
+
+    def __init__(self, core, accel=5, ang_accel=180, decay=.125, n_agents=None):
+        self.core = core
+        self.actions = torch.zeros((core.n_envs, core.n_agents), dtype=torch.int32, device=core.device)
+        self._plan = cuda.StepPlan(core.scenery, core.agents, core.params, actions=self.actions, accel=accel, ang_accel=ang_accel,
+                                   decay=decay, raw=False, subsample=None)
+        self.space = spaces.MultiDiscrete(n_agents or core.n_agents, 7)
+
+    def __call__(self, decision):
+        self.actions.copy_(decision.actions.reshape(self.actions.shape), non_blocking=True)
+        self._plan.move_only()
+        return arrdict(progress=self._plan.progress)
+
+
 def unpack(d):
     """`cuda` result objects -> arrdicts with the same attributes."""
     if isinstance(d, torch.Tensor):
@@ -311,9 +328,11 @@ def random_empty_positions(geometries, n_agents, n_points, random=np.random):
 
 class RandomSpawns:
 
-    def __init__(self, geometries, core, n_spawns=100):
-        """Respawns agents at random pre-computed free positions (modules.py:295-326)."""
+    def __init__(self, geometries, core, n_spawns=100, fused=False, seed=0):
+        """Respawns agents at random pre-computed free positions (modules.py:295-326). `fused`: the draw and the
+        update as one kernel (cuda.env_respawn; a counter-based hash of (seed, call number, agent) picks the spawn)."""
         self.core = core
+        self.fused, self.seed, self._calls = fused, seed, 0
         positions = random_empty_positions(geometries, core.n_agents, n_spawns)
         angles = core.random.uniform(-180, +180, (len(geometries), core.n_agents, n_spawns))
         self._spawns = torchify(arrdict(positions=positions, angles=angles)).to(core.device)
@@ -324,6 +343,12 @@ class RandomSpawns:
         Same effect as the reference (modules.py:312-326) without its `nonzero()` — a device-to-host sync in the middle
         of every step: a spawn is drawn for every agent and blended in under the mask, all on the device."""
         core = self.core
+        if self.fused:
+            if not hasattr(self, '_flat'):
+                self._flat = (self._spawns.positions.float().contiguous(), self._spawns.angles.float().contiguous())
+            self._calls += 1
+            cuda.env_respawn(core.scenery, core.agents, reset.reshape(core.n_envs, core.n_agents), self._flat[0], self._flat[1], self.seed, self._calls)
+            return
         choices = torch.randint(0, self._spawns.angles.shape[-1], reset.shape, device=reset.device)
         angles = self._spawns.angles.gather(-1, choices[..., None]).squeeze(-1)
         positions = self._spawns.positions.gather(2, choices[..., None, None].expand(-1, -1, 1, 2)).squeeze(2)

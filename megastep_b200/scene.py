@@ -115,6 +115,37 @@ def upload(arrays, device='cuda'):
         model=t('model', torch.float32))
 
 
+def tiled_scenery(arrays, n_envs, device='cuda', params=None):
+    """A baked `cuda.Scenery` of `n_envs` environments cycling through the envs of `arrays` (a `scene_arrays` result) —
+    the reference likewise cycles through its ~5k floorplans (cubicasa.py:218-224). The distinct envs are uploaded and
+    baked ONCE; the repetition happens on the device (torch `repeat`), so a 262,144-env scenery is built in seconds:
+    the host never holds more than the distinct envs, and `bake` (a pure function of an env's static lines and lights)
+    is not redone for the copies."""
+    import torch
+    from . import cuda
+    base = upload(arrays, device)
+    cuda.bake(base, params=params or cuda.make_params(core.AGENT_RADIUS, 64, 130., 10.))
+    u = len(base.lines)
+    if n_envs == u:
+        return base
+    reps, rest = divmod(n_envs, u)
+    lw, iw, tw = base.lines.widths, base.lights.widths, base.textures.widths
+    l_rest, i_rest = int(lw[:rest].sum()), int(iw[:rest].sum())
+    t_rest = int(tw[:l_rest].long().sum())
+
+    def cyc(t, n_rest):
+        return torch.cat([t.repeat(reps, *([1] * (t.dim() - 1))), t[:n_rest]]).contiguous()
+
+    s = cuda.Scenery(
+        n_agents=base.n_agents,
+        lights=cuda.Ragged2D(cyc(base.lights.vals, i_rest), cyc(iw, rest)),
+        lines=cuda.Ragged3D(cyc(base.lines.vals, l_rest), cyc(lw, rest)),
+        textures=cuda.Ragged2D(cyc(base.textures.vals, t_rest), cyc(tw, l_rest)),
+        model=base.model)
+    s.baked.vals.copy_(cyc(base.baked.vals, t_rest))
+    return s
+
+
 def scenery(geometries, n_agents=1, device='cuda', random=np.random):
     """Geometries -> baked `cuda.Scenery` (reference scene.py:75-100)."""
     from . import cuda

@@ -98,6 +98,27 @@ def reference_scenery(ref, arrays, device='cuda'):
     return s
 
 
+def reference_scenery_tiled(ref, arrays, n_envs, baked=None, device='cuda'):
+    """A reference Scenery of `n_envs` envs cycling through the envs of `arrays`, repeated on the device (what
+    megastep_b200.scene.tiled_scenery does for ours). `baked`: the distinct envs' baked light map, tiled the same way."""
+    import torch
+    t = lambda k, dtype: torch.as_tensor(arrays[k], dtype=dtype).contiguous().to(device)
+    lw, iw, tw = t('line_widths', torch.int32), t('light_widths', torch.int32), t('tex_widths', torch.int32)
+    u = lw.numel()
+    reps, rest = divmod(n_envs, u)
+    l_rest, i_rest = int(lw[:rest].sum()), int(iw[:rest].sum())
+    t_rest = int(tw[:l_rest].long().sum())
+    cyc = lambda x, n_rest: torch.cat([x.repeat(reps, *([1] * (x.dim() - 1))), x[:n_rest]]).contiguous()
+    s = ref.Scenery(n_agents=arrays['n_agents'],
+                    lights=ref.Ragged2D(cyc(t('lights', torch.float32), i_rest), cyc(iw, rest)),
+                    lines=ref.Ragged3D(cyc(t('lines', torch.float32), l_rest), cyc(lw, rest)),
+                    textures=ref.Ragged2D(cyc(t('textures', torch.float32), t_rest), cyc(tw, l_rest)),
+                    model=t('model', torch.float32))
+    if baked is not None:
+        s.baked.vals.copy_(cyc(torch.as_tensor(baked).to(device), t_rest))
+    return s
+
+
 def reference_agents(ref, st, device='cuda'):
     import torch
     return ref.Agents(**{k: torch.as_tensor(st[k]).contiguous().to(device) for k in ('angles', 'positions', 'angvelocity', 'velocity')})

@@ -394,7 +394,7 @@ def test_every_kernel_variant_gives_identical_results(res):
                         check(f'tick_kernel stage_rec={stage_rec} nch={nch} threads={threads} stages={stages}')
         _reset_options()
         for opts in ({'persist': 1, 'merge_dyn': 2}, {'persist': 1, 'dyn_groups': 1}, {'persist': 1, 'dyn_groups': 2},
-                     {'persist': 1, 'no_sched': 1}, {'persist': 1, 'stages': 4, 'threads': 128}, {'idx64': 1}, {'persist': 2, 'idx64': 1}, {}):
+                     {'persist': 1, 'no_sched': 1}, {'persist': 1, 'stages': 4, 'threads': 128}, {'persist': 1, 'idx64': 1}, {'idx64': 1}, {}):
             _reset_options()
             for name, v in opts.items():
                 cuda.set_option(name, v)
@@ -447,10 +447,10 @@ def test_second_pass_inline_and_overflow_paths_agree(sub):
     st['positions'] = (3.5 + rng.uniform(-.6, .6, st['positions'].shape)).astype(np.float32)
     res = 128
     outs = []
-    modes = {'tick': {}, 'tick-2-per-entry': {'dyn_groups': 2}, 'tick-1-per-entry': {'dyn_groups': 1}, 'tick+dyn_kernel': {'merge_dyn': 2},
-             'tick-inline': {}, 'tick-overflow': {}, 'tick+dyn_kernel-overflow': {'merge_dyn': 2},
-             'view+dyn': {'persist': 2}, 'view-inline': {'persist': 2}, 'view-overflow': {'persist': 2},
-             'view+dyn-1warp': {'persist': 2, 'dyn_warps': 1}, 'view+dyn-4warps': {'persist': 2, 'dyn_warps': 4}}
+    modes = {'view+dyn': {}, 'view-inline': {}, 'view-overflow': {}, 'view+dyn-1warp': {'dyn_warps': 1}, 'view+dyn-4warps': {'dyn_warps': 4},
+             'tick': {'persist': 1}, 'tick-2-per-entry': {'persist': 1, 'dyn_groups': 2}, 'tick-1-per-entry': {'persist': 1, 'dyn_groups': 1},
+             'tick+dyn_kernel': {'persist': 1, 'merge_dyn': 2}, 'tick-inline': {'persist': 1}, 'tick-overflow': {'persist': 1},
+             'tick+dyn_kernel-overflow': {'persist': 1, 'merge_dyn': 2}}
     for mode, opts in modes.items():
         cuda.USE_WORKSPACE = 'inline' not in mode
         _reset_options()

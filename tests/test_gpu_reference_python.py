@@ -249,3 +249,109 @@ def test_deathmatch_env_against_the_reference_env(pkg):
         actions = torch.as_tensor(rng.randint(0, 7, (N * A, 1))).cuda()
         a, b = ours.step(arrdict(actions=actions)), theirs.step(pkg.arrdict.arrdict(actions=actions))
     assert hits > 0, 'the packed agents should land some shots'
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the envs' fused paths (device kernels for the rules) against their op-for-op restatements
+# ----------------------------------------------------------------------------------------------------------------------
+def test_fused_explorer_equals_the_unfused_one():
+    """envs.Explorer(fused=True) — msb_move, RGBD heads, the bit ledger kernels — against fused=False (itself checked
+    against the reference's env above): observations, rewards, resets, potentials and the set of seen texels."""
+    from megastep_b200 import envs
+    from megastep_b200.arrdict import arrdict
+    N = 24
+    gs = _geometries(N)
+    np.random.seed(21)
+    a_env = envs.Explorer(gs, fused=True)
+    np.random.seed(21)
+    b_env = envs.Explorer(gs, fused=False)
+    assert a_env.fused and not b_env.fused
+    pos, ang = _spawn_table(gs, 1)
+    a_env._respawner, b_env._respawner = FixedSpawns(a_env.core, pos, ang), FixedSpawns(b_env.core, pos, ang)
+    rng = np.random.RandomState(2)
+    a, b = a_env.reset(), b_env.reset()
+    for tick in range(14):
+        torch.cuda.synchronize()
+        for k in ('rgb', 'd', 'imu'):
+            assert torch.equal(a.obs[k], b.obs[k]), f'tick {tick}: obs.{k}'
+        assert torch.equal(a.reset, b.reset) and torch.equal(a.reward, b.reward), f'tick {tick}'
+        assert torch.equal(a_env._ledger.potential, b_env._ledger.potential)
+        assert torch.equal(a_env._ledger.seen, b_env._ledger.seen), f'tick {tick}: seen texels'
+        actions = torch.as_tensor(rng.randint(0, 7, (N, 1))).cuda()
+        if tick in (5, 9):                                                   # resets through the rule itself, twice
+            a_env._lengths[3:9] += 1000
+            b_env._lengths[3:9] += 1000
+        a, b = a_env.step(arrdict(actions=actions)), b_env.step(arrdict(actions=actions))
+    assert float(a.reward.abs().sum()) > 0 and int(a_env._ledger.seen.sum()) > 100
+    st = a_env.state(2)
+    assert st.seen.shape == b_env.state(2).seen.shape
+
+
+def test_fused_deathmatch_equals_the_unfused_one():
+    from megastep_b200 import envs
+    from megastep_b200.arrdict import arrdict
+    N, A = 16, 4
+    gs = _geometries(N)
+    np.random.seed(22)
+    a_env = envs.Deathmatch(gs, A, fused=True)
+    np.random.seed(22)
+    b_env = envs.Deathmatch(gs, A, fused=False)
+    pos, ang = _spawn_table(gs, A)
+    rooms = np.stack([g.rooms[np.argmax((g.rooms[:, 2] - g.rooms[:, 0]) * (g.rooms[:, 3] - g.rooms[:, 1]))] for g in gs])
+    mid = torch.as_tensor(np.stack([(rooms[:, 0] + rooms[:, 2]) / 2, (rooms[:, 1] + rooms[:, 3]) / 2], -1)).float().cuda()
+    pos = mid[:, None, None, :] + torch.as_tensor(np.random.RandomState(1).uniform(-.8, .8, tuple(pos.shape))).float().cuda()
+    d = mid[:, None, None, :] - pos
+    ang = torch.rad2deg(torch.atan2(d[..., 1], d[..., 0]))
+    a_env._spawner, b_env._spawner = FixedSpawns(a_env.core, pos, ang), FixedSpawns(b_env.core, pos, ang)
+    rng = np.random.RandomState(2)
+    a, b = a_env.reset(), b_env.reset()
+    hits = 0.
+    for tick in range(12):
+        torch.cuda.synchronize()
+        for k in ('rgb', 'd', 'imu', 'health'):
+            assert _same(a.obs[k], b.obs[k]), f'tick {tick}: obs.{k}'
+        assert torch.equal(a.reset, b.reset) and torch.equal(a.reward, b.reward), f'tick {tick}'
+        assert _same(a_env._health, b_env._health) and _same(a_env._damage, b_env._damage)
+        assert torch.equal(a_env.matchings, b_env.matchings)
+        hits += float(a.reward.sum())
+        if tick == 5:
+            a_env._health[:3] = -1.
+            b_env._health[:3] = -1.
+        if tick == 7:                                                        # somebody wanders out of the building
+            a_env.core.agents.positions[5, 1] = -3.
+            b_env.core.agents.positions[5, 1] = -3.
+        actions = torch.as_tensor(rng.randint(0, 7, (N * A, 1))).cuda()
+        a, b = a_env.step(arrdict(actions=actions)), b_env.step(arrdict(actions=actions))
+    assert hits > 0
+
+
+def test_device_respawns_move_only_the_flagged_agents():
+    """cuda.env_respawn (RandomSpawns, modules.py:312-326, with the draw on the device): flagged agents land on one of
+    THEIR spawn points with zeroed velocities, the others are untouched; with explicit choices it equals the gather."""
+    from megastep_b200 import cuda, modules, scene
+    gs = _geometries(6)
+    arrays = scene.scene_arrays(gs, 3, np.random.RandomState(1))
+    st = common.random_state(gs, 3, seed=4)
+    c = common.to_device(arrays, st, 64, 90.)
+    spawner = modules.RandomSpawns(gs, c, n_spawns=20, fused=True, seed=5)
+    before = common.read_state(c)
+    reset = torch.as_tensor(np.random.RandomState(1).rand(6, 3) < .5).cuda()
+    spawner(reset)
+    after = common.read_state(c)
+    m = reset.cpu().numpy()
+    for k in before:
+        assert np.array_equal(before[k][~m], after[k][~m]), k
+    assert (after['velocity'][m] == 0).all() and (after['angvelocity'][m] == 0).all()
+    spawns = spawner._spawns.positions.float().cpu().numpy()
+    picked = set()
+    for n, a in zip(*m.nonzero()):
+        hit = (np.abs(spawns[n, a] - after['positions'][n, a]).sum(-1) == 0).nonzero()[0]
+        assert len(hit) > 0
+        picked.add(int(hit[0]))
+    assert len(picked) > 2, 'the draws should not all pick the same spawn'
+    # explicit choices
+    choices = torch.as_tensor(np.random.RandomState(2).randint(0, 20, (6, 3)).astype(np.int32)).cuda()
+    cuda.env_respawn(c.scenery, c.agents, torch.ones_like(reset), spawner._flat[0], spawner._flat[1], 0, 0, choices)
+    want = spawner._flat[0].gather(2, choices.long()[..., None, None].expand(-1, -1, 1, 2)).squeeze(2)
+    assert torch.equal(c.agents.positions, want)
+    assert torch.equal(c.agents.angles, spawner._flat[1].gather(2, choices.long()[..., None]).squeeze(2))
