@@ -105,10 +105,10 @@ def render_kernel_bytes(cfg, arrays, raw=True):
 
 def profiled_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of view_kernel, from the committed ncu --set full
-    capture of the same workload (profiles/r01_kernels_full_summary.json)."""
-    path = os.path.join(ROOT, 'profiles', 'r01_kernels_full_summary.json')
+    capture of the same workload (profiles/r02_kernels_full_summary.json, entry of full_view_kernel_raw.csv)."""
+    path = os.path.join(ROOT, 'profiles', 'r02_kernels_full_summary.json')
     try:
-        recs = [r for r in json.load(open(path)) if 'view_kernel' in r['Kernel Name']]
+        recs = [r for r in json.load(open(path)) if 'view_kernel' in r['Kernel Name'] and r.get('source') == 'full_view_kernel_raw.csv']
         mb = [float(r['dram__bytes_read.sum']) + float(r['dram__bytes_write.sum']) for r in recs]
         return sum(mb) / len(mb) * 1e6, os.path.relpath(path, ROOT)
     except (OSError, KeyError, ValueError, ZeroDivisionError):
@@ -504,7 +504,7 @@ def main():
                     'kernel_share_of_step': km['render'] / sum(km.values()), 'algorithmic_bytes_per_launch': rb,
                     'traffic_source': traffic_src, 'all_kernels_ms': km, 'peak_source': peak_src,
                     'whole_step': {'achieved': step_achieved, 'frac': step_achieved / peak, 'algorithmic_bytes_per_step': out['bytes_per_step']},
-                    'note': 'not HBM-bound: issue/latency-bound (ncu: issue-active 62%, DRAM ~15% of peak). Kernels are timed apart here (events between them); in the step dyn_kernel overlaps the tail of view_kernel, so all_kernels_ms sums to more than ms_per_step. See DESIGN.md'}
+                    'note': 'not HBM-bound: issue/latency-bound (ncu, profiles/r02_kernels_full_summary.json: issue-active 61%, DRAM 14% of peak, 61.6 M warp-instructions). Kernels are timed apart here (events between them); in the step dyn_kernel overlaps the tail of view_kernel, so all_kernels_ms sums to more than ms_per_step. See DESIGN.md'}
     else:
         roofline = {'bound': 'hbm', 'achieved': step_achieved, 'peak': peak, 'unit': 'GB/s', 'frac': step_achieved / peak, 'traffic': None,
                     'kernel': 'whole step (physics + render + ~40 ATen launches)', 'algorithmic_bytes_per_step': out['bytes_per_step'],

@@ -593,6 +593,16 @@ __device__ __noinline__ float dyn_inline(const float4* seg, int L, int AF, int n
     return intensity;
 }
 
+// The sum over each group of `sub` adjacent lanes (sub a power of two; every lane of the group gets it), added as a
+// butterfly from the widest stride down — (x0 + x2) + (x1 + x3) for sub = 4 — which is the order ATen's mean() adds the
+// `sub` values of a pooled pixel in (probed: scripts/mean_order_probe.py), so that the fused RGB / Depth heads equal
+// `downsample(x, sub).mean(-1)` (modules.py:181-183, 222-223) bit for bit (tests/test_gpu_reference_python.py).
+__device__ __forceinline__ float pool_sum(float x, int sub, int lane) {
+    (void)lane;
+    for (int o = sub >> 1; o > 0; o >>= 1) x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
 // What shading gathers for one ray: the two texels (and baked lights) around the hit, with the filter weights.
 struct Texels { float lw, rw, tl0, tl1, tl2, tr0, tr1, tr2, bl, br; };
 
@@ -770,13 +780,7 @@ __device__ __forceinline__ void shade_chunk(const KArgs& k, const VSmem& m, int 
             const float z = __fmul_rn(__fsub_rn(dist, k.p.agent_radius), k.inv_max_depth);
             d = __fsub_rn(1.f, fminf(fmaxf(z, 0.f), 1.f));
         }
-        float v0 = s0, v1 = s1, v2 = s2, v3 = d;
-        for (int o = 1; o < sub_; o <<= 1) {
-            v0 = __fadd_rn(v0, __shfl_xor_sync(0xffffffffu, v0, o));
-            v1 = __fadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, o));
-            v2 = __fadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
-            v3 = __fadd_rn(v3, __shfl_xor_sync(0xffffffffu, v3, o));
-        }
+        const float v0 = pool_sum(s0, sub_, lane), v1 = pool_sum(s1, sub_, lane), v2 = pool_sum(s2, sub_, lane), v3 = pool_sum(d, sub_, lane);
         if (live && lane == gl) {
             const int Ro = R >> k.sub_shift, ro = r >> k.sub_shift;         // subsample is a power of two
             const float inv = k.inv_sub;
@@ -1326,12 +1330,7 @@ __device__ __forceinline__ void dyn_finish(const KArgs& k, const DynEntry& d, un
         sc[0] = s0; sc[1] = s1; sc[2] = s2;
     }
     if (k.has_obs && k.obs.rgb) {
-        float v0 = d.have ? s0 : 0.f, v1 = d.have ? s1 : 0.f, v2 = d.have ? s2 : 0.f;
-        for (int o = 1; o < sub; o <<= 1) {
-            v0 = __fadd_rn(v0, __shfl_xor_sync(0xffffffffu, v0, o));
-            v1 = __fadd_rn(v1, __shfl_xor_sync(0xffffffffu, v1, o));
-            v2 = __fadd_rn(v2, __shfl_xor_sync(0xffffffffu, v2, o));
-        }
+        const float v0 = pool_sum(d.have ? s0 : 0.f, sub, lane), v1 = pool_sum(d.have ? s1 : 0.f, sub, lane), v2 = pool_sum(d.have ? s2 : 0.f, sub, lane);
         if (d.have && lane == gl) {
             const int Ro = R >> k.sub_shift, ro = (r0 + lane) >> k.sub_shift;
             float* q = k.obs.rgb + ag * 3 * Ro + ro;

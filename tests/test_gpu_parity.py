@@ -243,8 +243,13 @@ def test_bake_bit_exact_against_reference_build(ref):
 # ------------------------------------------------------------------------------------------------------------------
 # fused paths against the unfused ones
 # ------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('A,res,fov,sub', [(4, 128, 70., 1), (4, 512, 70., 4), (1, 256, 130., 4)])
+@pytest.mark.parametrize('A,res,fov,sub', [(4, 128, 70., 1), (4, 512, 70., 4), (1, 256, 130., 4), (3, 96, 100., 2)])
 def test_fused_step_equals_modules_pipeline(A, res, fov, sub):
+    """FusedStep (what bench.py times) against this package's unfused modules — MomentumMovement -> render -> RGB / Depth /
+    IMU, PyTorch ops around cuda.physics / cuda.render as in the reference — over 6 ticks from the same state with NO
+    resynchronisation: everything bit for bit (in-kernel movement restates torch's op order with rounding-explicit
+    intrinsics; the pooled heads add in ATen's order). The same comparison against the reference's OWN modules.py runs
+    in tests/test_gpu_reference_python.py."""
     from megastep_b200 import modules
     from megastep_b200.arrdict import arrdict
     gs, arrays, st = make('synthetic', 12, A, seed=31)
@@ -252,26 +257,20 @@ def test_fused_step_equals_modules_pipeline(A, res, fov, sub):
     mover, rgb, depth, imu = modules.MomentumMovement(c1), modules.RGB(c1, subsample=sub), modules.Depth(c1, subsample=sub), modules.IMU(c1)
     fused = modules.FusedStep(c2, subsample=sub, raw=True)
     rng = np.random.RandomState(3)
-    for tick in range(5):
+    for tick in range(6):
         actions = torch.as_tensor(rng.randint(0, 7, (12, A))).int().cuda()
         p = mover(arrdict(actions=actions))
         r = modules.render(c1)
         want = arrdict(rgb=rgb(r), d=depth(r), imu=imu())
         out = fused(actions)
         torch.cuda.synchronize()
-        assert torch.equal(out.progress < 1, p.progress < 1)
-        torch.testing.assert_close(out.progress, p.progress, rtol=0, atol=1e-6)
+        assert torch.equal(out.progress, p.progress), f'tick {tick}: progress'
         for k in ('positions', 'angles', 'velocity', 'angvelocity'):
-            torch.testing.assert_close(getattr(c2.agents, k), getattr(c1.agents, k), rtol=0, atol=1e-5, msg=lambda m: f'tick {tick} {k}: {m}')
-        same = out.render.indices == r.indices.squeeze(2)
-        assert same.float().mean() > .999
-        torch.testing.assert_close(out.obs.imu, want.imu, rtol=0, atol=1e-6)
-        ok = downsampled_all(same, sub)
-        torch.testing.assert_close(out.obs.d.squeeze(2).squeeze(2)[ok], want.d.squeeze(2).squeeze(2)[ok], rtol=0, atol=1e-5)
-        okc = ok[:, :, None, :].expand(-1, -1, 3, -1)
-        torch.testing.assert_close(out.obs.rgb.squeeze(3)[okc], want.rgb.squeeze(3)[okc], rtol=0, atol=1e-5)
-        # keep the two cores in lock step even if a near-tie made them diverge by an ulp
-        common.load_state(c2, common.read_state(c1))
+            assert torch.equal(getattr(c2.agents, k), getattr(c1.agents, k)), f'tick {tick}: {k}'
+        assert torch.equal(out.render.indices, r.indices.squeeze(2)), f'tick {tick}: indices'
+        for k in ('locations', 'dots', 'distances'):
+            assert _same(getattr(out.render, k), r[k].squeeze(2)), f'tick {tick}: {k}'
+        assert torch.equal(out.obs.imu, want.imu) and torch.equal(out.obs.d, want.d) and torch.equal(out.obs.rgb, want.rgb), f'tick {tick}: obs'
 
 
 def test_random_spawns_respawn_only_the_flagged_agents_on_the_device():
@@ -349,9 +348,7 @@ def test_rgbd_head_equals_rgb_and_depth_modules():
     obs = modules.RGBD(c, subsample=4)()
     torch.cuda.synchronize()
     assert obs.rgb.shape == want_rgb.shape and obs.d.shape == want_d.shape
-    torch.testing.assert_close(obs.rgb, want_rgb, rtol=0, atol=1e-6)
-    torch.testing.assert_close(obs.d, want_d, rtol=0, atol=1e-6)
-    torch.testing.assert_close(obs.imu, want_imu, rtol=0, atol=1e-6)
+    assert torch.equal(obs.rgb, want_rgb) and torch.equal(obs.d, want_d) and torch.equal(obs.imu, want_imu)
 
 
 OPTIONS = ('nch', 'threads', 'stage_rec', 'idx64', 'persist', 'merge_dyn', 'dyn_groups', 'stages', 'no_sched', 'dyn_warps')
