@@ -54,7 +54,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-raw', action='store_true', help='skip materialising the five Render tensors (obs heads only)')
     ap.add_argument('--gather', action='store_true', help='all-gather the observations to every rank each step (NCCL, side stream, overlapping the next step)')
-    ap.add_argument('--obs-dtype', default='float32', choices=['float32', 'float16'], help='precision of the gathered observations')
+    ap.add_argument('--obs-dtype', default='float32', choices=['float32', 'float16', 'uint8'], help='precision of the gathered observations (uint8: rgb and depth quantised to 8 bits, imu as fp16)')
+    ap.add_argument('--distinct-shards', action='store_true', help='every rank builds its own floorplans / poses / actions (seeds + rank) instead of a replica of rank 0\'s shard')
     ap.add_argument('--no-graph', action='store_true', help='e2e leg: plain launches instead of a CUDA-graph replay')
     ap.add_argument('--e2e', default='torch', choices=['native', 'torch'], help='e2e leg: the library\'s own host-driven graph (one call per tick) or a torch CUDA graph between PyTorch copies')
     ap.add_argument('--dry-run', action='store_true', help='build the scene and the CPU baseline only (no GPU)')
@@ -307,12 +308,15 @@ def run_gpu(args, cfg, arm_cls, rank, world, local_rank):
     device = torch.device('cuda', local_rank)
     torch.cuda.set_device(device)
     n_envs = args.envs or cfg['n_envs']
-    gs, arrays, pos, ang = build_scene(cfg, n_envs, args.unique, rank)
+    # Weak scaling = the SAME work on every GPU: each rank steps a replica of the same shard (same floorplans, poses and
+    # actions), so that the max-over-ranks time measures the system, not which rank drew the costliest floorplans.
+    seed_rank = rank if args.distinct_shards else 0
+    gs, arrays, pos, ang = build_scene(cfg, n_envs, args.unique, seed_rank)
     raw = not args.no_raw
     arm = arm_cls(cfg, arrays, pos, ang, device, raw)
     N, A = pos.shape[:2]
     K, W = args.steps, args.warmup
-    rng = np.random.RandomState(3 + rank)
+    rng = np.random.RandomState(3 + seed_rank)
     acts_host = torch.as_tensor(rng.randint(0, 7, (K + W, N, A)).astype(np.int32)).pin_memory()
     acts_dev = acts_host.to(device)
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=device)
@@ -473,7 +477,7 @@ def main():
     base_cfg = {'workload': f"{args.workload}: synthetic cubicasa-shaped floorplans, {n_envs} envs/GPU x {cfg['n_agents']} agents x "
                             f"{cfg['res']} rays, fov {cfg['fov']:g}, MomentumMovement + physics + render + RGB/Depth/IMU (subsample {cfg['subsample']})",
                 'envs_per_gpu': n_envs, 'n_agents': cfg['n_agents'], 'res': cfg['res'], 'fov': cfg['fov'], 'subsample': cfg['subsample'],
-                'raw_render_outputs': not args.no_raw, 'parallelism': f'env-sharded x{eff_world}, no per-step collective' + (' + obs all-gather' if args.gather else ''),
+                'raw_render_outputs': not args.no_raw, 'parallelism': f'env-sharded x{eff_world} ({"each rank its own floorplans" if args.distinct_shards else "each rank a replica of the same shard: identical work per GPU"}), no per-step collective' + (f' + obs all-gather ({args.obs_dtype})' if args.gather else ''),
                 'l2': f'flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write); per-step CUDA events'}
 
     if out is None:

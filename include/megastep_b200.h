@@ -4,8 +4,13 @@
  * pybind11/ATen extension (`megastepcuda`, megastep/src/wrappers.cpp:30-172); the entry points below are what a
  * binding for it binds, with every at::Tensor flattened to a raw DEVICE pointer plus sizes, and the reference's
  * process-global `initialize()` constants (megastep/src/kernels.cu:12-27) turned into an explicit per-call params
- * struct. No torch types, no globals, no allocation: the caller owns every buffer (scratch included); kernels are enqueued on the
+ * struct. No torch types, no allocation: the caller owns every buffer (scratch included); kernels are enqueued on the
  * caller's stream and return without synchronising (as the reference: kernels.cu:30-32, no device sync anywhere).
+ * Every entry point takes all of its state through its arguments and may be called from several threads (on different
+ * streams, each with its own workspace) — with three process-global exceptions, none of which changes results:
+ * msb_set_option / msb_get_option (tuning and diagnostics switches, the per-kernel timing ring and the stats counters:
+ * set them from one thread, while nothing else is launching), msb_launch_count (an atomic counter) and msb_last_error
+ * (thread-local).
  *
  * All functions return 0 on success, non-zero on failure (msb_last_error() describes it). Pointer arguments are
  * device pointers unless marked [host]. All float data is fp32; all index data int32 unless stated (texel
@@ -188,7 +193,9 @@ int msb_step_graph_destroy(msb_graph* g);
 /* [host] Recommended workspace size in bytes for this scene and observation subsample (1 when obs is NULL). */
 int64_t msb_workspace_bytes(const msb_params* p, const msb_scenery* s, int32_t subsample);
 
-/* Tuning/diagnostics: selects kernel variants (0 = default). Affects speed only, never results. */
+/* Tuning/diagnostics: selects kernel variants (0 = default). Affects speed only, never results. Process-global and NOT
+ * thread-safe (see the top of this header): "timing" records CUDA events around every kernel on the launching stream,
+ * "stats" allocates device counters the kernels add to. */
 int msb_set_option(const char* name, int64_t value);
 int64_t msb_get_option(const char* name);
 

@@ -2269,6 +2269,7 @@ static long long g_opt_dyn_warps = 0;    // warps sharing one queue entry in dyn
 static long long g_opt_fused_step = 0;   // 1: msb_step runs physics inside view_kernel (measured slower: the physics latency
                                          // chain adds to every CTA's life instead of running at its own high occupancy)
 static long long g_opt_bake_brute = 0;  // 1: bake tests every static line per (texel, light) like the reference, even when the spatial table exists
+static long long g_opt_view_ctas_per_sm = 0;   // view_kernel: cap the resident CTAs per SM (by padding its shared memory); 0: auto
 static long long g_opt_persist = 0;      // 1: render with tick_kernel (persistent grid) instead of view_kernel + dyn_kernel
 static long long g_opt_merge_dyn = 0;    // tick_kernel lights the agent-hit windows itself — 0 / 1: yes, 2: no (dyn_kernel follows)
 static long long g_opt_dyn_groups = 0;   // merged second pass: tickets per queue entry (1, 2 or 4; default 4)
@@ -2374,6 +2375,7 @@ extern "C" int msb_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "stage_rec")) { g_opt_stage_rec = value; return 0; }
     if (!strcmp(name, "idx64")) { g_opt_idx64 = value; return 0; }
     if (!strcmp(name, "persist")) { g_opt_persist = value; return 0; }
+    if (!strcmp(name, "view_ctas_per_sm")) { g_opt_view_ctas_per_sm = value; return 0; }
     if (!strcmp(name, "bake_brute")) { g_opt_bake_brute = value; return 0; }
     if (!strcmp(name, "merge_dyn")) { g_opt_merge_dyn = value; return 0; }
     if (!strcmp(name, "dyn_groups")) { g_opt_dyn_groups = value; return 0; }
@@ -2516,6 +2518,11 @@ static int launch_view(KArgs& k, bool phys, int nch, int threads, cudaStream_t s
         sm = vsmem_bytes(k.wcap, threads / 32, k.s.n_agents, k.s.n_agents * k.s.n_model, false);
     }
     if (sm > 227 * 1024) return fail("%s", "scene too large: an env's segments do not fit in shared memory (227 KB)");
+    if (g_opt_view_ctas_per_sm >= 1 && g_opt_view_ctas_per_sm <= 16) {
+        // fewer resident CTAs than the registers allow: the grid's last, partial wave is what it costs to have more
+        const size_t per = (size_t)(227 * 1024) / (size_t)g_opt_view_ctas_per_sm - 1024;
+        if (per > sm) sm = per & ~size_t(15);
+    }
 #define MSB_LAUNCH(N)                                                                                            \
     {                                                                                                            \
         auto fn = phys ? (k.stats ? view_kernel<N, true, true> : view_kernel<N, true, false>)                    \

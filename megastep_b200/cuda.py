@@ -279,8 +279,18 @@ class Scenery:
         return dotdict(n_agents=self._n_agents, lights=self._lights[e], lines=self._lines[e],
                        textures=self._textures[se:ee], model=self._model, baked=self._baked[se:ee])
 
+    def invalidate(self):
+        """Call after editing the STATIC geometry in place (`lines.vals` beyond the agents' rows, `lights`, the texture
+        widths): the side tables derived from it — the spatial table, the light-visibility grid, the launch order —
+        are built once and cached, so the kernels would otherwise keep seeing the old walls (the reference re-reads
+        `lines` on every call; here only the agents' rows, the texels and `baked` are re-read). Rebuilt on the next call;
+        re-bake if the lighting should follow."""
+        self._c = None
+        self._ws = {}
+
     def _struct(self):
-        """The msb_scenery view of this object; built once (device pointers are stable, we hold the tensors)."""
+        """The msb_scenery view of this object; built once (device pointers are stable, we hold the tensors). The static
+        arrays are treated as immutable from here on: see `invalidate`."""
         if self._c is None:
             for name, t in (('lines', self._lines.vals), ('lights', self._lights.vals), ('textures', self._textures.vals)):
                 _require(t.is_cuda, f'{name} must be a CUDA tensor')
@@ -333,6 +343,8 @@ def _shared_workspace(scenery, params):
     """The per-(scenery, res) scratch used by plain render() calls on the default stream."""
     key = (params.res, torch.cuda.current_stream(scenery.model.device).cuda_stream)
     if key not in scenery._ws:
+        while len(scenery._ws) >= 4:                    # a handful of (res, stream) pairs at most: drop the oldest
+            scenery._ws.pop(next(iter(scenery._ws)))
         scenery._ws[key] = make_workspace(scenery, params, 1)
     return scenery._ws[key][1]
 

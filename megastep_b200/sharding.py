@@ -117,15 +117,24 @@ def initialize(device=None, devices=None, backend=None):
 class PackedObs:
     """The observation heads of one rank packed per environment — one row [rgb | d | imu] per env — so that ONE
     all-gather of the rows gives every rank the whole batch, and each observation of the whole batch is a plain strided
-    view of the gathered rows (no unpacking pass). Optionally carried at reduced precision.
+    view of the gathered rows (no unpacking pass). Optionally carried at reduced precision: `torch.float16`, or
+    `torch.uint8` — rgb and depth (both in [0, 1]) quantised to 8 bits, what image observations are usually stored as
+    (the reference's own replay-buffer estimate assumes 64 px x 3 channels, docs/faq.rst:77-79), the imu kept as fp16.
 
-    layout(n_agents, ro) -> column ranges; views(rows) -> arrdict(rgb (N,A,3,1,ro), d (N,A,1,1,ro), imu (N,A,3))."""
+    views(rows) -> arrdict(rgb (N,A,3,1,ro), d (N,A,1,1,ro), imu (N,A,3))."""
 
     def __init__(self, n_agents, ro, dtype=torch.float32):
         self.A, self.ro, self.dtype = n_agents, ro, dtype
-        self.cols = {'rgb': (0, n_agents * 3 * ro), 'd': (n_agents * 3 * ro, n_agents * 4 * ro),
-                     'imu': (n_agents * 4 * ro, n_agents * 4 * ro + n_agents * 3)}
+        A = n_agents
+        if dtype == torch.uint8:
+            n_img = A * 4 * ro
+            pad = n_img % 2                                     # the fp16 imu starts on an even byte
+            self.cols = {'rgb': (0, A * 3 * ro), 'd': (A * 3 * ro, n_img), 'imu': (n_img + pad, n_img + pad + 2 * A * 3)}
+        else:
+            self.cols = {'rgb': (0, A * 3 * ro), 'd': (A * 3 * ro, A * 4 * ro), 'imu': (A * 4 * ro, A * 4 * ro + A * 3)}
         self.width = self.cols['imu'][1]
+        if dtype == torch.uint8:
+            self.width += self.width % 2                        # rows stay 2-byte aligned
 
     def empty(self, n_envs, device):
         return torch.empty((n_envs, self.width), dtype=self.dtype, device=device)
@@ -134,16 +143,26 @@ class PackedObs:
         """obs: arrdict(rgb, d, imu) of one rank (float32) -> out (n_local, width); three strided copies (with the cast)."""
         n = out.shape[0]
         for k, (a, b) in self.cols.items():
-            out[:, a:b].copy_(obs[k].reshape(n, -1))
+            src = obs[k].reshape(n, -1)
+            if self.dtype == torch.uint8:
+                if k == 'imu':
+                    out[:, a:b].view(torch.float16).copy_(src)
+                else:
+                    out[:, a:b].copy_((src * 255.).round_().clamp_(0., 255.))
+            else:
+                out[:, a:b].copy_(src)
         return out
 
     def views(self, rows):
         from .arrdict import arrdict
-        n, A, ro = rows.shape[0], self.A, self.ro
+        A, ro = self.A, self.ro
         c = self.cols
+        imu = rows[:, c['imu'][0]:c['imu'][1]]
+        if self.dtype == torch.uint8:
+            imu = imu.view(torch.float16)
         return arrdict(rgb=rows[:, c['rgb'][0]:c['rgb'][1]].unflatten(1, (A, 3, 1, ro)),
                        d=rows[:, c['d'][0]:c['d'][1]].unflatten(1, (A, 1, 1, ro)),
-                       imu=rows[:, c['imu'][0]:c['imu'][1]].unflatten(1, (A, 3)))
+                       imu=imu.unflatten(1, (A, 3)))
 
 
 class ShardedCore:

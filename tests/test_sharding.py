@@ -129,6 +129,13 @@ def test_packed_obs_round_trip_and_half_precision():
     h = sharding.PackedObs(4, 16, torch.float16)
     vh = h.views(h.pack(obs, h.empty(5, 'cpu')))
     assert vh.rgb.dtype == torch.float16 and all(torch.allclose(vh[k].float(), obs[k], atol=2e-3) for k in obs)
+    for A, ro in ((4, 16), (1, 5), (3, 7)):                      # 8-bit images, fp16 imu; odd widths exercise the alignment padding
+        obs = arrdict(rgb=torch.rand(5, A, 3, 1, ro), d=torch.rand(5, A, 1, 1, ro), imu=torch.randn(5, A, 3))
+        q = sharding.PackedObs(A, ro, torch.uint8)
+        vq = q.views(q.pack(obs, q.empty(5, 'cpu')))
+        assert vq.rgb.dtype == torch.uint8 and vq.imu.dtype == torch.float16 and q.width % 2 == 0
+        assert (vq.rgb.float() / 255 - obs.rgb).abs().max() <= .5 / 255 + 1e-6 and (vq.d.float() / 255 - obs.d).abs().max() <= .5 / 255 + 1e-6
+        assert torch.allclose(vq.imu.float(), obs.imu, atol=4e-3)
 
 
 def _scene_for_shards(n_envs, n_agents, seed=7):
@@ -169,7 +176,7 @@ def _nccl_worker(rank, world, port, q):
         N, A = 12, 4
         arrays, pos, ang = _scene_for_shards(N, A)
         ok = True
-        for dtype, tol in ((torch.float32, 0.), (torch.float16, 2e-3)):
+        for dtype, tol in ((torch.float32, 0.), (torch.float16, 2e-3), (torch.uint8, 2.1e-3)):
             sc = sharding.ShardedCore(arrays, N, res=128, fov=70., subsample=1, obs_dtype=dtype, positions=pos, angles=ang)
             # the same batch, whole, on this rank's GPU
             s = scene.upload(arrays)
@@ -187,7 +194,8 @@ def _nccl_worker(rank, world, port, q):
                 full = sc.gather_wait()
                 torch.cuda.synchronize()
                 for k in ('rgb', 'd', 'imu'):
-                    good = torch.equal(full[k], want.obs[k]) if tol == 0. else torch.allclose(full[k].float(), want.obs[k], atol=tol)
+                    got = full[k].float() / 255 if full[k].dtype == torch.uint8 else full[k].float()
+                    good = torch.equal(full[k], want.obs[k]) if tol == 0. else torch.allclose(got, want.obs[k], atol=tol if k != 'imu' else 4e-3)
                     ok = ok and bool(good) and full[k].shape == want.obs[k].shape
         q.put((rank, ok))
     finally:
