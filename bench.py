@@ -1,18 +1,22 @@
 #!/usr/bin/env python
 """bench.py — agent-frames/s of the physics()+render() hot path on synthetic cubicasa-shaped scenes.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload deathmatch|explorer]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload deathmatch|explorer|...]
+                    [--envs E] [--gather [--obs-dtype float32|float16|uint8]]
 
 A "step" is one whole environment tick over the batch: MomentumMovement (random actions) -> physics -> render (all
 five Render tensors materialised, as the reference's render() does) -> RGB/Depth/IMU observation heads.
   * ours:      msb_step through the C ABI: movement+physics kernel, render+heads kernel, agent-hit lighting kernel —
-               three back-to-back launches, no host round trip.
-  * reference: the reference's OWN kernels.cu/wrappers.cpp built unmodified for sm_100a (oracle/_ref), driven through
-               its own API (megastepcuda.physics / .render) plus the PyTorch elementwise ops its modules.py runs around
-               them. megastep has no CPU step path (docs/faq.rst:23-27), so this — not a CPU run — is the reference arm;
-               if oracle/_ref is not loadable the arm falls back to timing the CPU oracle port on the host cores.
+               three back-to-back launches (replayed as one CUDA graph), no host round trip.
+  * reference: the reference's OWN kernels.cu/wrappers.cpp built unmodified for sm_100a (oracle/_ref) driven by the
+               reference's OWN unmodified Python (oracle/_ref/site: core.Core, modules.MomentumMovement / render / RGB /
+               Depth / IMU) through tests/common.py::reference_package — the same shim the parity tests use. megastep
+               has no CPU step path (docs/faq.rst:23-27), so this — not a CPU run — is the reference arm; if oracle/_ref
+               is not loadable the arm falls back to timing the CPU oracle port on the host cores.
+Under torchrun (N > 1) every rank steps a replica of the same shard (identical work per GPU: weak scaling; --distinct-shards
+gives each rank its own floorplans); no per-step collective unless --gather (ShardedCore's packed all-gather).
 
-Prints ONE JSON line (rank 0). See DESIGN.md §Measurement for what each key means.
+Prints ONE JSON line (rank 0), the last line of stdout. See DESIGN.md §5 for what each key means.
 """
 import argparse
 import json

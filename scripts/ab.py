@@ -20,7 +20,7 @@ import bench                                                    # noqa: E402
 from megastep_b200 import cuda, modules, scene, core as core_   # noqa: E402
 
 ALL = ('nch', 'threads', 'stage_rec', 'idx64', 'persist', 'merge_dyn', 'dyn_groups', 'stages', 'no_sched', 'dyn_warps', 'pdl',
-       'no_prefetch', 'no_env_order', 'dyn_window', 'debug_skip_dyn', 'no_vis')
+       'no_prefetch', 'no_env_order', 'dyn_window', 'debug_skip_dyn', 'no_vis', 'fused_step', 'view_ctas_per_sm', 'bake_brute')
 
 
 def main():
