@@ -1993,6 +1993,7 @@ __global__ void __launch_bounds__(256) vis_kernel(const __grid_constant__ KArgs 
     const int I = __ldg(k.s.light_widths + n);
     const float* lt = k.s.lights + 3 * (int64_t)__ldg(k.s.light_starts + n);
     const float vmax = __ldg(k.s.occ_meta + 2 * n), diam = __ldg(k.s.occ_meta + 2 * n + 1);
+    const float4* boxes = reinterpret_cast<const float4*>(k.s.occ_boxes) + __ldg(k.s.box_starts + n);
     const bool real = lane < I;
     const float Ix = real ? __ldg(lt + 3 * lane) : 0.f, Iy = real ? __ldg(lt + 3 * lane + 1) : 0.f;
     for (int cell = warp; cell < gx * gy; cell += nwarps) {
@@ -2005,21 +2006,27 @@ __global__ void __launch_bounds__(256) vis_kernel(const __grid_constant__ KArgs 
         const float thr2 = thr * thr;
         const float bx0 = fminf(Ix, Cx) - thr, bx1 = fmaxf(Ix, Cx) + thr, by0 = fminf(Iy, Cy) - thr, by1 = fmaxf(Iy, Cy) + thr;
         bool sure = real;
-        for (int l = 0; l < W; l++) {
-            const float4 s4 = seg[l];                                               // (uniform address: a broadcast)
-            // nowhere near the box around light -> centre: the common case
-            const bool far = fmaxf(s4.x, s4.z) < bx0 || fminf(s4.x, s4.z) > bx1 || fmaxf(s4.y, s4.w) < by0 || fminf(s4.y, s4.w) > by1;
-            if (sure && !far) {
-                const float Vx = s4.z - s4.x, Vy = s4.w - s4.y;
-                // do they cross? (orientation signs; a near-miss shows up in the end-point distances below)
-                const float o1 = Ux * (s4.y - Iy) - Uy * (s4.x - Ix), o2 = Ux * (s4.w - Iy) - Uy * (s4.z - Ix);
-                const float o3 = Vx * (Iy - s4.y) - Vy * (Ix - s4.x), o4 = Vx * (Cy - s4.y) - Vy * (Cx - s4.x);
-                const bool cross = (o1 * o2 <= 0.f) && (o3 * o4 <= 0.f);
-                const float d2 = fminf(fminf(pt_seg_d2(s4.x, s4.y, Ix, Iy, Ux, Uy), pt_seg_d2(s4.z, s4.w, Ix, Iy, Ux, Uy)),
-                                       fminf(pt_seg_d2(Ix, Iy, s4.x, s4.y, Vx, Vy), pt_seg_d2(Cx, Cy, s4.x, s4.y, Vx, Vy)));
-                if (cross || !(d2 > thr2)) sure = false;                            // (NaN: not sure)
+        for (int b = 0; b < nb; b++) {
+            // the run's box against the box around light -> centre: a run no light's query comes near is skipped whole
+            const float4 bx = __ldg(boxes + b);                                     // (uniform address: a broadcast)
+            const bool near = sure && !(bx.z < bx0 || bx.x > bx1 || bx.w < by0 || bx.y > by1);
+            if (!__any_sync(0xffffffffu, near)) continue;
+            for (int l = VRUN * b; l < VRUN * (b + 1) && l < W; l++) {
+                const float4 s4 = seg[l];                                           // (uniform address: a broadcast)
+                // nowhere near the box around light -> centre: the common case
+                const bool far = fmaxf(s4.x, s4.z) < bx0 || fminf(s4.x, s4.z) > bx1 || fmaxf(s4.y, s4.w) < by0 || fminf(s4.y, s4.w) > by1;
+                if (sure && !far) {
+                    const float Vx = s4.z - s4.x, Vy = s4.w - s4.y;
+                    // do they cross? (orientation signs; a near-miss shows up in the end-point distances below)
+                    const float o1 = Ux * (s4.y - Iy) - Uy * (s4.x - Ix), o2 = Ux * (s4.w - Iy) - Uy * (s4.z - Ix);
+                    const float o3 = Vx * (Iy - s4.y) - Vy * (Ix - s4.x), o4 = Vx * (Cy - s4.y) - Vy * (Cx - s4.x);
+                    const bool cross = (o1 * o2 <= 0.f) && (o3 * o4 <= 0.f);
+                    const float d2 = fminf(fminf(pt_seg_d2(s4.x, s4.y, Ix, Iy, Ux, Uy), pt_seg_d2(s4.z, s4.w, Ix, Iy, Ux, Uy)),
+                                           fminf(pt_seg_d2(Ix, Iy, s4.x, s4.y, Vx, Vy), pt_seg_d2(Cx, Cy, s4.x, s4.y, Vx, Vy)));
+                    if (cross || !(d2 > thr2)) sure = false;                        // (NaN: not sure)
+                }
             }
-            if ((l & 7) == 7 && !__any_sync(0xffffffffu, sure)) break;             // (l is warp-uniform)
+            if (!__any_sync(0xffffffffu, sure)) break;
         }
         const unsigned word = __ballot_sync(0xffffffffu, sure);
         if (lane == 0) out[cell] = word;
@@ -2168,13 +2175,15 @@ __global__ void __launch_bounds__(256) ledger_mark_kernel(const int32_t* __restr
             fresh = !(atomicOr(seen + (texel >> 5), bit) & bit);
         }
     }
-    // one add per env and warp (a warp's rays belong to one env, or two at an env boundary)
-    const unsigned active = __activemask();
-    const int n0 = __shfl_sync(active, n, __ffs(active) - 1);
-    const unsigned first = __ballot_sync(active, fresh && n == n0), second = __ballot_sync(active, fresh && n != n0);
+    // one add per env and warp (a warp's rays belong to one env, or a few at env boundaries)
     const int lane = threadIdx.x & 31;
-    if (lane == __ffs(active) - 1 && first) { atomicAdd(potential + n0, __popc(first)); atomicAdd(gained + n0, __popc(first)); }
-    if (second && lane == __ffs(second) - 1) { atomicAdd(potential + n, __popc(second)); atomicAdd(gained + n, __popc(second)); }
+    unsigned todo = __ballot_sync(0xffffffffu, fresh);
+    while (todo) {
+        const int env = __shfl_sync(0xffffffffu, n, __ffs(todo) - 1);
+        const unsigned same = __ballot_sync(0xffffffffu, fresh && n == env);
+        if (lane == __ffs(same) - 1) { atomicAdd(potential + env, __popc(same)); atomicAdd(gained + env, __popc(same)); }
+        todo &= ~same;
+    }
 }
 
 // one CTA per env: if the env resets, its texels' bits — a range of the scene-wide bit array, not word-aligned — are cleared

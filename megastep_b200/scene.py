@@ -134,7 +134,8 @@ def tiled_scenery(arrays, n_envs, device='cuda', params=None):
     t_rest = int(tw[:l_rest].long().sum())
 
     def cyc(t, n_rest):
-        return torch.cat([t.repeat(reps, *([1] * (t.dim() - 1))), t[:n_rest]]).contiguous()
+        whole = t.repeat(reps, *([1] * (t.dim() - 1)))
+        return whole if n_rest == 0 else torch.cat([whole, t[:n_rest]]).contiguous()
 
     s = cuda.Scenery(
         n_agents=base.n_agents,

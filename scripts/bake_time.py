@@ -33,7 +33,10 @@ def main():
            'lines': int(len(arrays['lines']))}
     params = cuda.make_params(bench.AGENT_RADIUS, cfg['res'], cfg['fov'], bench.FPS)
     s, out['upload_ms'] = timed(lambda: scene.upload(arrays))
+    cuda.set_option('timing', 1)
     _, out['table_and_visibility_ms'] = timed(lambda: s._struct())
+    out['vis_kernel_ms'] = cuda.get_option('time_ns_bake') / 1e6
+    cuda.set_option('timing', 0)
     _, _ = timed(lambda: cuda.bake(s, params=params))                       # warm-up (attribute set-up)
     _, out['bake_table_ms'] = timed(lambda: cuda.bake(s, params=params))
     ours = s.baked.vals.clone()

@@ -560,6 +560,37 @@ def test_visibility_grid_is_conservative_and_changes_nothing():
             assert bits > .3 * total, (bits, total)
 
 
+def test_more_than_2_to_31_texels_copies_of_an_env_render_and_move_alike():
+    """64-bit texel offsets in their true regime (the reference's 32-bit accessors stop at 2^31 elements, common.h:30,43):
+    a scenery of > 2^31 texels — 256 floorplans repeated on the device, scene.tiled_scenery — in which every copy of a
+    floorplan holds its agent in the same pose: the last copies must render and move exactly like the first."""
+    from megastep_b200 import core as core_, scene, synthetic
+    if torch.cuda.mem_get_info()[1] < 120e9:
+        pytest.skip('needs ~80 GB of device memory')
+    gs = synthetic.sample(256, seed=5)
+    base = scene.scene_arrays(gs, 1, np.random.RandomState(5))
+    reps = int(np.ceil((2 ** 31 + 2 ** 27) / len(base['textures'])))
+    N = 256 * reps
+    s = scene.tiled_scenery(base, N)
+    assert s.textures.vals.size(0) > 2 ** 31 and int(s.textures._long_starts()[-1]) > 2 ** 31
+    c = core_.Core(s, res=32, fov=130., fps=10.)
+    pos, ang = synthetic.spawns(gs, 1, np.random.RandomState(6))
+    c.agents.positions.copy_(torch.as_tensor(pos).cuda().repeat(reps, 1, 1))
+    c.agents.angles.copy_(torch.as_tensor(ang).cuda().repeat(reps, 1))
+    c.agents.velocity.copy_(torch.as_tensor((2 * np.random.RandomState(7).normal(size=(256, 1, 2))).astype(np.float32)).cuda().repeat(reps, 1, 1))
+    for tick in range(2):
+        p = c.physics()
+        r = c.render()
+        torch.cuda.synchronize()
+        assert torch.equal(p.progress[:256], p.progress[-256:]) and torch.equal(c.agents.positions[:256], c.agents.positions[-256:])
+        for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
+            a, b = getattr(r, k)[:256], getattr(r, k)[-256:]
+            assert _same(a, b), f'tick {tick}: {k} of the last copies differs from the first'
+        assert (r.indices >= 0).float().mean() > .9 and float(r.screen[-256:].sum()) > 0
+    del c, s, r
+    torch.cuda.empty_cache()
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # 3. properties at the benchmark's full size (Deathmatch 4096 x 4 x 128)
 # ------------------------------------------------------------------------------------------------------------------
