@@ -1431,22 +1431,20 @@ __global__ void __launch_bounds__(128, MSB_DYN_BLOCKS) dyn_kernel(const __grid_c
 
 // ---------------------------------------------------------------------------------------------------------------
 // tick_kernel: view_kernel as a persistent grid — one CTA per resident slot, looping over environments — with the
-// second pass (dyn_kernel's work) taken on by the same warps.
-//
-// Why: a one-shot CTA per env spends its first microseconds waiting (table copy, agent state, draw: three barriers) and
-// its last ones with most warps parked at the final barrier while the slowest (agent, ray block) item finishes, holding
-// registers and shared memory all the while (ncu, round 1: 25 % of the stall samples in 9 % of the instructions; stall
-// `barrier` 1.9 per issue; 15 % of the SM cycles idle in the grid's tail). Here
-//   * each CTA keeps a ring of S shared-memory STAGES, one env each. The warp that finishes the last item of the env in
-//     stage s refills it: takes the next env off a global counter (costliest first), starts the three bulk (TMA) copies
-//     of its table, loads and draws its agents, waits for the copies' mbarrier and publishes the stage — while the other
-//     warps are busy with the envs in the other stages. No CTA-wide barrier anywhere after the first;
-//   * items are handed out by one ticket counter per CTA, env after env: a warp that runs out of items of one env moves
-//     on to the next staged one instead of waiting for its siblings;
-//   * the queue of agent-hit pixel windows is drained by the same warps: every warp holds a TICKET for one (entry,
-//     light group) and looks at that entry's flag between two ray items — a published entry is lit right away by the
-//     `dyn_groups` warps holding its tickets (their finds OR-ed into the entry, the last one sums the lights and writes
-//     the pixels); once the rays are done the warps drain what is left. No second kernel, no tail of idle CTAs.
+// second pass (dyn_kernel's work) optionally taken on by the same warps. OPT-IN (option "persist" = 1): built to hide the
+// one-shot CTAs' prologue / epilogue stalls, measured slower than view_kernel + dyn_kernel at the benchmark's size
+// (DESIGN.md §4 has the counters), kept as a tested variant.
+//   * each CTA keeps a POOL of S shared-memory STAGES, one env each. The warp that finishes the last item of the env in
+//     a stage restages it: the next env's descriptor (fetched off a global counter, costliest first, while the previous
+//     tenant was being worked on, its table prefetched into L2), three bulk (TMA) copies on the stage's mbarrier, the
+//     agents loaded and drawn, the stage published — while the other warps are busy with the other stages. No CTA-wide
+//     barrier anywhere after the first;
+//   * a warp looking for work takes an item of the staged env that was published first and still has items to hand
+//     out: an item that takes long keeps its own stage, the others go on being refilled around it;
+//   * merged second pass: every warp holds a TICKET for one (queue entry, light group) and looks at that entry's flag
+//     between two ray items — a published entry is lit by the `dyn_groups` warps holding its tickets (their finds OR-ed
+//     into the entry, the last one sums the lights and writes the pixels); once the rays are done the warps drain what
+//     is left. The entries are counted per ENV (dyn_ctrl[3]), so nothing waits on a CTA that is yet to be scheduled.
 // Results are those of view_kernel + dyn_kernel, bit for bit (same item code, same per-entry scan).
 // ---------------------------------------------------------------------------------------------------------------
 enum { PMAXS = 8, META_N = 16, META_G0 = 17, META_L = 19, META_PAR = 20, META_INTS = 24 };
