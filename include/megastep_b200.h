@@ -228,6 +228,13 @@ int msb_env_respawn(const msb_scenery* s, const msb_agents* a, const uint8_t* re
                     const float* spawn_angles, int32_t n_spawns, uint32_t seed, uint32_t tick, const int32_t* choices,
                     void* cuda_stream);
 
+/* The three observation heads of a batch (msb_obs_out's rgb (N, A, 3, ro), depth (N, A, ro), imu (N, A, 3)) packed into
+ * one row per env, [rgb | depth | imu], in one pass: the send buffer of the multi-GPU observation all-gather
+ * (megastep_b200/sharding.py). mode 0: fp32 rows; 1: fp16 rows; 2: rgb and depth as uint8 = clamp(round(255 x), 0, 255),
+ * the imu as fp16 starting at byte `imu_offset` of the row. `row_bytes` is the row pitch. */
+int msb_pack_obs(const float* rgb, const float* depth, const float* imu, int64_t n_envs, int32_t n_agents, int32_t ro,
+                 void* rows, int64_t row_bytes, int32_t mode, int32_t imu_offset, void* cuda_stream);
+
 /* Number of kernels launched by this library since load (bench.py's `gpu_launches`). */
 int64_t msb_launch_count(void);
 

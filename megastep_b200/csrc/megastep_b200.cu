@@ -2259,6 +2259,32 @@ __global__ void __launch_bounds__(256) respawn_kernel(const uint8_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// pack_obs_kernel: the three observation heads of a batch into one row per env, [rgb | d | imu], in one pass — the send
+// buffer of ShardedCore's all-gather (sharding.PackedObs) — as fp32, fp16, or 8-bit images with an fp16 imu.
+// One thread per row element. Same values as the PyTorch form: x -> half by round-to-nearest-even; x -> uint8 as
+// clamp(round_half_even(255 x), 0, 255).
+// ---------------------------------------------------------------------------------------------------------------
+#include <cuda_fp16.h>
+__global__ void __launch_bounds__(256) pack_obs_kernel(const float* __restrict__ rgb, const float* __restrict__ d,
+                                                       const float* __restrict__ imu, unsigned char* rows, int64_t n_envs, int n_img_rgb,
+                                                       int n_img_d, int n_imu, int64_t row_bytes, int mode, int imu_off) {
+    const int per_env = n_img_rgb + n_img_d + n_imu;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_envs * per_env) return;
+    const int64_t n = i / per_env;
+    const int e = (int)(i - n * per_env);
+    float x;
+    if (e < n_img_rgb) x = __ldg(rgb + n * n_img_rgb + e);
+    else if (e < n_img_rgb + n_img_d) x = __ldg(d + n * n_img_d + (e - n_img_rgb));
+    else x = __ldg(imu + n * n_imu + (e - n_img_rgb - n_img_d));
+    unsigned char* row = rows + n * row_bytes;
+    if (mode == 0) reinterpret_cast<float*>(row)[e] = x;
+    else if (mode == 1) reinterpret_cast<__half*>(row)[e] = __float2half_rn(x);
+    else if (e < n_img_rgb + n_img_d) row[e] = (unsigned char)fminf(fmaxf(rintf(__fmul_rn(x, 255.f)), 0.f), 255.f);
+    else reinterpret_cast<__half*>(row + imu_off)[e - n_img_rgb - n_img_d] = __float2half_rn(x);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side: C ABI
 // ---------------------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -3010,4 +3036,16 @@ extern "C" int msb_env_respawn(const msb_scenery* s, const msb_agents* a, const 
                                                                                        seed, tick, const_cast<int32_t*>(choices));
     g_launches++;
     return check(cudaGetLastError(), "respawn_kernel launch");
+}
+
+extern "C" int msb_pack_obs(const float* rgb, const float* depth, const float* imu, int64_t n_envs, int32_t n_agents, int32_t ro,
+                            void* rows, int64_t row_bytes, int32_t mode, int32_t imu_offset, void* cuda_stream) {
+    if (!rgb || !depth || !imu || !rows || mode < 0 || mode > 2) return fail("%s", "msb_pack_obs: bad argument");
+    if (n_envs == 0) return 0;
+    const int n_rgb = n_agents * 3 * ro, n_d = n_agents * ro, n_imu = n_agents * 3;
+    const int64_t total = n_envs * (int64_t)(n_rgb + n_d + n_imu);
+    pack_obs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(rgb, depth, imu, reinterpret_cast<unsigned char*>(rows),
+                                                                                         n_envs, n_rgb, n_d, n_imu, row_bytes, mode, imu_offset);
+    g_launches++;
+    return check(cudaGetLastError(), "pack_obs_kernel launch");
 }

@@ -104,6 +104,8 @@ def _load():
                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.msb_env_respawn.argtypes = [P(_Scenery), P(_Agents), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                     ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
+    lib.msb_pack_obs.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                 ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
     lib.msb_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
     lib.msb_get_option.argtypes = [ctypes.c_char_p]
     lib.msb_get_option.restype = ctypes.c_int64
@@ -723,6 +725,16 @@ def env_respawn(scenery, agents, reset, spawn_positions, spawn_angles, seed, tic
         _check(_lib.msb_env_respawn(ctypes.byref(s), ctypes.byref(agents._c), reset.contiguous().data_ptr(), spawn_positions.data_ptr(),
                                     spawn_angles.data_ptr(), spawn_angles.shape[-1], int(seed) & 0xffffffff, int(tick) & 0xffffffff,
                                     choices.data_ptr() if choices is not None else None, stream))
+
+
+def pack_obs(rgb, depth, imu, rows, mode, imu_offset=0):
+    """rgb (N, A, 3, 1, ro), depth (N, A, 1, 1, ro), imu (N, A, 3), all fp32 -> rows (N, width): one launch (msb_pack_obs)."""
+    n, a, ro = rgb.shape[0], rgb.shape[1], rgb.shape[-1]
+    _require(rgb.is_contiguous() and depth.is_contiguous() and imu.is_contiguous() and rows.is_contiguous(), 'pack_obs needs contiguous tensors')
+    _require(rgb.dtype == torch.float32 and depth.dtype == torch.float32 and imu.dtype == torch.float32, 'pack_obs packs fp32 observations')
+    with _on_device(rows) as stream:
+        _check(_lib.msb_pack_obs(rgb.data_ptr(), depth.data_ptr(), imu.data_ptr(), n, a, ro, rows.data_ptr(), rows.stride(0) * rows.element_size(),
+                                 int(mode), int(imu_offset), stream))
 
 
 def set_option(name, value):

@@ -219,3 +219,18 @@ def test_sharded_core_two_ranks_over_nccl():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert results == [(0, True), (1, True)]
+
+
+@pytest.mark.gpu
+def test_pack_obs_kernel_equals_the_torch_packing():
+    """msb_pack_obs (one launch) against PackedObs.pack's PyTorch form, for the three row formats and an odd width."""
+    torch.manual_seed(0)
+    for A, ro in ((4, 128), (3, 7), (1, 5)):
+        obs = arrdict(rgb=torch.rand(33, A, 3, 1, ro) * 1.2 - .1, d=torch.rand(33, A, 1, 1, ro), imu=torch.randn(33, A, 3))
+        for dtype in (torch.float32, torch.float16, torch.uint8):
+            p = sharding.PackedObs(A, ro, dtype)
+            want = p.pack(obs, p.empty(33, 'cpu'))
+            got = p.pack(arrdict({k: v.cuda() for k, v in obs.items()}), torch.zeros((33, p.width), dtype=dtype, device='cuda'))
+            v, w = p.views(got.cpu()), p.views(want)
+            for k in ('rgb', 'd', 'imu'):
+                assert torch.equal(v[k], w[k]), (A, ro, dtype, k)
