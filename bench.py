@@ -59,6 +59,7 @@ def parse():
     ap.add_argument('--no-raw', action='store_true', help='skip materialising the five Render tensors (obs heads only)')
     ap.add_argument('--gather', action='store_true', help='all-gather the observations to every rank each step (NCCL, side stream, overlapping the next step)')
     ap.add_argument('--obs-dtype', default='float32', choices=['float32', 'float16', 'uint8'], help='precision of the gathered observations (uint8: rgb and depth quantised to 8 bits, imu as fp16)')
+    ap.add_argument('--gather-transport', default='nccl', choices=['nccl', 'p2p'], help='nccl: all_gather_into_tensor; p2p: symmetric memory + copy-engine peer copies (no SMs)')
     ap.add_argument('--distinct-shards', action='store_true', help='every rank builds its own floorplans / poses / actions (seeds + rank) instead of a replica of rank 0\'s shard')
     ap.add_argument('--no-graph', action='store_true', help='e2e leg: plain launches instead of a CUDA-graph replay')
     ap.add_argument('--e2e', default='torch', choices=['native', 'torch'], help='e2e leg: the library\'s own host-driven graph (one call per tick) or a torch CUDA graph between PyTorch copies')
@@ -331,7 +332,7 @@ def run_gpu(args, cfg, arm_cls, rank, world, local_rank):
         arm.step()
         # ShardedCore's collective: rows packed per env, ONE all_gather_into_tensor on a side stream, double-buffered
         packing = sharding.PackedObs(A, cfg['res'] // cfg['subsample'], getattr(torch, args.obs_dtype))
-        gather = sharding.RowGather(packing, N, device)
+        gather = sharding.RowGather(packing, N, device, transport=args.gather_transport)
 
     def barrier():
         if world > 1:
@@ -532,7 +533,7 @@ def main():
         'step_ms_percentiles': {p: float(np.percentile(out['per_step_ms'], p)) for p in (5, 50, 95)},
     }
     if out.get('gather_bytes') is not None:
-        line['gather'] = {'what': 'observations packed per env, one NCCL all_gather_into_tensor per step on a side stream (overlaps the next step), every rank receives the whole batch', 'dtype': args.obs_dtype, 'bytes_received_per_rank_per_step': out['gather_bytes'],
+        line['gather'] = {'what': 'observations packed per env (one launch), ' + ('one NCCL all_gather_into_tensor' if args.gather_transport == 'nccl' else 'copy-engine peer copies out of symmetric memory between two barriers') + ' per step on a side stream (overlaps the next step), every rank receives the whole batch', 'transport': args.gather_transport, 'dtype': args.obs_dtype, 'bytes_received_per_rank_per_step': out['gather_bytes'],
                           'achieved_GBps_per_rank': out['gather_bytes'] / (out['step_ms'] / K * 1e-3) / 1e9}
     if reference:
         line['cpu_baseline'] = {'value': value, 'unit': 'agent-frames/s', 'cores': 0, 'kind': 'reference',

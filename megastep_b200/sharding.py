@@ -182,12 +182,12 @@ class ShardedCore:
     `(lo, hi) -> arrays` that builds only this rank's envs. Envs are split into contiguous ranges (`shard_range`); each
     rank owns its scenery, agents and parameters. The only collective is `gather()`: the observation heads are packed
     one row per env (`PackedObs`) and all-gathered with ONE `all_gather_into_tensor` on a side stream, so that it
-    overlaps the next `step()`; `gather_start()` / `gather_wait()` split it. `obs_dtype=torch.float16` halves the bytes
-    on the wire.
+    overlaps the next `step()`; `gather_start()` / `gather_wait()` split it. `obs_dtype=torch.float16` / `torch.uint8`
+    halve / quarter the bytes on the wire; `transport='p2p'` moves them with the copy engines (see `RowGather`).
     """
 
     def __init__(self, arrays, n_envs, n_agents=None, res=64, fov=130., fps=10., subsample=1, raw=False, obs_dtype=torch.float32,
-                 group=None, device=None, graph=False, positions=None, angles=None):
+                 group=None, device=None, graph=False, positions=None, angles=None, transport='nccl'):
         from . import core as core_, cuda, modules, scene
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -211,6 +211,7 @@ class ShardedCore:
             self.core.agents.angles.copy_(torch.as_tensor(angles[self.lo:self.hi]))
         self.stepper = modules.FusedStep(self.core, subsample=subsample, raw=raw, graph=graph)
         self.packing = PackedObs(self.core.n_agents, res // subsample, obs_dtype)
+        self.transport = transport
         self._gatherer = None
         self._out = None
 
@@ -226,7 +227,7 @@ class ShardedCore:
     def gather_start(self):
         """Pack the latest observations and start all-gathering them on the side stream."""
         if self._gatherer is None:
-            self._gatherer = RowGather(self.packing, self.n_local, self.device, self.group)
+            self._gatherer = RowGather(self.packing, self.n_local, self.device, self.group, self.transport)
         self._gatherer.start(self._out.obs)
 
     def gather_wait(self):
@@ -239,14 +240,31 @@ class ShardedCore:
 
 
 class RowGather:
-    """One `all_gather_into_tensor` of per-env packed rows, double-buffered so that the gather of tick t may still be in
-    flight (side stream) while tick t+1 runs and packs into the other buffer."""
+    """The all-gather of per-env packed rows, double-buffered so that the gather of tick t may still be in flight (side
+    stream) while tick t+1 runs and packs into the other buffer. Two transports:
 
-    def __init__(self, packing, n_local, device, group=None):
-        self.packing, self.group = packing, group
+      'nccl'  one `all_gather_into_tensor` per step (NCCL over NVLink / NVSwitch): its kernel shares the SMs with the step;
+      'p2p'   the rows live in symmetric memory (torch.distributed._symmetric_memory: every rank maps every peer's
+              buffer) and each rank PULLS its peers' rows with plain device-to-device copies between two barriers — the
+              copy engines move the bytes over NVLink, no SM is taken from the step that runs meanwhile (the pattern of
+              torch's own `_low_contention_all_gather`).
+    """
+
+    def __init__(self, packing, n_local, device, group=None, transport='nccl'):
+        self.packing, self.group, self.transport = packing, group, transport
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.cuda = torch.device(device).type == 'cuda'
-        self.rows = [packing.empty(n_local, device) for _ in range(2)]
+        if transport == 'p2p' and not (self.cuda and self.world > 1):
+            self.transport = transport = 'nccl'
+        self.handles = None
+        if transport == 'p2p':
+            import torch.distributed._symmetric_memory as symm
+            pg = group if group is not None else dist.group.WORLD
+            self.rows = [symm.empty((n_local, packing.width), dtype=packing.dtype, device=torch.device(device)) for _ in range(2)]
+            self.handles = [symm.rendezvous(r, pg) for r in self.rows]
+        else:
+            self.rows = [packing.empty(n_local, device) for _ in range(2)]
         self.full = [packing.empty(n_local * self.world, device) for _ in range(2)]
         self.stream = torch.cuda.Stream(device=device, priority=-1) if self.cuda else None
         self.done = [None, None]
@@ -262,10 +280,18 @@ class RowGather:
             self.packing.pack(obs, self.rows[i])
             self.stream.wait_stream(main)
             with torch.cuda.stream(self.stream):
-                if self.world > 1:
-                    dist.all_gather_into_tensor(self.full[i], self.rows[i], group=self.group)
-                else:
+                if self.world == 1:
                     self.full[i].copy_(self.rows[i])
+                elif self.transport == 'p2p':
+                    h, rows = self.handles[i], self.rows[i]
+                    chunks = self.full[i].chunk(self.world)
+                    h.barrier()                                # every rank has packed its rows
+                    for step in range(self.world):             # own rows first, then the peers', each rank starting elsewhere
+                        r = (self.rank - step) % self.world
+                        chunks[r].copy_(h.get_buffer(r, rows.shape, rows.dtype))
+                    h.barrier()                                # every rank has read them: they may be packed over
+                else:
+                    dist.all_gather_into_tensor(self.full[i], self.rows[i], group=self.group)
                 self.done[i] = torch.cuda.Event()
                 self.done[i].record(self.stream)
         else:

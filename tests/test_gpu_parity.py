@@ -473,6 +473,28 @@ def test_second_pass_inline_and_overflow_paths_agree(sub):
         assert _same(outs[0][1], screen) and _same(outs[0][2], rgb), mode
 
 
+def test_static_geometry_edited_in_place_is_seen_after_invalidate():
+    """The side tables (spatial table, visibility grid) are built once per Scenery: after moving a wall in place,
+    Scenery.invalidate() makes the kernels see it — same results as a scenery built from the edited arrays."""
+    gs, arrays, st = make('synthetic', 5, 2, seed=81)
+    c = common.to_device(arrays, st, 64, 100.)
+    before = c.render()
+    AF = 2 * 8
+    lo = int(c.scenery.lines.starts[0]) + AF
+    c.scenery.lines.vals[lo:lo + 40] += .37                      # shift forty walls of env 0
+    c.scenery.invalidate()
+    fresh = c.render()
+    edited = dict(arrays)
+    edited['lines'] = arrays['lines'].copy()
+    edited['lines'][lo:lo + 40] += np.float32(.37)
+    c2 = common.to_device(edited, st, 64, 100.)
+    want = c2.render()
+    torch.cuda.synchronize()
+    assert not torch.equal(fresh.indices[0], before.indices[0])
+    for k in ('indices', 'locations', 'dots', 'distances', 'screen'):
+        assert _same(getattr(fresh, k), getattr(want, k)), k
+
+
 def test_native_table_builder_equals_the_torch_restatement():
     """msb_build_table (sort-tile-recursive packing by two shared-memory sorts) against cuda._occluder_table, bit for
     bit: rows, records, run boxes, per-env summary; ragged envs including ones with no static line at all."""

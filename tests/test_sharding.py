@@ -176,8 +176,9 @@ def _nccl_worker(rank, world, port, q):
         N, A = 12, 4
         arrays, pos, ang = _scene_for_shards(N, A)
         ok = True
-        for dtype, tol in ((torch.float32, 0.), (torch.float16, 2e-3), (torch.uint8, 2.1e-3)):
-            sc = sharding.ShardedCore(arrays, N, res=128, fov=70., subsample=1, obs_dtype=dtype, positions=pos, angles=ang)
+        for dtype, tol, transport in ((torch.float32, 0., 'nccl'), (torch.float16, 2e-3, 'nccl'), (torch.uint8, 2.1e-3, 'nccl'),
+                                      (torch.float32, 0., 'p2p'), (torch.uint8, 2.1e-3, 'p2p')):
+            sc = sharding.ShardedCore(arrays, N, res=128, fov=70., subsample=1, obs_dtype=dtype, positions=pos, angles=ang, transport=transport)
             # the same batch, whole, on this rank's GPU
             s = scene.upload(arrays)
             cuda.bake(s, params=cuda.make_params(common.AGENT_RADIUS, 128, 70., 10.))
