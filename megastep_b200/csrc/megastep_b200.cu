@@ -2261,27 +2261,57 @@ __global__ void __launch_bounds__(256) respawn_kernel(const uint8_t* __restrict_
 // ---------------------------------------------------------------------------------------------------------------
 // pack_obs_kernel: the three observation heads of a batch into one row per env, [rgb | d | imu], in one pass — the send
 // buffer of ShardedCore's all-gather (sharding.PackedObs) — as fp32, fp16, or 8-bit images with an fp16 imu.
-// One thread per row element. Same values as the PyTorch form: x -> half by round-to-nearest-even; x -> uint8 as
+// Same values as the PyTorch form: x -> half by round-to-nearest-even; x -> uint8 as
 // clamp(round_half_even(255 x), 0, 255).
 // ---------------------------------------------------------------------------------------------------------------
 #include <cuda_fp16.h>
+template <typename T> struct Pack4 { T v[4]; };
+
+__device__ __forceinline__ unsigned char quant8(float x) { return (unsigned char)fminf(fmaxf(rintf(__fmul_rn(x, 255.f)), 0.f), 255.f); }
+
+// grid (ceil(units / 256), N): blockIdx.y = env, no division anywhere. VEC: the image part moves four pixels per thread
+// (float4 in, 4 / 8 / 16 bytes out) — needs 4 | A * 3 * ro and 4 | A * ro; the imu (3 A values) goes one per thread.
+template <bool VEC>
 __global__ void __launch_bounds__(256) pack_obs_kernel(const float* __restrict__ rgb, const float* __restrict__ d,
-                                                       const float* __restrict__ imu, unsigned char* rows, int64_t n_envs, int n_img_rgb,
-                                                       int n_img_d, int n_imu, int64_t row_bytes, int mode, int imu_off) {
-    const int per_env = n_img_rgb + n_img_d + n_imu;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_envs * per_env) return;
-    const int64_t n = i / per_env;
-    const int e = (int)(i - n * per_env);
-    float x;
-    if (e < n_img_rgb) x = __ldg(rgb + n * n_img_rgb + e);
-    else if (e < n_img_rgb + n_img_d) x = __ldg(d + n * n_img_d + (e - n_img_rgb));
-    else x = __ldg(imu + n * n_imu + (e - n_img_rgb - n_img_d));
+                                                       const float* __restrict__ imu, unsigned char* rows, int n_img_rgb, int n_img_d,
+                                                       int n_imu, int64_t row_bytes, int mode, int imu_off) {
+    const int64_t n = blockIdx.y;
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned char* row = rows + n * row_bytes;
-    if (mode == 0) reinterpret_cast<float*>(row)[e] = x;
-    else if (mode == 1) reinterpret_cast<__half*>(row)[e] = __float2half_rn(x);
-    else if (e < n_img_rgb + n_img_d) row[e] = (unsigned char)fminf(fmaxf(rintf(__fmul_rn(x, 255.f)), 0.f), 255.f);
-    else reinterpret_cast<__half*>(row + imu_off)[e - n_img_rgb - n_img_d] = __float2half_rn(x);
+    const int n_img = n_img_rgb + n_img_d;
+    const int W = VEC ? 4 : 1;
+    const int img_units = n_img / W;
+    if (u < img_units) {
+        const int e = u * W;
+        const float* src = e < n_img_rgb ? rgb + n * n_img_rgb + e : d + n * n_img_d + (e - n_img_rgb);
+        float x[4];
+        if (VEC) { const float4 v = __ldg(reinterpret_cast<const float4*>(src)); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+        else x[0] = __ldg(src);
+        if (mode == 0) {
+            if (VEC) *reinterpret_cast<float4*>(row + 4 * (size_t)e) = make_float4(x[0], x[1], x[2], x[3]);
+            else reinterpret_cast<float*>(row)[e] = x[0];
+        } else if (mode == 1) {
+            if (VEC) {
+                Pack4<__half> h;
+#pragma unroll
+                for (int i = 0; i < 4; i++) h.v[i] = __float2half_rn(x[i]);
+                *reinterpret_cast<uint2*>(row + 2 * (size_t)e) = *reinterpret_cast<uint2*>(&h);
+            } else reinterpret_cast<__half*>(row)[e] = __float2half_rn(x[0]);
+        } else {
+            if (VEC) {
+                Pack4<unsigned char> q;
+#pragma unroll
+                for (int i = 0; i < 4; i++) q.v[i] = quant8(x[i]);
+                *reinterpret_cast<uint32_t*>(row + e) = *reinterpret_cast<uint32_t*>(&q);
+            } else row[e] = quant8(x[0]);
+        }
+    } else if (u < img_units + n_imu) {
+        const int j = u - img_units;
+        const float x = __ldg(imu + n * n_imu + j);
+        if (mode == 0) reinterpret_cast<float*>(row)[n_img + j] = x;
+        else if (mode == 1) reinterpret_cast<__half*>(row)[n_img + j] = __float2half_rn(x);
+        else reinterpret_cast<__half*>(row + imu_off)[j] = __float2half_rn(x);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -3043,9 +3073,19 @@ extern "C" int msb_pack_obs(const float* rgb, const float* depth, const float* i
     if (!rgb || !depth || !imu || !rows || mode < 0 || mode > 2) return fail("%s", "msb_pack_obs: bad argument");
     if (n_envs == 0) return 0;
     const int n_rgb = n_agents * 3 * ro, n_d = n_agents * ro, n_imu = n_agents * 3;
-    const int64_t total = n_envs * (int64_t)(n_rgb + n_d + n_imu);
-    pack_obs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(rgb, depth, imu, reinterpret_cast<unsigned char*>(rows),
-                                                                                         n_envs, n_rgb, n_d, n_imu, row_bytes, mode, imu_offset);
-    g_launches++;
+    if (n_envs > 65535 * 1024ll) return fail("%s", "msb_pack_obs: too many envs for one launch");
+    const int64_t out_align = mode == 0 ? 16 : (mode == 1 ? 8 : 4);          // four pixels of output
+    const bool vec = n_rgb % 4 == 0 && n_d % 4 == 0 && row_bytes % out_align == 0 && ((uintptr_t)rows % out_align) == 0 &&
+                     ((uintptr_t)rgb % 16) == 0 && ((uintptr_t)depth % 16) == 0;
+    const int units = (n_rgb + n_d) / (vec ? 4 : 1) + n_imu;
+    // (gridDim.y is capped at 65535: fold the envs of a larger batch into successive launches)
+    for (int64_t n0 = 0; n0 < n_envs; n0 += 65535) {
+        const int64_t nn = n_envs - n0 < 65535 ? n_envs - n0 : 65535;
+        dim3 grid((unsigned)((units + 255) / 256), (unsigned)nn);
+        unsigned char* out = reinterpret_cast<unsigned char*>(rows) + n0 * row_bytes;
+        if (vec) pack_obs_kernel<true><<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(rgb + n0 * n_rgb, depth + n0 * n_d, imu + n0 * n_imu, out, n_rgb, n_d, n_imu, row_bytes, mode, imu_offset);
+        else pack_obs_kernel<false><<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(rgb + n0 * n_rgb, depth + n0 * n_d, imu + n0 * n_imu, out, n_rgb, n_d, n_imu, row_bytes, mode, imu_offset);
+        g_launches++;
+    }
     return check(cudaGetLastError(), "pack_obs_kernel launch");
 }
