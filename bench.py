@@ -9,7 +9,7 @@ five Render tensors materialised, as the reference's render() does) -> RGB/Depth
   * ours:      msb_step through the C ABI: movement+physics kernel, render+heads kernel, agent-hit lighting kernel —
                three back-to-back launches (replayed as one CUDA graph), no host round trip.
   * reference: the reference's OWN kernels.cu/wrappers.cpp built unmodified for sm_100a (oracle/_ref) driven by the
-               reference's OWN unmodified Python (oracle/_ref/site: core.Core, modules.MomentumMovement / render / RGB /
+               reference's OWN unmodified Python (baseline/_ref: core.Core, modules.MomentumMovement / render / RGB /
                Depth / IMU) through tests/common.py::reference_package — the same shim the parity tests use. megastep
                has no CPU step path (docs/faq.rst:23-27), so this — not a CPU run — is the reference arm; if oracle/_ref
                is not loadable the arm falls back to timing the CPU oracle port on the host cores.
@@ -265,7 +265,7 @@ class Ours:
 
 class Reference:
     """The reference's own CUDA build (oracle/_ref/megastepcuda*.so) driven by the reference's own, unmodified Python
-    (oracle/_ref/site/megastep: core.Core, modules.MomentumMovement :106-118, modules.render :126-136, Depth :170-184,
+    (baseline/_ref/megastep: core.Core, modules.MomentumMovement :106-118, modules.render :126-136, Depth :170-184,
     RGB :211-224, IMU :263-270) — through tests/common.py::reference_package, the same shim the parity tests use.
     Nothing of this repository's library is on that path (it is not even loaded into the process)."""
     name = 'reference'

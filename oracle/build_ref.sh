@@ -17,15 +17,18 @@ if [ ! -f "$SRC/kernels.cu" ]; then
 fi
 mkdir -p "$OUT"
 PY=${PYTHON:-python}
-# The reference's PYTHON package (megastep/, rebar/), installed — not copied into the repo — next to the extension:
-# the parity tests and `bench.py --impl reference` drive the reference's own unmodified modules.py / core.py / scene.py
-# / demo envs through it (tests/common.py::reference_package). pip builds in the source tree, so install from a copy.
-if [ ! -f "$OUT/site/megastep/modules.py" ] || [ "$REF/megastep/modules.py" -nt "$OUT/site/megastep/modules.py" ]; then
+# The reference's PYTHON package (megastep/, rebar/), pip-installed — not copied into the repo — into baseline/_ref (the
+# git-ignored directory the bench contract names for the installed reference; it travels to the GPU box): the parity tests
+# and `bench.py --impl reference` drive the reference's own unmodified modules.py / core.py / scene.py / demo envs through
+# it (tests/common.py::reference_package). pip builds in the source tree, so install from a copy under /tmp.
+SITE="$HERE/../baseline/_ref"
+if [ ! -f "$SITE/megastep/modules.py" ] || [ "$REF/megastep/modules.py" -nt "$SITE/megastep/modules.py" ]; then
     TMP=$(mktemp -d)
     cp -r "$REF" "$TMP/reference"
-    rm -rf "$OUT/site"
+    rm -rf "$SITE" "$OUT/site"
+    mkdir -p "$SITE"
     $PY -m pip install --quiet --no-index --no-build-isolation --no-deps --find-links /opt/wheelhouse \
-        --target "$OUT/site" "$TMP/reference" >/dev/null 2>&1 && echo "build_ref: installed the reference package into $OUT/site" \
+        --target "$SITE" "$TMP/reference" >/dev/null 2>&1 && echo "build_ref: installed the reference package into baseline/_ref" \
         || echo "build_ref: pip install of the reference package failed (tests that drive its Python will skip)" >&2
     rm -rf "$TMP"
 fi

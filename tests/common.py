@@ -138,7 +138,7 @@ def index_agreement(a, b, dist_a, dist_b, tol=2e-3):
 
 # ----------------------------------------------------------------------------------------------------------------------
 # The reference's own PYTHON package as a checker: megastep/{core,modules,scene,ragged}.py and the demo
-# envs, unmodified, as pip-installed by oracle/build_ref.sh into oracle/_ref/site (git-ignored, travels to the GPU box),
+# envs, unmodified, as pip-installed by oracle/build_ref.sh into baseline/_ref (git-ignored, travels to the GPU box),
 # running on the reference's own extension build (oracle/_ref/megastepcuda*.so). The package's __init__ (a JIT build
 # with -std=c++14 that torch >= 2 rejects) is bypassed; matplotlib / rasterio / shapely / bs4, absent from this image
 # and used by none of the code the checker runs, are stubbed.
@@ -183,13 +183,13 @@ def _stub_absent_modules():
 
 def reference_package():
     """Namespace with the reference's own `core`, `modules`, `scene`, `ragged`, `spaces`, `cuda` (its extension) and
-    `envs` (explorer / deathmatch modules), or None when oracle/_ref (extension + site) is not built."""
+    `envs` (explorer / deathmatch modules), or None when oracle/_ref (extension) or baseline/_ref (package) is not built."""
     global _REFPKG
     if _REFPKG is not None:
         return _REFPKG or None
     import sys
     import types
-    site = os.path.join(ROOT, 'oracle', '_ref', 'site')
+    site = os.path.join(ROOT, 'baseline', '_ref')
     ext = reference_module()
     if ext is None or not os.path.exists(os.path.join(site, 'megastep', 'modules.py')):
         _REFPKG = False

@@ -1,7 +1,7 @@
 """Parity against the reference's OWN Python + its OWN CUDA build (tests/common.py::reference_package).
 
 The checker here is the unmodified megastep/{core,modules,scene}.py and megastep/demo/envs/{explorer,deathmatch}.py of
-the reference (pip-installed by oracle/build_ref.sh into oracle/_ref/site), driving the reference's own extension
+the reference (pip-installed by oracle/build_ref.sh into baseline/_ref), driving the reference's own extension
 (oracle/_ref/megastepcuda*.so). Compared with it, from identical state and with no resynchronisation in between:
 
   * `modules.FusedStep` — the path bench.py times — at BASELINE.json's full sizes (Deathmatch 4096 x 4 x 128 and
