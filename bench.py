@@ -352,6 +352,10 @@ def run_gpu(args, cfg, arm_cls, rank, world, local_rank):
     for i in range(W):
         arm.actions.copy_(acts_dev[i])
         arm.step()
+        if gather is not None:
+            gather.start(arm.obs())           # (the collective's first calls set up its channels / peer mappings)
+    if gather is not None:
+        gather.wait()
     barrier()
     if sampler:
         sampler.mark()
