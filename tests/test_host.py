@@ -497,3 +497,66 @@ def test_demo_envs_wiring_on_a_fake_core(monkeypatch):
     assert (dm._health <= 1).all() and dm.matchings.shape == (3, 2, 2)
     # health only ever drops between respawns: by 0.001 per step plus 0.05 per wound
     assert (dm._health < 1).all()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# round 2 host logic
+# ----------------------------------------------------------------------------------------------------------------------
+def test_tile_arrays_cycles_through_the_envs():
+    import numpy as np
+    from megastep_b200 import scene, sharding, synthetic
+    gs = synthetic.sample(5, seed=3)
+    base = scene.scene_arrays(gs, 2, np.random.RandomState(0))
+    base['baked'] = np.arange(len(base['textures']), dtype=np.float32)
+    for n in (5, 7, 10, 13):
+        tiled = synthetic.tile_arrays(base, n)
+        assert len(tiled['line_widths']) == n
+        for i in range(n):
+            one, ref = sharding.shard_arrays(tiled, i, i + 1), sharding.shard_arrays(base, i % 5, i % 5 + 1)
+            for k in ('lines', 'line_widths', 'lights', 'light_widths', 'textures', 'tex_widths', 'baked'):
+                np.testing.assert_array_equal(one[k], ref[k])
+
+
+def test_spawns_land_inside_rooms_whether_or_not_envs_share_a_floorplan():
+    import numpy as np
+    from megastep_b200 import synthetic
+    for n_unique in (6, 2):
+        gs = synthetic.sample(6, seed=4, n_unique=n_unique)
+        pos, ang = synthetic.spawns(gs, 3, np.random.RandomState(1))
+        assert pos.shape == (6, 3, 2) and ang.shape == (6, 3) and (ang >= -180).all() and (ang < 180).all()
+        for n, g in enumerate(gs):
+            r = g['rooms']
+            inside = ((pos[n, :, None, 0] >= r[None, :, 0]) & (pos[n, :, None, 0] <= r[None, :, 2]) &
+                      (pos[n, :, None, 1] >= r[None, :, 1]) & (pos[n, :, None, 1] <= r[None, :, 3])).any(1)
+            assert inside.all()
+        if n_unique == 2:                                       # copies of a floorplan still get their own poses
+            assert not np.array_equal(pos[0], pos[2])
+
+
+def test_scene_building_does_not_load_the_native_library():
+    """bench.py's reference arm builds its scenes with this package: that must not map libmegastep_b200.so."""
+    import subprocess
+    import sys
+    code = ("import sys, numpy as np; from megastep_b200 import scene, synthetic, sharding, geometry, toys; "
+            "scene.scene_arrays(synthetic.sample(2, seed=1), 2, np.random.RandomState(0)); "
+            "assert 'megastep_b200.cuda' not in sys.modules and 'megastep_b200.core' not in sys.modules; print('clean')")
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd=common.ROOT)
+    assert out.returncode == 0 and 'clean' in out.stdout, out.stderr[-500:]
+
+
+def test_package_exposes_its_submodules_lazily():
+    import megastep_b200
+    for name in ('envs', 'cubicasa', 'sharding', 'synthetic', 'constants'):
+        assert getattr(megastep_b200, name).__name__ == f'megastep_b200.{name}'
+
+
+def test_spawn_points_without_masks_fall_back_to_the_rooms():
+    import numpy as np
+    from megastep_b200 import modules, synthetic
+    gs = synthetic.sample(3, seed=2)                            # no masks
+    pts = modules.random_empty_positions(gs, 2, 7, random=np.random.RandomState(0))
+    assert pts.shape == (3, 2, 7, 2)
+    for n, g in enumerate(gs):
+        r = g['rooms']
+        p = pts[n].reshape(-1, 2)
+        assert ((p[:, None, 0] >= r[None, :, 0]) & (p[:, None, 0] <= r[None, :, 2]) & (p[:, None, 1] >= r[None, :, 1]) & (p[:, None, 1] <= r[None, :, 3])).any(1).all()
