@@ -91,6 +91,8 @@ def item(rows, boxes, pos, ang, r0, nch, R, hs, run, per_batch, others, model_ra
     bsmin = np.maximum(xmin - 1e-3 - 1e-4 * np.maximum(np.abs(xmin), np.abs(xmax)), 0.)
     todo = bcm.any(1)
     groups = tests = 0
+    whatif = np.zeros(4)        # tests that moved some ray's hit; tests left if culled against the span's own farthest hit;
+                                # iterations if candidates with disjoint ray spans shared one (= deepest overlap); chunks
     segX, segY = camera(rows.reshape(-1, 2, 2))                            # (W, 2 endpoints)
     seg_cm = masks(segX, segY) & ~((segX < xclip).all(1))[:, None]
     seg_smin = segX.min(1) - 1e-3 - 1e-4 * np.abs(segX).max(1)
@@ -110,15 +112,23 @@ def item(rows, boxes, pos, ang, r0, nch, R, hs, run, per_batch, others, model_ra
             cand = segs[seg_cm[segs, c] & ~(seg_smin[segs] > cmax[c] + CULL_EPS)]
             tests += len(cand)
             lanes = slice(32 * c, 32 * c + 32)
+            depth = np.zeros(32, int)
             for j in cand:
                 UxV = ru[lanes, 0] * V[j, 1] - ru[lanes, 1] * V[j, 0]
                 with np.errstate(divide='ignore', invalid='ignore'):
                     s = snum[j] / UxV
                     t = (ru[lanes, 1] * PQ[j, 0] - ru[lanes, 0] * PQ[j, 1]) / UxV
-                hit = (np.abs(UxV) >= 1e-3) & (t >= 0) & (t <= 1) & (nearp[lanes] < s) & (s < best[lanes])
+                span = (np.abs(UxV) >= 1e-3) & (t >= 0) & (t <= 1)
+                hit = span & (nearp[lanes] < s) & (s < best[lanes])
+                whatif[0] += hit.any()
+                if span.any() and not (seg_smin[j] > best[lanes][span].max() + CULL_EPS):
+                    whatif[1] += 1
+                    depth += span
                 best[lanes] = np.where(hit, s, best[lanes])
             if len(cand):
                 cmax[c] = best[lanes].max()
+                whatif[2] += depth.max()
+                whatif[3] += 1
     # the agents' own batch: skipped unless another agent's disc is in sight (view_agent's test)
     rho = model_radius * 1.001 + 1e-3
     Bn = bounds[-1]
@@ -132,7 +142,7 @@ def item(rows, boxes, pos, ang, r0, nch, R, hs, run, per_batch, others, model_ra
         if not (behind or left or right or hidden):
             agent_groups = 1
             break
-    return groups, tests, agent_groups, best
+    return groups, tests, agent_groups, best, whatif
 
 
 def main():
@@ -153,6 +163,7 @@ def main():
     model_radius = np.abs(scene.agent_model()).reshape(-1, 2)
     model_radius = np.hypot(model_radius[:, 0], model_radius[:, 1]).max()
     tot = np.zeros(3)
+    wi = np.zeros(4)
     items = 0
     for n, g in enumerate(gs):
         walls = np.asarray(g.walls, dtype=np.float64).reshape(-1, 4)
@@ -166,11 +177,15 @@ def main():
                 if args.hint:
                     res = item(*common_args, hint=res[3])
                 tot += res[:3]
+                wi += res[4]
                 items += 1
     g, t, ag = tot / items
     print(f'{vars(args)}\nitems {items}: static batches {g:.2f} + agent batches {ag:.2f} = {g + ag:.2f} per item '
           f'({(g + ag) * items / (args.envs * args.agents):.2f} per agent); candidate tests {t:.1f} per item ({t * items / (args.envs * args.agents):.1f} per agent) '
           f'[static only]; segments binned {g * args.run * args.runs_per_batch:.0f} per item')
+    print(f'what if, per item: tests that move some ray\'s hit {wi[0] / items:.1f}; tests left when a segment is culled against the farthest hit '
+          f'of ITS OWN ray span {wi[1] / items:.1f}; iterations if span-disjoint candidates shared one {wi[2] / items:.1f} '
+          f'(over {wi[3] / items:.2f} non-empty chunk rounds per item)')
 
 
 if __name__ == '__main__':
